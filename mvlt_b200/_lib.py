@@ -1,0 +1,84 @@
+"""ctypes binding of the C-ABI library (``include/mvlt_b200.h``).
+
+There is NO CPU fallback: every op in this package enqueues hand-written sm_100a kernels from
+``libmvlt_b200.so`` on the current CUDA stream. Loading fails loudly when the library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_LIBPATH = Path(__file__).resolve().parent / "lib" / "libmvlt_b200.so"
+_lib = None
+
+
+class MvltError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("B", C.c_void_p), ("D", C.c_void_p), ("D2", C.c_void_p),
+        ("bias", C.c_void_p), ("aux", C.c_void_p), ("residual", C.c_void_p), ("rowscale", C.c_void_p),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("a_mn", C.c_int32), ("b_mn", C.c_int32),
+        ("lda", C.c_int64), ("ldb", C.c_int64), ("ldd", C.c_int64),
+        ("batch1", C.c_int32), ("batch2", C.c_int32),
+        ("sA1", C.c_int64), ("sA2", C.c_int64), ("sB1", C.c_int64), ("sB2", C.c_int64),
+        ("sD1", C.c_int64), ("sD2", C.c_int64),
+        ("alpha", C.c_float),
+        ("act", C.c_int32), ("out_f32", C.c_int32), ("atomic_add", C.c_int32),
+        ("rows_per_scale", C.c_int32), ("split_k", C.c_int32), ("block_n", C.c_int32),
+    ]
+
+
+ACT_NONE, ACT_GELU, ACT_DGELU = 0, 1, 2
+
+
+def lib_path() -> Path:
+    return _LIBPATH
+
+
+def load():
+    """dlopen the C-ABI library (once). Raises MvltError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIBPATH.exists():
+        raise MvltError(
+            f"{_LIBPATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(mvlt_b200 has no CPU / eager fallback)")
+    _lib = C.CDLL(str(_LIBPATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
+    _lib.mvlt_last_error.restype = C.c_char_p
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().mvlt_last_error().decode(errors="replace")
+        raise MvltError(f"{what} failed (rc={rc}): {msg}")
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MvltError("mvlt_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
+
+
+def call(name: str, *args):
+    """Call ``int mvlt_<name>(..., void* stream)`` with the current torch stream appended."""
+    fn = getattr(load(), "mvlt_" + name)
+    check(fn(*args, stream_ptr()), "mvlt_" + name)

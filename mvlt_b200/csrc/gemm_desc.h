@@ -1,0 +1,49 @@
+// Plain-C description of one (strided-batched) GEMM launch. Shared by include/mvlt_b200.h (C-ABI),
+// the tcgen05 kernel and the SIMT cross-check kernel.
+//
+//   D[b1,b2][m,n] = epilogue( alpha * sum_k A[b1,b2][m,k] * B[b1,b2][n,k] )
+//
+// A is M x K, B is N x K (i.e. D = A * B^T in BLAS terms). Each operand is bf16 and either
+//   K-major  (x_mn = 0): element (r,k) at  base + r*ld + k      (the reference's nn.Linear weight layout)
+//   MN-major (x_mn = 1): element (r,k) at  base + k*ld + r      (a transposed view, no copy)
+// so the three GEMMs of a Linear layer (y = x W^T, dx = dy W, dW = dy^T x) and the four batched
+// products of attention all map onto this one descriptor without materialising a transpose.
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  MVLT_ACT_NONE = 0,
+  MVLT_ACT_GELU = 1,   // D = gelu_erf(v); optional D2 = v (pre-activation, bf16) for the backward pass
+  MVLT_ACT_DGELU = 2,  // D = v * gelu_erf'(aux[m,n])   (aux = saved pre-activation, bf16)
+};
+
+typedef struct mvlt_gemm_desc {
+  const void* A;  // bf16
+  const void* B;  // bf16
+  void* D;        // bf16 or fp32 (out_f32)
+  void* D2;       // optional second bf16 output (pre-activation) or NULL
+  const float* bias;      // [N] fp32 or NULL; added after alpha scaling
+  const void* aux;        // bf16 [.., M, N] with D's strides, for MVLT_ACT_DGELU
+  const float* residual;  // fp32 with D's strides or NULL:  D = residual + rowscale * v
+  const float* rowscale;  // fp32 [ceil(M / rows_per_scale)] or NULL (drop-path keep/scale per sample)
+  int32_t M, N, K;
+  int32_t a_mn, b_mn;
+  int64_t lda, ldb, ldd;  // leading dimensions in ELEMENTS
+  int32_t batch1, batch2;  // >= 1 each; total batch = batch1 * batch2
+  int64_t sA1, sA2, sB1, sB2, sD1, sD2;  // batch strides in elements (0 allowed = broadcast)
+  float alpha;
+  int32_t act;
+  int32_t out_f32;         // 1: D is fp32, 0: bf16
+  int32_t atomic_add;      // 1: D (fp32) += v via red.global.add (split-K / grad accumulation)
+  int32_t rows_per_scale;  // rows of D per rowscale entry
+  int32_t split_k;         // 0/1 = no split; >1 requires atomic_add
+  int32_t block_n;         // 0 = auto
+} mvlt_gemm_desc;
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,156 @@
+"""tcgen05 GEMM (csrc/gemm_tcgen05.cu) vs torch fp32 matmul of the same bf16 operands, through the C-ABI."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _rand(shape, g, scale=1.0):
+    return (torch.randn(shape, generator=g, device="cuda", dtype=F32) * scale).to(BF16)
+
+
+def _ref(a, b):
+    return torch.matmul(a.float(), b.float().transpose(-1, -2))
+
+
+def _check(out, ref, K, tag, atol_scale=1.0):
+    err = (out.float() - ref).abs().max().item()
+    mag = ref.abs().max().item()
+    tol = atol_scale * (1e-2 * mag + 1e-3) if out.dtype == BF16 else atol_scale * (2e-3 * mag + 1e-3)
+    assert err <= tol, f"{tag}: max err {err:.4g} (ref max {mag:.4g}, tol {tol:.4g})"
+
+
+LAYOUTS = [(0, 0), (0, 1), (1, 0), (1, 1)]
+SHAPES = [(128, 64, 64), (256, 128, 128), (300, 192, 200), (1000, 320, 48), (128, 512, 1024), (77, 64, 4096)]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("out_dtype", [BF16, F32])
+def test_gemm_layouts(a_mn, b_mn, M, N, K, out_dtype):
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + a_mn * 2 + b_mn)
+    # storage dims padded to multiples of 8 elements so that the TMA stride rule (16 B) holds
+    def mk(rows, cols, mn):
+        if not mn:
+            st = _rand((rows, (cols + 7) // 8 * 8), g)
+            return st[:, :cols]
+        st = _rand((cols, (rows + 7) // 8 * 8), g)
+        return st[:, :rows].t()
+    a = mk(M, K, a_mn)
+    b = mk(N, K, b_mn)
+    ldd = (N + 7) // 8 * 8
+    out = torch.full((M, ldd), float("nan"), device="cuda", dtype=out_dtype)[:, :N]
+    k.gemm(a, b, out)
+    torch.cuda.synchronize()
+    _check(out, _ref(a, b), K, f"layout a_mn={a_mn} b_mn={b_mn} {M}x{N}x{K}")
+
+
+def test_gemm_matches_simt_ref_bitwise_structure():
+    """Same descriptor through the SIMT cross-check kernel and the tcgen05 kernel."""
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a, b = _rand((512, 256), g), _rand((384, 256), g)
+    o1 = torch.empty((512, 384), device="cuda", dtype=F32)
+    o2 = torch.empty_like(o1)
+    k.gemm(a, b, o1)
+    k.gemm(a, b, o2, impl="ref")
+    torch.cuda.synchronize()
+    assert (o1 - o2).abs().max().item() < 1e-2
+
+
+def test_gemm_epilogues():
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K = 640, 256, 192
+    a, b = _rand((M, K), g, 0.5), _rand((N, K), g, 0.2)
+    bias = torch.randn(N, generator=g, device="cuda")
+    ref = _ref(a, b) * 0.5 + bias
+    # bias + alpha
+    out = torch.empty((M, N), device="cuda", dtype=F32)
+    k.gemm(a, b, out, alpha=0.5, bias=bias)
+    _check(out, ref, K, "bias")
+    # gelu + preact
+    out = torch.empty((M, N), device="cuda", dtype=BF16)
+    pre = torch.empty((M, N), device="cuda", dtype=BF16)
+    k.gemm(a, b, out, alpha=0.5, bias=bias, act=k.ACT_GELU, preact_out=pre)
+    _check(pre, ref, K, "preact")
+    _check(out, torch.nn.functional.gelu(ref), K, "gelu")
+    # dgelu
+    x = ref.to(BF16)
+    xr = x.float().requires_grad_(True)
+    torch.nn.functional.gelu(xr).sum().backward()
+    out = torch.empty((M, N), device="cuda", dtype=BF16)
+    k.gemm(a, b, out, act=k.ACT_DGELU, aux=x)
+    _check(out, _ref(a, b) * xr.grad, K, "dgelu")
+    # residual + rowscale
+    res = torch.randn((M, N), generator=g, device="cuda")
+    rs = torch.rand(M // 64, generator=g, device="cuda")
+    out = torch.empty((M, N), device="cuda", dtype=F32)
+    k.gemm(a, b, out, alpha=0.5, bias=bias, residual=res, rowscale=rs, rows_per_scale=64)
+    _check(out, res + rs.repeat_interleave(64)[:, None] * ref, K, "residual")
+    # in-place residual
+    buf = res.clone()
+    k.gemm(a, b, buf, alpha=0.5, bias=bias, residual=buf)
+    _check(buf, res + ref, K, "residual-inplace")
+    torch.cuda.synchronize()
+
+
+def test_gemm_splitk_atomic():
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(13)
+    Ntok, Co, Ci = 20000, 512, 64
+    dy, x = _rand((Ntok, Co), g, 0.1), _rand((Ntok, Ci), g, 0.1)
+    out = torch.ones((Co, Ci), device="cuda", dtype=F32)
+    k.gemm(dy.t(), x.t(), out, atomic_add=True, split_k=37)
+    torch.cuda.synchronize()
+    ref = 1.0 + dy.float().t() @ x.float()
+    _check(out, ref, Ntok, "splitk")
+
+
+def test_gemm_batched_attention_views():
+    """The four attention products on head-strided views (no permute copies)."""
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(17)
+    B, H, Nq, Nk, D = 3, 5, 384, 192, 64
+    C = H * D
+    q = _rand((B * Nq, C), g, 0.3)
+    kv = _rand((B * Nk, 2 * C), g, 0.3)
+    q4 = q.view(B, Nq, H, D).permute(0, 2, 1, 3)                 # [B,H,Nq,D] K-major
+    k4 = kv.view(B, Nk, 2, H, D)[:, :, 0].permute(0, 2, 1, 3)    # [B,H,Nk,D]
+    v4 = kv.view(B, Nk, 2, H, D)[:, :, 1].permute(0, 2, 1, 3)
+    s = torch.empty((B, H, Nq, Nk), device="cuda", dtype=BF16)
+    k.gemm(q4, k4, s, alpha=0.125)
+    _check(s, 0.125 * q4.float() @ k4.float().transpose(-1, -2), D, "S=QK^T")
+    p = torch.softmax(s.float(), -1).to(BF16)
+    o = torch.empty((B * Nq, C), device="cuda", dtype=BF16)
+    o4 = o.view(B, Nq, H, D).permute(0, 2, 1, 3)
+    k.gemm(p, v4.transpose(-1, -2), o4)                           # B operand logical [D, Nk] MN-major
+    _check(o4, p.float() @ v4.float(), Nk, "O=PV")
+    do = _rand((B * Nq, C), g, 0.3).view(B, Nq, H, D).permute(0, 2, 1, 3)
+    dkv = torch.zeros((B * Nk, 2 * C), device="cuda", dtype=BF16)
+    dv4 = dkv.view(B, Nk, 2, H, D)[:, :, 1].permute(0, 2, 1, 3)
+    k.gemm(p.transpose(-1, -2), do.transpose(-1, -2), dv4)        # dV = P^T dO  (MN, MN)
+    _check(dv4, p.float().transpose(-1, -2) @ do.float(), Nq, "dV=P^T dO")
+    dq = torch.empty((B * Nq, C), device="cuda", dtype=BF16).view(B, Nq, H, D).permute(0, 2, 1, 3)
+    k.gemm(p, k4.transpose(-1, -2), dq)                           # stand-in for dS K
+    _check(dq, p.float() @ k4.float(), Nk, "dQ=dS K")
+    torch.cuda.synchronize()
+
+
+def test_gemm_vocab_shape():
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(19)
+    M, V, H = 1024, 30522, 768
+    h, e = _rand((M, H), g, 0.5), _rand((V, H), g, 0.05)
+    ldd = (V + 7) // 8 * 8
+    logits = torch.empty((M, ldd), device="cuda", dtype=BF16)[:, :V]
+    bias = torch.randn(V, generator=g, device="cuda") * 0.1
+    k.gemm(h, e, logits, bias=bias)
+    _check(logits, _ref(h, e) + bias, H, "vocab fwd")
+    dh = torch.empty((M, H), device="cuda", dtype=F32)
+    k.gemm(logits, e.t(), dh)                                      # dH = dlogits E   (K = vocab, B MN-major)
+    _check(dh, logits.float() @ e.float(), V, "vocab dH", atol_scale=2.0)
+    torch.cuda.synchronize()
