@@ -109,8 +109,7 @@ def make_state_dict(model: str = "pvlt_tiny", loss_type: Optional[Dict[str, int]
     sd["text_embeddings.position_embeddings.weight"] = _tn((MAX_POS, HIDDEN), seed, "position_embeddings", 1.0) * 0.05
     sd["text_embeddings.token_type_embeddings.weight"] = _tn((2, HIDDEN), seed, "token_type_embeddings", 1.0) * 0.05
     lnorm("text_embeddings.LayerNorm", HIDDEN)
-    sd["text_embeddings.position_ids"] = torch.arange(MAX_POS).unsqueeze(0)
-    sd["text_embeddings.token_type_ids"] = torch.zeros((1, MAX_POS), dtype=torch.long)
+    # (position_ids / token_type_ids are non-persistent buffers in transformers >= 4.31: not in the state_dict)
 
     def head_embed(prefix):
         linear(prefix + ".0", HIDDEN, EMBED_DIMS[-1])
@@ -200,7 +199,8 @@ def _lin(x, sd, prefix):
 def bert_embeddings(sd, ids, p_drop=0.0, training=False):
     """transformers BertEmbeddings.forward (absolute positions, token type 0); call site pvlt.py:326."""
     T = ids.shape[1]
-    x = (sd["text_embeddings.word_embeddings.weight"][ids]
+    # padding_idx=0 (BertConfig.pad_token_id): pad rows get no gradient from the gather (SURVEY H6)
+    x = (F.embedding(ids, sd["text_embeddings.word_embeddings.weight"], padding_idx=0)
          + sd["text_embeddings.token_type_embeddings.weight"][0]
          + sd["text_embeddings.position_embeddings.weight"][:T])
     x = _ln(x, sd, "text_embeddings.LayerNorm", 1e-12)

@@ -1,0 +1,94 @@
+"""Pins the oracle (oracle/) against golden vectors recorded from the UNMODIFIED reference
+(tests/golden/make_golden.py, run in the build container where /root/reference exists)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grid_mask as gm
+from oracle import pvlt_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_grid_mask_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "grid_mask_golden.npz"))
+    for seed, grid in zip(g["seeds"], g["grids"]):
+        assert (gm.grid_c(int(seed)) == grid).all(), f"C oracle differs at seed {seed}"
+        assert (gm.grid_py(int(seed)) == grid).all(), f"python oracle differs at seed {seed}"
+    for s, grid in enumerate(g["extra_352_075"]):
+        assert (gm.grid_c(s, (352, 352), 16, 0.75) == grid).all()
+        assert (gm.grid_py(s, (352, 352), 16, 0.75) == grid).all()
+
+
+def test_grid_mask_sliding_window_quirk_statistics():
+    """only the first nh+nw-1 shuffled patches are used -> realised fraction varies widely."""
+    fr = [gm.grid_c(s).mean() for s in range(200)]
+    assert min(fr) < 0.35 and max(fr) > 0.65 and abs(np.mean(fr) - 0.5) < 0.05
+
+
+def test_masked_fill_semantics():
+    img = np.random.RandomState(0).rand(3, 256, 256).astype(np.float32)
+    m = gm.expand(gm.grid_c(3))
+    out = gm.masked_fill(img, m)
+    assert out.dtype == np.float32
+    assert (out[:, m[0] == 1] == np.float32(1e-6)).all() and (out[:, m[0] == 0] == img[:, m[0] == 0]).all()
+
+
+@pytest.mark.parametrize("tag,loss_type", [("pre", {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0}),
+                                           ("cls", {"itm": 0, "mlm": 0, "t2i": 0, "cls": 1})])
+def test_pvlt_oracle_matches_reference_golden(tag, loss_type):
+    g = np.load(os.path.join(GOLD, "pvlt_tiny_golden.npz"))
+    sd = O.make_state_dict("pvlt_tiny", loss_type, seed=0)
+    batch = O.make_inputs(2, seed=0)
+    ls, grads, out = O.train_step_grads(sd, batch, loss_type)
+    for k in ("mlm", "itm", "t2i", "sup_cls", "sub_cls", "total"):
+        if f"{tag}_loss_{k}" in g:
+            assert abs(ls[k] - float(g[f"{tag}_loss_{k}"])) < 2e-5 * max(1.0, abs(ls[k])), k
+    cmp = lambda a, b, tol: np.testing.assert_allclose(a.detach().numpy(), b, rtol=tol, atol=tol)
+    if loss_type["mlm"]:
+        cmp(out["mlm_logits"][:, :8, ::257], g[f"{tag}_mlm_logits_sub"], 2e-5)
+        cmp(torch.logsumexp(out["mlm_logits"], -1), g[f"{tag}_mlm_logits_lse"], 2e-5)
+    if loss_type["itm"]:
+        cmp(out["itm_logits"], g[f"{tag}_itm_logits"], 2e-5)
+    if loss_type["cls"]:
+        cmp(out["sup_cls_logits"], g[f"{tag}_sup_cls_logits"], 2e-5)
+        cmp(out["sub_cls_logits"], g[f"{tag}_sub_cls_logits"], 2e-5)
+    if loss_type["t2i"]:
+        cmp(out["t2i_logits"][:, :, ::16, ::16], g[f"{tag}_t2i_logits_sub"], 5e-5)
+    names = [str(n) for n in g[f"{tag}_grad_names"]]
+    gsum, gabs = g[f"{tag}_grad_sum"], g[f"{tag}_grad_abs"]
+    assert len(names) > 100
+    for n, s, a in zip(names, gsum, gabs):
+        if n == "mlm_head.mlm_decoder.weight":
+            n = "text_embeddings.word_embeddings.weight"
+        mine = grads[n].double()
+        assert abs(mine.abs().sum().item() - a) <= 1e-3 * a + 1e-7, (n, mine.abs().sum().item(), a)
+        assert abs(mine.sum().item() - s) <= 1e-3 * a + 1e-7, (n, mine.sum().item(), s)
+    # eval-mode path (BatchNorm running stats) used by retrieval
+    # (the golden script ran its train-mode forward first, so the reference's BN buffers had one
+    #  momentum-0.1 update; replay that update through the oracle's bn_stats hook)
+    with torch.no_grad():
+        stats = {}
+        O.forward(sd, batch["images"], batch["input_ids"], loss_type, training=True, bn_stats=stats)
+        sde = dict(sd)
+        for p, (rm, rv) in stats.items():
+            sde[p + ".1.running_mean"], sde[p + ".1.running_var"] = rm, rv
+        oe = O.forward(sde, batch["images"], batch["input_ids"], loss_type, training=False)
+    if loss_type["itm"]:
+        cmp(oe["itm_logits"], g[f"{tag}_eval_itm_logits"], 2e-5)
+    if loss_type["t2i"]:
+        cmp(oe["t2i_logits"][:, :, ::16, ::16], g[f"{tag}_eval_t2i_logits_sub"], 5e-5)
+
+
+def test_scores_and_rank():
+    logits = torch.tensor([[[0.1, 0.9]], [[0.8, 0.2]], [[0.3, 0.7]]])
+    assert O.retrieval_rank(logits) == 0
+    logits = torch.tensor([[[0.9, 0.1]], [[0.1, 0.9]], [[0.3, 0.7]]])
+    assert O.retrieval_rank(logits) == 2
+    lg = torch.zeros(1, 4, 10)
+    lg[0, 1, 3] = 1
+    lg[0, 2, 5] = 1
+    assert O.compute_mlm_score(lg, torch.tensor([[-1, 3, 4, -1]])) == 0.5
+    assert O.compute_psnr(torch.zeros(2, 2), torch.zeros(2, 2)) == 100
