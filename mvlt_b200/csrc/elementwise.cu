@@ -1,0 +1,460 @@
+// Memory-bound glue kernels: casts, column sums (bias grads), patchify/unpatchify for the k=s convolutions,
+// strided row copies, batch reductions and the bilinear position-embedding resize (fwd + bwd).
+// All are coalesced and 128-bit vectorised where the layout allows; grids are capped at a multiple of the SM count.
+//
+// Reference ops replaced: the permute/reshape/contiguous copies around /root/reference/libs/pvlt.py:102-104,168,
+// 350-352, F.interpolate at :295-297, torch.cat/split at :107,:346 and autograd's bias/broadcast reductions.
+#include "common.cuh"
+
+namespace {
+
+inline int cap_grid(long long work_items, int threads, int per_sm = 8) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = (long long)mvlt_num_sms() * per_sm;
+  if (b < 1) b = 1;
+  return (int)(b < cap ? b : cap);
+}
+
+// ---- dst_bf16[i] = bf16(src_f32[i] * scale[row / rows_per_scale]) -------------------------------------------
+__global__ void __launch_bounds__(256) cast_scale_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                         long long n8, int C, const float* __restrict__ rowscale,
+                                                         int rows_per_scale, float alpha) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 8;
+    float s = alpha;
+    if (rowscale) s *= rowscale[(e / C) / rows_per_scale];
+    const float4 a = *reinterpret_cast<const float4*>(src + e);
+    const float4 b = *reinterpret_cast<const float4*>(src + e + 4);
+    uint4 u;
+    u.x = pack_bf16x2(a.x * s, a.y * s); u.y = pack_bf16x2(a.z * s, a.w * s);
+    u.z = pack_bf16x2(b.x * s, b.y * s); u.w = pack_bf16x2(b.z * s, b.w * s);
+    *reinterpret_cast<uint4*>(dst + e) = u;
+  }
+}
+
+// ---- out[c] (+)= sum_r x[r*ld + c] ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int C, long long ld,
+                                                     float* __restrict__ out, long long rows_per_block) {
+  __shared__ float sh[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + tx * 2;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      if constexpr (sizeof(T) == 2) {
+        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
+        a0 += f.x; a1 += f.y;
+      } else {
+        const float2 f = *reinterpret_cast<const float2*>(x + r * ld + c);
+        a0 += f.x; a1 += f.y;
+      }
+    }
+  }
+  sh[ty][tx * 2] = a0;
+  sh[ty][tx * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < C) atomicAdd(out + cc, s);
+  }
+}
+
+// ---- patchify: NHWC tokens -> [B*oh*ow, R*R*C] bf16 (k index = (ky*R+kx)*C + c) ------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ src, long long src_batch_stride,
+                                                       __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C,
+                                                       int R) {
+  const int c8n = C / 8;
+  const long long total = (long long)B * H * W * c8n;
+  const int ow = W / R, oh = H / R;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    long long t = i / c8n;
+    const int xw = (int)(t % W); t /= W;
+    const int yh = (int)(t % H);
+    const int b = (int)(t / H);
+    const T* s = src + (long long)b * src_batch_stride + ((long long)yh * W + xw) * C + c8 * 8;
+    uint4 u;
+    if constexpr (sizeof(T) == 2) {
+      u = *reinterpret_cast<const uint4*>(s);
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(s);
+      const float4 bb = *reinterpret_cast<const float4*>(s + 4);
+      u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+      u.z = pack_bf16x2(bb.x, bb.y); u.w = pack_bf16x2(bb.z, bb.w);
+    }
+    const int oy = yh / R, ky = yh % R, ox = xw / R, kx = xw % R;
+    const long long drow = ((long long)b * oh + oy) * ow + ox;
+    *reinterpret_cast<uint4*>(dst + drow * ((long long)R * R * C) + (long long)(ky * R + kx) * C + c8 * 8) = u;
+  }
+}
+
+// inverse: dpatch bf16 [B*oh*ow, R*R*C] -> dst fp32 NHWC rows (writes, does not accumulate)
+__global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                                                         long long dst_batch_stride, int B, int H, int W, int C, int R) {
+  const int c8n = C / 8;
+  const long long total = (long long)B * H * W * c8n;
+  const int ow = W / R, oh = H / R;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    long long t = i / c8n;
+    const int xw = (int)(t % W); t /= W;
+    const int yh = (int)(t % H);
+    const int b = (int)(t / H);
+    const int oy = yh / R, ky = yh % R, ox = xw / R, kx = xw % R;
+    const long long srow = ((long long)b * oh + oy) * ow + ox;
+    const uint4 u = *reinterpret_cast<const uint4*>(src + srow * ((long long)R * R * C) + (long long)(ky * R + kx) * C + c8 * 8);
+    float* d = dst + (long long)b * dst_batch_stride + ((long long)yh * W + xw) * C + c8 * 8;
+    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    *reinterpret_cast<float4*>(d) = make_float4(f0.x, f0.y, f1.x, f1.y);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+  }
+}
+
+// stage-1 patch embed: NCHW fp32 image -> bf16 [B*(H/P)*(W/P), Kpad], k = (ci*P + ky)*P + kx (the conv weight's own
+// flattening), zero padded to Kpad
+__global__ void __launch_bounds__(256) patchify_nchw_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ dst,
+                                                            int B, int Cin, int H, int W, int P, int Kpad) {
+  const int ow = W / P, oh = H / P;
+  const long long total = (long long)B * oh * ow * Cin * P;  // one thread per (patch, ci, ky): P contiguous pixels
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // ox fastest so that consecutive threads read consecutive image columns
+    const int ox = (int)(i % ow);
+    long long t = i / ow;
+    const int ky = (int)(t % P); t /= P;
+    const int ci = (int)(t % Cin); t /= Cin;
+    const int oy = (int)(t % oh);
+    const int b = (int)(t / oh);
+    const float* s = img + (((long long)b * Cin + ci) * H + (oy * P + ky)) * W + ox * P;
+    __nv_bfloat16* d = dst + (((long long)b * oh + oy) * ow + ox) * Kpad + (ci * P + ky) * P;
+    for (int kx = 0; kx < P; ++kx) d[kx] = __float2bfloat16(s[kx]);
+  }
+}
+
+// ---- generic strided row copy with dtype conversion ----------------------------------------------------------
+struct RowMap2 { int group, stride, offset; };
+__device__ __forceinline__ long long map_row2(const RowMap2& m, long long r) {
+  return (r / m.group) * m.stride + m.offset + (r % m.group);
+}
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) copy_rows_kernel(const TI* __restrict__ src, RowMap2 sm, long long lds,
+                                                        TO* __restrict__ dst, RowMap2 dm, long long ldd, long long rows,
+                                                        int C, int accumulate) {
+  const int c4n = C / 4;
+  const long long total = rows * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    const long long r = i / c4n;
+    const TI* s = src + map_row2(sm, r) * lds + c;
+    TO* d = dst + map_row2(dm, r) * ldd + c;
+    float4 v;
+    if constexpr (sizeof(TI) == 2) {
+      const uint2 u = *reinterpret_cast<const uint2*>(s);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      v = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      v = *reinterpret_cast<const float4*>(s);
+    }
+    if constexpr (sizeof(TO) == 2) {
+      if (accumulate) {
+        const uint2 u0 = *reinterpret_cast<const uint2*>(d);
+        const float2 a = unpack_bf16x2(u0.x), b = unpack_bf16x2(u0.y);
+        v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+      }
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(d) = u;
+    } else {
+      if (accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(d);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *reinterpret_cast<float4*>(d) = v;
+    }
+  }
+}
+
+// ---- out[r, c] (+)= sum_b x[b*batch_stride + r*C + c]  (position-embedding gradients) -------------------------
+__global__ void __launch_bounds__(256) batch_reduce_kernel(const float* __restrict__ x, long long batch_stride, int B,
+                                                           long long n4, float* __restrict__ out, int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (long long)b * batch_stride + i * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out + i * 4);
+    if (accumulate) {
+      const float4 p = *o;
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    *o = acc;
+  }
+}
+
+// ---- bilinear resize of a [h*w, C] table to [H*W, C], align_corners=False (torch upsample_bilinear2d) ---------
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float s = ((float)dst + 0.5f) * scale - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+__global__ void pos_resize_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst, int h, int w, int H, int W,
+                                      int C) {
+  const long long total = (long long)H * W * C;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int X = (int)((i / C) % W), Y = (int)(i / ((long long)C * W));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    src_index(Y, sy, h, y0, y1, ly);
+    src_index(X, sx, w, x0, x1, lx);
+    const float v00 = src[((long long)y0 * w + x0) * C + c], v01 = src[((long long)y0 * w + x1) * C + c];
+    const float v10 = src[((long long)y1 * w + x0) * C + c], v11 = src[((long long)y1 * w + x1) * C + c];
+    dst[i] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  }
+}
+__global__ void pos_resize_bwd_kernel(const float* __restrict__ dsrc_resized, float* __restrict__ dtable, int h, int w,
+                                      int H, int W, int C) {
+  const long long total = (long long)H * W * C;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int X = (int)((i / C) % W), Y = (int)(i / ((long long)C * W));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    src_index(Y, sy, h, y0, y1, ly);
+    src_index(X, sx, w, x0, x1, lx);
+    const float g = dsrc_resized[i];
+    atomicAdd(dtable + ((long long)y0 * w + x0) * C + c, g * (1.f - ly) * (1.f - lx));
+    atomicAdd(dtable + ((long long)y0 * w + x1) * C + c, g * (1.f - ly) * lx);
+    atomicAdd(dtable + ((long long)y1 * w + x0) * C + c, g * ly * (1.f - lx));
+    atomicAdd(dtable + ((long long)y1 * w + x1) * C + c, g * ly * lx);
+  }
+}
+
+// ---- weight preparation: fp32 master -> bf16 compute copy, optionally permuting conv [Co,Ci,kh,kw] -> [Co,kh,kw,Ci]
+__global__ void cast_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+__global__ void cast_conv_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Co, int Ci,
+                                        int KK, int dst_ld) {
+  const long long n = (long long)Co * Ci * KK;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Ci);
+    const int kk = (int)((i / Ci) % KK);
+    const int co = (int)(i / ((long long)Ci * KK));
+    dst[(long long)co * dst_ld + (long long)kk * Ci + ci] = __float2bfloat16(src[((long long)co * Ci + ci) * KK + kk]);
+  }
+}
+// gradient of the permuted copy back to the master layout: dW[co,ci,kk] += dWp[co,kk,ci]
+__global__ void uncast_conv_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int KK,
+                                         int src_ld) {
+  const long long n = (long long)Co * Ci * KK;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % KK);
+    const int ci = (int)((i / KK) % Ci);
+    const int co = (int)(i / ((long long)Ci * KK));
+    dw[i] += dwp[(long long)co * src_ld + (long long)kk * Ci + ci];
+  }
+}
+
+// ---- out = dy * gelu_erf'(pre), all bf16 -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pre,
+                                                       __nv_bfloat16* __restrict__ out, long long n2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const float2 d = unpack_bf16x2(reinterpret_cast<const uint32_t*>(dy)[i]);
+    const float2 x = unpack_bf16x2(reinterpret_cast<const uint32_t*>(pre)[i]);
+    reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(d.x * dgelu_erf(x.x), d.y * dgelu_erf(x.y));
+  }
+}
+
+// ---- generic 2-D cast with arbitrary (unaligned) widths: dst[r*ldd + c] = (TO) src[r*lds + c] * alpha ----------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast2d_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst,
+                                                     long long ldd, long long rows, int C, float alpha) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i % C);
+    float v;
+    if constexpr (sizeof(TI) == 2) v = __bfloat162float(src[r * lds + c]);
+    else v = src[r * lds + c];
+    v *= alpha;
+    if constexpr (sizeof(TO) == 2) dst[r * ldd + c] = __float2bfloat16(v);
+    else dst[r * ldd + c] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int mvlt_gelu_bwd(const void* dy_bf16, const void* pre_bf16, void* out_bf16, long long n, void* stream_) {
+  MVLT_CHECK_ARG(n % 2 == 0, "gelu_bwd: n must be even");
+  gelu_bwd_kernel<<<cap_grid(n / 2, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(pre_bf16),
+      reinterpret_cast<__nv_bfloat16*>(out_bf16), n / 2);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_cast2d(const void* src, int src_f32, long long lds, void* dst, int dst_f32, long long ldd,
+                           long long rows, int C, float alpha, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  const int grid = cap_grid(rows * C, 256);
+#define LAUNCH(TI, TO) cast2d_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(src), lds, reinterpret_cast<TO*>(dst), ldd, rows, C, alpha)
+  if (src_f32 && dst_f32) LAUNCH(float, float);
+  else if (src_f32) LAUNCH(float, __nv_bfloat16);
+  else if (dst_f32) LAUNCH(__nv_bfloat16, float);
+  else LAUNCH(__nv_bfloat16, __nv_bfloat16);
+#undef LAUNCH
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_memset_zero(void* p, long long bytes, void* stream_) {
+  cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, reinterpret_cast<cudaStream_t>(stream_));
+  if (e != cudaSuccess) {
+    mvlt_set_error("memset failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+extern "C" int mvlt_cast_scale_bf16(const float* src, void* dst, long long rows, int C, const float* rowscale,
+                                    int rows_per_scale, float alpha, void* stream_) {
+  MVLT_CHECK_ARG(C % 8 == 0, "cast_scale: C=%d must be a multiple of 8", C);
+  const long long n8 = rows * C / 8;
+  cast_scale_kernel<<<cap_grid(n8, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n8, C, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, alpha);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_colsum(const void* x, int x_f32, long long rows, int C, long long ld, float* out, void* stream_) {
+  MVLT_CHECK_ARG(C % 2 == 0 && ld % 2 == 0, "colsum: C and ld must be even");
+  const int gx = (C + 63) / 64;
+  long long gy = (long long)mvlt_num_sms() * 4 / gx;
+  if (gy < 1) gy = 1;
+  long long rpb = (rows + gy - 1) / gy;
+  if (rpb < 64) rpb = 64;
+  gy = (rows + rpb - 1) / rpb;
+  dim3 grid(gx, (unsigned)gy);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  if (x_f32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), rows, C, ld, out, rpb);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, ld, out, rpb);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_patchify(const void* src, int src_f32, long long src_batch_stride, void* dst, int B, int H, int W,
+                             int C, int R, void* stream_) {
+  MVLT_CHECK_ARG(C % 8 == 0 && H % R == 0 && W % R == 0, "patchify: bad shape H=%d W=%d C=%d R=%d", H, W, C, R);
+  const long long total = (long long)B * H * W * (C / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  if (src_f32)
+    patchify_kernel<float><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(src), src_batch_stride,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C, R);
+  else
+    patchify_kernel<__nv_bfloat16><<<cap_grid(total, 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(src), src_batch_stride, reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C, R);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_unpatchify(const void* src_bf16, float* dst, long long dst_batch_stride, int B, int H, int W, int C,
+                               int R, void* stream_) {
+  MVLT_CHECK_ARG(C % 8 == 0 && H % R == 0 && W % R == 0, "unpatchify: bad shape");
+  const long long total = (long long)B * H * W * (C / 8);
+  unpatchify_kernel<<<cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src_bf16), dst, dst_batch_stride, B, H, W, C, R);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_patchify_nchw(const float* img, void* dst_bf16, int B, int Cin, int H, int W, int P, int Kpad,
+                                  void* stream_) {
+  MVLT_CHECK_ARG(H % P == 0 && W % P == 0 && Kpad >= Cin * P * P, "patchify_nchw: bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  if (Kpad > Cin * P * P) cudaMemsetAsync(dst_bf16, 0, (size_t)B * (H / P) * (W / P) * Kpad * 2, st);
+  const long long total = (long long)B * (H / P) * (W / P) * Cin * P;
+  patchify_nchw_kernel<<<cap_grid(total, 256), 256, 0, st>>>(img, reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, Cin, H,
+                                                             W, P, Kpad);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_copy_rows(const void* src, int src_f32, const int* smap, long long lds, void* dst, int dst_f32,
+                              const int* dmap, long long ldd, long long rows, int C, int accumulate, void* stream_) {
+  MVLT_CHECK_ARG(C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "copy_rows: C/ld must be multiples of 4");
+  auto mk = [&](const int* m) {
+    const int big = 1 << 30;
+    return RowMap2{m && m[0] > 0 ? m[0] : big, m && m[0] > 0 ? m[1] : big, m && m[0] > 0 ? m[2] : 0};
+  };
+  RowMap2 sm = mk(smap), dm = mk(dmap);
+  const long long total = rows * (C / 4);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  const int grid = cap_grid(total, 256);
+#define LAUNCH(TI, TO)                                                                                          \
+  copy_rows_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(src), sm, lds,                     \
+                                                 reinterpret_cast<TO*>(dst), dm, ldd, rows, C, accumulate)
+  if (src_f32 && dst_f32) LAUNCH(float, float);
+  else if (src_f32) LAUNCH(float, __nv_bfloat16);
+  else if (dst_f32) LAUNCH(__nv_bfloat16, float);
+  else LAUNCH(__nv_bfloat16, __nv_bfloat16);
+#undef LAUNCH
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_batch_reduce(const float* x, long long batch_stride, int B, long long n, float* out, int accumulate,
+                                 void* stream_) {
+  MVLT_CHECK_ARG(n % 4 == 0 && batch_stride % 4 == 0, "batch_reduce: n must be a multiple of 4");
+  batch_reduce_kernel<<<cap_grid(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, batch_stride, B,
+                                                                                                n / 4, out, accumulate);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_pos_resize_fwd(const float* table, float* out, int h, int w, int H, int W, int C, void* stream_) {
+  const long long total = (long long)H * W * C;
+  pos_resize_fwd_kernel<<<cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(table, out, h, w, H, W, C);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int mvlt_pos_resize_bwd(const float* dout, float* dtable, int h, int w, int H, int W, int C, void* stream_) {
+  const long long total = (long long)H * W * C;
+  pos_resize_bwd_kernel<<<cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(dout, dtable, h, w, H, W, C);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_cast_weight(const float* src, void* dst_bf16, long long n, void* stream_) {
+  cast_weight_kernel<<<cap_grid(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int mvlt_cast_conv_weight(const float* src, void* dst_bf16, int Co, int Ci, int KK, int dst_ld, void* stream_) {
+  cast_conv_weight_kernel<<<cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), Co, Ci, KK, dst_ld);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int mvlt_uncast_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KK, int src_ld, void* stream_) {
+  uncast_conv_wgrad_kernel<<<cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      dwp, dw, Co, Ci, KK, src_ld);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}

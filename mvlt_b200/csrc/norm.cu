@@ -1,0 +1,337 @@
+// LayerNorm forward/backward and the K/V-side softmax forward/backward: memory-bound, one warp per row,
+// 128-bit vectorised, warp-shuffle reductions, fp32 statistics.
+//
+// Reference ops replaced: nn.LayerNorm at /root/reference/libs/pvlt.py:93,105,129,136,141-142,163,169,208 and
+// libs/vl_heads.py:28,33; attn.softmax at libs/pvlt.py:114.
+//
+// Row maps let one launch read/write a strided sub-range of a token buffer, e.g. "rows [HW, HW+T) of every
+// sample" or "write the normalised patch rows at b*N + r and add the (resized) position embedding", which is
+// how the reference's x + pos / torch.cat (pvlt.py:346) and torch.split (:102,:350) disappear.
+#include "common.cuh"
+
+struct RowMap {  // physical_row(r) = (r / group) * stride + offset + (r % group)
+  int group, stride, offset;
+};
+__device__ __forceinline__ long long map_row(const RowMap& m, int r) {
+  return (long long)(r / m.group) * m.stride + m.offset + (r % m.group);
+}
+
+namespace {
+
+constexpr int LN_MAX_VEC = 6;  // C <= 768 (6 x 128 columns per warp pass)
+
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, RowMap xm, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, TO* __restrict__ y, RowMap ym,
+                                                     const float* __restrict__ post_add, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out, int rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int nvec = (C + 127) / 128;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    const TI* xr = x + map_row(xm, r) * C;
+    float4 v[LN_MAX_VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = i * 128 + lane * 4;
+      if (i < nvec && c < C) {
+        v[i] = load4<TI>(xr + c);
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+      } else {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = i * 128 + lane * 4;
+      if (i < nvec && c < C) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + b * b + cc * cc + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (lane == 0 && mean_out != nullptr) {
+      mean_out[r] = mean;
+      rstd_out[r] = rstd;
+    }
+    TO* yr = y + map_row(ym, r) * C;
+    const float* pa = post_add ? post_add + (long long)(r % ym.group) * C : nullptr;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = i * 128 + lane * 4;
+      if (i < nvec && c < C) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (pa) {
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(pa + c));
+          o.x += p4.x; o.y += p4.y; o.z += p4.z; o.w += p4.w;
+        }
+        store4<TO>(yr + c, o);
+      }
+    }
+  }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))  [+ dx_add];   dgamma += dy*xhat ; dbeta += dy
+template <typename TDY, typename TX, typename TDX>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, RowMap dym, const TX* __restrict__ x,
+                                                     RowMap xm, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                     TDX* __restrict__ dx, RowMap dxm, const float* __restrict__ dx_add,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
+                                                     int C) {
+  extern __shared__ float sh[];  // [2][warps][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int nvec = (C + 127) / 128;
+  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = blockIdx.x * warps_per_block + warp; r < rows; r += gridDim.x * warps_per_block) {
+    const TDY* dyr = dy + map_row(dym, r) * C;
+    const TX* xr = x + map_row(xm, r) * C;
+    const float mu = mean[r], rs = rstd[r];
+    float4 vdy[LN_MAX_VEC], vxh[LN_MAX_VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = i * 128 + lane * 4;
+      if (i < nvec && c < C) {
+        const float4 d = load4<TDY>(dyr + c);
+        const float4 xv = load4<TX>(xr + c);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        float4 xh;
+        xh.x = (xv.x - mu) * rs; xh.y = (xv.y - mu) * rs; xh.z = (xv.z - mu) * rs; xh.w = (xv.w - mu) * rs;
+        ag[i].x += d.x * xh.x; ag[i].y += d.y * xh.y; ag[i].z += d.z * xh.z; ag[i].w += d.w * xh.w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        float4 gd;
+        gd.x = d.x * g.x; gd.y = d.y * g.y; gd.z = d.z * g.z; gd.w = d.w * g.w;
+        s1 += gd.x + gd.y + gd.z + gd.w;
+        s2 += gd.x * xh.x + gd.y * xh.y + gd.z * xh.z + gd.w * xh.w;
+        vdy[i] = gd;
+        vxh[i] = xh;
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    const long long drow = map_row(dxm, r) * C;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = i * 128 + lane * 4;
+      if (i < nvec && c < C) {
+        float4 o;
+        o.x = rs * (vdy[i].x - s1 - vxh[i].x * s2);
+        o.y = rs * (vdy[i].y - s1 - vxh[i].y * s2);
+        o.z = rs * (vdy[i].z - s1 - vxh[i].z * s2);
+        o.w = rs * (vdy[i].w - s1 - vxh[i].w * s2);
+        if (dx_add) {
+          const float4 a = *reinterpret_cast<const float4*>(dx_add + drow + c);
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        store4<TDX>(dx + drow + c, o);
+      }
+    }
+  }
+  if (dgamma == nullptr) return;
+  // block reduction of the per-warp partials, then one atomic per column per block
+  float* shg = sh;
+  float* shb = sh + warps_per_block * C;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = i * 128 + lane * 4;
+    if (i < nvec && c < C) {
+      *reinterpret_cast<float4*>(shg + warp * C + c) = ag[i];
+      *reinterpret_cast<float4*>(shb + warp * C + c) = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float g = 0.f, b = 0.f;
+    for (int w = 0; w < warps_per_block; ++w) {
+      g += shg[w * C + c];
+      b += shb[w * C + c];
+    }
+    atomicAdd(dgamma + c, g);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
+// ---- softmax over the (short) key axis: one warp per row, in place on bf16 ------------------------------
+constexpr int SM_MAX_PAIRS = 8;  // Nk <= 512
+
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(__nv_bfloat16* __restrict__ s, long long rows, int nk) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int npair = nk / 64;  // each lane owns bf16x2 at column lane*2 + 64*j
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    uint32_t* row = reinterpret_cast<uint32_t*>(s + r * nk);
+    float2 v[SM_MAX_PAIRS];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SM_MAX_PAIRS; ++j)
+      if (j < npair) {
+        v[j] = unpack_bf16x2(row[lane + 32 * j]);
+        m = fmaxf(m, fmaxf(v[j].x, v[j].y));
+      }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < SM_MAX_PAIRS; ++j)
+      if (j < npair) {
+        v[j].x = __expf(v[j].x - m);
+        v[j].y = __expf(v[j].y - m);
+        sum += v[j].x + v[j].y;
+      }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < SM_MAX_PAIRS; ++j)
+      if (j < npair) row[lane + 32 * j] = pack_bf16x2(v[j].x * inv, v[j].y * inv);
+  }
+}
+
+// dS = scale * P * (dP - sum_k P dP), written in place over dP
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p,
+                                                          __nv_bfloat16* __restrict__ dp, long long rows, int nk,
+                                                          float scale) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int npair = nk / 64;
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    const uint32_t* prow = reinterpret_cast<const uint32_t*>(p + r * nk);
+    uint32_t* drow = reinterpret_cast<uint32_t*>(dp + r * nk);
+    float2 pv[SM_MAX_PAIRS], dv[SM_MAX_PAIRS];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < SM_MAX_PAIRS; ++j)
+      if (j < npair) {
+        pv[j] = unpack_bf16x2(prow[lane + 32 * j]);
+        dv[j] = unpack_bf16x2(drow[lane + 32 * j]);
+        dot += pv[j].x * dv[j].x + pv[j].y * dv[j].y;
+      }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int j = 0; j < SM_MAX_PAIRS; ++j)
+      if (j < npair)
+        drow[lane + 32 * j] = pack_bf16x2(scale * pv[j].x * (dv[j].x - dot), scale * pv[j].y * (dv[j].y - dot));
+  }
+}
+
+int ln_grid(int rows, int wpb) {
+  long long b = ((long long)rows + wpb - 1) / wpb;
+  const long long cap = (long long)mvlt_num_sms() * 8;
+  return (int)(b < cap ? b : cap);
+}
+
+}  // namespace
+
+// x_f32 / y_f32: 1 = fp32, 0 = bf16.  map arrays are {group, stride, offset}; group <= 0 means identity.
+extern "C" int mvlt_layernorm_fwd(const void* x, int x_f32, const int* xmap, const float* gamma, const float* beta,
+                                  void* y, int y_f32, const int* ymap, const float* post_add, float* mean,
+                                  float* rstd, int rows, int C, float eps, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MVLT_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && C <= 128 * LN_MAX_VEC, "layernorm_fwd: unsupported C=%d", C);
+  RowMap xm{xmap && xmap[0] > 0 ? xmap[0] : rows, xmap && xmap[0] > 0 ? xmap[1] : rows, xmap && xmap[0] > 0 ? xmap[2] : 0};
+  RowMap ym{ymap && ymap[0] > 0 ? ymap[0] : rows, ymap && ymap[0] > 0 ? ymap[1] : rows, ymap && ymap[0] > 0 ? ymap[2] : 0};
+  const int grid = ln_grid(rows, 8);
+#define LAUNCH(TI, TO)                                                                                         \
+  ln_fwd_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,                 \
+                                              reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps)
+  if (x_f32 && y_f32) LAUNCH(float, float);
+  else if (x_f32 && !y_f32) LAUNCH(float, __nv_bfloat16);
+  else if (!x_f32 && y_f32) LAUNCH(__nv_bfloat16, float);
+  else LAUNCH(__nv_bfloat16, __nv_bfloat16);
+#undef LAUNCH
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_layernorm_bwd(const void* dy, int dy_f32, const int* dymap, const void* x, int x_f32,
+                                  const int* xmap, const float* mean, const float* rstd, const float* gamma,
+                                  void* dx, int dx_f32, const int* dxmap, const float* dx_add, float* dgamma,
+                                  float* dbeta, int rows, int C, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MVLT_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && C <= 128 * LN_MAX_VEC, "layernorm_bwd: unsupported C=%d", C);
+  auto mk = [&](const int* m) {
+    return RowMap{m && m[0] > 0 ? m[0] : rows, m && m[0] > 0 ? m[1] : rows, m && m[0] > 0 ? m[2] : 0};
+  };
+  RowMap dym = mk(dymap), xm = mk(xmap), dxm = mk(dxmap);
+  const int wpb = 8;
+  long long b = ((long long)rows + wpb * 4 - 1) / (wpb * 4);  // >= 4 rows per warp to amortise the atomics
+  const long long cap = (long long)mvlt_num_sms() * 4;
+  const int grid = (int)(b < cap ? (b > 0 ? b : 1) : cap);
+  const size_t smem = (size_t)2 * wpb * C * sizeof(float);
+#define LAUNCH(TDY, TX, TDX)                                                                                    \
+  ln_bwd_kernel<TDY, TX, TDX><<<grid, 256, smem, st>>>(reinterpret_cast<const TDY*>(dy), dym,                   \
+                                                       reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma,   \
+                                                       reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta,  \
+                                                       rows, C)
+  const int key = (dy_f32 ? 4 : 0) | (x_f32 ? 2 : 0) | (dx_f32 ? 1 : 0);
+  switch (key) {
+    case 0: LAUNCH(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16); break;
+    case 1: LAUNCH(__nv_bfloat16, __nv_bfloat16, float); break;
+    case 2: LAUNCH(__nv_bfloat16, float, __nv_bfloat16); break;
+    case 3: LAUNCH(__nv_bfloat16, float, float); break;
+    case 4: LAUNCH(float, __nv_bfloat16, __nv_bfloat16); break;
+    case 5: LAUNCH(float, __nv_bfloat16, float); break;
+    case 6: LAUNCH(float, float, __nv_bfloat16); break;
+    default: LAUNCH(float, float, float); break;
+  }
+#undef LAUNCH
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_softmax_fwd(void* s_bf16, long long rows, int nk, void* stream_) {
+  MVLT_CHECK_ARG(nk % 64 == 0 && nk <= 64 * SM_MAX_PAIRS, "softmax_fwd: Nk=%d must be a multiple of 64 and <= 512", nk);
+  long long b = (rows + 7) / 8;
+  const long long cap = (long long)mvlt_num_sms() * 16;
+  softmax_fwd_kernel<<<(int)(b < cap ? b : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<__nv_bfloat16*>(s_bf16), rows, nk);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mvlt_softmax_bwd(const void* p_bf16, void* dp_bf16, long long rows, int nk, float scale,
+                                void* stream_) {
+  MVLT_CHECK_ARG(nk % 64 == 0 && nk <= 64 * SM_MAX_PAIRS, "softmax_bwd: Nk=%d must be a multiple of 64 and <= 512", nk);
+  long long b = (rows + 7) / 8;
+  const long long cap = (long long)mvlt_num_sms() * 16;
+  softmax_bwd_kernel<<<(int)(b < cap ? b : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(p_bf16), reinterpret_cast<__nv_bfloat16*>(dp_bf16), rows, nk, scale);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}

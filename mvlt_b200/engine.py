@@ -1,0 +1,550 @@
+"""Hand-scheduled forward/backward of the PVLT hot path on top of the C-ABI kernels.
+
+No autograd graph is built inside: ``forward`` records exactly the buffers its ``backward`` needs, and both
+enqueue only ``libmvlt_b200.so`` kernels on the current stream (tensors are device-memory handles).
+The whole thing is exposed to PyTorch as ONE autograd node (``mvlt_b200/libs/pvlt.py``), so ``nn.Parameter``
+ownership, ``state_dict`` names, optimizers and ``DistributedDataParallel`` work unchanged.
+
+Reference path restated (file:line relative to /root/reference):
+  libs/pvlt.py:322-356  forward_pyramid_features_vl      -> PVLTEngine._stage_fwd / _block_fwd
+  libs/pvlt.py:95-121   Attention.forward (SR attention)  -> _block_fwd (q / sr / kv / softmax / proj)
+  libs/pvlt.py:65-71    Mlp.forward                       -> _block_fwd (fc1+GELU epilogue, fc2+residual epilogue)
+  libs/pvlt.py:358-401  forward (heads)                   -> heads_fwd
+  libs/vl_heads.py      MLMHead / ITMHead / CLSHead / ITGHead
+  engine_grid_masking.py:81-102 losses                    -> fused loss path (CE / SmoothL1 kernels)
+
+dtype policy (== the reference under torch.cuda.amp.autocast): fp32 master weights, fp32
+residual stream, LayerNorm / softmax / losses in fp32, bf16 GEMM operands with fp32 (TMEM) accumulation.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import kernels as k
+from ._lib import MvltError
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+EMBED_DIMS = [64, 128, 320, 512]
+NUM_HEADS = [1, 2, 5, 8]
+MLP_RATIOS = [8, 8, 4, 4]
+SR_RATIOS = [8, 4, 2, 1]
+PATCH = [4, 2, 2, 2]
+DEPTHS = {"pvlt_tiny": [2, 2, 2, 2], "pvlt_small": [3, 4, 6, 3], "pvlt_medium": [3, 4, 18, 3],
+          "pvlt_large": [3, 8, 27, 3]}
+VOCAB, HIDDEN = 30522, 768
+VOCAB_PAD = 30528  # leading dimension of logits buffers (TMA needs 16-byte row strides)
+HEAD_DIM = 64
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def _split_k(M, N, K):
+    """split-K factor for dW-type GEMMs (tiny M x N output, huge K): fill ~2 waves of SMs."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 256 else 1)
+    kb = (K + 63) // 64
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return max(1, min(want, kb // 4 if kb >= 8 else 1))
+
+
+class PVLTEngine:
+    def __init__(self, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor], depths: List[int],
+                 loss_type: Dict[str, int], num_text_tokens: int = 128, drop_path_rate: float = 0.0,
+                 embed_dropout: float = 0.1):
+        self.P = params          # name -> fp32 parameter tensor (live nn.Parameter data)
+        self.Bf = buffers        # name -> buffer (BatchNorm running stats)
+        self.depths = depths
+        self.loss_type = loss_type
+        self.T = num_text_tokens
+        self.embed_dropout = embed_dropout
+        nblk = sum(depths)
+        self.dpr = [drop_path_rate * i / max(nblk - 1, 1) for i in range(nblk)]  # torch.linspace(0, r, n)
+        self.W: Dict[str, torch.Tensor] = {}   # bf16 compute copies (conv weights permuted to [Co, kh, kw, Ci])
+        self._w_version = None
+        self._pos_cache = {}
+        self._step = 0
+        from . import t2i as _t2i
+        self.t2i = _t2i.T2IHead(self) if loss_type.get("t2i") else None
+
+    # ------------------------------------------------------------------------------------------------
+    # weights
+    # ------------------------------------------------------------------------------------------------
+    def _conv_names(self):
+        names = {}
+        for i in range(4):
+            s = i + 1
+            if i > 0:
+                names[f"patch_embed{s}.proj.weight"] = PATCH[i] * PATCH[i]
+            if SR_RATIOS[i] > 1:
+                for j in range(self.depths[i]):
+                    names[f"block{s}.{j}.attn.sr.weight"] = SR_RATIOS[i] * SR_RATIOS[i]
+        return names
+
+    def prepare_weights(self):
+        """fp32 master -> bf16 compute copies, refreshed only when a parameter changed (optimizer step / load)."""
+        ver = tuple(p._version for p in self.P.values())
+        dev = next(iter(self.P.values())).device
+        if self._w_version == ver and self.W:
+            return
+        convs = self._conv_names()
+        for name, p in self.P.items():
+            if p.dim() < 2 or name.startswith("pos_embed") or name.startswith("text_pos_embed"):
+                continue
+            if name.startswith("t2i_head."):
+                continue  # handled by the t2i module (3x3 layout)
+            if name in ("text_embeddings.position_embeddings.weight", "text_embeddings.token_type_embeddings.weight"):
+                continue
+            if name.endswith("linear.weight") and ("itm_head" in name or "cls_head" in name):
+                continue  # small heads read fp32 weights directly
+            if name not in self.W:
+                shape = (p.shape[0], p[0].numel())
+                self.W[name] = _empty(shape, BF16, dev)
+            if name in convs:
+                k.cast_conv_weight(p, self.W[name], p.shape[0], p.shape[1], convs[name], self.W[name].shape[1])
+            else:
+                k.cast_weight(p, self.W[name])
+        if self.t2i is not None:
+            self.t2i.prepare_weights()
+        self._w_version = ver
+
+    # ------------------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------------------
+    def _lin_param_grads(self, G, wname, bname, dy, x, wgrad=None):
+        """dW += dy^T x (split-K, fp32 atomics straight into the gradient buffer); db += column sums of dy."""
+        rows, co = dy.shape
+        ci = x.shape[1]
+        tgt = wgrad if wgrad is not None else G[wname].view(co, -1)
+        k.gemm(dy.t(), x.t(), tgt, atomic_add=True, split_k=_split_k(co, ci, rows))
+        if bname is not None:
+            k.colsum(dy, rows, co, dy.stride(0), G[bname])
+
+    def _pos(self, stage, H, W, dev):
+        """pvlt.py:291-297,341-344: bilinear resize of the position table (cached per weight version)."""
+        key = (stage, H, W, self.P[f"pos_embed{stage}"]._version)
+        if key in self._pos_cache:
+            return self._pos_cache[key]
+        pe = self.P[f"pos_embed{stage}"]
+        C = pe.shape[-1]
+        tab = pe[0, 1:] if stage == 4 else pe[0]
+        side = int(round(math.sqrt(tab.shape[0])))
+        n1 = self.P["pos_embed1"].shape[1]
+        if H * W == n1:
+            out = tab
+        else:
+            out = _empty((H * W, C), F32, dev)
+            k.pos_resize_fwd(tab, out, side, side, H, W, C)
+        self._pos_cache = {kk: v for kk, v in self._pos_cache.items() if kk[0] != stage}
+        self._pos_cache[key] = out
+        return out
+
+    # ------------------------------------------------------------------------------------------------
+    # transformer block
+    # ------------------------------------------------------------------------------------------------
+    def _block_fwd(self, X, pfx, i, B, H, W, dp, save):
+        P, Wb, T = self.P, self.W, self.T
+        C, R, heads = EMBED_DIMS[i], SR_RATIOS[i], NUM_HEADS[i]
+        HW, N = H * W, H * W + T
+        M = B * N
+        dev = X.device
+        hidden = C * MLP_RATIOS[i]
+        c = {}
+        # ---- attention branch
+        xn = _empty((M, C), BF16, dev)
+        mean1, rstd1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
+        k.layernorm_fwd(X, P[pfx + ".norm1.weight"], P[pfx + ".norm1.bias"], xn, 1e-6, M, C, mean=mean1, rstd=rstd1)
+        q = _empty((M, C), BF16, dev)
+        k.gemm(xn, Wb[pfx + ".attn.q.weight"], q, bias=P[pfx + ".attn.q.bias"])
+        if R > 1:
+            oh, ow = H // R, W // R
+            Nk = oh * ow + T
+            patches = _empty((B * oh * ow, R * R * C), BF16, dev)
+            k.patchify(xn, N * C, patches, B, H, W, C, R)
+            sr = _empty((B * oh * ow, C), BF16, dev)
+            k.gemm(patches, Wb[pfx + ".attn.sr.weight"], sr, bias=P[pfx + ".attn.sr.bias"])
+            kvin = _empty((B * Nk, C), BF16, dev)
+            srm, srr = _empty((B * oh * ow,), F32, dev), _empty((B * oh * ow,), F32, dev)
+            k.layernorm_fwd(sr, P[pfx + ".attn.norm.weight"], P[pfx + ".attn.norm.bias"], kvin, 1e-5, B * oh * ow, C,
+                            ymap=(oh * ow, Nk, 0), mean=srm, rstd=srr)
+            k.copy_rows(xn, kvin, B * T, C, smap=(T, N, HW), dmap=(T, Nk, oh * ow))
+            c.update(patches=patches, sr=sr, srm=srm, srr=srr)
+        else:
+            Nk = N
+            kvin = xn
+        if Nk % 64 != 0 or Nk > 512:
+            raise MvltError(f"K/V length {Nk} unsupported by the softmax kernel (need a multiple of 64, <= 512)")
+        kv = _empty((B * Nk, 2 * C), BF16, dev)
+        k.gemm(kvin, Wb[pfx + ".attn.kv.weight"], kv, bias=P[pfx + ".attn.kv.bias"])
+        q4 = q.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3)
+        kv5 = kv.view(B, Nk, 2, heads, HEAD_DIM)
+        k4, v4 = kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3)
+        Pm = _empty((B, heads, N, Nk), BF16, dev)
+        k.gemm(q4, k4, Pm, alpha=HEAD_DIM ** -0.5)
+        k.softmax_fwd(Pm, B * heads * N, Nk)
+        o = _empty((M, C), BF16, dev)
+        k.gemm(Pm, v4.transpose(-1, -2), o.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3))
+        X1 = _empty((B, N, C), F32, dev)
+        k.gemm(o, Wb[pfx + ".attn.proj.weight"], X1.view(M, C), bias=P[pfx + ".attn.proj.bias"],
+               residual=X.view(M, C), rowscale=dp[0] if dp else None, rows_per_scale=N)
+        # ---- MLP branch
+        xn2 = _empty((M, C), BF16, dev)
+        mean2, rstd2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
+        k.layernorm_fwd(X1, P[pfx + ".norm2.weight"], P[pfx + ".norm2.bias"], xn2, 1e-6, M, C, mean=mean2, rstd=rstd2)
+        act = _empty((M, hidden), BF16, dev)
+        hpre = _empty((M, hidden), BF16, dev) if save else None
+        k.gemm(xn2, Wb[pfx + ".mlp.fc1.weight"], act, bias=P[pfx + ".mlp.fc1.bias"], act=k.ACT_GELU, preact_out=hpre)
+        X2 = _empty((B, N, C), F32, dev)
+        k.gemm(act, Wb[pfx + ".mlp.fc2.weight"], X2.view(M, C), bias=P[pfx + ".mlp.fc2.bias"],
+               residual=X1.view(M, C), rowscale=dp[1] if dp else None, rows_per_scale=N)
+        if save:
+            c.update(X=X, xn=xn, mean1=mean1, rstd1=rstd1, q=q, kvin=kvin, kv=kv, Pm=Pm, o=o, X1=X1, xn2=xn2,
+                     mean2=mean2, rstd2=rstd2, act=act, hpre=hpre, dp=dp, Nk=Nk)
+        return X2, c
+
+    def _block_bwd(self, dX2, c, pfx, i, B, H, W, G):
+        P, Wb, T = self.P, self.W, self.T
+        C, R, heads = EMBED_DIMS[i], SR_RATIOS[i], NUM_HEADS[i]
+        HW, N = H * W, H * W + T
+        M = B * N
+        Nk = c["Nk"]
+        dev = dX2.device
+        hidden = C * MLP_RATIOS[i]
+        dp = c["dp"]
+        # ---- MLP branch
+        dy2 = _empty((M, C), BF16, dev)
+        k.cast_scale_bf16(dX2, dy2, M, C, rowscale=dp[1] if dp else None, rows_per_scale=N)
+        self._lin_param_grads(G, pfx + ".mlp.fc2.weight", pfx + ".mlp.fc2.bias", dy2, c["act"])
+        dh = _empty((M, hidden), BF16, dev)
+        k.gemm(dy2, Wb[pfx + ".mlp.fc2.weight"].t(), dh, act=k.ACT_DGELU, aux=c["hpre"])
+        self._lin_param_grads(G, pfx + ".mlp.fc1.weight", pfx + ".mlp.fc1.bias", dh, c["xn2"])
+        dxn2 = dy2  # reuse
+        k.gemm(dh, Wb[pfx + ".mlp.fc1.weight"].t(), dxn2)
+        del dh
+        dX1 = _empty((B, N, C), F32, dev)
+        k.layernorm_bwd(dxn2, c["X1"], c["mean2"], c["rstd2"], P[pfx + ".norm2.weight"], dX1, M, C, dx_add=dX2,
+                        dgamma=G[pfx + ".norm2.weight"], dbeta=G[pfx + ".norm2.bias"])
+        # ---- attention branch
+        dyp = dxn2
+        k.cast_scale_bf16(dX1, dyp, M, C, rowscale=dp[0] if dp else None, rows_per_scale=N)
+        self._lin_param_grads(G, pfx + ".attn.proj.weight", pfx + ".attn.proj.bias", dyp, c["o"])
+        do = _empty((M, C), BF16, dev)
+        k.gemm(dyp, Wb[pfx + ".attn.proj.weight"].t(), do)
+        do4 = do.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3)
+        q4 = c["q"].view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3)
+        kv5 = c["kv"].view(B, Nk, 2, heads, HEAD_DIM)
+        k4, v4 = kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3)
+        dkv = _empty((B * Nk, 2 * C), BF16, dev)
+        dkv5 = dkv.view(B, Nk, 2, heads, HEAD_DIM)
+        dk4, dv4 = dkv5[:, :, 0].permute(0, 2, 1, 3), dkv5[:, :, 1].permute(0, 2, 1, 3)
+        Pm = c["Pm"]
+        k.gemm(Pm.transpose(-1, -2), do4.transpose(-1, -2), dv4)          # dV = P^T dO
+        dS = _empty((B, heads, N, Nk), BF16, dev)
+        k.gemm(do4, v4, dS)                                               # dP = dO V^T
+        k.softmax_bwd(Pm, dS, B * heads * N, Nk, HEAD_DIM ** -0.5)        # dS (includes the qk scale)
+        dq = dyp  # reuse
+        k.gemm(dS, k4.transpose(-1, -2), dq.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3))   # dQ = dS K
+        k.gemm(dS.transpose(-1, -2), q4.transpose(-1, -2), dk4)           # dK = dS^T Q
+        del dS
+        self._lin_param_grads(G, pfx + ".attn.kv.weight", pfx + ".attn.kv.bias", dkv, c["kvin"])
+        dxn = _empty((M, C), F32, dev)
+        if R > 1:
+            oh, ow = H // R, W // R
+            dkvin = _empty((B * Nk, C), BF16, dev)
+            k.gemm(dkv, Wb[pfx + ".attn.kv.weight"].t(), dkvin)
+            k.copy_rows(dkvin, dxn, B * T, C, smap=(T, Nk, oh * ow), dmap=(T, N, HW))
+            dsr = _empty((B * oh * ow, C), BF16, dev)
+            k.layernorm_bwd(dkvin, c["sr"], c["srm"], c["srr"], P[pfx + ".attn.norm.weight"], dsr, B * oh * ow, C,
+                            dymap=(oh * ow, Nk, 0), dgamma=G[pfx + ".attn.norm.weight"],
+                            dbeta=G[pfx + ".attn.norm.bias"])
+            self._lin_param_grads(G, None, pfx + ".attn.sr.bias", dsr, c["patches"],
+                                  wgrad=self._conv_wgrad(G, pfx + ".attn.sr.weight"))
+            dpatch = _empty((B * oh * ow, R * R * C), BF16, dev)
+            k.gemm(dsr, Wb[pfx + ".attn.sr.weight"].t(), dpatch)
+            k.unpatchify(dpatch, dxn, N * C, B, H, W, C, R)
+            k.gemm(dq, Wb[pfx + ".attn.q.weight"].t(), dxn, residual=dxn)
+        else:
+            k.gemm(dkv, Wb[pfx + ".attn.kv.weight"].t(), dxn)
+            k.gemm(dq, Wb[pfx + ".attn.q.weight"].t(), dxn, residual=dxn)
+        self._lin_param_grads(G, pfx + ".attn.q.weight", pfx + ".attn.q.bias", dq, c["xn"])
+        dX = _empty((B, N, C), F32, dev)
+        k.layernorm_bwd(dxn, c["X"], c["mean1"], c["rstd1"], P[pfx + ".norm1.weight"], dX, M, C, dx_add=dX1,
+                        dgamma=G[pfx + ".norm1.weight"], dbeta=G[pfx + ".norm1.bias"])
+        return dX
+
+    def _conv_wgrad(self, G, name):
+        """fp32 gradient buffer in the permuted [Co, kh*kw*Ci] layout; folded back into the master layout at the end."""
+        key = "__perm__" + name
+        if key not in G:
+            w = self.W[name]
+            G[key] = torch.zeros(w.shape, dtype=F32, device=w.device)
+        return G[key]
+
+    # ------------------------------------------------------------------------------------------------
+    # encoder
+    # ------------------------------------------------------------------------------------------------
+    def encoder_fwd(self, images, ids, training, save):
+        P, Wb, T = self.P, self.W, self.T
+        dev = images.device
+        B, Cin, IH, IW = images.shape
+        if ids.shape != (B, T):
+            raise MvltError(f"input_ids must be [B, {T}], got {tuple(ids.shape)}")
+        ctx = {"B": B, "stages": [], "IH": IH, "IW": IW}
+        self._step += 1
+        # --- BERT embeddings (pvlt.py:326)
+        p_drop = self.embed_dropout if training else 0.0
+        seed = (self._step * 0x9E3779B1) & 0xFFFFFFFFFFFF
+        y768 = _empty((B * T, HIDDEN), BF16, dev)
+        em, er = _empty((B * T,), F32, dev), _empty((B * T,), F32, dev)
+        ids = ids.contiguous()
+        k.bert_embed_fwd(ids, P["text_embeddings.word_embeddings.weight"], P["text_embeddings.position_embeddings.weight"],
+                         P["text_embeddings.token_type_embeddings.weight"], P["text_embeddings.LayerNorm.weight"],
+                         P["text_embeddings.LayerNorm.bias"], y768, em, er, B * T, T, 1e-12, p_drop, seed)
+        ctx.update(ids=ids, em=em, er=er, p_drop=p_drop, seed=seed)
+        # --- drop path factors: one [2*nblocks, B] draw per step
+        nblk = sum(self.depths)
+        dps = None
+        if training and any(r > 0 for r in self.dpr):
+            keep = torch.tensor([1.0 - r for r in self.dpr for _ in (0, 1)], device=dev, dtype=F32).view(-1, 1)
+            dps = (torch.rand((2 * nblk, B), device=dev) < keep).to(F32) / keep
+        Xprev, Hp, Wp = None, IH, IW
+        te_in = y768
+        blk = 0
+        for i in range(4):
+            s = i + 1
+            C, p = EMBED_DIMS[i], PATCH[i]
+            H, W = Hp // p, Wp // p
+            HW, N = H * W, H * W + T
+            sc = {"H": H, "W": W}
+            # patch embed (pvlt.py:165-172): conv k=s=p as patchify + GEMM, LN(1e-5) + pos add written in place
+            if i == 0:
+                Kp = Cin * p * p
+                patches = _empty((B * HW, Kp), BF16, dev)
+                k.patchify_nchw(images, patches, B, Cin, IH, IW, p, Kp)
+            else:
+                Cp = EMBED_DIMS[i - 1]
+                Np = Hp * Wp + T
+                patches = _empty((B * HW, p * p * Cp), BF16, dev)
+                k.patchify(Xprev, Np * Cp, patches, B, Hp, Wp, Cp, p)
+            pe = _empty((B * HW, C), BF16, dev)
+            k.gemm(patches, Wb[f"patch_embed{s}.proj.weight"], pe, bias=P[f"patch_embed{s}.proj.bias"])
+            X = _empty((B, N, C), F32, dev)
+            pem, per = _empty((B * HW,), F32, dev), _empty((B * HW,), F32, dev)
+            k.layernorm_fwd(pe, P[f"patch_embed{s}.norm.weight"], P[f"patch_embed{s}.norm.bias"], X, 1e-5, B * HW, C,
+                            ymap=(HW, N, 0), post_add=self._pos(s, H, W, dev), mean=pem, rstd=per)
+            # text embed (pvlt.py:205-208,339)
+            if i > 0:
+                Cp = EMBED_DIMS[i - 1]
+                Np = Hp * Wp + T
+                te_in = _empty((B * T, Cp), BF16, dev)
+                k.copy_rows(Xprev, te_in, B * T, Cp, smap=(T, Np, Hp * Wp))
+            te = _empty((B * T, C), BF16, dev)
+            k.gemm(te_in, Wb[f"text_embed{s}.0.weight"], te, bias=P[f"text_embed{s}.0.bias"])
+            tem, ter = _empty((B * T,), F32, dev), _empty((B * T,), F32, dev)
+            k.layernorm_fwd(te, P[f"text_embed{s}.1.weight"], P[f"text_embed{s}.1.bias"], X, 1e-5, B * T, C,
+                            ymap=(T, N, HW), post_add=P[f"text_pos_embed{s}"], mean=tem, rstd=ter)
+            if save:
+                sc.update(patches=patches, pe=pe, pem=pem, per=per, te_in=te_in, te=te, tem=tem, ter=ter)
+            sc["blocks"] = []
+            for j in range(self.depths[i]):
+                dp = (dps[2 * blk], dps[2 * blk + 1]) if dps is not None else None
+                X, bc = self._block_fwd(X, f"block{s}.{j}", i, B, H, W, dp, save)
+                sc["blocks"].append(bc)
+                blk += 1
+            sc["out"] = X
+            ctx["stages"].append(sc)
+            Xprev, Hp, Wp = X, H, W
+        return ctx
+
+    def encoder_bwd(self, ctx, dXs, G):
+        """dXs[i]: fp32 gradient wrt the output token buffer of stage i (or None). Accumulates into G."""
+        P, Wb, T = self.P, self.W, self.T
+        B = ctx["B"]
+        dev = ctx["ids"].device
+        dX = dXs[3]
+        for i in (3, 2, 1, 0):
+            s = i + 1
+            sc = ctx["stages"][i]
+            C, p = EMBED_DIMS[i], PATCH[i]
+            H, W = sc["H"], sc["W"]
+            HW, N = H * W, H * W + T
+            if dX is None:
+                dX = torch.zeros((B, N, C), dtype=F32, device=dev)
+            for j in reversed(range(self.depths[i])):
+                dX = self._block_bwd(dX, sc["blocks"][j], f"block{s}.{j}", i, B, H, W, G)
+            # position embeddings (pvlt.py:341-346): batch-sum of the token grads, image part through the
+            # transposed bilinear resize
+            pe_tab = P[f"pos_embed{s}"]
+            side = int(round(math.sqrt(pe_tab.shape[1] - (1 if s == 4 else 0))))
+            gtab = G[f"pos_embed{s}"][0, 1:] if s == 4 else G[f"pos_embed{s}"][0]
+            if HW == P["pos_embed1"].shape[1]:
+                k.batch_reduce(dX, N * C, B, HW * C, gtab, accumulate=True)
+            else:
+                dpos = _empty((HW, C), F32, dev)
+                k.batch_reduce(dX, N * C, B, HW * C, dpos)
+                k.pos_resize_bwd(dpos, gtab, side, side, H, W, C)
+            k.batch_reduce(dX.view(-1)[HW * C:], N * C, B, T * C, G[f"text_pos_embed{s}"], accumulate=True)
+            # patch embed backward
+            dpe = _empty((B * HW, C), BF16, dev)
+            k.layernorm_bwd(dX, sc["pe"], sc["pem"], sc["per"], P[f"patch_embed{s}.norm.weight"], dpe, B * HW, C,
+                            dymap=(HW, N, 0), dgamma=G[f"patch_embed{s}.norm.weight"],
+                            dbeta=G[f"patch_embed{s}.norm.bias"])
+            if i == 0:
+                self._lin_param_grads(G, f"patch_embed{s}.proj.weight", f"patch_embed{s}.proj.bias", dpe, sc["patches"])
+            else:
+                self._lin_param_grads(G, None, f"patch_embed{s}.proj.bias", dpe, sc["patches"],
+                                      wgrad=self._conv_wgrad(G, f"patch_embed{s}.proj.weight"))
+            # text embed backward
+            dte = _empty((B * T, C), BF16, dev)
+            k.layernorm_bwd(dX, sc["te"], sc["tem"], sc["ter"], P[f"text_embed{s}.1.weight"], dte, B * T, C,
+                            dymap=(T, N, HW), dgamma=G[f"text_embed{s}.1.weight"], dbeta=G[f"text_embed{s}.1.bias"])
+            self._lin_param_grads(G, f"text_embed{s}.0.weight", f"text_embed{s}.0.bias", dte, sc["te_in"])
+            if i > 0:
+                Cp = EMBED_DIMS[i - 1]
+                Hp, Wp = ctx["stages"][i - 1]["H"], ctx["stages"][i - 1]["W"]
+                Np = Hp * Wp + T
+                dXp = _empty((B, Np, Cp), F32, dev)
+                dpatch = _empty((B * HW, p * p * Cp), BF16, dev)
+                k.gemm(dpe, Wb[f"patch_embed{s}.proj.weight"].t(), dpatch)
+                k.unpatchify(dpatch, dXp, Np * Cp, B, Hp, Wp, Cp, p)
+                k.gemm(dte.view(B, T, C), Wb[f"text_embed{s}.0.weight"].t(), dXp[:, Hp * Wp:, :])
+                if dXs[i - 1] is not None:   # t2i head gradients: fp32 [B, HWp, Cp], image rows of the previous stage
+                    k.copy_rows(dXs[i - 1], dXp, B * Hp * Wp, Cp, dmap=(Hp * Wp, Np, 0), accumulate=True)
+                dX = dXp
+            else:
+                dy768 = _empty((B * T, HIDDEN), BF16, dev)
+                k.gemm(dte, Wb["text_embed1.0.weight"].t(), dy768)
+                k.bert_embed_bwd(dy768, ctx["ids"], P["text_embeddings.word_embeddings.weight"],
+                                 P["text_embeddings.position_embeddings.weight"],
+                                 P["text_embeddings.token_type_embeddings.weight"], P["text_embeddings.LayerNorm.weight"],
+                                 ctx["em"], ctx["er"], G["text_embeddings.word_embeddings.weight"],
+                                 G["text_embeddings.position_embeddings.weight"],
+                                 G["text_embeddings.token_type_embeddings.weight"], G["text_embeddings.LayerNorm.weight"],
+                                 G["text_embeddings.LayerNorm.bias"], B * T, T, ctx["p_drop"], ctx["seed"])
+        # fold the permuted conv-weight gradients back into the master [Co, Ci, kh, kw] layout
+        for key in [kk for kk in G if kk.startswith("__perm__")]:
+            name = key[len("__perm__"):]
+            if name.startswith("t2i_head."):
+                continue
+            w = P[name]
+            KK = w.shape[2] * w.shape[3]
+            k.uncast_conv_wgrad(G[key], G[name], w.shape[0], w.shape[1], KK, G[key].shape[1])
+
+    # ------------------------------------------------------------------------------------------------
+    # heads (pvlt.py:365-397)
+    # ------------------------------------------------------------------------------------------------
+    def _head_embed_fwd(self, feat, name, rows):
+        """Linear(512->768) + LayerNorm(1e-5): pvlt.py:244-248,253-257,262-273."""
+        P, Wb = self.P, self.W
+        dev = feat.device
+        he = _empty((rows, HIDDEN), BF16, dev)
+        k.gemm(feat, Wb[name + ".0.weight"], he, bias=P[name + ".0.bias"])
+        hn = _empty((rows, HIDDEN), BF16, dev)
+        m, r = _empty((rows,), F32, dev), _empty((rows,), F32, dev)
+        k.layernorm_fwd(he, P[name + ".1.weight"], P[name + ".1.bias"], hn, 1e-5, rows, HIDDEN, mean=m, rstd=r)
+        return hn, dict(feat=feat, he=he, m=m, r=r)
+
+    def _head_embed_bwd(self, dhn, c, name, rows, G):
+        P, Wb = self.P, self.W
+        dhe = _empty((rows, HIDDEN), BF16, dhn.device)
+        k.layernorm_bwd(dhn, c["he"], c["m"], c["r"], P[name + ".1.weight"], dhe, rows, HIDDEN,
+                        dgamma=G[name + ".1.weight"], dbeta=G[name + ".1.bias"])
+        self._lin_param_grads(G, name + ".0.weight", name + ".0.bias", dhe, c["feat"])
+        dfeat = _empty((rows, EMBED_DIMS[-1]), BF16, dhn.device)
+        k.gemm(dhe, Wb[name + ".0.weight"].t(), dfeat)
+        return dfeat
+
+    def small_head_fwd(self, X4, B, HW4, name):
+        """ITM / CLS heads on text token 0 (vl_heads.py:84-87,101-104: linear.bias + linear_bias)."""
+        P = self.P
+        N4 = HW4 + self.T
+        dev = X4.device
+        feat = _empty((B, EMBED_DIMS[-1]), BF16, dev)
+        k.copy_rows(X4, feat, B, EMBED_DIMS[-1], smap=(1, N4, HW4))
+        hn, c = self._head_embed_fwd(feat, name + "_head_embed", B)
+        n = P[name + "_head.linear.weight"].shape[0]
+        logits = _empty((B, n), F32, dev)
+        k.small_linear_fwd(hn, P[name + "_head.linear.weight"], P[name + "_head.linear.bias"],
+                           P[name + "_head.linear_bias"], logits, B, n, HIDDEN)
+        c.update(hn=hn, n=n)
+        return logits, c
+
+    def small_head_bwd(self, dlogits, c, name, B, HW4, dX4, G):
+        P = self.P
+        N4 = HW4 + self.T
+        n = c["n"]
+        dhn = _empty((B, HIDDEN), BF16, dlogits.device)
+        k.small_linear_bwd(dlogits, c["hn"], P[name + "_head.linear.weight"], dhn, G[name + "_head.linear.weight"],
+                           G[name + "_head.linear.bias"], G[name + "_head.linear_bias"], B, n, HIDDEN)
+        dfeat = self._head_embed_bwd(dhn, c, name + "_head_embed", B, G)
+        k.copy_rows(dfeat, dX4, B, EMBED_DIMS[-1], dmap=(1, N4, HW4), accumulate=True)
+
+    def mlm_fwd(self, X4, B, HW4, idx, n_rows, out_f32=False):
+        """MLM head (pvlt.py:368-369, vl_heads.py:30-35,65-70) on the rows listed in ``idx`` (None = all B*T)."""
+        P, Wb, T = self.P, self.W, self.T
+        N4 = HW4 + T
+        dev = X4.device
+        feat = _empty((n_rows, EMBED_DIMS[-1]), BF16, dev)
+        if idx is None:
+            k.copy_rows(X4, feat, n_rows, EMBED_DIMS[-1], smap=(T, N4, HW4))
+        else:
+            k.gather_rows(X4, idx, n_rows, feat, EMBED_DIMS[-1], smap=(T, N4, HW4))
+        hn, c = self._head_embed_fwd(feat, "mlm_head_embed", n_rows)
+        ha = _empty((n_rows, HIDDEN), BF16, dev)
+        hpre = _empty((n_rows, HIDDEN), BF16, dev)
+        k.gemm(hn, Wb["mlm_head.transform.dense.weight"], ha, bias=P["mlm_head.transform.dense.bias"],
+               act=k.ACT_GELU, preact_out=hpre)
+        hl = _empty((n_rows, HIDDEN), BF16, dev)
+        m2, r2 = _empty((n_rows,), F32, dev), _empty((n_rows,), F32, dev)
+        k.layernorm_fwd(ha, P["mlm_head.transform.LayerNorm.weight"], P["mlm_head.transform.LayerNorm.bias"], hl,
+                        1e-5, n_rows, HIDDEN, mean=m2, rstd=r2)
+        logits = _empty((n_rows, VOCAB_PAD), F32 if out_f32 else BF16, dev)[:, :VOCAB]
+        k.gemm(hl, Wb["text_embeddings.word_embeddings.weight"], logits, bias=P["mlm_head.bias"])
+        c.update(hn=hn, ha=ha, hpre=hpre, hl=hl, m2=m2, r2=r2, idx=idx, n_rows=n_rows)
+        return logits, c
+
+    def mlm_bwd(self, dlogits, c, B, HW4, dX4, G):
+        """dlogits: bf16 [n_rows, VOCAB] view with leading dimension VOCAB_PAD."""
+        P, Wb, T = self.P, self.W, self.T
+        N4 = HW4 + T
+        n_rows = c["n_rows"]
+        dev = dlogits.device
+        # tied decoder: dE += dlogits^T hl  (lands in word_embeddings.grad next to the gather's scatter-add)
+        k.gemm(dlogits.t(), c["hl"].t(), G["text_embeddings.word_embeddings.weight"], atomic_add=True,
+               split_k=_split_k(VOCAB, HIDDEN, n_rows))
+        k.colsum(dlogits, n_rows, VOCAB, VOCAB_PAD, G["mlm_head.bias"])
+        dhl = _empty((n_rows, HIDDEN), BF16, dev)
+        k.gemm(dlogits, Wb["text_embeddings.word_embeddings.weight"].t(), dhl)
+        dha = _empty((n_rows, HIDDEN), BF16, dev)
+        k.layernorm_bwd(dhl, c["ha"], c["m2"], c["r2"], P["mlm_head.transform.LayerNorm.weight"], dha, n_rows, HIDDEN,
+                        dgamma=G["mlm_head.transform.LayerNorm.weight"], dbeta=G["mlm_head.transform.LayerNorm.bias"])
+        # GELU backward as an elementwise pass folded into the dense GEMM pair: dpre = dha * gelu'(hpre)
+        dpre = dhl
+        k.gelu_bwd(dha, c["hpre"], dpre, n_rows * HIDDEN)
+        self._lin_param_grads(G, "mlm_head.transform.dense.weight", "mlm_head.transform.dense.bias", dpre, c["hn"])
+        dhn = dha
+        k.gemm(dpre, Wb["mlm_head.transform.dense.weight"].t(), dhn)
+        dfeat = self._head_embed_bwd(dhn, c, "mlm_head_embed", n_rows, G)
+        if c["idx"] is None:
+            k.copy_rows(dfeat, dX4, n_rows, EMBED_DIMS[-1], dmap=(T, N4, HW4), accumulate=True)
+        else:
+            k.scatter_rows(dfeat, c["idx"], n_rows, dX4, EMBED_DIMS[-1], dmap=(T, N4, HW4), accumulate=True)
+
+    # ------------------------------------------------------------------------------------------------
+    # gradient buffers
+    # ------------------------------------------------------------------------------------------------
+    def new_grads(self):
+        """One flat zeroed fp32 buffer, viewed per parameter (the tied decoder weight has no separate entry)."""
+        dev = next(iter(self.P.values())).device
+        total = sum((p.numel() + 3) // 4 * 4 for p in self.P.values())
+        flat = torch.zeros(total, dtype=F32, device=dev)
+        G, off = {}, 0
+        for name, p in self.P.items():
+            G[name] = flat[off:off + p.numel()].view(p.shape)
+            off += (p.numel() + 3) // 4 * 4
+        G["__flat__"] = flat
+        return G

@@ -103,3 +103,249 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
             raise _lib.MvltError("gemm aux/preact must be bf16 with out's strides")
     call("gemm" if impl == "tcgen05" else "gemm_ref", C.byref(d))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# Non-GEMM kernels
+# ------------------------------------------------------------------------------------------------------
+_I3 = C.c_int * 3
+
+
+def _map(m):
+    """(group, stride, offset) row map -> C int[3]; None = identity."""
+    if m is None:
+        return _I3(0, 0, 0)
+    return _I3(int(m[0]), int(m[1]), int(m[2]))
+
+
+def _f32(t):
+    if t.dtype == F32:
+        return 1
+    if t.dtype == BF16:
+        return 0
+    raise _lib.MvltError(f"expected fp32/bf16 tensor, got {t.dtype}")
+
+
+def layernorm_fwd(x, gamma, beta, y, eps, rows, Cdim, xmap=None, ymap=None, post_add=None, mean=None, rstd=None):
+    require_cuda(x, y)
+    call("layernorm_fwd", ptr(x), _f32(x), _map(xmap), ptr(gamma), ptr(beta), ptr(y), _f32(y), _map(ymap),
+         ptr(post_add), ptr(mean), ptr(rstd), C.c_int(rows), C.c_int(Cdim), C.c_float(eps))
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, rows, Cdim, dymap=None, xmap=None, dxmap=None, dx_add=None,
+                  dgamma=None, dbeta=None):
+    require_cuda(dy, x, dx)
+    call("layernorm_bwd", ptr(dy), _f32(dy), _map(dymap), ptr(x), _f32(x), _map(xmap), ptr(mean), ptr(rstd),
+         ptr(gamma), ptr(dx), _f32(dx), _map(dxmap), ptr(dx_add), ptr(dgamma), ptr(dbeta), C.c_int(rows),
+         C.c_int(Cdim))
+
+
+def softmax_fwd(s, rows, nk):
+    call("softmax_fwd", ptr(s), C.c_longlong(rows), C.c_int(nk))
+
+
+def softmax_bwd(p, dp, rows, nk, scale):
+    call("softmax_bwd", ptr(p), ptr(dp), C.c_longlong(rows), C.c_int(nk), C.c_float(scale))
+
+
+def cast_scale_bf16(src, dst, rows, Cdim, rowscale=None, rows_per_scale=0, alpha=1.0):
+    call("cast_scale_bf16", ptr(src), ptr(dst), C.c_longlong(rows), C.c_int(Cdim), ptr(rowscale),
+         C.c_int(rows_per_scale), C.c_float(alpha))
+
+
+def colsum(x, rows, Cdim, ld, out):
+    call("colsum", ptr(x), _f32(x), C.c_longlong(rows), C.c_int(Cdim), C.c_longlong(ld), ptr(out))
+
+
+def patchify(src, src_batch_stride, dst, B, H, W, Cdim, R):
+    call("patchify", ptr(src), _f32(src), C.c_longlong(src_batch_stride), ptr(dst), C.c_int(B), C.c_int(H),
+         C.c_int(W), C.c_int(Cdim), C.c_int(R))
+
+
+def unpatchify(src, dst, dst_batch_stride, B, H, W, Cdim, R):
+    call("unpatchify", ptr(src), ptr(dst), C.c_longlong(dst_batch_stride), C.c_int(B), C.c_int(H), C.c_int(W),
+         C.c_int(Cdim), C.c_int(R))
+
+
+def patchify_nchw(img, dst, B, Cin, H, W, P, Kpad):
+    call("patchify_nchw", ptr(img), ptr(dst), C.c_int(B), C.c_int(Cin), C.c_int(H), C.c_int(W), C.c_int(P),
+         C.c_int(Kpad))
+
+
+def copy_rows(src, dst, rows, Cdim, smap=None, dmap=None, lds=None, ldd=None, accumulate=False):
+    call("copy_rows", ptr(src), _f32(src), _map(smap), C.c_longlong(lds or Cdim), ptr(dst), _f32(dst), _map(dmap),
+         C.c_longlong(ldd or Cdim), C.c_longlong(rows), C.c_int(Cdim), C.c_int(1 if accumulate else 0))
+
+
+def batch_reduce(x, batch_stride, B, n, out, accumulate=False):
+    call("batch_reduce", ptr(x), C.c_longlong(batch_stride), C.c_int(B), C.c_longlong(n), ptr(out),
+         C.c_int(1 if accumulate else 0))
+
+
+def pos_resize_fwd(table, out, h, w, H, W, Cdim):
+    call("pos_resize_fwd", ptr(table), ptr(out), C.c_int(h), C.c_int(w), C.c_int(H), C.c_int(W), C.c_int(Cdim))
+
+
+def pos_resize_bwd(dout, dtable, h, w, H, W, Cdim):
+    call("pos_resize_bwd", ptr(dout), ptr(dtable), C.c_int(h), C.c_int(w), C.c_int(H), C.c_int(W), C.c_int(Cdim))
+
+
+def cast_weight(src, dst):
+    call("cast_weight", ptr(src), ptr(dst), C.c_longlong(src.numel()))
+
+
+def cast_conv_weight(src, dst, Co, Ci, KK, dst_ld):
+    call("cast_conv_weight", ptr(src), ptr(dst), C.c_int(Co), C.c_int(Ci), C.c_int(KK), C.c_int(dst_ld))
+
+
+def uncast_conv_wgrad(dwp, dw, Co, Ci, KK, src_ld):
+    call("uncast_conv_wgrad", ptr(dwp), ptr(dw), C.c_int(Co), C.c_int(Ci), C.c_int(KK), C.c_int(src_ld))
+
+
+def bert_embed_fwd(ids, word, pos, typ, gamma, beta, out, mean, rstd, rows, T, eps, p_drop, seed):
+    call("bert_embed_fwd", ptr(ids), ptr(word), ptr(pos), ptr(typ), ptr(gamma), ptr(beta), ptr(out), ptr(mean),
+         ptr(rstd), C.c_int(rows), C.c_int(T), C.c_float(eps), C.c_float(p_drop), C.c_ulonglong(seed))
+
+
+def bert_embed_bwd(dy, ids, word, pos, typ, gamma, mean, rstd, dword, dpos, dtype_, dgamma, dbeta, rows, T, p_drop,
+                   seed, pad_id=0):
+    call("bert_embed_bwd", ptr(dy), ptr(ids), ptr(word), ptr(pos), ptr(typ), ptr(gamma), ptr(mean), ptr(rstd),
+         ptr(dword), ptr(dpos), ptr(dtype_), ptr(dgamma), ptr(dbeta), C.c_int(rows), C.c_int(T), C.c_float(p_drop),
+         C.c_ulonglong(seed), C.c_int(pad_id))
+
+
+def compact_labels(labels, n, ignore, idx_out, labels_out, count_out):
+    call("compact_labels", ptr(labels), C.c_int(n), C.c_longlong(ignore), ptr(idx_out), ptr(labels_out),
+         ptr(count_out))
+
+
+def gather_rows(src, idx, n_idx, dst, Cdim, smap=None, lds=None):
+    call("gather_rows", ptr(src), _map(smap), C.c_longlong(lds or Cdim), ptr(idx), C.c_int(n_idx), ptr(dst),
+         _f32(dst), C.c_int(Cdim))
+
+
+def scatter_rows(src, idx, n_idx, dst, Cdim, dmap=None, ldd=None, accumulate=False):
+    call("scatter_rows", ptr(src), _f32(src), ptr(idx), C.c_int(n_idx), ptr(dst), _map(dmap),
+         C.c_longlong(ldd or Cdim), C.c_int(Cdim), C.c_int(1 if accumulate else 0))
+
+
+def ce_fwd(logits, ld, labels, rows, n_cls, ignore, lse, loss_sum, scale, total_sum=None, argmax_out=None,
+           correct=None):
+    call("ce_fwd", ptr(logits), _f32(logits), C.c_longlong(ld), ptr(labels), C.c_int(rows), C.c_int(n_cls),
+         C.c_longlong(ignore), ptr(lse), ptr(loss_sum), ptr(total_sum), C.c_float(scale), ptr(argmax_out),
+         ptr(correct))
+
+
+def ce_bwd(logits, ld, labels, rows, n_cls, ignore, lse, dlogits, ldd, scale, gscale=None):
+    call("ce_bwd", ptr(logits), _f32(logits), C.c_longlong(ld), ptr(labels), C.c_int(rows), C.c_int(n_cls),
+         C.c_longlong(ignore), ptr(lse), ptr(dlogits), C.c_longlong(ldd), C.c_float(scale), ptr(gscale))
+
+
+def small_linear_fwd(h, W, b1, b2, out, M, n, K):
+    call("small_linear_fwd", ptr(h), ptr(W), ptr(b1), ptr(b2), ptr(out), C.c_int(M), C.c_int(n), C.c_int(K))
+
+
+def small_linear_bwd(dlogits, h, W, dh, dW, db1, db2, M, n, K):
+    call("small_linear_bwd", ptr(dlogits), ptr(h), ptr(W), ptr(dh), ptr(dW), ptr(db1), ptr(db2), C.c_int(M),
+         C.c_int(n), C.c_int(K))
+
+
+def itm_rank(logits, n_query, n_cand, rank_out, prob_out=None):
+    call("itm_rank", ptr(logits), C.c_int(n_query), C.c_int(n_cand), ptr(rank_out), ptr(prob_out))
+
+
+def grid_mask(seeds_u32, grid_out, B, size_w, size_h, patch, ratio):
+    call("grid_mask", ptr(seeds_u32), ptr(grid_out), C.c_int(B), C.c_int(size_w), C.c_int(size_h), C.c_int(patch),
+         C.c_double(ratio))
+
+
+def masked_fill(img, grid, out, mask_out, B, Cc, H, W, patch, fill=1e-6):
+    call("masked_fill", ptr(img), ptr(grid), ptr(out), ptr(mask_out), C.c_int(B), C.c_int(Cc), C.c_int(H),
+         C.c_int(W), C.c_int(patch), C.c_float(fill))
+
+
+def gelu_bwd(dy, pre, out, n):
+    call("gelu_bwd", ptr(dy), ptr(pre), ptr(out), C.c_longlong(n))
+
+
+def cast2d(src, lds, dst, ldd, rows, Cdim, alpha=1.0):
+    call("cast2d", ptr(src), _f32(src), C.c_longlong(lds), ptr(dst), _f32(dst), C.c_longlong(ldd),
+         C.c_longlong(rows), C.c_int(Cdim), C.c_float(alpha))
+
+
+def zeros(shape, dtype, dev):
+    t = torch.empty(shape, dtype=dtype, device=dev)
+    call("memset_zero", ptr(t), C.c_longlong(t.numel() * t.element_size()))
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------
+# t2i (MVM) head kernels
+# ------------------------------------------------------------------------------------------------------
+def im2col3x3(src, batch_stride, pix_stride, col, B, H, W, Cdim):
+    call("im2col3x3", ptr(src), _f32(src), C.c_longlong(batch_stride), C.c_int(pix_stride), ptr(col), C.c_int(B),
+         C.c_int(H), C.c_int(W), C.c_int(Cdim))
+
+
+def col2im3x3(dcol, dst, batch_stride, pix_stride, B, H, W, Cdim, accumulate=False):
+    call("col2im3x3", ptr(dcol), ptr(dst), _f32(dst), C.c_longlong(batch_stride), C.c_int(pix_stride), C.c_int(B),
+         C.c_int(H), C.c_int(W), C.c_int(Cdim), C.c_int(1 if accumulate else 0))
+
+
+def bn_stats(x, rows, Cdim, s, ss):
+    call("bn_stats", ptr(x), C.c_longlong(rows), C.c_int(Cdim), ptr(s), ptr(ss))
+
+
+def bn_finalize(s, ss, rows, gamma, beta, rmean, rvar, momentum, eps, training, scale, shift, mean, invstd, Cdim):
+    call("bn_finalize", ptr(s), ptr(ss), C.c_longlong(rows), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar),
+         C.c_float(momentum), C.c_float(eps), C.c_int(1 if training else 0), ptr(scale), ptr(shift), ptr(mean),
+         ptr(invstd), C.c_int(Cdim))
+
+
+def bn_apply(x, scale, shift, out, out_ld, out_coff, rows, Cdim, m1=None, m1_ld=0, m2=None, m2_ld=0):
+    call("bn_apply", ptr(x), ptr(scale), ptr(shift), ptr(m1), C.c_int(m1_ld), ptr(m2), C.c_int(m2_ld), ptr(out),
+         C.c_int(out_ld), C.c_int(out_coff), C.c_longlong(rows), C.c_int(Cdim))
+
+
+def bn_bwd(dy, x, scale, mean, invstd, sum_dy, sum_dy_xhat, dx, rows, Cdim, training):
+    call("bn_bwd", ptr(dy), ptr(x), ptr(scale), ptr(mean), ptr(invstd), ptr(sum_dy), ptr(sum_dy_xhat), ptr(dx),
+         C.c_longlong(rows), C.c_int(Cdim), C.c_int(1 if training else 0))
+
+
+def ew_mul(a, a_ld, a_coff, dst, d_ld, d_coff, rows, Cdim, b=None, b_ld=0, c2=None, c2_ld=0, accumulate=False):
+    call("ew_mul", ptr(a), _f32(a), C.c_int(a_ld), C.c_int(a_coff), ptr(b), C.c_int(b_ld), ptr(c2), C.c_int(c2_ld),
+         ptr(dst), _f32(dst), C.c_int(d_ld), C.c_int(d_coff), C.c_longlong(rows), C.c_int(Cdim),
+         C.c_int(1 if accumulate else 0))
+
+
+def upsample2x_fwd(src, batch_stride, pix_stride, dst, B, h, w, Cdim):
+    call("upsample2x_fwd", ptr(src), _f32(src), C.c_longlong(batch_stride), C.c_int(pix_stride), ptr(dst), C.c_int(B),
+         C.c_int(h), C.c_int(w), C.c_int(Cdim))
+
+
+def upsample2x_bwd(dy, dx, batch_stride, pix_stride, B, h, w, Cdim, accumulate=False):
+    call("upsample2x_bwd", ptr(dy), ptr(dx), _f32(dx), C.c_longlong(batch_stride), C.c_int(pix_stride), C.c_int(B),
+         C.c_int(h), C.c_int(w), C.c_int(Cdim), C.c_int(1 if accumulate else 0))
+
+
+def score_fwd(x, W, bias, out, rows, Cin):
+    call("score_fwd", ptr(x), ptr(W), ptr(bias), ptr(out), C.c_longlong(rows), C.c_int(Cin))
+
+
+def score_bwd(dscore, x, W, dx, dW, db, rows, Cin):
+    call("score_bwd", ptr(dscore), ptr(x), ptr(W), ptr(dx), ptr(dW), ptr(db), C.c_longlong(rows), C.c_int(Cin))
+
+
+def upsample8_fwd(score, out, B, h, w, S):
+    call("upsample8_fwd", ptr(score), ptr(out), C.c_int(B), C.c_int(h), C.c_int(w), C.c_int(S))
+
+
+def t2i_up_loss(score, target, dpred, dscore, loss_sum, total_sum, loss_scale, grad_scale, gscale, B, h, w, S, mode,
+                want_grad):
+    call("t2i_up_loss", ptr(score), ptr(target), ptr(dpred), ptr(dscore), ptr(loss_sum), ptr(total_sum),
+         C.c_float(loss_scale), C.c_float(grad_scale), ptr(gscale), C.c_int(B), C.c_int(h), C.c_int(w), C.c_int(S),
+         C.c_int(mode), C.c_int(1 if want_grad else 0))
+
+
+def sq_diff_sum(a, b, n, out):
+    call("sq_diff_sum", ptr(a), ptr(b), C.c_longlong(n), ptr(out))

@@ -1,0 +1,207 @@
+"""MVM / text-to-image head (the reference's ITGHead, /root/reference/libs/vl_heads.py:107-165) scheduled
+by hand on the C-ABI kernels: im2col + tcgen05 GEMM for the eleven 3x3 convolutions, train-mode BatchNorm,
+x2 bilinear upsampling, elementwise products written into channel slices of the concat buffers, the 1x1 score
+conv, and the x8 upsample fused with the SmoothL1 loss (engine_grid_masking.py:101).
+
+Activations are NHWC bf16; the three inputs are read in place from the fp32 token buffers of stages 2-4
+(image rows are already NHWC, so the reference's permute+contiguous at pvlt.py:352 disappears).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels as k
+
+BF16, F32 = torch.bfloat16, torch.float32
+CH = 64
+UNITS = ["reduction1", "reduction2", "reduction3", "conv_upsample1", "conv_upsample2", "conv_upsample3",
+         "conv_upsample4", "conv_upsample5", "conv_concat2", "conv_concat3", "conv4"]
+
+
+def _split_k(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 256 else 1)
+    kb = (K + 63) // 64
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return max(1, min(want, kb // 4 if kb >= 8 else 1))
+
+
+class T2IHead:
+    def __init__(self, engine):
+        self.e = engine
+        self.W = {}
+        self.nbt_pending = {}
+
+    def sync_buffers(self):
+        """BatchNorm's num_batches_tracked is bookkeeping only (momentum is fixed): counted on the host and written
+        to the registered buffers when a state_dict is taken."""
+        for pfx, n in self.nbt_pending.items():
+            self.e.Bf[pfx + ".1.num_batches_tracked"] += n
+        self.nbt_pending = {}
+
+    def prepare_weights(self):
+        P = self.e.P
+        for u in UNITS:
+            w = P[f"t2i_head.{u}.0.weight"]
+            name = f"t2i_head.{u}.0.weight"
+            if name not in self.W:
+                self.W[name] = torch.empty((w.shape[0], 9 * w.shape[1]), dtype=BF16, device=w.device)
+            k.cast_conv_weight(w, self.W[name], w.shape[0], w.shape[1], 9, 9 * w.shape[1])
+
+    # ---- conv3x3 (no bias) + BatchNorm ----------------------------------------------------------------
+    def _convbn_fwd(self, u, src, batch_stride, pix_stride, B, H, W, Ci, training, out=None, out_ld=None, out_coff=0):
+        P, Bf = self.e.P, self.e.Bf
+        pfx = f"t2i_head.{u}"
+        Wp = self.W[pfx + ".0.weight"]
+        Co = Wp.shape[0]
+        rows = B * H * W
+        dev = Wp.device
+        col = torch.empty((rows, 9 * Ci), dtype=BF16, device=dev)
+        k.im2col3x3(src, batch_stride, pix_stride, col, B, H, W, Ci)
+        y = torch.empty((rows, Co), dtype=BF16, device=dev)
+        k.gemm(col, Wp, y)
+        st = k.zeros((2, Co), F32, dev)
+        if training:
+            k.bn_stats(y, rows, Co, st[0], st[1])
+        aff = torch.empty((4, Co), dtype=F32, device=dev)  # scale, shift, mean, invstd
+        k.bn_finalize(st[0], st[1], rows, P[pfx + ".1.weight"], P[pfx + ".1.bias"], Bf[pfx + ".1.running_mean"],
+                      Bf[pfx + ".1.running_var"], 0.1, 1e-5, training, aff[0], aff[1], aff[2], aff[3], Co)
+        if training:
+            self.nbt_pending[pfx] = self.nbt_pending.get(pfx, 0) + 1   # folded into the buffer by sync_buffers()
+        if out is None:
+            out = torch.empty((rows, Co), dtype=BF16, device=dev)
+            out_ld = Co
+        k.bn_apply(y, aff[0], aff[1], out, out_ld, out_coff, rows, Co)
+        return out, dict(col=col, y=y, aff=aff, B=B, H=H, W=W, Ci=Ci, Co=Co, training=training)
+
+    def _convbn_bwd(self, u, dout, c, G, dst, dst_batch_stride, dst_pix_stride, accumulate=False):
+        """dout: contiguous bf16 [rows, Co]. Writes/accumulates the input gradient into ``dst`` (NHWC, fp32 or bf16)."""
+        pfx = f"t2i_head.{u}"
+        Wp = self.W[pfx + ".0.weight"]
+        B, H, W, Ci, Co = c["B"], c["H"], c["W"], c["Ci"], c["Co"]
+        rows = B * H * W
+        dev = dout.device
+        aff = c["aff"]
+        dy = torch.empty((rows, Co), dtype=BF16, device=dev)
+        red = k.zeros((2, Co), F32, dev)
+        # aff[0] = gamma * invstd is exactly the leading factor of the BatchNorm backward formula
+        k.bn_bwd(dout, c["y"], aff[0], aff[2], aff[3], red[0], red[1], dy, rows, Co, c["training"])
+        k.copy_rows(red[0:1], G[pfx + ".1.bias"].view(1, Co), 1, Co, accumulate=True)
+        k.copy_rows(red[1:2], G[pfx + ".1.weight"].view(1, Co), 1, Co, accumulate=True)
+        key = "__perm__" + pfx + ".0.weight"
+        if key not in G:
+            G[key] = k.zeros(tuple(Wp.shape), F32, dev)
+        k.gemm(dy.t(), c["col"].t(), G[key], atomic_add=True, split_k=_split_k(Co, 9 * Ci, rows))
+        if dst is not None:
+            dcol = torch.empty((rows, 9 * Ci), dtype=BF16, device=dev)
+            k.gemm(dy, Wp.t(), dcol)
+            k.col2im3x3(dcol, dst, dst_batch_stride, dst_pix_stride, B, H, W, Ci, accumulate)
+
+    def _slice(self, t, ld, coff, rows, Cdim):
+        out = torch.empty((rows, Cdim), dtype=t.dtype, device=t.device)
+        k.cast2d(t.view(-1)[coff:], ld, out, Cdim, rows, Cdim)
+        return out
+
+    # ---- forward ------------------------------------------------------------------------------------
+    def forward(self, feats, B, training):
+        """feats: [(X fp32 [B,N,C], H, W, C)] for stages 2, 3, 4. Returns (score fp32 [B*h*w, 3], ctx)."""
+        (Xl, Hl, Wl, Cl), (Xm, Hm, Wm, Cm), (Xh, Hh, Wh, Chh) = feats
+        T = self.e.T
+        dev = Xl.device
+        c = {}
+        low, c["r1"] = self._convbn_fwd("reduction1", Xl, (Hl * Wl + T) * Cl, Cl, B, Hl, Wl, Cl, training)
+        mid, c["r2"] = self._convbn_fwd("reduction2", Xm, (Hm * Wm + T) * Cm, Cm, B, Hm, Wm, Cm, training)
+        high, c["r3"] = self._convbn_fwd("reduction3", Xh, (Hh * Wh + T) * Chh, Chh, B, Hh, Wh, Chh, training)
+        rows_m, rows_l = B * Hm * Wm, B * Hl * Wl
+        up_high = torch.empty((rows_m, CH), dtype=BF16, device=dev)
+        k.upsample2x_fwd(high, Hh * Wh * CH, CH, up_high, B, Hh, Wh, CH)
+        cat2 = torch.empty((rows_m, 2 * CH), dtype=BF16, device=dev)
+        A1, c["u1"] = self._convbn_fwd("conv_upsample1", up_high, Hm * Wm * CH, CH, B, Hm, Wm, CH, training)
+        k.ew_mul(A1, CH, 0, cat2, 2 * CH, 0, rows_m, CH, b=mid, b_ld=CH)                     # x2_1
+        _, c["u4"] = self._convbn_fwd("conv_upsample4", up_high, Hm * Wm * CH, CH, B, Hm, Wm, CH, training,
+                                      out=cat2, out_ld=2 * CH, out_coff=CH)
+        x2_2, c["c2"] = self._convbn_fwd("conv_concat2", cat2, Hm * Wm * 2 * CH, 2 * CH, B, Hm, Wm, 2 * CH, training)
+        up_mid = torch.empty((rows_l, CH), dtype=BF16, device=dev)
+        k.upsample2x_fwd(mid, Hm * Wm * CH, CH, up_mid, B, Hm, Wm, CH)
+        A2, c["u2"] = self._convbn_fwd("conv_upsample2", up_mid, Hl * Wl * CH, CH, B, Hl, Wl, CH, training)
+        up_x21 = torch.empty((rows_l, CH), dtype=BF16, device=dev)
+        k.upsample2x_fwd(cat2, Hm * Wm * 2 * CH, 2 * CH, up_x21, B, Hm, Wm, CH)
+        A3, c["u3"] = self._convbn_fwd("conv_upsample3", up_x21, Hl * Wl * CH, CH, B, Hl, Wl, CH, training)
+        cat3 = torch.empty((rows_l, 3 * CH), dtype=BF16, device=dev)
+        k.ew_mul(A2, CH, 0, cat3, 3 * CH, 0, rows_l, CH, b=A3, b_ld=CH, c2=low, c2_ld=CH)    # x3_1
+        up_x22 = torch.empty((rows_l, 2 * CH), dtype=BF16, device=dev)
+        k.upsample2x_fwd(x2_2, Hm * Wm * 2 * CH, 2 * CH, up_x22, B, Hm, Wm, 2 * CH)
+        _, c["u5"] = self._convbn_fwd("conv_upsample5", up_x22, Hl * Wl * 2 * CH, 2 * CH, B, Hl, Wl, 2 * CH, training,
+                                      out=cat3, out_ld=3 * CH, out_coff=CH)
+        x3_2, c["c3"] = self._convbn_fwd("conv_concat3", cat3, Hl * Wl * 3 * CH, 3 * CH, B, Hl, Wl, 3 * CH, training)
+        r, c["c4"] = self._convbn_fwd("conv4", x3_2, Hl * Wl * 3 * CH, 3 * CH, B, Hl, Wl, 3 * CH, training)
+        P = self.e.P
+        score = torch.empty((rows_l, 3), dtype=F32, device=dev)
+        k.score_fwd(r, P["t2i_head.score.0.weight"], P["t2i_head.score.0.bias"], score, rows_l, 3 * CH)
+        c.update(low=low, mid=mid, A1=A1, A2=A2, A3=A3, cat2=cat2, r=r, dims=(B, Hl, Wl, Hm, Wm, Hh, Wh),
+                 chans=(Cl, Cm, Chh))
+        return score, c
+
+    # ---- backward -----------------------------------------------------------------------------------
+    def backward(self, dscore, c, G, dX4):
+        """dscore fp32 [B*Hl*Wl, 3]. Returns (dfeat2 fp32 [B,Hl*Wl,Cl], dfeat3 fp32 [B,Hm*Wm,Cm]) and accumulates the
+        stage-4 image-row gradient into dX4 (fp32 [B, N4, C4])."""
+        P = self.e.P
+        T = self.e.T
+        B, Hl, Wl, Hm, Wm, Hh, Wh = c["dims"]
+        Cl, Cm, Chh = c["chans"]
+        rows_l, rows_m, rows_h = B * Hl * Wl, B * Hm * Wm, B * Hh * Wh
+        dev = dscore.device
+        new = lambda rows, ch: torch.empty((rows, ch), dtype=BF16, device=dev)
+        dr = new(rows_l, 3 * CH)
+        k.score_bwd(dscore, c["r"], P["t2i_head.score.0.weight"], dr, G["t2i_head.score.0.weight"],
+                    G["t2i_head.score.0.bias"], rows_l, 3 * CH)
+        d_x32 = new(rows_l, 3 * CH)
+        self._convbn_bwd("conv4", dr, c["c4"], G, d_x32, Hl * Wl * 3 * CH, 3 * CH)
+        d_cat3 = new(rows_l, 3 * CH)
+        self._convbn_bwd("conv_concat3", d_x32, c["c3"], G, d_cat3, Hl * Wl * 3 * CH, 3 * CH)
+        # cat3 = [x3_1 | bn(conv_upsample5(up(x2_2)))]
+        d_u5 = self._slice(d_cat3, 3 * CH, CH, rows_l, 2 * CH)
+        d_up_x22 = new(rows_l, 2 * CH)
+        self._convbn_bwd("conv_upsample5", d_u5, c["u5"], G, d_up_x22, Hl * Wl * 2 * CH, 2 * CH)
+        d_x22 = new(rows_m, 2 * CH)
+        k.upsample2x_bwd(d_up_x22, d_x22, Hm * Wm * 2 * CH, 2 * CH, B, Hm, Wm, 2 * CH)
+        # x3_1 = A2 * A3 * low
+        dA2, dA3, g_low = new(rows_l, CH), new(rows_l, CH), new(rows_l, CH)
+        k.ew_mul(d_cat3, 3 * CH, 0, dA2, CH, 0, rows_l, CH, b=c["A3"], b_ld=CH, c2=c["low"], c2_ld=CH)
+        k.ew_mul(d_cat3, 3 * CH, 0, dA3, CH, 0, rows_l, CH, b=c["A2"], b_ld=CH, c2=c["low"], c2_ld=CH)
+        k.ew_mul(d_cat3, 3 * CH, 0, g_low, CH, 0, rows_l, CH, b=c["A2"], b_ld=CH, c2=c["A3"], c2_ld=CH)
+        d_up_x21 = new(rows_l, CH)
+        self._convbn_bwd("conv_upsample3", dA3, c["u3"], G, d_up_x21, Hl * Wl * CH, CH)
+        g_x21 = new(rows_m, CH)
+        k.upsample2x_bwd(d_up_x21, g_x21, Hm * Wm * CH, CH, B, Hm, Wm, CH)
+        d_up_mid = new(rows_l, CH)
+        self._convbn_bwd("conv_upsample2", dA2, c["u2"], G, d_up_mid, Hl * Wl * CH, CH)
+        g_mid = new(rows_m, CH)
+        k.upsample2x_bwd(d_up_mid, g_mid, Hm * Wm * CH, CH, B, Hm, Wm, CH)
+        # cat2 = [x2_1 | bn(conv_upsample4(up(high)))]
+        d_cat2 = new(rows_m, 2 * CH)
+        self._convbn_bwd("conv_concat2", d_x22, c["c2"], G, d_cat2, Hm * Wm * 2 * CH, 2 * CH)
+        d_u4 = self._slice(d_cat2, 2 * CH, CH, rows_m, CH)
+        d_up_high = new(rows_m, CH)
+        self._convbn_bwd("conv_upsample4", d_u4, c["u4"], G, d_up_high, Hm * Wm * CH, CH)
+        # x2_1 = A1 * mid ; total gradient of x2_1 = g_x21 + d_cat2[:, :CH]
+        k.ew_mul(d_cat2, 2 * CH, 0, g_x21, CH, 0, rows_m, CH, accumulate=True)
+        dA1 = new(rows_m, CH)
+        k.ew_mul(g_x21, CH, 0, dA1, CH, 0, rows_m, CH, b=c["mid"], b_ld=CH)
+        k.ew_mul(g_x21, CH, 0, g_mid, CH, 0, rows_m, CH, b=c["A1"], b_ld=CH, accumulate=True)
+        self._convbn_bwd("conv_upsample1", dA1, c["u1"], G, d_up_high, Hm * Wm * CH, CH, accumulate=True)
+        g_high = new(rows_h, CH)
+        k.upsample2x_bwd(d_up_high, g_high, Hh * Wh * CH, CH, B, Hh, Wh, CH)
+        # reductions back into the encoder's token-gradient buffers
+        N4 = Hh * Wh + T
+        self._convbn_bwd("reduction3", g_high, c["r3"], G, dX4, N4 * Chh, Chh, accumulate=True)
+        dfeat3 = torch.empty((B, Hm * Wm, Cm), dtype=F32, device=dev)
+        self._convbn_bwd("reduction2", g_mid, c["r2"], G, dfeat3, Hm * Wm * Cm, Cm)
+        dfeat2 = torch.empty((B, Hl * Wl, Cl), dtype=F32, device=dev)
+        self._convbn_bwd("reduction1", g_low, c["r1"], G, dfeat2, Hl * Wl * Cl, Cl)
+        # fold the permuted 3x3 weight gradients back to [Co, Ci, 3, 3]
+        for u in UNITS:
+            name = f"t2i_head.{u}.0.weight"
+            w = P[name]
+            k.uncast_conv_wgrad(G["__perm__" + name], G[name], w.shape[0], w.shape[1], 9, 9 * w.shape[1])
+        return dfeat2, dfeat3
