@@ -78,7 +78,21 @@ def require_cuda(*tensors):
             raise MvltError("mvlt_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
 
 
-def call(name: str, *args):
+LAUNCHES = 0          # number of C-ABI kernel entry points invoked (bench.py's gpu_launches)
+GEMM_FLOPS = 0.0      # executed GEMM flops accumulated while PROFILE is active
+PROFILE = None        # when a dict: name -> list of (start_event, end_event) recorded around every call
+
+
+def call(name: str, *args, tag: str = None):
     """Call ``int mvlt_<name>(..., void* stream)`` with the current torch stream appended."""
+    global LAUNCHES
     fn = getattr(load(), "mvlt_" + name)
+    LAUNCHES += 1
+    if PROFILE is None:
+        check(fn(*args, stream_ptr()), "mvlt_" + name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(fn(*args, stream_ptr()), "mvlt_" + name)
+    e1.record()
+    PROFILE.setdefault(tag or name, []).append((e0, e1))

@@ -101,6 +101,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
     for t in (aux, preact_out):
         if t is not None and (t.dtype != BF16 or t.stride() != out.stride()):
             raise _lib.MvltError("gemm aux/preact must be bf16 with out's strides")
+    if _lib.PROFILE is not None:
+        _lib.GEMM_FLOPS += 2.0 * M * N * K * b1 * b2
     call("gemm" if impl == "tcgen05" else "gemm_ref", C.byref(d))
     return out
 

@@ -205,7 +205,10 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
         lab_c = torch.empty((B * T,), dtype=torch.int64, device=dev)
         cnt = torch.empty((1,), dtype=torch.int32, device=dev)
         k.compact_labels(lab_dev, B * T, -1, idx, lab_c, cnt)
-        n = int((labels != -1).sum()) if not labels.is_cuda else int(cnt.item())
+        if batch.get("mlm_count") is not None:
+            n = int(batch["mlm_count"])          # supplied by the data pipeline: no device->host sync
+        else:
+            n = int((labels != -1).sum()) if not labels.is_cuda else int(cnt.item())
         if n > 0:
             lg, c = eng.mlm_fwd(X4, B, HW4, idx, n)
             lse = torch.empty((n,), dtype=F32, device=dev)
@@ -386,13 +389,29 @@ class PyramidVisionLanguageTransformer(nn.Module):
                     sup_cls_logits=sup if lt['cls'] else None, sub_cls_logits=sub if lt['cls'] else None,
                     t2i_logits=t2i if lt['t2i'] else None)
 
+    @torch.no_grad()
+    def itm_logits(self, input_images, input_ids):
+        """Retrieval fast path: encoder + ITM head only (the reference also runs its unused MLM / t2i heads,
+        engine_grid_masking.py:356-358). Returns fp32 [B, 2]."""
+        if not self.loss_type['itm']:
+            raise MvltError("this model was built without the ITM head")
+        eng = self._engine()
+        eng.prepare_weights()
+        images = input_images.contiguous().to(F32)
+        enc = eng.encoder_fwd(images, input_ids, False, False)
+        X4, HW4 = _heads_common_fwd(eng, enc, images.shape[0])
+        lg, _ = eng.small_head_fwd(X4, images.shape[0], HW4, "itm")
+        return lg
+
     def forward_losses(self, input_images, input_ids, *, mlm_labels=None, itm_labels=None, sup_cls_labels=None,
-                       sub_cls_labels=None, target_images=None, weights: Optional[Dict[str, float]] = None):
+                       sub_cls_labels=None, target_images=None, weights: Optional[Dict[str, float]] = None,
+                       mlm_count: Optional[int] = None):
         """Fused step: heads + losses of engine_grid_masking.py:81-102. Returns (total_loss, stats[8])."""
         self._engine()
         params = [p for _, p in self.named_parameters()]
         batch = dict(mlm_labels=mlm_labels, itm_labels=itm_labels, sup_cls_labels=sup_cls_labels,
-                     sub_cls_labels=sub_cls_labels, target_images=target_images, weights=weights or {})
+                     sub_cls_labels=sub_cls_labels, target_images=target_images, weights=weights or {},
+                     mlm_count=mlm_count)
         return _PVLTFunction.apply(self, ("losses", torch.is_grad_enabled()), batch, input_images, input_ids, *params)
 
 

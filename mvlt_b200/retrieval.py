@@ -1,0 +1,132 @@
+"""Candidate-sharded ITM retrieval sweep (zero-shot ITR / TIR).
+
+Reference: /root/reference/engine_grid_masking.py:336-393 scores the 101 (query, candidate) pairs of one query per
+forward on EVERY rank redundantly and also runs the unused MLM + t2i heads. Here the pairs of a chunk of queries
+are block-partitioned across the ranks of one NVSwitch box, each rank runs encoder + ITM head only, the [.,2]
+logits are all-gathered (a few hundred bytes per query over NCCL/NVLink) and the rank of candidate 0 is computed
+by the ``itm_rank`` kernel (softmax p(match), descending, engine_grid_masking.py:360-384).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as k
+
+F32 = torch.float32
+
+
+def shard_bounds(n_pairs: int, rank: int, world: int):
+    """Balanced contiguous block partition of the flattened pair list (101 is prime: per-query splits would not be)."""
+    per = (n_pairs + world - 1) // world
+    lo = min(rank * per, n_pairs)
+    return lo, min(lo + per, n_pairs), per
+
+
+@torch.no_grad()
+def score_pairs(model, images, input_ids):
+    """ITM logits fp32 [n, 2] for n aligned (image, text) pairs: encoder + ITM head only."""
+    return model.itm_logits(images, input_ids)
+
+
+@torch.no_grad()
+def rank_queries(model, images, input_ids, n_cand, rank=0, world=1, group=None):
+    """images [Q*n_cand, 3, H, W], input_ids [Q*n_cand, T] (flattened query-major; candidate 0 is the positive).
+    Every rank passes the SAME full tensors' shard-local view via ``shard_bounds``; returns int32 ranks [Q]."""
+    n = images.shape[0]
+    Q = n // n_cand
+    dev = images.device
+    lo, hi, per = shard_bounds(n, rank, world)
+    local = torch.zeros((per, 2), dtype=F32, device=dev)
+    if hi > lo:
+        local[: hi - lo] = score_pairs(model, images[lo:hi], input_ids[lo:hi])
+    if world > 1:
+        full = torch.empty((world * per, 2), dtype=F32, device=dev)
+        dist.all_gather_into_tensor(full, local, group=group)
+        logits = full[:n].contiguous()
+    else:
+        logits = local[:n]
+    ranks = torch.empty((Q,), dtype=torch.int32, device=dev)
+    k.itm_rank(logits, Q, n_cand, ranks)
+    return ranks, logits.view(Q, n_cand, 2)
+
+
+def accuracy_at(ranks, ks=(1, 5, 10)):
+    """acc@k as engine_grid_masking.py:380-393 counts it (index < k)."""
+    r = ranks.cpu()
+    return {kk: float((r < kk).sum()) / max(r.numel(), 1) for kk in ks}
+
+
+def bench_sweep(dev, rank, world, n_query=1000, n_cand=101, queries_per_step=4, warmup=1, pool=512):
+    """Synthetic TIR protocol: per query one id row repeated n_cand times against n_cand images drawn
+    from a device-resident pool. Returns the JSON sub-object bench.py prints."""
+    import mvlt_b200
+    from .synthetic import make_batch
+    torch.manual_seed(4321)
+    model = mvlt_b200.create_model("pvlt_tiny", pretrained=True, num_classes=1000, drop_rate=0.0, drop_path_rate=0.1,
+                                   drop_block_rate=None, token_hidden_size=768, num_text_tokens=128,
+                                   loss_type={"itm": 1, "mlm": 0, "t2i": 0, "cls": 0}, pretrained_pth="").to(dev).eval()
+    if world > 1:   # identical weights on every rank
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    b = make_batch(pool, seed=99)
+    img_pool = b["images"].to(dev)
+    ids_pool = b["ori_input_ids"].to(dev)
+    qps = queries_per_step * world
+    n_steps = (n_query + qps - 1) // qps
+    cand = torch.arange(n_cand, device=dev)
+
+    def one(step):
+        q0 = step * qps
+        qs = torch.arange(q0, q0 + qps, device=dev)
+        img_idx = ((qs.unsqueeze(1) * 37 + cand.unsqueeze(0) * 11) % pool).reshape(-1)
+        ids_idx = (qs % pool).repeat_interleave(n_cand)
+        lo, hi, _ = shard_bounds(qps * n_cand, rank, world)
+        # only this rank's shard is materialised; rank_queries slices [lo:hi] of a virtual full tensor
+        images = img_pool[img_idx[lo:hi]]
+        ids = ids_pool[ids_idx[lo:hi]]
+        return _rank_shard(model, images, ids, qps, n_cand, lo, hi, rank, world)
+
+    for s in range(warmup):
+        one(s)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    acc1 = 0
+    for s in range(n_steps):
+        ranks = one(s)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    pairs = n_steps * qps * n_cand
+    v = pairs / (ms / 1e3)
+    return {"metric": "itm_retrieval_pairs_per_s", "value": round(v, 1), "unit": "pairs/s", "n_query": n_steps * qps,
+            "n_cand": n_cand, "pairs": pairs, "ms_total": round(ms, 2), "scaling": "strong (candidate pairs sharded)",
+            "model_tflops": round(v * 8.33 / 1e3, 2), "config": "BASELINE configs[2], ITM-only forward, bf16 operands"}
+
+
+@torch.no_grad()
+def _rank_shard(model, images, ids, Q, n_cand, lo, hi, rank, world):
+    dev = images.device
+    n = Q * n_cand
+    per = (n + world - 1) // world
+    local = torch.zeros((per, 2), dtype=F32, device=dev)
+    if hi > lo:
+        local[: hi - lo] = score_pairs(model, images, ids)
+    if world > 1:
+        full = torch.empty((world * per, 2), dtype=F32, device=dev)
+        dist.all_gather_into_tensor(full, local)
+        logits = full[:n].contiguous()
+    else:
+        logits = local[:n]
+    ranks = torch.empty((Q,), dtype=torch.int32, device=dev)
+    k.itm_rank(logits, Q, n_cand, ranks)
+    return ranks
