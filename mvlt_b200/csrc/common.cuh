@@ -83,6 +83,33 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return cdf + x * pdf;
 }
 
+// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner chain
+// instead of erff()'s ~60 instructions; the outputs below are rounded to bf16 anyway.
+__device__ __forceinline__ float erf_poly_tail(float ax, float e) {  // returns (1 - erf(ax)) given e = exp(-ax^2)
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  return poly * t * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  const float e = __expf(-az * az);
+  const float tail = erf_poly_tail(az, e);           // 1 - erf(|z|)
+  const float erfz = copysignf(1.0f - tail, z);
+  return 0.5f * x * (1.0f + erfz);
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  const float e = __expf(-az * az);                   // = exp(-x^2 / 2)
+  const float tail = erf_poly_tail(az, e);
+  const float cdf = 0.5f * (1.0f + copysignf(1.0f - tail, z));
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -32,36 +32,43 @@ __global__ void __launch_bounds__(256) cast_scale_kernel(const float* __restrict
   }
 }
 
-// ---- out[c] (+)= sum_r x[r*ld + c] ---------------------------------------------------------------------------
+// ---- out[c] += sum_r x[r*ld + c]: each thread owns 8 consecutive columns (one 16 B load for bf16) ---------------
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int C, long long ld,
-                                                     float* __restrict__ out, long long rows_per_block) {
-  __shared__ float sh[8][64];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 64 + tx * 2;
+                                                     float* __restrict__ out, long long rows_per_block, int tx_n) {
+  __shared__ float sh[256 * 8];
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+  const int ry = blockDim.x / tx_n;
+  const int c = (blockIdx.x * tx_n + tx) * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
-  float a0 = 0.f, a1 = 0.f;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c < C) {
-    for (long long r = r0 + ty; r < r1; r += 8) {
+#pragma unroll 4
+    for (long long r = r0 + ty; r < r1; r += ry) {
       if constexpr (sizeof(T) == 2) {
-        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
-        a0 += f.x; a1 += f.y;
+        const uint4 u = *reinterpret_cast<const uint4*>(x + r * ld + c);
+        float2 f;
+        f = unpack_bf16x2(u.x); a[0] += f.x; a[1] += f.y;
+        f = unpack_bf16x2(u.y); a[2] += f.x; a[3] += f.y;
+        f = unpack_bf16x2(u.z); a[4] += f.x; a[5] += f.y;
+        f = unpack_bf16x2(u.w); a[6] += f.x; a[7] += f.y;
       } else {
-        const float2 f = *reinterpret_cast<const float2*>(x + r * ld + c);
-        a0 += f.x; a1 += f.y;
+        const float4 f0 = *reinterpret_cast<const float4*>(x + r * ld + c);
+        const float4 f1 = *reinterpret_cast<const float4*>(x + r * ld + c + 4);
+        a[0] += f0.x; a[1] += f0.y; a[2] += f0.z; a[3] += f0.w;
+        a[4] += f1.x; a[5] += f1.y; a[6] += f1.z; a[7] += f1.w;
       }
     }
   }
-  sh[ty][tx * 2] = a0;
-  sh[ty][tx * 2 + 1] = a1;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
-    const int cc = blockIdx.x * 64 + threadIdx.x;
+  for (int j = 0; j < 8; ++j) sh[(ty * tx_n + tx) * 8 + j] = a[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < tx_n * 8; i += blockDim.x) {
+    float s = 0.f;
+    for (int y = 0; y < ry; ++y) s += sh[(y * tx_n) * 8 + i];
+    const int cc = blockIdx.x * tx_n * 8 + i;
     if (cc < C) atomicAdd(out + cc, s);
   }
 }
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __re
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const float2 d = unpack_bf16x2(reinterpret_cast<const uint32_t*>(dy)[i]);
     const float2 x = unpack_bf16x2(reinterpret_cast<const uint32_t*>(pre)[i]);
-    reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(d.x * dgelu_erf(x.x), d.y * dgelu_erf(x.y));
+    reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(d.x * dgelu_fast(x.x), d.y * dgelu_fast(x.y));
   }
 }
 
@@ -343,17 +350,21 @@ extern "C" int mvlt_cast_scale_bf16(const float* src, void* dst, long long rows,
 }
 
 extern "C" int mvlt_colsum(const void* x, int x_f32, long long rows, int C, long long ld, float* out, void* stream_) {
-  MVLT_CHECK_ARG(C % 2 == 0 && ld % 2 == 0, "colsum: C and ld must be even");
-  const int gx = (C + 63) / 64;
-  long long gy = (long long)mvlt_num_sms() * 4 / gx;
+  MVLT_CHECK_ARG(ld % 8 == 0 && (((uintptr_t)x) & 15) == 0, "colsum: ld must be a multiple of 8 and x 16-byte aligned");
+  const int groups = (C + 7) / 8;           // 8-column groups (reads may touch the ld padding, results are masked)
+  int tx_n = groups < 32 ? groups : 32;
+  while (256 % tx_n != 0) --tx_n;
+  const int gx = (groups + tx_n - 1) / tx_n;
+  long long gy = (long long)mvlt_num_sms() * 8 / gx;
   if (gy < 1) gy = 1;
+  const int ry = 256 / tx_n;
   long long rpb = (rows + gy - 1) / gy;
-  if (rpb < 64) rpb = 64;
+  if (rpb < 4LL * ry) rpb = 4LL * ry;
   gy = (rows + rpb - 1) / rpb;
   dim3 grid(gx, (unsigned)gy);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  if (x_f32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), rows, C, ld, out, rpb);
-  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, ld, out, rpb);
+  if (x_f32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), rows, C, ld, out, rpb, tx_n);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, ld, out, rpb, tx_n);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -2,7 +2,7 @@
 //
 //   warp 0      : TMA producer (cp.async.bulk.tensor.4d, SWIZZLE_128B boxes, mbarrier complete_tx)
 //   warp 1      : TMEM owner + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, bf16 -> fp32)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> 128-bit global stores)
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> 128-bit global stores)
 //
 // Accumulators live in TMEM and are double-buffered (2 x BLOCK_N <= 512 columns) so the epilogue of tile
 // i overlaps the mainloop of tile i+1. Tiles are scheduled round-robin over a grid of <= #SM CTAs.
@@ -25,7 +25,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 200 * 1024;
@@ -89,6 +89,117 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
   return c;
 }
 
+// Fused epilogue for one thread's 32 consecutive output columns of one row. Every loop is fully unrolled so that
+// v[] stays in registers (a dynamically indexed tail loop would demote it to local memory).
+__device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t (&r)[32], long long row_off, int col0,
+                                               float rs, bool aligned) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  const bool full = (col0 + 32 <= p.N);
+  const bool vec_ok = full && aligned && ((col0 & 7) == 0);
+  if (p.bias != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+    }
+  }
+  if (p.act == MVLT_ACT_GELU) {
+    if (p.D2 != nullptr) {
+      __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.D2) + row_off + col0;
+      if (vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+          u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(d2 + j) = u;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) d2[j] = __float2bfloat16(v[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+  } else if (p.act == MVLT_ACT_DGELU) {
+    const __nv_bfloat16* ax = p.aux + row_off + col0;
+    if (vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(ax + j);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[j] *= dgelu_fast(f.x); v[j + 1] *= dgelu_fast(f.y);
+        f = unpack_bf16x2(u.y); v[j + 2] *= dgelu_fast(f.x); v[j + 3] *= dgelu_fast(f.y);
+        f = unpack_bf16x2(u.z); v[j + 4] *= dgelu_fast(f.x); v[j + 5] *= dgelu_fast(f.y);
+        f = unpack_bf16x2(u.w); v[j + 6] *= dgelu_fast(f.x); v[j + 7] *= dgelu_fast(f.y);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] *= dgelu_fast(__bfloat162float(ax[j]));
+    }
+  }
+  if (p.residual != nullptr) {
+    const float* rp = p.residual + row_off + col0;
+    if (vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+        v[j] = r4.x + rs * v[j]; v[j + 1] = r4.y + rs * v[j + 1];
+        v[j + 2] = r4.z + rs * v[j + 2]; v[j + 3] = r4.w + rs * v[j + 3];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] = rp[j] + rs * v[j];
+    }
+  } else if (p.rowscale != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rs;
+  }
+  if (p.atomic_add) {
+    float* d = reinterpret_cast<float*>(p.D) + row_off + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < p.N) atomicAdd(d + j, v[j]);
+  } else if (p.out_f32) {
+    float* d = reinterpret_cast<float*>(p.D) + row_off + col0;
+    if (vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) d[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + row_off + col0;
+    if (vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(d + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) d[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const KParams p) {
@@ -113,7 +224,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one elected lane per epilogue warp
+      mbar_init(&tempty_bar[a], 8);  // one elected lane per epilogue warp
     }
     fence_barrier_init();
   }
@@ -212,7 +323,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===================== epilogue warps =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // Two warps share each TMEM lane quarter and interleave the 32-column chunks of the accumulator.
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;      // 0: chunks 0,2,4..   1: chunks 1,3,5..
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -224,114 +337,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long row_off = batch_off + (long long)row * p.ldd;
       float rs = 1.f;
       if (p.rowscale != nullptr && row_ok) rs = p.rowscale[row / p.rows_per_scale];
+      const bool aligned = ((p.ldd & 7) == 0) && ((batch_off & 7) == 0);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n);
-      for (int c = 0; c < p.block_n; c += 32) {
+      for (int c = half * 32; c < p.block_n; c += 64) {
         uint32_t r[32];
         tmem_ld_32x32(taddr0 + (uint32_t)c, r);
         tmem_ld_wait();
         const int col0 = n0 + c;
-        if (!row_ok || col0 >= p.N) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        const bool full = (col0 + 32 <= p.N);
-        if (p.bias != nullptr) {
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-          }
-        }
-        const bool vec_ok = full && ((p.ldd & 7) == 0) && ((batch_off & 7) == 0) && ((col0 & 7) == 0);
-        if (p.act == MVLT_ACT_GELU) {
-          if (p.D2 != nullptr) {
-            __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.D2) + row_off + col0;
-            if (vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(d2 + j) = u;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) d2[j] = __float2bfloat16(v[j]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (p.act == MVLT_ACT_DGELU) {
-          const __nv_bfloat16* ax = p.aux + row_off + col0;
-          if (vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(ax + j);
-              float2 f;
-              f = unpack_bf16x2(u.x); v[j] *= dgelu_erf(f.x); v[j + 1] *= dgelu_erf(f.y);
-              f = unpack_bf16x2(u.y); v[j + 2] *= dgelu_erf(f.x); v[j + 3] *= dgelu_erf(f.y);
-              f = unpack_bf16x2(u.z); v[j + 4] *= dgelu_erf(f.x); v[j + 5] *= dgelu_erf(f.y);
-              f = unpack_bf16x2(u.w); v[j + 6] *= dgelu_erf(f.x); v[j + 7] *= dgelu_erf(f.y);
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] *= dgelu_erf(__bfloat162float(ax[j]));
-          }
-        }
-        if (p.residual != nullptr) {
-          const float* rp = p.residual + row_off + col0;
-          if (vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-              v[j] = r4.x + rs * v[j]; v[j + 1] = r4.y + rs * v[j + 1];
-              v[j + 2] = r4.z + rs * v[j + 2]; v[j + 3] = r4.w + rs * v[j + 3];
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] = rp[j] + rs * v[j];
-          }
-        } else if (p.rowscale != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= rs;
-        }
-        if (p.atomic_add) {
-          float* d = reinterpret_cast<float*>(p.D) + row_off + col0;
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) atomicAdd(d + j, v[j]);
-        } else if (p.out_f32) {
-          float* d = reinterpret_cast<float*>(p.D) + row_off + col0;
-          if (vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) d[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + row_off + col0;
-          if (vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(d + j) = u;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) d[j] = __float2bfloat16(v[j]);
-          }
-        }
+        if (row_ok && col0 < p.N) epilogue_chunk(p, r, row_off, col0, rs, aligned);
       }
       // all of this warp's TMEM reads are complete (wait::ld above): release the accumulator buffer
       tc_fence_before();

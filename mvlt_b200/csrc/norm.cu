@@ -46,40 +46,53 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v
   *reinterpret_cast<uint2*>(p) = u;
 }
 
-template <typename TI, typename TO>
+// G = lanes that share one row (32, or 16 for C == 64 so that a warp normalises two rows at once)
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TI, typename TO, int G>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, RowMap xm, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, TO* __restrict__ y, RowMap ym,
                                                      const float* __restrict__ post_add, float* __restrict__ mean_out,
                                                      float* __restrict__ rstd_out, int rows, int C, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int nvec = (C + 127) / 128;
-  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
-    const TI* xr = x + map_row(xm, r) * C;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, sub = lane % G;
+  const int rows_per_block = (blockDim.x >> 5) * RPW;
+  const int nvec = (C + 4 * G - 1) / (4 * G);
+  const float inv_c = 1.f / (float)C;
+  for (int r0 = blockIdx.x * rows_per_block; r0 < rows; r0 += gridDim.x * rows_per_block) {
+    const int r = r0 + (threadIdx.x >> 5) * RPW + lane / G;
+    const bool ok = r < rows;
+    const TI* xr = x + (ok ? map_row(xm, r) : 0) * C;
     float4 v[LN_MAX_VEC];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAX_VEC; ++i) {
-      const int c = i * 128 + lane * 4;
-      if (i < nvec && c < C) {
+      const int c = i * 4 * G + sub * 4;
+      if (ok && i < nvec && c < C) {
         v[i] = load4<TI>(xr + c);
         s += v[i].x + v[i].y + v[i].z + v[i].w;
       } else {
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    const float mean = warp_sum(s) / (float)C;
+    const float mean = group_sum<G>(s) * inv_c;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAX_VEC; ++i) {
-      const int c = i * 128 + lane * 4;
+      const int c = i * 4 * G + sub * 4;
       if (i < nvec && c < C) {
         const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
         q += a * a + b * b + cc * cc + d * d;
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-    if (lane == 0 && mean_out != nullptr) {
+    const float rstd = rsqrtf(group_sum<G>(q) * inv_c + eps);
+    if (!ok) continue;
+    if (sub == 0 && mean_out != nullptr) {
       mean_out[r] = mean;
       rstd_out[r] = rstd;
     }
@@ -87,7 +100,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, R
     const float* pa = post_add ? post_add + (long long)(r % ym.group) * C : nullptr;
 #pragma unroll
     for (int i = 0; i < LN_MAX_VEC; ++i) {
-      const int c = i * 128 + lane * 4;
+      const int c = i * 4 * G + sub * 4;
       if (i < nvec && c < C) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
         const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
@@ -107,30 +120,35 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, R
 }
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))  [+ dx_add];   dgamma += dy*xhat ; dbeta += dy
-template <typename TDY, typename TX, typename TDX>
+template <typename TDY, typename TX, typename TDX, int G>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, RowMap dym, const TX* __restrict__ x,
                                                      RowMap xm, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                      TDX* __restrict__ dx, RowMap dxm, const float* __restrict__ dx_add,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
                                                      int C) {
-  extern __shared__ float sh[];  // [2][warps][C]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  const int nvec = (C + 127) / 128;
+  extern __shared__ float sh[];  // [2][warps * RPW][C]
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % G;
+  const int wpb = blockDim.x >> 5;
+  const int rows_per_block = wpb * RPW;
+  const int nvec = (C + 4 * G - 1) / (4 * G);
+  const float inv_c = 1.f / (float)C;
   float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
 #pragma unroll
   for (int i = 0; i < LN_MAX_VEC; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = blockIdx.x * warps_per_block + warp; r < rows; r += gridDim.x * warps_per_block) {
-    const TDY* dyr = dy + map_row(dym, r) * C;
-    const TX* xr = x + map_row(xm, r) * C;
-    const float mu = mean[r], rs = rstd[r];
+  for (int r0 = blockIdx.x * rows_per_block; r0 < rows; r0 += gridDim.x * rows_per_block) {
+    const int r = r0 + warp * RPW + lane / G;
+    const bool ok = r < rows;
+    const TDY* dyr = dy + (ok ? map_row(dym, r) : 0) * C;
+    const TX* xr = x + (ok ? map_row(xm, r) : 0) * C;
+    const float mu = ok ? mean[r] : 0.f, rs = ok ? rstd[r] : 0.f;
     float4 vdy[LN_MAX_VEC], vxh[LN_MAX_VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAX_VEC; ++i) {
-      const int c = i * 128 + lane * 4;
-      if (i < nvec && c < C) {
+      const int c = i * 4 * G + sub * 4;
+      if (ok && i < nvec && c < C) {
         const float4 d = load4<TDY>(dyr + c);
         const float4 xv = load4<TX>(xr + c);
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -146,12 +164,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
         vxh[i] = xh;
       }
     }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
+    s1 = group_sum<G>(s1) * inv_c;
+    s2 = group_sum<G>(s2) * inv_c;
+    if (!ok) continue;
     const long long drow = map_row(dxm, r) * C;
 #pragma unroll
     for (int i = 0; i < LN_MAX_VEC; ++i) {
-      const int c = i * 128 + lane * 4;
+      const int c = i * 4 * G + sub * 4;
       if (i < nvec && c < C) {
         float4 o;
         o.x = rs * (vdy[i].x - s1 - vxh[i].x * s2);
@@ -167,21 +186,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
     }
   }
   if (dgamma == nullptr) return;
-  // block reduction of the per-warp partials, then one atomic per column per block
+  // block reduction of the per-row-group partials, then one atomic per column per block
+  const int slots = wpb * RPW;
   float* shg = sh;
-  float* shb = sh + warps_per_block * C;
+  float* shb = sh + slots * C;
+  const int slot = warp * RPW + lane / G;
 #pragma unroll
   for (int i = 0; i < LN_MAX_VEC; ++i) {
-    const int c = i * 128 + lane * 4;
+    const int c = i * 4 * G + sub * 4;
     if (i < nvec && c < C) {
-      *reinterpret_cast<float4*>(shg + warp * C + c) = ag[i];
-      *reinterpret_cast<float4*>(shb + warp * C + c) = ab[i];
+      *reinterpret_cast<float4*>(shg + slot * C + c) = ag[i];
+      *reinterpret_cast<float4*>(shb + slot * C + c) = ab[i];
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float g = 0.f, b = 0.f;
-    for (int w = 0; w < warps_per_block; ++w) {
+    for (int w = 0; w < slots; ++w) {
       g += shg[w * C + c];
       b += shb[w * C + c];
     }
@@ -266,10 +287,16 @@ extern "C" int mvlt_layernorm_fwd(const void* x, int x_f32, const int* xmap, con
   MVLT_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && C <= 128 * LN_MAX_VEC, "layernorm_fwd: unsupported C=%d", C);
   RowMap xm{xmap && xmap[0] > 0 ? xmap[0] : rows, xmap && xmap[0] > 0 ? xmap[1] : rows, xmap && xmap[0] > 0 ? xmap[2] : 0};
   RowMap ym{ymap && ymap[0] > 0 ? ymap[0] : rows, ymap && ymap[0] > 0 ? ymap[1] : rows, ymap && ymap[0] > 0 ? ymap[2] : 0};
-  const int grid = ln_grid(rows, 8);
-#define LAUNCH(TI, TO)                                                                                         \
-  ln_fwd_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,                 \
-                                              reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps)
+  const int grid = ln_grid(rows, C <= 64 ? 16 : 8);
+#define LAUNCH(TI, TO)                                                                                           \
+  do {                                                                                                           \
+    if (C <= 64)                                                                                                 \
+      ln_fwd_kernel<TI, TO, 16><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,            \
+                                                      reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps); \
+    else                                                                                                         \
+      ln_fwd_kernel<TI, TO, 32><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,            \
+                                                      reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps); \
+  } while (0)
   if (x_f32 && y_f32) LAUNCH(float, float);
   else if (x_f32 && !y_f32) LAUNCH(float, __nv_bfloat16);
   else if (!x_f32 && y_f32) LAUNCH(__nv_bfloat16, float);
@@ -289,16 +316,22 @@ extern "C" int mvlt_layernorm_bwd(const void* dy, int dy_f32, const int* dymap, 
     return RowMap{m && m[0] > 0 ? m[0] : rows, m && m[0] > 0 ? m[1] : rows, m && m[0] > 0 ? m[2] : 0};
   };
   RowMap dym = mk(dymap), xm = mk(xmap), dxm = mk(dxmap);
-  const int wpb = 8;
-  long long b = ((long long)rows + wpb * 4 - 1) / (wpb * 4);  // >= 4 rows per warp to amortise the atomics
-  const long long cap = (long long)mvlt_num_sms() * 4;
+  const int wpb = 8, rpw = C <= 64 ? 2 : 1;
+  long long b = ((long long)rows + wpb * rpw * 4 - 1) / (wpb * rpw * 4);  // >= 4 row passes per warp to amortise the atomics
+  const long long cap = (long long)mvlt_num_sms() * 6;
   const int grid = (int)(b < cap ? (b > 0 ? b : 1) : cap);
-  const size_t smem = (size_t)2 * wpb * C * sizeof(float);
-#define LAUNCH(TDY, TX, TDX)                                                                                    \
-  ln_bwd_kernel<TDY, TX, TDX><<<grid, 256, smem, st>>>(reinterpret_cast<const TDY*>(dy), dym,                   \
-                                                       reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma,   \
-                                                       reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta,  \
-                                                       rows, C)
+  const size_t smem = (size_t)2 * wpb * rpw * C * sizeof(float);
+#define LAUNCH(TDY, TX, TDX)                                                                                      \
+  do {                                                                                                            \
+    if (C <= 64)                                                                                                  \
+      ln_bwd_kernel<TDY, TX, TDX, 16><<<grid, 256, smem, st>>>(reinterpret_cast<const TDY*>(dy), dym,              \
+                                                               reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma, \
+                                                               reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta, rows, C); \
+    else                                                                                                          \
+      ln_bwd_kernel<TDY, TX, TDX, 32><<<grid, 256, smem, st>>>(reinterpret_cast<const TDY*>(dy), dym,              \
+                                                               reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma, \
+                                                               reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta, rows, C); \
+  } while (0)
   const int key = (dy_f32 ? 4 : 0) | (x_f32 ? 2 : 0) | (dx_f32 ? 1 : 0);
   switch (key) {
     case 0: LAUNCH(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16); break;
