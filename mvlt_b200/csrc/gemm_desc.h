@@ -19,6 +19,8 @@ enum {
   MVLT_ACT_NONE = 0,
   MVLT_ACT_GELU = 1,   // D = gelu_erf(v); optional D2 = v (pre-activation, bf16) for the backward pass
   MVLT_ACT_DGELU = 2,  // D = v * gelu_erf'(aux[m,n])   (aux = saved pre-activation, bf16)
+  MVLT_ACT_GELU_SAVE_GRAD = 3,  // D = gelu_erf(v); D2 = gelu_erf'(v) (bf16): the backward pass is then a plain multiply
+  MVLT_ACT_MUL_AUX = 4,         // D = v * aux[m,n]        (aux = saved gelu'(pre-activation), bf16)
 };
 
 typedef struct mvlt_gemm_desc {

@@ -30,6 +30,11 @@ __global__ void gemm_ref_kernel(const mvlt_gemm_desc g) {
     if (g.act == MVLT_ACT_GELU) {
       if (g.D2) reinterpret_cast<__nv_bfloat16*>(g.D2)[off] = __float2bfloat16(v);
       v = gelu_erf(v);
+    } else if (g.act == MVLT_ACT_GELU_SAVE_GRAD) {
+      reinterpret_cast<__nv_bfloat16*>(g.D2)[off] = __float2bfloat16(dgelu_erf(v));
+      v = gelu_erf(v);
+    } else if (g.act == MVLT_ACT_MUL_AUX) {
+      v *= __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g.aux)[off]);
     } else if (g.act == MVLT_ACT_DGELU) {
       v *= dgelu_erf(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g.aux)[off]));
     }

@@ -196,8 +196,10 @@ class PVLTEngine:
         mean2, rstd2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
         k.layernorm_fwd(X1, P[pfx + ".norm2.weight"], P[pfx + ".norm2.bias"], xn2, 1e-6, M, C, mean=mean2, rstd=rstd2)
         act = _empty((M, hidden), BF16, dev)
+        # training: the epilogue also stores gelu'(pre-activation) so that the backward GEMM epilogue is a multiply
         hpre = _empty((M, hidden), BF16, dev) if save else None
-        k.gemm(xn2, Wb[pfx + ".mlp.fc1.weight"], act, bias=P[pfx + ".mlp.fc1.bias"], act=k.ACT_GELU, preact_out=hpre)
+        k.gemm(xn2, Wb[pfx + ".mlp.fc1.weight"], act, bias=P[pfx + ".mlp.fc1.bias"],
+               act=k.ACT_GELU_SAVE_GRAD if save else k.ACT_GELU, preact_out=hpre)
         X2 = _empty((B, N, C), F32, dev)
         k.gemm(act, Wb[pfx + ".mlp.fc2.weight"], X2.view(M, C), bias=P[pfx + ".mlp.fc2.bias"],
                residual=X1.view(M, C), rowscale=dp[1] if dp else None, rows_per_scale=N)
@@ -220,7 +222,7 @@ class PVLTEngine:
         k.cast_scale_bf16(dX2, dy2, M, C, rowscale=dp[1] if dp else None, rows_per_scale=N)
         self._lin_param_grads(G, pfx + ".mlp.fc2.weight", pfx + ".mlp.fc2.bias", dy2, c["act"])
         dh = _empty((M, hidden), BF16, dev)
-        k.gemm(dy2, Wb[pfx + ".mlp.fc2.weight"].t(), dh, act=k.ACT_DGELU, aux=c["hpre"])
+        k.gemm(dy2, Wb[pfx + ".mlp.fc2.weight"].t(), dh, act=k.ACT_MUL_AUX, aux=c["hpre"])
         self._lin_param_grads(G, pfx + ".mlp.fc1.weight", pfx + ".mlp.fc1.bias", dh, c["xn2"])
         dxn2 = dy2  # reuse
         k.gemm(dh, Wb[pfx + ".mlp.fc1.weight"].t(), dxn2)
@@ -497,7 +499,7 @@ class PVLTEngine:
         ha = _empty((n_rows, HIDDEN), BF16, dev)
         hpre = _empty((n_rows, HIDDEN), BF16, dev)
         k.gemm(hn, Wb["mlm_head.transform.dense.weight"], ha, bias=P["mlm_head.transform.dense.bias"],
-               act=k.ACT_GELU, preact_out=hpre)
+               act=k.ACT_GELU_SAVE_GRAD, preact_out=hpre)
         hl = _empty((n_rows, HIDDEN), BF16, dev)
         m2, r2 = _empty((n_rows,), F32, dev), _empty((n_rows,), F32, dev)
         k.layernorm_fwd(ha, P["mlm_head.transform.LayerNorm.weight"], P["mlm_head.transform.LayerNorm.bias"], hl,
@@ -522,9 +524,9 @@ class PVLTEngine:
         dha = _empty((n_rows, HIDDEN), BF16, dev)
         k.layernorm_bwd(dhl, c["ha"], c["m2"], c["r2"], P["mlm_head.transform.LayerNorm.weight"], dha, n_rows, HIDDEN,
                         dgamma=G["mlm_head.transform.LayerNorm.weight"], dbeta=G["mlm_head.transform.LayerNorm.bias"])
-        # GELU backward as an elementwise pass folded into the dense GEMM pair: dpre = dha * gelu'(hpre)
+        # GELU backward: dpre = dha * gelu'(pre), with gelu' saved by the forward epilogue
         dpre = dhl
-        k.gelu_bwd(dha, c["hpre"], dpre, n_rows * HIDDEN)
+        k.ew_mul(dha, HIDDEN, 0, dpre, HIDDEN, 0, n_rows, HIDDEN, b=c["hpre"], b_ld=HIDDEN)
         self._lin_param_grads(G, "mlm_head.transform.dense.weight", "mlm_head.transform.dense.bias", dpre, c["hn"])
         dhn = dha
         k.gemm(dpre, Wb["mlm_head.transform.dense.weight"].t(), dhn)

@@ -85,6 +85,17 @@ def test_gemm_epilogues():
     out = torch.empty((M, N), device="cuda", dtype=BF16)
     k.gemm(a, b, out, act=k.ACT_DGELU, aux=x)
     _check(out, _ref(a, b) * xr.grad, K, "dgelu")
+    # gelu + saved derivative, then multiply-by-aux backward epilogue
+    out = torch.empty((M, N), device="cuda", dtype=BF16)
+    dg = torch.empty((M, N), device="cuda", dtype=BF16)
+    k.gemm(a, b, out, alpha=0.5, bias=bias, act=k.ACT_GELU_SAVE_GRAD, preact_out=dg)
+    refr = ref.clone().requires_grad_(True)
+    torch.nn.functional.gelu(refr).sum().backward()
+    _check(out, torch.nn.functional.gelu(ref), K, "gelu(save_grad)")
+    _check(dg, refr.grad, K, "gelu'")
+    out2 = torch.empty((M, N), device="cuda", dtype=BF16)
+    k.gemm(a, b, out2, act=k.ACT_MUL_AUX, aux=dg)
+    _check(out2, _ref(a, b) * dg.float(), K, "mul_aux")
     # residual + rowscale
     res = torch.randn((M, N), generator=g, device="cuda")
     rs = torch.rand(M // 64, generator=g, device="cuda")
