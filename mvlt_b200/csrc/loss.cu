@@ -106,7 +106,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                                                      int n_cls, long long ignore, float* __restrict__ lse_out,
                                                      float* __restrict__ loss_sum, float* __restrict__ total_sum, float scale,
-                                                     int* __restrict__ argmax_out, int* __restrict__ correct) {
+                                                     int* __restrict__ argmax_out, float* __restrict__ correct) {
   __shared__ float sh[32];
   __shared__ int shi[32];
   const int r = blockIdx.x;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logit
       const float l = (lse - ldf(row + lab)) * scale;
       atomicAdd(loss_sum, l);
       if (total_sum) atomicAdd(total_sum, l);
-      if (correct && am == (int)lab) atomicAdd(correct, 1);
+      if (correct && am == (int)lab) atomicAdd(correct, 1.0f);
     }
   }
 }
@@ -305,7 +305,7 @@ extern "C" int mvlt_scatter_rows(const void* src, int src_f32, const int* idx, i
 
 extern "C" int mvlt_ce_fwd(const void* logits, int logits_f32, long long ld, const long long* labels, int rows, int n_cls,
                            long long ignore, float* lse, float* loss_sum, float* total_sum, float scale, int* argmax_out,
-                           int* correct, void* stream_) {
+                           float* correct, void* stream_) {
   MVLT_CHECK_ARG(rows > 0 && n_cls > 0, "ce_fwd: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (logits_f32)

@@ -188,7 +188,8 @@ def eng_backward_logits(eng: PVLTEngine, saved, gouts, G):
 
 def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
     """engine_grid_masking.py:81-102 fused onto the heads. ``batch`` carries labels / target images / weights.
-    Returns (total_loss [], stats fp32 [8] = [total, mlm, itm, sup_cls, sub_cls, t2i, mlm_correct, mlm_count])."""
+    Returns (total_loss [], stats fp32 [12] = [total, mlm, itm, sup_cls, sub_cls, t2i, mlm_correct, mlm_count,
+    itm_correct, sup_cls_correct, sub_cls_correct, 0])."""
     B = images.shape[0]
     T = eng.T
     dev = images.device
@@ -196,9 +197,11 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
     X4, HW4 = _heads_common_fwd(eng, enc, B)
     lt = eng.loss_type
     w = batch.get("weights", {})
-    stats = k.zeros((8,), F32, dev)
+    stats = k.zeros((12,), F32, dev)
     hc = {}
-    if lt.get("mlm"):
+    only = batch.get("only")
+    want = lambda name: only is None or name in only
+    if lt.get("mlm") and want("mlm") and batch.get("mlm_labels") is not None:
         labels = batch["mlm_labels"]
         lab_dev = labels.to(dev, non_blocking=True).contiguous().view(-1)
         idx = torch.empty((B * T,), dtype=torch.int32, device=dev)
@@ -212,15 +215,16 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
         if n > 0:
             lg, c = eng.mlm_fwd(X4, B, HW4, idx, n)
             lse = torch.empty((n,), dtype=F32, device=dev)
-            corr = torch.zeros((1,), dtype=torch.int32, device=dev)
             wm = w.get("mlm", MLM_LOSS_WEIGHT)
-            k.ce_fwd(lg, VOCAB_PAD, lab_c, n, VOCAB, -1, lse, stats[1:2], wm / n, total_sum=stats[0:1], correct=corr)
-            c.update(logits=lg, lse=lse, labels=lab_c, scale=wm / n, corr=corr, n=n)
+            k.ce_fwd(lg, VOCAB_PAD, lab_c, n, VOCAB, -1, lse, stats[1:2], wm / n, total_sum=stats[0:1],
+                     correct=stats[6:7])
+            stats[7:8].fill_(float(n))
+            c.update(logits=lg, lse=lse, labels=lab_c, scale=wm / n, n=n)
             hc["mlm"] = c
     for name, key, wkey in (("itm", "itm_labels", "itm"), ("sup_cls", "sup_cls_labels", "cls"),
                             ("sub_cls", "sub_cls_labels", "cls")):
         on = lt.get("itm") if name == "itm" else lt.get("cls")
-        if not on:
+        if not on or not want(wkey) or batch.get(key) is None:
             continue
         lab = batch[key].to(dev, non_blocking=True).contiguous().view(-1)
         lg, c = eng.small_head_fwd(X4, B, HW4, name)
@@ -228,10 +232,11 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
         lse = torch.empty((B,), dtype=F32, device=dev)
         wt = w.get(wkey, ITM_LOSS_WEIGHT if name == "itm" else 1.0)
         slot = {"itm": 2, "sup_cls": 3, "sub_cls": 4}[name]
-        k.ce_fwd(lg, n_cls, lab, B, n_cls, -100, lse, stats[slot:slot + 1], wt / B, total_sum=stats[0:1])
+        k.ce_fwd(lg, n_cls, lab, B, n_cls, -100, lse, stats[slot:slot + 1], wt / B, total_sum=stats[0:1],
+                 correct=stats[slot + 6:slot + 7])
         c.update(logits=lg, lse=lse, labels=lab, scale=wt / B)
         hc[name] = c
-    if lt.get("t2i"):
+    if lt.get("t2i") and want("t2i") and batch.get("target_images") is not None:
         feats = [(enc["stages"][i]["out"], enc["stages"][i]["H"], enc["stages"][i]["W"], EMBED_DIMS[i]) for i in (1, 2, 3)]
         score, c = eng.t2i.forward(feats, B, training)
         h, wd = feats[0][1], feats[0][2]
@@ -405,13 +410,13 @@ class PyramidVisionLanguageTransformer(nn.Module):
 
     def forward_losses(self, input_images, input_ids, *, mlm_labels=None, itm_labels=None, sup_cls_labels=None,
                        sub_cls_labels=None, target_images=None, weights: Optional[Dict[str, float]] = None,
-                       mlm_count: Optional[int] = None):
+                       mlm_count: Optional[int] = None, only=None):
         """Fused step: heads + losses of engine_grid_masking.py:81-102. Returns (total_loss, stats[8])."""
         self._engine()
         params = [p for _, p in self.named_parameters()]
         batch = dict(mlm_labels=mlm_labels, itm_labels=itm_labels, sup_cls_labels=sup_cls_labels,
                      sub_cls_labels=sub_cls_labels, target_images=target_images, weights=weights or {},
-                     mlm_count=mlm_count)
+                     mlm_count=mlm_count, only=only)
         return _PVLTFunction.apply(self, ("losses", torch.is_grad_enabled()), batch, input_images, input_ids, *params)
 
 

@@ -30,7 +30,7 @@ def compute_mlm_score(logits, target, index=-1):
     dev = lg.device
     lse = torch.empty((rows,), dtype=F32, device=dev)
     dummy = k.zeros((1,), F32, dev)
-    correct = torch.zeros((1,), dtype=torch.int32, device=dev)
+    correct = k.zeros((1,), F32, dev)
     k.ce_fwd(lg, ld, target, rows, V, index, lse, dummy, 0.0, correct=correct)
     total = int((target != index).sum())
     return float(correct.item()) / total if total > 0 else float("nan")

@@ -23,6 +23,15 @@ def shard_bounds(n_pairs: int, rank: int, world: int):
     return lo, min(lo + per, n_pairs), per
 
 
+def gather_shards(local, n, world, group=None):
+    """local: [per, 2] logits of this rank's block (zero padded); returns the [n, 2] logits in global pair order."""
+    if world == 1:
+        return local[:n]
+    full = torch.empty((world * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, local.contiguous(), group=group)
+    return full[:n].contiguous()
+
+
 @torch.no_grad()
 def score_pairs(model, images, input_ids):
     """ITM logits fp32 [n, 2] for n aligned (image, text) pairs: encoder + ITM head only."""
@@ -40,12 +49,7 @@ def rank_queries(model, images, input_ids, n_cand, rank=0, world=1, group=None):
     local = torch.zeros((per, 2), dtype=F32, device=dev)
     if hi > lo:
         local[: hi - lo] = score_pairs(model, images[lo:hi], input_ids[lo:hi])
-    if world > 1:
-        full = torch.empty((world * per, 2), dtype=F32, device=dev)
-        dist.all_gather_into_tensor(full, local, group=group)
-        logits = full[:n].contiguous()
-    else:
-        logits = local[:n]
+    logits = gather_shards(local, n, world, group)
     ranks = torch.empty((Q,), dtype=torch.int32, device=dev)
     k.itm_rank(logits, Q, n_cand, ranks)
     return ranks, logits.view(Q, n_cand, 2)
@@ -121,12 +125,7 @@ def _rank_shard(model, images, ids, Q, n_cand, lo, hi, rank, world):
     local = torch.zeros((per, 2), dtype=F32, device=dev)
     if hi > lo:
         local[: hi - lo] = score_pairs(model, images, ids)
-    if world > 1:
-        full = torch.empty((world * per, 2), dtype=F32, device=dev)
-        dist.all_gather_into_tensor(full, local)
-        logits = full[:n].contiguous()
-    else:
-        logits = local[:n]
+    logits = gather_shards(local, n, world)
     ranks = torch.empty((Q,), dtype=torch.int32, device=dev)
     k.itm_rank(logits, Q, n_cand, ranks)
     return ranks

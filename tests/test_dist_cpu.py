@@ -1,0 +1,73 @@
+"""Host-side multi-process logic on CPU (gloo, world_size 2): candidate-pair sharding + score gather of the retrieval
+sweep, and the metric reduction of the train/eval loops. The CUDA side of the same paths is covered by -m gpu tests."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mvlt_b200 import retrieval
+        from mvlt_b200.utils import MetricLogger
+        from oracle import pvlt_oracle as O
+        n_cand, Q = 101, 3
+        n = n_cand * Q
+        g = torch.Generator().manual_seed(0)
+        truth = torch.randn((n, 2), generator=g)                  # the logits every pair "should" get
+        lo, hi, per = retrieval.shard_bounds(n, rank, world)
+        local = torch.zeros((per, 2))
+        local[: hi - lo] = truth[lo:hi]                            # this rank scores only its block
+        full = retrieval.gather_shards(local, n, world)
+        assert torch.equal(full, truth)
+        ranks = [O.retrieval_rank(full.view(Q, n_cand, 2)[i]) for i in range(Q)]
+        ml = MetricLogger()
+        ml.update(loss=float(rank + 1), n=2)
+        ml.synchronize_between_processes()
+        q.put((rank, lo, hi, ranks, ml.meters["loss"].global_avg))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_retrieval_sharding_and_metric_reduce_gloo_world2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, lo0, hi0, ranks0, avg0), (r1, lo1, hi1, ranks1, avg1) = res
+    assert lo0 == 0 and hi0 == lo1 and hi1 == 303          # contiguous, disjoint, complete cover of 3 x 101 pairs
+    assert abs((hi0 - lo0) - (hi1 - lo1)) <= 1              # balanced although 101 is prime
+    assert ranks0 == ranks1                                 # every rank derives identical rankings
+    assert avg0 == avg1 == pytest.approx(1.5)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_shard_bounds_cover(world):
+    from mvlt_b200 import retrieval
+    n = 101 * 4
+    seen = []
+    for r in range(world):
+        lo, hi, per = retrieval.shard_bounds(n, r, world)
+        assert hi - lo <= per
+        seen += list(range(lo, hi))
+    assert seen == list(range(n))

@@ -1,0 +1,130 @@
+"""The reference-named train / eval loops (engine_grid_masking.py) on synthetic loaders, plus size-independent
+properties at the BASELINE batch size (determinism, candidate-permutation equivariance, shard equivalence)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PRE = {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0}
+CLS = {"itm": 0, "mlm": 0, "t2i": 0, "cls": 1}
+
+
+def _model(loss_type, drop_path=0.1, seed=0):
+    import mvlt_b200
+    torch.manual_seed(seed)
+    return mvlt_b200.create_model("pvlt_tiny", pretrained=True, num_classes=1000, drop_rate=0.0, drop_path_rate=drop_path,
+                                  drop_block_rate=None, token_hidden_size=768, num_text_tokens=128,
+                                  loss_type=dict(loss_type), pretrained_pth="").cuda()
+
+
+def _loader(n, B, keys_eval=False):
+    from mvlt_b200.synthetic import make_batch
+    out = []
+    for i in range(n):
+        b = make_batch(B, seed=i)
+        b["image"] = b.pop("images")
+        if keys_eval:
+            b["images"] = b["image"]
+        out.append(b)
+    return out
+
+
+class _Args:
+    loss_type = PRE
+    eval_retrieval_tir = True
+    eval_retrieval_itr = False
+
+
+def test_train_and_eval_loops_run_and_learn():
+    import engine_grid_masking as E
+    m = _model(PRE, drop_path=0.0)
+    m.text_embeddings.dropout.p = 0.0
+    opt = torch.optim.AdamW(m.parameters(), lr=2e-4)
+    data = _loader(2, 8) * 6                        # 12 steps over two fixed batches: the loss must go down
+    s0 = E.train_one_epoch_vl(m, None, data[:2], opt, torch.device("cuda"), 0, None, args=_Args())
+    for ep in range(1, 5):
+        s1 = E.train_one_epoch_vl(m, None, data[:2], opt, torch.device("cuda"), ep, None, args=_Args())
+    assert all(math.isfinite(v) for v in s1.values())
+    assert s1["total_loss"] < s0["total_loss"] - 0.2, (s0, s1)
+    ev = E.evaluate_vl(_loader(2, 8), m, torch.device("cuda"), _Args())
+    assert set(ev) >= {"mlm_acc", "itm_acc", "t2i_psnr", "total_loss"} and 0 <= ev["mlm_acc"] <= 1 and ev["t2i_psnr"] > 0
+    sd = m.state_dict()
+    assert int(sd["t2i_head.conv4.1.num_batches_tracked"]) == 10   # one BatchNorm update per training forward
+
+
+def test_eval_fused_metrics_equal_dict_path_metrics():
+    """evaluate_vl takes accuracies from the fused kernels; they must equal vl_scores on materialised logits."""
+    from mvlt_b200.libs.vl_scores import compute_mlm_score, compute_score_with_logits
+    m = _model(PRE).eval()
+    b = _loader(1, 16)[0]
+    with torch.no_grad():
+        out = m(b["image"].cuda(), b["input_ids"].cuda())
+        _, st = m.forward_losses(b["image"].cuda(), b["input_ids"].cuda(), mlm_labels=b["mlm_labels"],
+                                 itm_labels=b["itm_labels"], only=("mlm", "itm"))
+    s = st.tolist()
+    acc = compute_mlm_score(out["mlm_logits"], b["mlm_labels"].cuda())
+    assert abs(acc - s[6] / s[7]) < 1e-6
+    itm = compute_score_with_logits(out["itm_logits"].view(-1, 2), b["itm_labels"].view(-1).cuda()).sum().item()
+    assert itm == s[8]
+    ce = torch.nn.functional.cross_entropy(out["mlm_logits"].float().view(-1, 30522), b["mlm_labels"].view(-1).cuda(),
+                                           ignore_index=-1).item()
+    assert abs(ce - s[1]) < 2e-2 * ce          # fused path scores bf16 logits, dict path fp32 logits
+
+
+def test_retrieval_loop_ranks_identical_to_oracle_ranking_of_same_logits():
+    import engine_grid_masking as E
+    from mvlt_b200 import retrieval
+    from mvlt_b200.synthetic import make_batch
+    from oracle import pvlt_oracle as O
+    m = _model({"itm": 1, "mlm": 0, "t2i": 0, "cls": 0}).eval()
+    pool = make_batch(101, seed=5)
+    loader = []
+    for q in range(3):
+        ids = pool["ori_input_ids"][q:q + 1].repeat(101, 1)
+        loader.append({"images_101": pool["images"].unsqueeze(0), "ori_input_ids_101": ids.unsqueeze(0), "info_list": []})
+    res = E.evaluate_retrieval(loader, m, torch.device("cuda"), _Args())
+    assert set(res) == {"acc@1", "acc@5", "acc@10"}
+    imgs = pool["images"].cuda()
+    for q in range(3):
+        ids = loader[q]["ori_input_ids_101"][0].cuda()
+        ranks, logits = retrieval.rank_queries(m, imgs, ids, 101)
+        assert int(ranks[0]) == O.retrieval_rank(logits[0].cpu())          # identical ranking (same logits)
+        # shard equivalence: scoring the two halves separately gives bit-identical logits => identical ranks
+        lo, hi, _ = retrieval.shard_bounds(101, 0, 2)
+        a = retrieval.score_pairs(m, imgs[lo:hi], ids[lo:hi])
+        b = retrieval.score_pairs(m, imgs[hi:], ids[hi:])
+        assert torch.equal(torch.cat([a, b]), logits[0])
+        # permutation equivariance of the candidate axis
+        perm = torch.randperm(101, generator=torch.Generator().manual_seed(q))
+        lp = retrieval.score_pairs(m, imgs[perm.cuda()], ids[perm.cuda()])
+        assert torch.equal(lp, logits[0][perm.cuda()])
+
+
+def test_recognition_loop():
+    import engine_grid_masking as E
+    m = _model(CLS).eval()
+    res = E.evaluate_recognition(_loader(2, 8, keys_eval=True), m, torch.device("cuda"), _Args())
+    assert 0 <= res["sup"][0] <= 1 and 0 <= res["sub"][0] <= 1
+
+
+def test_full_batch_properties_b128():
+    """BASELINE configs[1] size (B=128): finite step, MLM loss ~ ln(30522) at random init, forward repeatable."""
+    from mvlt_b200.synthetic import make_batch
+    m = _model(PRE, drop_path=0.0)
+    m.text_embeddings.dropout.p = 0.0
+    m.train()
+    b = make_batch(128, seed=1)
+    img, ids = b["images"].cuda(), b["input_ids"].cuda()
+    kw = dict(mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=img)
+    t1, s1 = m(img, ids, **kw)
+    t1.backward()
+    g1 = m.block1[0].mlp.fc1.weight.grad.clone()
+    m.zero_grad(set_to_none=True)
+    t2, s2 = m(img, ids, **kw)
+    assert torch.isfinite(s1).all() and torch.isfinite(g1).all()
+    assert abs(s1[1].item() - math.log(30522)) < 0.5
+    # repeatable up to the summation order of the fp32 atomics (loss / BatchNorm-statistic accumulators)
+    assert abs(s1[1].item() - s2[1].item()) < 1e-4 and abs(s1[2].item() - s2[2].item()) < 1e-4
+    assert float(g1.abs().sum()) > 0
