@@ -133,14 +133,15 @@ def run_ours(args):
     devb = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in h.items()} for h in host]
     seeds = torch.tensor([masking.sample_seed(rank, i) for i in range(B)], dtype=torch.int64, device=dev)
 
-    def step(i, b):
+    def step(i, b, fwd=None):
+        fwd = fwd or net
         img = b["images"]
         if i % 2 == 1:   # engine_grid_masking.py:72-78: odd steps feed the grid-masked image
             grid = masking.grid_mask_batch(seeds + i * B, (img.shape[3], img.shape[2]), 0.5, 16, device=dev)
             x = masking.apply_grid_mask(img, grid, 16)
         else:
             x = img
-        total, stats = net(x, b["input_ids"], mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=img,
+        total, stats = fwd(x, b["input_ids"], mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=img,
                            mlm_count=b["mlm_count"])
         total.backward()
         opt.step()
@@ -197,7 +198,7 @@ def run_ours(args):
         _lib.PROFILE, _lib.GEMM_FLOPS = {}, 0.0
         nprof = 2
         for i in range(nprof):
-            step(i, devb[i % 2])
+            step(i, devb[i % 2], fwd=model)      # the bare module: rank 0 alone must not enter DDP's collectives
         torch.cuda.synchronize()
         prof, flops = _lib.PROFILE, _lib.GEMM_FLOPS
         _lib.PROFILE = None

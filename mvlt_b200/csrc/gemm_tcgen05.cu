@@ -91,8 +91,33 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
 
 // Fused epilogue for one thread's 32 consecutive output columns of one row. Every loop is fully unrolled so that
 // v[] stays in registers (a dynamically indexed tail loop would demote it to local memory).
-__device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t (&r)[32], long long row_off, int col0,
-                                               float rs, bool aligned) {
+// ex[] holds this chunk's residual (32 fp32 words) or aux (16 words of bf16 pairs), loaded ahead of time by
+// issue_extra() so that their DRAM latency overlaps the MMA wait / the previous chunk.
+__device__ __forceinline__ bool chunk_vec_ok(const KParams& p, int col0, bool aligned) {
+  return (col0 + 32 <= p.N) && aligned && ((col0 & 7) == 0);
+}
+__device__ __forceinline__ void issue_extra(const KParams& p, long long row_off, int col0, bool use, uint32_t (&ex)[32]) {
+  if (!use) return;
+  if (p.residual != nullptr) {
+    const float4* rp = reinterpret_cast<const float4*>(p.residual + row_off + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = rp[j];
+      ex[4 * j] = __float_as_uint(t.x); ex[4 * j + 1] = __float_as_uint(t.y);
+      ex[4 * j + 2] = __float_as_uint(t.z); ex[4 * j + 3] = __float_as_uint(t.w);
+    }
+  } else if (p.aux != nullptr) {
+    const uint4* ap = reinterpret_cast<const uint4*>(p.aux + row_off + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 t = ap[j];
+      ex[4 * j] = t.x; ex[4 * j + 1] = t.y; ex[4 * j + 2] = t.z; ex[4 * j + 3] = t.w;
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t (&r)[32], const uint32_t (&ex)[32],
+                                               long long row_off, int col0, float rs, bool aligned) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
@@ -152,13 +177,9 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
     const __nv_bfloat16* ax = p.aux + row_off + col0;
     if (vec_ok) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(ax + j);
-        float2 f;
-        f = unpack_bf16x2(u.x); v[j] *= f.x; v[j + 1] *= f.y;
-        f = unpack_bf16x2(u.y); v[j + 2] *= f.x; v[j + 3] *= f.y;
-        f = unpack_bf16x2(u.z); v[j + 4] *= f.x; v[j + 5] *= f.y;
-        f = unpack_bf16x2(u.w); v[j + 6] *= f.x; v[j + 7] *= f.y;
+      for (int j = 0; j < 16; ++j) {
+        const float2 f = unpack_bf16x2(ex[j]);
+        v[2 * j] *= f.x; v[2 * j + 1] *= f.y;
       }
     } else {
 #pragma unroll
@@ -169,13 +190,9 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
     const __nv_bfloat16* ax = p.aux + row_off + col0;
     if (vec_ok) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(ax + j);
-        float2 f;
-        f = unpack_bf16x2(u.x); v[j] *= dgelu_fast(f.x); v[j + 1] *= dgelu_fast(f.y);
-        f = unpack_bf16x2(u.y); v[j + 2] *= dgelu_fast(f.x); v[j + 3] *= dgelu_fast(f.y);
-        f = unpack_bf16x2(u.z); v[j + 4] *= dgelu_fast(f.x); v[j + 5] *= dgelu_fast(f.y);
-        f = unpack_bf16x2(u.w); v[j + 6] *= dgelu_fast(f.x); v[j + 7] *= dgelu_fast(f.y);
+      for (int j = 0; j < 16; ++j) {
+        const float2 f = unpack_bf16x2(ex[j]);
+        v[2 * j] *= dgelu_fast(f.x); v[2 * j + 1] *= dgelu_fast(f.y);
       }
     } else {
 #pragma unroll
@@ -187,11 +204,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
     const float* rp = p.residual + row_off + col0;
     if (vec_ok) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-        v[j] = r4.x + rs * v[j]; v[j + 1] = r4.y + rs * v[j + 1];
-        v[j + 2] = r4.z + rs * v[j + 2]; v[j + 3] = r4.w + rs * v[j + 3];
-      }
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(rs, v[j], __uint_as_float(ex[j]));
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -267,7 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);  // one elected lane per epilogue warp
+      mbar_init(&tempty_bar[a], 4);  // one elected lane per warp of the owning epilogue group
     }
     fence_barrier_init();
   }
@@ -366,12 +379,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===================== epilogue warps =====================
-    // Two warps share each TMEM lane quarter and interleave the 32-column chunks of the accumulator.
+    // Two groups of four warps (one warp per TMEM lane quarter). Group g drains accumulator buffer g, i.e. every
+    // second tile of this CTA, so the (latency-bound) epilogues of consecutive tiles overlap each other as well as
+    // the mainloop. Residual / aux operands of a chunk are fetched one chunk ahead (and, for the first chunk,
+    // before waiting for the MMA).
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;      // 0: chunks 0,2,4..   1: chunks 1,3,5..
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int group = (warp - 2) >> 2;     // accumulator buffer / tile parity owned by this warp
+    const bool has_extra = (p.residual != nullptr) || (p.aux != nullptr);
+    uint32_t phase = 0;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      if ((local & 1) != group) continue;
       const TileCoord tc = decode_tile(p, t);
       const int row = tc.m_blk * BLOCK_M + quarter * 32 + lane;
       const int n0 = tc.n_blk * p.block_n;
@@ -382,24 +400,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (p.rowscale != nullptr && row_ok) rs = p.rowscale[row / p.rows_per_scale];
       const bool aligned = ((p.ldd & 7) == 0) && ((batch_off & 7) == 0);
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      uint32_t exA[32], exB[32];
+      issue_extra(p, row_off, n0, has_extra && row_ok && chunk_vec_ok(p, n0, aligned), exA);
+      mbar_wait(&tfull_bar[group], phase);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n);
-      for (int c = half * 32; c < p.block_n; c += 64) {
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * p.block_n);
+      for (int c = 0; c < p.block_n; c += 64) {
         uint32_t r[32];
-        tmem_ld_32x32(taddr0 + (uint32_t)c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (row_ok && col0 < p.N) epilogue_chunk(p, r, row_off, col0, rs, aligned);
+        {
+          tmem_ld_32x32(taddr0 + (uint32_t)c, r);
+          const int cn = n0 + c + 32;
+          if (c + 32 < p.block_n) issue_extra(p, row_off, cn, has_extra && row_ok && chunk_vec_ok(p, cn, aligned), exB);
+          tmem_ld_wait();
+          const int col0 = n0 + c;
+          if (row_ok && col0 < p.N) epilogue_chunk(p, r, exA, row_off, col0, rs, aligned);
+        }
+        if (c + 32 < p.block_n) {
+          tmem_ld_32x32(taddr0 + (uint32_t)(c + 32), r);
+          const int cn = n0 + c + 64;
+          if (c + 64 < p.block_n) issue_extra(p, row_off, cn, has_extra && row_ok && chunk_vec_ok(p, cn, aligned), exA);
+          tmem_ld_wait();
+          const int col0 = n0 + c + 32;
+          if (row_ok && col0 < p.N) epilogue_chunk(p, r, exB, row_off, col0, rs, aligned);
+        }
       }
       // all of this warp's TMEM reads are complete (wait::ld above): release the accumulator buffer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
+      if (lane == 0) mbar_arrive(&tempty_bar[group]);
+      phase ^= 1;
     }
   }
 

@@ -18,7 +18,7 @@ __device__ __forceinline__ long long map_row(const RowMap& m, int r) {
 
 namespace {
 
-constexpr int LN_MAX_VEC = 6;  // C <= 768 (6 x 128 columns per warp pass)
+constexpr int LN_MAX_VEC = 6;  // C <= 768 (6 x 128 columns per warp pass); kernels are instantiated for NV in {1,3,4,6}
 
 template <typename T>
 __device__ __forceinline__ float4 load4(const T* p);
@@ -54,7 +54,7 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <typename TI, typename TO, int G>
+template <typename TI, typename TO, int G, int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, RowMap xm, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, TO* __restrict__ y, RowMap ym,
                                                      const float* __restrict__ post_add, float* __restrict__ mean_out,
@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, R
     const int r = r0 + (threadIdx.x >> 5) * RPW + lane / G;
     const bool ok = r < rows;
     const TI* xr = x + (ok ? map_row(xm, r) : 0) * C;
-    float4 v[LN_MAX_VEC];
+    float4 v[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = i * 4 * G + sub * 4;
       if (ok && i < nvec && c < C) {
         v[i] = load4<TI>(xr + c);
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, R
     const float mean = group_sum<G>(s) * inv_c;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = i * 4 * G + sub * 4;
       if (i < nvec && c < C) {
         const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, R
     TO* yr = y + map_row(ym, r) * C;
     const float* pa = post_add ? post_add + (long long)(r % ym.group) * C : nullptr;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = i * 4 * G + sub * 4;
       if (i < nvec && c < C) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, R
 }
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))  [+ dx_add];   dgamma += dy*xhat ; dbeta += dy
-template <typename TDY, typename TX, typename TDX, int G>
+template <typename TDY, typename TX, typename TDX, int G, int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, RowMap dym, const TX* __restrict__ x,
                                                      RowMap xm, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -134,19 +134,19 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
   const int rows_per_block = wpb * RPW;
   const int nvec = (C + 4 * G - 1) / (4 * G);
   const float inv_c = 1.f / (float)C;
-  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
+  float4 ag[NV], ab[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r0 = blockIdx.x * rows_per_block; r0 < rows; r0 += gridDim.x * rows_per_block) {
     const int r = r0 + warp * RPW + lane / G;
     const bool ok = r < rows;
     const TDY* dyr = dy + (ok ? map_row(dym, r) : 0) * C;
     const TX* xr = x + (ok ? map_row(xm, r) : 0) * C;
     const float mu = ok ? mean[r] : 0.f, rs = ok ? rstd[r] : 0.f;
-    float4 vdy[LN_MAX_VEC], vxh[LN_MAX_VEC];
+    float4 vdy[NV], vxh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = i * 4 * G + sub * 4;
       if (ok && i < nvec && c < C) {
         const float4 d = load4<TDY>(dyr + c);
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
     if (!ok) continue;
     const long long drow = map_row(dxm, r) * C;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = i * 4 * G + sub * 4;
       if (i < nvec && c < C) {
         float4 o;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
   float* shb = sh + slots * C;
   const int slot = warp * RPW + lane / G;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = i * 4 * G + sub * 4;
     if (i < nvec && c < C) {
       *reinterpret_cast<float4*>(shg + slot * C + c) = ag[i];
@@ -288,14 +288,16 @@ extern "C" int mvlt_layernorm_fwd(const void* x, int x_f32, const int* xmap, con
   RowMap xm{xmap && xmap[0] > 0 ? xmap[0] : rows, xmap && xmap[0] > 0 ? xmap[1] : rows, xmap && xmap[0] > 0 ? xmap[2] : 0};
   RowMap ym{ymap && ymap[0] > 0 ? ymap[0] : rows, ymap && ymap[0] > 0 ? ymap[1] : rows, ymap && ymap[0] > 0 ? ymap[2] : 0};
   const int grid = ln_grid(rows, C <= 64 ? 16 : 8);
-#define LAUNCH(TI, TO)                                                                                           \
-  do {                                                                                                           \
-    if (C <= 64)                                                                                                 \
-      ln_fwd_kernel<TI, TO, 16><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,            \
-                                                      reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps); \
-    else                                                                                                         \
-      ln_fwd_kernel<TI, TO, 32><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,            \
-                                                      reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps); \
+#define LN_FWD_CALL(TI, TO, G, NV)                                                                              \
+  ln_fwd_kernel<TI, TO, G, NV><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,               \
+                                                     reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps)
+#define LAUNCH(TI, TO)                                 \
+  do {                                                 \
+    if (C <= 64) LN_FWD_CALL(TI, TO, 16, 1);           \
+    else if (C <= 128) LN_FWD_CALL(TI, TO, 32, 1);     \
+    else if (C <= 384) LN_FWD_CALL(TI, TO, 32, 3);     \
+    else if (C <= 512) LN_FWD_CALL(TI, TO, 32, 4);     \
+    else LN_FWD_CALL(TI, TO, 32, 6);                   \
   } while (0)
   if (x_f32 && y_f32) LAUNCH(float, float);
   else if (x_f32 && !y_f32) LAUNCH(float, __nv_bfloat16);
@@ -321,16 +323,17 @@ extern "C" int mvlt_layernorm_bwd(const void* dy, int dy_f32, const int* dymap, 
   const long long cap = (long long)mvlt_num_sms() * 6;
   const int grid = (int)(b < cap ? (b > 0 ? b : 1) : cap);
   const size_t smem = (size_t)2 * wpb * rpw * C * sizeof(float);
-#define LAUNCH(TDY, TX, TDX)                                                                                      \
-  do {                                                                                                            \
-    if (C <= 64)                                                                                                  \
-      ln_bwd_kernel<TDY, TX, TDX, 16><<<grid, 256, smem, st>>>(reinterpret_cast<const TDY*>(dy), dym,              \
-                                                               reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma, \
-                                                               reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta, rows, C); \
-    else                                                                                                          \
-      ln_bwd_kernel<TDY, TX, TDX, 32><<<grid, 256, smem, st>>>(reinterpret_cast<const TDY*>(dy), dym,              \
-                                                               reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma, \
-                                                               reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta, rows, C); \
+#define LN_BWD_CALL(TDY, TX, TDX, G, NV)                                                                         \
+  ln_bwd_kernel<TDY, TX, TDX, G, NV><<<grid, 256, smem, st>>>(reinterpret_cast<const TDY*>(dy), dym,                 \
+                                                              reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma, \
+                                                              reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta, rows, C)
+#define LAUNCH(TDY, TX, TDX)                                  \
+  do {                                                        \
+    if (C <= 64) LN_BWD_CALL(TDY, TX, TDX, 16, 1);            \
+    else if (C <= 128) LN_BWD_CALL(TDY, TX, TDX, 32, 1);      \
+    else if (C <= 384) LN_BWD_CALL(TDY, TX, TDX, 32, 3);      \
+    else if (C <= 512) LN_BWD_CALL(TDY, TX, TDX, 32, 4);      \
+    else LN_BWD_CALL(TDY, TX, TDX, 32, 6);                    \
   } while (0)
   const int key = (dy_f32 ? 4 : 0) | (x_f32 ? 2 : 0) | (dx_f32 ? 1 : 0);
   switch (key) {
