@@ -28,7 +28,8 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 190 * 1024;  // pipeline stages; + 32 KB epilogue store staging + barriers <= 227 KB
+constexpr int STAGING_BYTES = 8 * 4096;
 
 struct KParams {
   int M, N, K;
@@ -116,13 +117,50 @@ __device__ __forceinline__ void issue_extra(const KParams& p, long long row_off,
   }
 }
 
+// Warp-cooperative, fully coalesced store of a 32-row x (P*16)-byte chunk: every lane holds one row in registers;
+// the rows go through a swizzled (bank-conflict-free) per-warp smem tile so that each global store instruction
+// writes whole contiguous row segments (64 B for bf16, 128 B for fp32) instead of 16 B slivers of 32 different rows.
+template <int P>
+__device__ __forceinline__ void staged_store(uint8_t* stage, const uint4 (&pieces)[P], uint8_t* gbase, long long ld_bytes,
+                                             int lane, int rows_valid) {
+  constexpr int W = P * 16;
+  const int swz_w = (P == 8) ? (lane & 7) : ((lane >> 1) & 3);
+  uint8_t* wrow = stage + lane * W;
+#pragma unroll
+  for (int q = 0; q < P; ++q) *reinterpret_cast<uint4*>(wrow + ((q ^ swz_w) << 4)) = pieces[q];
+  __syncwarp();
+  constexpr int RPI = 32 / P;  // rows covered by one store instruction
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    const int row = q * RPI + lane / P, pc = lane % P;
+    const int swz_r = (P == 8) ? (row & 7) : ((row >> 1) & 3);
+    const uint4 val = *reinterpret_cast<const uint4*>(stage + row * W + ((pc ^ swz_r) << 4));
+    if (row < rows_valid) *reinterpret_cast<uint4*>(gbase + (long long)row * ld_bytes + pc * 16) = val;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void pack_bf16_row(const float (&v)[32], uint4 (&out)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    out[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]); out[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+    out[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); out[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+  }
+}
+
+// Fused epilogue for one warp's 32 rows x 32 columns (one row per lane). Called warp-uniformly; every loop is fully
+// unrolled so that v[] stays in registers.
+template <bool kHasExtra>
 __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t (&r)[32], const uint32_t (&ex)[32],
-                                               long long row_off, int col0, float rs, bool aligned) {
+                                               long long row_base_off, int lane, int rows_valid, int col0, float rs,
+                                               bool aligned, uint8_t* stage) {
+  const bool row_ok = lane < rows_valid;
+  const long long row_off = row_base_off + (long long)lane * p.ldd;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
   const bool full = (col0 + 32 <= p.N);
-  const bool vec_ok = full && aligned && ((col0 & 7) == 0);
+  const bool vec_ok = full && aligned && ((col0 & 7) == 0);   // warp-uniform
   if (p.bias != nullptr) {
     if (full) {
 #pragma unroll
@@ -136,76 +174,61 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
         if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
     }
   }
-  if (p.act == MVLT_ACT_GELU) {
-    if (p.D2 != nullptr) {
-      __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.D2) + row_off + col0;
-      if (vec_ok) {
+  if (!kHasExtra && (p.act == MVLT_ACT_GELU || p.act == MVLT_ACT_GELU_SAVE_GRAD)) {
+    float d2v[32];
+    if (p.act == MVLT_ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-          u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-          *reinterpret_cast<uint4*>(d2 + j) = u;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) d2[j] = __float2bfloat16(v[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-  } else if (p.act == MVLT_ACT_GELU_SAVE_GRAD) {
-    float dg[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) gelu_and_grad(v[j], v[j], dg[j]);
-    __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.D2) + row_off + col0;
-    if (vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(dg[j], dg[j + 1]); u.y = pack_bf16x2(dg[j + 2], dg[j + 3]);
-        u.z = pack_bf16x2(dg[j + 4], dg[j + 5]); u.w = pack_bf16x2(dg[j + 6], dg[j + 7]);
-        *reinterpret_cast<uint4*>(d2 + j) = u;
-      }
+      for (int j = 0; j < 32; ++j) { d2v[j] = v[j]; v[j] = gelu_fast(v[j]); }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) d2[j] = __float2bfloat16(dg[j]);
+      for (int j = 0; j < 32; ++j) gelu_and_grad(v[j], v[j], d2v[j]);
     }
-  } else if (p.act == MVLT_ACT_MUL_AUX) {
-    const __nv_bfloat16* ax = p.aux + row_off + col0;
+    if (p.D2 != nullptr) {
+      __nv_bfloat16* d2base = reinterpret_cast<__nv_bfloat16*>(p.D2) + row_base_off + col0;
+      if (vec_ok) {
+        uint4 pk[4];
+        pack_bf16_row(d2v, pk);
+        staged_store<4>(stage, pk, reinterpret_cast<uint8_t*>(d2base), p.ldd * 2, lane, rows_valid);
+      } else if (row_ok) {
+        __nv_bfloat16* d2 = d2base + (long long)lane * p.ldd;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) d2[j] = __float2bfloat16(d2v[j]);
+      }
+    }
+  } else if (kHasExtra && p.act == MVLT_ACT_MUL_AUX) {
     if (vec_ok) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float2 f = unpack_bf16x2(ex[j]);
         v[2 * j] *= f.x; v[2 * j + 1] *= f.y;
       }
-    } else {
+    } else if (row_ok) {
+      const __nv_bfloat16* ax = p.aux + row_off + col0;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.N) v[j] *= __bfloat162float(ax[j]);
     }
-  } else if (p.act == MVLT_ACT_DGELU) {
-    const __nv_bfloat16* ax = p.aux + row_off + col0;
+  } else if (kHasExtra && p.act == MVLT_ACT_DGELU) {
     if (vec_ok) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float2 f = unpack_bf16x2(ex[j]);
         v[2 * j] *= dgelu_fast(f.x); v[2 * j + 1] *= dgelu_fast(f.y);
       }
-    } else {
+    } else if (row_ok) {
+      const __nv_bfloat16* ax = p.aux + row_off + col0;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.N) v[j] *= dgelu_fast(__bfloat162float(ax[j]));
     }
   }
-  if (p.residual != nullptr) {
-    const float* rp = p.residual + row_off + col0;
+  if (kHasExtra && p.residual != nullptr) {
     if (vec_ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaf(rs, v[j], __uint_as_float(ex[j]));
-    } else {
+    } else if (row_ok) {
+      const float* rp = p.residual + row_off + col0;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.N) v[j] = rp[j] + rs * v[j];
@@ -215,40 +238,43 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
     for (int j = 0; j < 32; ++j) v[j] *= rs;
   }
   if (p.atomic_add) {
-    float* d = reinterpret_cast<float*>(p.D) + row_off + col0;
-    if (vec_ok) {   // 128-bit vector reductions: 4x fewer L2 atomic operations for the split-K dW GEMMs
+    if (row_ok) {
+      float* d = reinterpret_cast<float*>(p.D) + row_off + col0;
+      if (vec_ok) {   // 128-bit vector reductions: 4x fewer L2 atomic operations for the split-K dW GEMMs
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
-                     "f"(v[j + 3])
-                     : "memory");
-    } else {
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(v[j]), "f"(v[j + 1]),
+                       "f"(v[j + 2]), "f"(v[j + 3])
+                       : "memory");
+      } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) atomicAdd(d + j, v[j]);
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) atomicAdd(d + j, v[j]);
+      }
     }
   } else if (p.out_f32) {
-    float* d = reinterpret_cast<float*>(p.D) + row_off + col0;
+    float* dbase = reinterpret_cast<float*>(p.D) + row_base_off + col0;
     if (vec_ok) {
+      uint4 pk[8];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
+      for (int j = 0; j < 8; ++j)
+        pk[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                           __float_as_uint(v[4 * j + 3]));
+      staged_store<8>(stage, pk, reinterpret_cast<uint8_t*>(dbase), p.ldd * 4, lane, rows_valid);
+    } else if (row_ok) {
+      float* d = dbase + (long long)lane * p.ldd;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.N) d[j] = v[j];
     }
   } else {
-    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + row_off + col0;
+    __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0;
     if (vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(d + j) = u;
-      }
-    } else {
+      uint4 pk[4];
+      pack_bf16_row(v, pk);
+      staged_store<4>(stage, pk, reinterpret_cast<uint8_t*>(dbase), p.ldd * 2, lane, rows_valid);
+    } else if (row_ok) {
+      __nv_bfloat16* d = dbase + (long long)lane * p.ldd;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.N) d[j] = __float2bfloat16(v[j]);
@@ -256,6 +282,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t 
   }
 }
 
+template <bool kHasExtra>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const KParams p) {
@@ -272,6 +299,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full_bar) + 256;   // 8 x 4 KB per-warp store staging tiles
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -385,7 +413,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // before waiting for the MMA).
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int group = (warp - 2) >> 2;     // accumulator buffer / tile parity owned by this warp
-    const bool has_extra = (p.residual != nullptr) || (p.aux != nullptr);
+    constexpr bool has_extra = kHasExtra;
     uint32_t phase = 0;
     int local = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
@@ -394,14 +422,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = tc.m_blk * BLOCK_M + quarter * 32 + lane;
       const int n0 = tc.n_blk * p.block_n;
       const bool row_ok = row < p.M;
+      const int row_base = tc.m_blk * BLOCK_M + quarter * 32;
+      const int rows_valid = min(32, p.M - row_base);          // <= 0 when the whole warp is past the M tail
       const long long batch_off = (long long)tc.b1 * p.sD1 + (long long)tc.b2 * p.sD2;
-      const long long row_off = batch_off + (long long)row * p.ldd;
+      const long long row_base_off = batch_off + (long long)row_base * p.ldd;
+      const long long row_off = row_base_off + (long long)lane * p.ldd;
       float rs = 1.f;
       if (p.rowscale != nullptr && row_ok) rs = p.rowscale[row / p.rows_per_scale];
       const bool aligned = ((p.ldd & 7) == 0) && ((batch_off & 7) == 0);
+      uint8_t* stage = stage_base + (warp - 2) * 4096;
 
       uint32_t exA[32], exB[32];
-      issue_extra(p, row_off, n0, has_extra && row_ok && chunk_vec_ok(p, n0, aligned), exA);
+      if (kHasExtra) issue_extra(p, row_off, n0, row_ok && chunk_vec_ok(p, n0, aligned), exA);
       mbar_wait(&tfull_bar[group], phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * p.block_n);
@@ -410,18 +442,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         {
           tmem_ld_32x32(taddr0 + (uint32_t)c, r);
           const int cn = n0 + c + 32;
-          if (c + 32 < p.block_n) issue_extra(p, row_off, cn, has_extra && row_ok && chunk_vec_ok(p, cn, aligned), exB);
+          if (kHasExtra && c + 32 < p.block_n) issue_extra(p, row_off, cn, row_ok && chunk_vec_ok(p, cn, aligned), exB);
           tmem_ld_wait();
           const int col0 = n0 + c;
-          if (row_ok && col0 < p.N) epilogue_chunk(p, r, exA, row_off, col0, rs, aligned);
+          if (rows_valid > 0 && col0 < p.N) epilogue_chunk<kHasExtra>(p, r, exA, row_base_off, lane, rows_valid, col0, rs, aligned, stage);
         }
         if (c + 32 < p.block_n) {
           tmem_ld_32x32(taddr0 + (uint32_t)(c + 32), r);
           const int cn = n0 + c + 64;
-          if (c + 64 < p.block_n) issue_extra(p, row_off, cn, has_extra && row_ok && chunk_vec_ok(p, cn, aligned), exA);
+          if (kHasExtra && c + 64 < p.block_n) issue_extra(p, row_off, cn, row_ok && chunk_vec_ok(p, cn, aligned), exA);
           tmem_ld_wait();
           const int col0 = n0 + c + 32;
-          if (row_ok && col0 < p.N) epilogue_chunk(p, r, exB, row_off, col0, rs, aligned);
+          if (rows_valid > 0 && col0 < p.N) epilogue_chunk<kHasExtra>(p, r, exB, row_base_off, lane, rows_valid, col0, rs, aligned, stage);
         }
       }
       // all of this warp's TMEM reads are complete (wait::ld above): release the accumulator buffer
@@ -589,6 +621,8 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   MVLT_CHECK_ARG(!((g->act == MVLT_ACT_DGELU || g->act == MVLT_ACT_MUL_AUX) && g->aux == nullptr),
                  "mvlt_gemm: dgelu / mul_aux epilogue needs aux");
   MVLT_CHECK_ARG(!(g->act == MVLT_ACT_GELU_SAVE_GRAD && g->D2 == nullptr), "mvlt_gemm: gelu_save_grad needs D2");
+  MVLT_CHECK_ARG(!((g->act == MVLT_ACT_GELU || g->act == MVLT_ACT_GELU_SAVE_GRAD) && (g->residual || g->aux)),
+                 "mvlt_gemm: the GELU epilogues do not combine with residual / aux operands");
   MVLT_CHECK_ARG(!(g->rowscale && g->rows_per_scale <= 0), "mvlt_gemm: rowscale needs rows_per_scale");
 
   KParams p;
@@ -626,18 +660,20 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   if (rc) return rc;
 
   // > half of the SM's shared memory so two CTAs (each wanting all 512 TMEM columns) never share an SM
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
   if (smem < 120 * 1024) smem = 120 * 1024;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   const long long total_tiles =
       (long long)p.batch1 * p.batch2 * p.split_k * p.num_m_blocks * p.num_n_blocks;
   MVLT_CHECK_ARG(total_tiles < (1ll << 31), "mvlt_gemm: too many tiles");
   int grid = mvlt_num_sms();
   if (total_tiles < grid) grid = (int)total_tiles;
-  gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  if (p.residual != nullptr || p.aux != nullptr) gemm_tcgen05_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  else gemm_tcgen05_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
