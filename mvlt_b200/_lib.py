@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
     ]
 
 
-ACT_NONE, ACT_GELU, ACT_DGELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU, ACT_DGELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_SOFTMAX, ACT_SOFTMAX_BWD = 0, 1, 2, 3, 4, 5, 6
 
 
 def lib_path() -> Path:

@@ -125,6 +125,78 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
   dg = fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2/FMUL2/FADD2: one issue slot for two fp32 lanes) ------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_splat(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// gelu_erf(x) and gelu_erf'(x) for two values at once. Same Abramowitz-Stegun 7.1.26 erfc tail as gelu_and_grad
+// (|error| <= 1.5e-7) but evaluated with packed fp32x2 FMAs and approximate MUFU ex2 / rcp:
+// 14 packed FP ops + 4 MUFU + ~8 ALU per PAIR instead of ~38 instructions per ELEMENT.
+__device__ __forceinline__ void gelu_and_grad2(f32x2_t x, f32x2_t& g, f32x2_t& dg) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  const f32x2_t ax = f2_pack(fabsf(x0), fabsf(x1));
+  const f32x2_t nw = f2_mul(f2_mul(x, x), f2_splat(-0.72134752044448170368f));   // -x^2/2 * log2(e)
+  float n0, n1;
+  f2_unpack(nw, n0, n1);
+  const float e0 = ex2_approx(n0), e1 = ex2_approx(n1);                           // exp(-x^2/2)
+  const f32x2_t e = f2_pack(e0, e1);
+  const f32x2_t den = f2_fma(ax, f2_splat(0.23164189f), f2_splat(1.0f));         // 1 + 0.3275911 |x|/sqrt(2)
+  float d0, d1;
+  f2_unpack(den, d0, d1);
+  const f32x2_t t = f2_pack(rcp_approx(d0), rcp_approx(d1));
+  f32x2_t poly = f2_fma(f2_splat(0.5307027145f), t, f2_splat(-0.7265760135f));   // coefficients pre-multiplied by 0.5
+  poly = f2_fma(poly, t, f2_splat(0.7107068705f));
+  poly = f2_fma(poly, t, f2_splat(-0.142248368f));
+  poly = f2_fma(poly, t, f2_splat(0.127414796f));
+  const f32x2_t h = f2_mul(f2_mul(poly, t), e);                                  // 0.5 * erfc(|x|/sqrt(2))
+  const f32x2_t omh = f2_fma(h, f2_splat(-1.0f), f2_splat(1.0f));                // 1 - h
+  float h0, h1, m0, m1;
+  f2_unpack(h, h0, h1);
+  f2_unpack(omh, m0, m1);
+  const f32x2_t cdf = f2_pack(x0 >= 0.f ? m0 : h0, x1 >= 0.f ? m1 : h1);
+  g = f2_mul(x, cdf);
+  dg = f2_fma(f2_mul(x, e), f2_splat(0.39894228040143267794f), cdf);
+}
+__device__ __forceinline__ f32x2_t gelu2(f32x2_t x) {
+  f32x2_t g, dg;
+  gelu_and_grad2(x, g, dg);   // the derivative tail is dead code here and is eliminated
+  return g;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -252,6 +324,24 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+// TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+  return r;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

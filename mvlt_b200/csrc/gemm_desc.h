@@ -21,6 +21,9 @@ enum {
   MVLT_ACT_DGELU = 2,  // D = v * gelu_erf'(aux[m,n])   (aux = saved pre-activation, bf16)
   MVLT_ACT_GELU_SAVE_GRAD = 3,  // D = gelu_erf(v); D2 = gelu_erf'(v) (bf16): the backward pass is then a plain multiply
   MVLT_ACT_MUL_AUX = 4,         // D = v * aux[m,n]        (aux = saved gelu'(pre-activation), bf16)
+  // Row-wise epilogues; need the whole row in one tile (N <= 256, N % 32 == 0) and a bf16 output:
+  MVLT_ACT_SOFTMAX = 5,         // D = softmax_n(alpha * acc)                        (attention probabilities)
+  MVLT_ACT_SOFTMAX_BWD = 6,     // D = alpha * aux * (acc - sum_n aux * acc)         (aux = P; acc = dP -> dS)
 };
 
 typedef struct mvlt_gemm_desc {

@@ -2,10 +2,15 @@
 //
 //   warp 0      : TMA producer (cp.async.bulk.tensor.4d, SWIZZLE_128B boxes, mbarrier complete_tx)
 //   warp 1      : TMEM owner + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, bf16 -> fp32)
-//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> 128-bit global stores)
+//   warps 2, 3  : idle (they only pad warpgroup 0 so that setmaxnreg can hand its registers to the epilogue)
+//   warps 4..19 : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> smem-staged coalesced global I/O)
 //
-// Accumulators live in TMEM and are double-buffered (2 x BLOCK_N <= 512 columns) so the epilogue of tile
-// i overlaps the mainloop of tile i+1. Tiles are scheduled round-robin over a grid of <= #SM CTAs.
+// Accumulators live in TMEM and are multi-buffered (2 x BLOCK_N, or 4 x BLOCK_N when BLOCK_N <= 128, of the 512
+// columns) so the epilogue of tile i overlaps the mainloop of tiles i+1.. . Tiles are scheduled round-robin over a
+// grid of <= #SM CTAs. Most PVLT-tiny GEMMs have K = 64..512 and are bound by their epilogue / HBM traffic, not by
+// the tensor pipe: every accumulator is therefore drained by EIGHT warps (4 TMEM lane quarters x 2 column halves),
+// 16 epilogue warps = 4 per SM sub-partition, and the kernel is specialised per epilogue kind so that the inner
+// loops carry no runtime dispatch.
 // Operands may be K-major or MN-major (see gemm_desc.h); MN-major tiles are fetched as 64x64 swizzle
 // atoms and described to the tensor core with the MN-major canonical layout (LBO = atom stride).
 //
@@ -25,17 +30,41 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int FIRST_EPI_WARP = 4;
+constexpr int NUM_THREADS = 32 * (FIRST_EPI_WARP + NUM_EPI_WARPS);  // warpgroup 0 (TMA, MMA, 2 idle) + 16 epilogue warps
+// Register budget: 640 threads launch with 96 registers each (61440 = the CTA's pool; setmaxnreg can only move
+// registers inside that pool, an over-subscribed .inc blocks forever). Warpgroup 0 shrinks to 32 and the four
+// epilogue warpgroups grow to 112: 128 * 32 + 512 * 112 = 61440.
+constexpr int LAUNCH_REGS = 96;
+constexpr int PRODUCER_REGS = 32;
+constexpr int EPILOGUE_REGS = 112;
+static_assert(128 * PRODUCER_REGS + (NUM_THREADS - 128) * EPILOGUE_REGS <= NUM_THREADS * LAUNCH_REGS,
+              "setmaxnreg budget exceeds the registers the CTA is launched with");
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
-constexpr int SMEM_BUDGET = 190 * 1024;  // pipeline stages; + 32 KB epilogue store staging + barriers <= 227 KB
-constexpr int STAGING_BYTES = 8 * 4096;
+constexpr int MAX_ACC = 4;
+constexpr int SMEM_BUDGET = 160 * 1024;  // pipeline stages; + 64 KB epilogue staging + barriers <= 227 KB
+constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096;
+
+// epilogue kinds the kernel is specialised on
+enum { EPI_PLAIN = 0, EPI_GELU = 1, EPI_AUX = 2, EPI_RESID = 3, EPI_SOFTMAX = 4, EPI_SOFTMAX_BWD = 5 };
+
+// n / d for 0 <= n < 2^31 with a host-computed magic number (no integer division in the tile loops)
+struct FastDiv {
+  uint32_t d, m, sh;
+};
+__device__ __forceinline__ void fast_divmod(const FastDiv& f, uint32_t n, uint32_t& q, uint32_t& r) {
+  q = (f.d == 1u) ? n : (__umulhi(n, f.m) >> f.sh);
+  r = n - q * f.d;
+}
 
 struct KParams {
   int M, N, K;
-  int block_n, stages;
+  int block_n, stages, num_acc;
   int num_m_blocks, num_n_blocks, num_k_blocks, kb_per_split, split_k;
   int batch1, batch2;
+  FastDiv div_n, div_m, div_s, div_b2;
   int a_mn, b_mn;
   int a_b1, a_b2, b_b1, b_b2;  // 1 if the batch coordinate is used for that operand, 0 if broadcast
   void* D;
@@ -79,213 +108,397 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
   TileCoord c;
-  c.n_blk = t % p.num_n_blocks;
-  t /= p.num_n_blocks;
-  c.m_blk = t % p.num_m_blocks;
-  t /= p.num_m_blocks;
-  c.split = t % p.split_k;
-  t /= p.split_k;
-  c.b2 = t % p.batch2;
-  c.b1 = t / p.batch2;
+  uint32_t q = (uint32_t)t, r;
+  fast_divmod(p.div_n, q, q, r);
+  c.n_blk = (int)r;
+  fast_divmod(p.div_m, q, q, r);
+  c.m_blk = (int)r;
+  fast_divmod(p.div_s, q, q, r);
+  c.split = (int)r;
+  fast_divmod(p.div_b2, q, q, r);
+  c.b2 = (int)r;
+  c.b1 = (int)q;
   return c;
 }
 
-// Fused epilogue for one thread's 32 consecutive output columns of one row. Every loop is fully unrolled so that
-// v[] stays in registers (a dynamically indexed tail loop would demote it to local memory).
-// ex[] holds this chunk's residual (32 fp32 words) or aux (16 words of bf16 pairs), loaded ahead of time by
-// issue_extra() so that their DRAM latency overlaps the MMA wait / the previous chunk.
-__device__ __forceinline__ bool chunk_vec_ok(const KParams& p, int col0, bool aligned) {
-  return (col0 + 32 <= p.N) && aligned && ((col0 & 7) == 0);
+// ---- epilogue building blocks -------------------------------------------------------------------------------------
+// Every epilogue warp owns a 4 KB staging tile in shared memory: 32 rows x 128 B (P = 8 sixteen-byte pieces per row:
+// 32 fp32 or 64 bf16 columns) or 32 rows x 64 B (P = 4: 32 bf16 columns). A lane reads/writes ITS row (one TMEM lane)
+// as 16-byte pieces, XOR-swizzled by row so that both the row-per-lane side and the coalesced side are bank-conflict
+// free. Global memory is only ever touched on the coalesced side: one instruction moves whole contiguous row
+// segments (4 rows x 128 B), never 16-byte slivers of 32 different rows. On B200 the L1/L2 request rate, not bytes,
+// bounds these thin-K GEMMs, so every operand of the epilogue (D, D2, residual, aux) goes through the tile.
+//
+// piece(row, q) lives at tile + row * 16P + ((q ^ swz(row)) << 4), swz = row & 7 (P = 8) or (row >> 1) & 3 (P = 4).
+// All lane-dependent parts of these addresses are computed once per warp (StageAddr); the per-piece part is an
+// immediate.
+struct StageAddr {
+  uint32_t w8;    // row-per-lane side, P = 8: tile + lane * 128 (128-byte aligned)
+  uint32_t wx8;   // (lane & 7) << 4
+  uint32_t f8e;   // coalesced side, P = 8, even q: tile + (lane >> 3) * 128 + (((lane & 7) ^ (lane >> 3)) << 4)
+  uint32_t f8o;   // odd q: f8e ^ 64
+  uint32_t w4;    // row-per-lane side, P = 4: tile + lane * 64 (64-byte aligned)
+  uint32_t wx4;   // ((lane >> 1) & 3) << 4
+  uint32_t f4;    // coalesced side, P = 4: tile + (lane >> 2) * 64 + (((lane & 3) ^ ((lane >> 3) & 3)) << 4)
+};
+__device__ __forceinline__ StageAddr make_stage_addr(uint32_t tile_s, int lane) {
+  StageAddr s;
+  s.w8 = tile_s + (uint32_t)lane * 128u;
+  s.wx8 = (uint32_t)(lane & 7) << 4;
+  s.f8e = tile_s + (uint32_t)(lane >> 3) * 128u + ((uint32_t)((lane & 7) ^ (lane >> 3)) << 4);
+  s.f8o = s.f8e ^ 64u;
+  s.w4 = tile_s + (uint32_t)lane * 64u;
+  s.wx4 = (uint32_t)((lane >> 1) & 3) << 4;
+  s.f4 = tile_s + (uint32_t)(lane >> 2) * 64u + ((uint32_t)((lane & 3) ^ ((lane >> 3) & 3)) << 4);
+  return s;
 }
-__device__ __forceinline__ void issue_extra(const KParams& p, long long row_off, int col0, bool use, uint32_t (&ex)[32]) {
-  if (!use) return;
-  if (p.residual != nullptr) {
-    const float4* rp = reinterpret_cast<const float4*>(p.residual + row_off + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 t = rp[j];
-      ex[4 * j] = __float_as_uint(t.x); ex[4 * j + 1] = __float_as_uint(t.y);
-      ex[4 * j + 2] = __float_as_uint(t.z); ex[4 * j + 3] = __float_as_uint(t.w);
-    }
-  } else if (p.aux != nullptr) {
-    const uint4* ap = reinterpret_cast<const uint4*>(p.aux + row_off + col0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 t = ap[j];
-      ex[4 * j] = t.x; ex[4 * j + 1] = t.y; ex[4 * j + 2] = t.z; ex[4 * j + 3] = t.w;
-    }
-  }
+template <int P>
+__device__ __forceinline__ uint32_t own_piece(const StageAddr& s, int q) {   // piece q of this lane's row
+  return (P == 8) ? (s.w8 | (((uint32_t)q << 4) ^ s.wx8)) : (s.w4 | (((uint32_t)q << 4) ^ s.wx4));
+}
+template <int P>
+__device__ __forceinline__ uint32_t co_piece(const StageAddr& s, int q) {    // piece handled by this lane in coalesced pass q
+  return (P == 8) ? (((q & 1) ? s.f8o : s.f8e) + (uint32_t)q * 512u) : (s.f4 + (uint32_t)q * 512u);
+}
+// this lane's global byte offset inside a 32-row unit for coalesced pass 0; pass q adds q * (32 / P) rows
+template <int P>
+__device__ __forceinline__ long long co_goff(int lane, long long ld_bytes) {
+  return (P == 8) ? ((long long)(lane >> 3) * ld_bytes + (lane & 7) * 16) : ((long long)(lane >> 2) * ld_bytes + (lane & 3) * 16);
 }
 
-// Warp-cooperative, fully coalesced store of a 32-row x (P*16)-byte chunk: every lane holds one row in registers;
-// the rows go through a swizzled (bank-conflict-free) per-warp smem tile so that each global store instruction
-// writes whole contiguous row segments (64 B for bf16, 128 B for fp32) instead of 16 B slivers of 32 different rows.
-template <int P>
-__device__ __forceinline__ void staged_store(uint8_t* stage, const uint4 (&pieces)[P], uint8_t* gbase, long long ld_bytes,
-                                             int lane, int rows_valid) {
-  constexpr int W = P * 16;
-  const int swz_w = (P == 8) ? (lane & 7) : ((lane >> 1) & 3);
-  uint8_t* wrow = stage + lane * W;
-#pragma unroll
-  for (int q = 0; q < P; ++q) *reinterpret_cast<uint4*>(wrow + ((q ^ swz_w) << 4)) = pieces[q];
+// staging tile -> global (plain stores, or vector fp32 reductions for the split-K dW GEMMs)
+template <int P, bool kRed>
+__device__ __forceinline__ void stage_flush(const StageAddr& s, uint8_t* gbase, long long ld_bytes, int lane, int rows_valid) {
+  constexpr int RPI = 32 / P;  // rows covered by one instruction
+  uint8_t* g = gbase + co_goff<P>(lane, ld_bytes);
+  const int row0 = (P == 8) ? (lane >> 3) : (lane >> 2);
   __syncwarp();
-  constexpr int RPI = 32 / P;  // rows covered by one store instruction
 #pragma unroll
   for (int q = 0; q < P; ++q) {
-    const int row = q * RPI + lane / P, pc = lane % P;
-    const int swz_r = (P == 8) ? (row & 7) : ((row >> 1) & 3);
-    const uint4 val = *reinterpret_cast<const uint4*>(stage + row * W + ((pc ^ swz_r) << 4));
-    if (row < rows_valid) *reinterpret_cast<uint4*>(gbase + (long long)row * ld_bytes + pc * 16) = val;
+    const uint4 val = ld_shared_v4(co_piece<P>(s, q));
+    if (rows_valid == 32 || q * RPI + row0 < rows_valid) {
+      uint8_t* gq = g + (long long)(q * RPI) * ld_bytes;
+      if (kRed)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gq), "f"(__uint_as_float(val.x)),
+                     "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w))
+                     : "memory");
+      else
+        *reinterpret_cast<uint4*>(gq) = val;
+    }
   }
   __syncwarp();
 }
-
-__device__ __forceinline__ void pack_bf16_row(const float (&v)[32], uint4 (&out)[4]) {
+// global -> staging tile (coalesced) -> this lane's row in registers
+template <int P>
+__device__ __forceinline__ void load_rows_via_stage(const StageAddr& s, const uint8_t* gbase, long long ld_bytes, int lane,
+                                                    int rows_valid, uint32_t (&ex)[P * 4]) {
+  constexpr int RPI = 32 / P;
+  const uint8_t* g = gbase + co_goff<P>(lane, ld_bytes);
+  const int row0 = (P == 8) ? (lane >> 3) : (lane >> 2);
+  uint4 t[P];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    out[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]); out[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-    out[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); out[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+  for (int q = 0; q < P; ++q) {
+    t[q] = make_uint4(0u, 0u, 0u, 0u);
+    if (rows_valid == 32 || q * RPI + row0 < rows_valid)
+      t[q] = *reinterpret_cast<const uint4*>(g + (long long)(q * RPI) * ld_bytes);
   }
+#pragma unroll
+  for (int q = 0; q < P; ++q) st_shared_v4(co_piece<P>(s, q), t[q].x, t[q].y, t[q].z, t[q].w);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    const uint4 v = ld_shared_v4(own_piece<P>(s, q));
+    ex[4 * q] = v.x; ex[4 * q + 1] = v.y; ex[4 * q + 2] = v.z; ex[4 * q + 3] = v.w;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_f2(f32x2_t v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+// 16 bf16 columns (8 packed pairs) of this lane's row -> pieces (2*i16, 2*i16+1) of its staging row
+template <int P>
+__device__ __forceinline__ void stage_put_bf16(const StageAddr& s, int i16, const uint32_t (&pk)[8]) {
+  st_shared_v4(own_piece<P>(s, 2 * i16), pk[0], pk[1], pk[2], pk[3]);
+  st_shared_v4(own_piece<P>(s, 2 * i16 + 1), pk[4], pk[5], pk[6], pk[7]);
 }
 
-// Fused epilogue for one warp's 32 rows x 32 columns (one row per lane). Called warp-uniformly; every loop is fully
-// unrolled so that v[] stays in registers.
-template <bool kHasExtra>
-__device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t (&r)[32], const uint32_t (&ex)[32],
-                                               long long row_base_off, int lane, int rows_valid, int col0, float rs,
-                                               bool aligned, uint8_t* stage) {
-  const bool row_ok = lane < rows_valid;
-  const long long row_off = row_base_off + (long long)lane * p.ldd;
-  float v[32];
+// alpha * acc + bias for 16 columns of this lane's row, as 8 packed fp32 pairs (FFMA2)
+template <bool kFull>
+__device__ __forceinline__ void scale_bias16(const KParams& p, const uint32_t (&r)[16], int c0, f32x2_t (&v2)[8]) {
+  const f32x2_t alpha2 = f2_splat(p.alpha);
+  if (p.bias == nullptr) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-  const bool full = (col0 + 32 <= p.N);
-  const bool vec_ok = full && aligned && ((col0 & 7) == 0);   // warp-uniform
-  if (p.bias != nullptr) {
-    if (full) {
+    for (int j = 0; j < 8; ++j) v2[j] = f2_mul(f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), alpha2);
+  } else if (kFull) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-    }
-  }
-  if (!kHasExtra && (p.act == MVLT_ACT_GELU || p.act == MVLT_ACT_GELU_SAVE_GRAD)) {
-    float d2v[32];
-    if (p.act == MVLT_ACT_GELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { d2v[j] = v[j]; v[j] = gelu_fast(v[j]); }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) gelu_and_grad(v[j], v[j], d2v[j]);
-    }
-    if (p.D2 != nullptr) {
-      __nv_bfloat16* d2base = reinterpret_cast<__nv_bfloat16*>(p.D2) + row_base_off + col0;
-      if (vec_ok) {
-        uint4 pk[4];
-        pack_bf16_row(d2v, pk);
-        staged_store<4>(stage, pk, reinterpret_cast<uint8_t*>(d2base), p.ldd * 2, lane, rows_valid);
-      } else if (row_ok) {
-        __nv_bfloat16* d2 = d2base + (long long)lane * p.ldd;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) d2[j] = __float2bfloat16(d2v[j]);
-      }
-    }
-  } else if (kHasExtra && p.act == MVLT_ACT_MUL_AUX) {
-    if (vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float2 f = unpack_bf16x2(ex[j]);
-        v[2 * j] *= f.x; v[2 * j + 1] *= f.y;
-      }
-    } else if (row_ok) {
-      const __nv_bfloat16* ax = p.aux + row_off + col0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] *= __bfloat162float(ax[j]);
-    }
-  } else if (kHasExtra && p.act == MVLT_ACT_DGELU) {
-    if (vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float2 f = unpack_bf16x2(ex[j]);
-        v[2 * j] *= dgelu_fast(f.x); v[2 * j + 1] *= dgelu_fast(f.y);
-      }
-    } else if (row_ok) {
-      const __nv_bfloat16* ax = p.aux + row_off + col0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] *= dgelu_fast(__bfloat162float(ax[j]));
-    }
-  }
-  if (kHasExtra && p.residual != nullptr) {
-    if (vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaf(rs, v[j], __uint_as_float(ex[j]));
-    } else if (row_ok) {
-      const float* rp = p.residual + row_off + col0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] = rp[j] + rs * v[j];
-    }
-  } else if (p.rowscale != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= rs;
-  }
-  if (p.atomic_add) {
-    if (row_ok) {
-      float* d = reinterpret_cast<float*>(p.D) + row_off + col0;
-      if (vec_ok) {   // 128-bit vector reductions: 4x fewer L2 atomic operations for the split-K dW GEMMs
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(v[j]), "f"(v[j + 1]),
-                       "f"(v[j + 2]), "f"(v[j + 3])
-                       : "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) atomicAdd(d + j, v[j]);
-      }
-    }
-  } else if (p.out_f32) {
-    float* dbase = reinterpret_cast<float*>(p.D) + row_base_off + col0;
-    if (vec_ok) {
-      uint4 pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        pk[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                           __float_as_uint(v[4 * j + 3]));
-      staged_store<8>(stage, pk, reinterpret_cast<uint8_t*>(dbase), p.ldd * 4, lane, rows_valid);
-    } else if (row_ok) {
-      float* d = dbase + (long long)lane * p.ldd;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) d[j] = v[j];
+    for (int j = 0; j < 4; ++j) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
+      v2[2 * j] = f2_fma(f2_pack(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), alpha2, f2_pack(b4.x, b4.y));
+      v2[2 * j + 1] = f2_fma(f2_pack(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), alpha2, f2_pack(b4.z, b4.w));
     }
   } else {
-    __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0;
-    if (vec_ok) {
-      uint4 pk[4];
-      pack_bf16_row(v, pk);
-      staged_store<4>(stage, pk, reinterpret_cast<uint8_t*>(dbase), p.ldd * 2, lane, rows_valid);
-    } else if (row_ok) {
-      __nv_bfloat16* d = dbase + (long long)lane * p.ldd;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) d[j] = __float2bfloat16(v[j]);
+    for (int j = 0; j < 8; ++j) {   // N tail: predicated scalar bias loads
+      float b0 = 0.f, b1 = 0.f;
+      if (c0 + 2 * j < p.N) b0 = __ldg(p.bias + c0 + 2 * j);
+      if (c0 + 2 * j + 1 < p.N) b1 = __ldg(p.bias + c0 + 2 * j + 1);
+      v2[j] = f2_fma(f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), alpha2, f2_pack(b0, b1));
+    }
+  }
+}
+// multiply by aux (MUL_AUX) or by gelu'(aux) (DGELU); ax = 8 bf16 pairs
+__device__ __forceinline__ void apply_aux16(int act, const uint32_t* ax, f32x2_t (&v2)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 f = unpack_bf16x2(ax[j]);
+    f32x2_t m = f2_pack(f.x, f.y);
+    if (act == MVLT_ACT_DGELU) {
+      f32x2_t g;
+      gelu_and_grad2(m, g, m);
+    }
+    v2[j] = f2_mul(v2[j], m);
+  }
+}
+
+// Vector path of the fused epilogue for one "unit" of this warp: 32 rows x (32 fp32 | 64 bf16 | 32 bf16) columns,
+// i.e. one staging tile with P pieces per row. All columns of the unit are inside N and 16-byte aligned.
+// The TMEM accumulator is read 16 columns at a time to keep the register footprint small (no spills at 112
+// registers: local memory has almost no L1 behind it in this kernel). Warp-uniform; loops fully unrolled.
+template <int kEpi, bool kOutF32, int P>
+__device__ __forceinline__ void epilogue_unit_vec(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
+                                                  int rows_valid, int col0, float rs, const StageAddr& s) {
+  constexpr int COLS = kOutF32 ? 32 : P * 8;
+  constexpr int N16 = COLS / 16;
+  static_assert(!kOutF32 || P == 8, "fp32 units are 32 columns = 128-byte rows");
+  const long long ld_bytes = p.ldd * (kOutF32 ? 4 : 2);
+  uint32_t ex[P * 4];
+  if constexpr (kEpi == EPI_RESID || kEpi == EPI_AUX) {   // residual (fp32 out) / aux (bf16 out): geometry of the output unit
+    const uint8_t* g = (kEpi == EPI_RESID) ? reinterpret_cast<const uint8_t*>(p.residual + row_base_off + col0)
+                                           : reinterpret_cast<const uint8_t*>(p.aux + row_base_off + col0);
+    load_rows_via_stage<P>(s, g, ld_bytes, lane, rows_valid, ex);
+  }
+  uint32_t d2pk[P * 4];   // second bf16 output of the GELU epilogues, flushed after D (dead otherwise)
+#pragma unroll
+  for (int i = 0; i < N16; ++i) {
+    uint32_t r[16];
+    tmem_ld_32x16(taddr + (uint32_t)(16 * i), r);
+    tmem_ld_wait();
+    f32x2_t v2[8];
+    scale_bias16<true>(p, r, col0 + 16 * i, v2);
+    if constexpr (kEpi == EPI_GELU) {
+      if (p.act == MVLT_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { d2pk[8 * i + j] = pack_bf16x2_f2(v2[j]); v2[j] = gelu2(v2[j]); }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f32x2_t dg;
+          gelu_and_grad2(v2[j], v2[j], dg);
+          d2pk[8 * i + j] = pack_bf16x2_f2(dg);
+        }
+      }
+    } else if constexpr (kEpi == EPI_PLAIN && kOutF32) {
+      if (p.act == MVLT_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v2[j] = gelu2(v2[j]);
+      }
+    }
+    if constexpr (kEpi == EPI_AUX) apply_aux16(p.act, &ex[8 * i], v2);
+    if constexpr (kEpi == EPI_RESID) {
+      const f32x2_t rs2 = f2_splat(rs);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v2[j] = f2_fma(rs2, v2[j], f2_pack(__uint_as_float(ex[16 * i + 2 * j]), __uint_as_float(ex[16 * i + 2 * j + 1])));
+    } else if (p.rowscale != nullptr) {
+      const f32x2_t rs2 = f2_splat(rs);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v2[j] = f2_mul(v2[j], rs2);
+    }
+    if constexpr (kOutF32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a, b, c, d;
+        f2_unpack(v2[2 * j], a, b);
+        f2_unpack(v2[2 * j + 1], c, d);
+        st_shared_v4(own_piece<8>(s, 4 * i + j), __float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d));
+      }
+    } else {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2_f2(v2[j]);
+      stage_put_bf16<P>(s, i, pk);
+    }
+  }
+  if constexpr (kOutF32) {
+    uint8_t* g = reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(p.D) + row_base_off + col0);
+    if (kEpi == EPI_PLAIN && p.atomic_add) stage_flush<8, true>(s, g, ld_bytes, lane, rows_valid);
+    else stage_flush<8, false>(s, g, ld_bytes, lane, rows_valid);
+  } else {
+    stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), ld_bytes,
+                          lane, rows_valid);
+    if constexpr (kEpi == EPI_GELU) {
+      if (p.D2 != nullptr) {
+#pragma unroll
+        for (int i = 0; i < N16; ++i) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = d2pk[8 * i + j];
+          stage_put_bf16<P>(s, i, pk);
+        }
+        stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D2) + row_base_off + col0),
+                              ld_bytes, lane, rows_valid);
+      }
     }
   }
 }
 
-template <bool kHasExtra>
+// Tail path (N not a multiple of 32 / unaligned rows): one 32-column chunk with per-element predicates and
+// row-per-lane global accesses. Only the last column block of odd-sized problems (vocabulary 30522) gets here.
+__device__ __noinline__ void epilogue_chunk_tail(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
+                                                 int rows_valid, int col0, float rs) {
+  const bool row_ok = lane < rows_valid;
+  const long long row_off = row_base_off + (long long)lane * p.ldd;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const int c0 = col0 + 16 * h;
+    uint32_t r[16];
+    tmem_ld_32x16(taddr + (uint32_t)(16 * h), r);
+    tmem_ld_wait();
+    f32x2_t v2[8];
+    scale_bias16<false>(p, r, c0, v2);
+    if (p.act == MVLT_ACT_GELU || p.act == MVLT_ACT_GELU_SAVE_GRAD) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f32x2_t g, dg;
+        gelu_and_grad2(v2[j], g, dg);
+        const uint32_t second = pack_bf16x2_f2(p.act == MVLT_ACT_GELU ? v2[j] : dg);
+        v2[j] = g;
+        if (p.D2 != nullptr && row_ok) {
+          __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.D2) + row_off + c0;
+          const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&second);
+          if (c0 + 2 * j < p.N) d2[2 * j] = hv.x;
+          if (c0 + 2 * j + 1 < p.N) d2[2 * j + 1] = hv.y;
+        }
+      }
+    }
+    if (p.aux != nullptr) {
+      uint32_t ax[8];
+      const __nv_bfloat16* ap = p.aux + row_off + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a0 = 0.f, a1 = 0.f;
+        if (row_ok && c0 + 2 * j < p.N) a0 = __bfloat162float(ap[2 * j]);
+        if (row_ok && c0 + 2 * j + 1 < p.N) a1 = __bfloat162float(ap[2 * j + 1]);
+        ax[j] = pack_bf16x2(a0, a1);
+      }
+      apply_aux16(p.act, ax, v2);
+    }
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f2_unpack(v2[j], v[2 * j], v[2 * j + 1]);
+    if (p.residual != nullptr) {
+      const float* rp = p.residual + row_off + c0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (row_ok && c0 + j < p.N) v[j] = fmaf(rs, v[j], rp[j]);
+    } else if (p.rowscale != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= rs;
+    }
+    if (row_ok) {
+      if (p.out_f32) {
+        float* d = reinterpret_cast<float*>(p.D) + row_off + c0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < p.N) {
+            if (p.atomic_add) atomicAdd(d + j, v[j]);
+            else d[j] = v[j];
+          }
+        }
+      } else {
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + row_off + c0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < p.N) d[j] = __float2bfloat16(v[j]);
+      }
+    }
+  }
+}
+
+// Exchange of per-row partial results between the two column-half warps of one (accumulator, lane-quarter) pair:
+// each writes its value(s) to the head of its own staging tile, the pair meets on a named barrier, each reads the
+// partner's, and a second barrier protects the staging tile before it is reused.
+__device__ __forceinline__ float2 pair_exchange(uint32_t my_stage_s, uint32_t partner_stage_s, int bar_id, int lane, float2 mine) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(my_stage_s + lane * 8), "f"(mine.x), "f"(mine.y) : "memory");
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  float2 other;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(other.x), "=f"(other.y) : "r"(partner_stage_s + lane * 8) : "memory");
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  return other;
+}
+
+// ---- fused row softmax (forward): pass 2 for one unit of P*8 bf16 columns: P = exp2(a2 * acc - mx) * inv
+template <int P>
+__device__ __forceinline__ void softmax_unit(const KParams& p, uint32_t taddr, long long row_base_off, int lane, int rows_valid,
+                                             int col0, float a2, float mx, float inv, const StageAddr& s) {
+#pragma unroll
+  for (int i = 0; i < P / 2; ++i) {
+    uint32_t r[16];
+    tmem_ld_32x16(taddr + (uint32_t)(16 * i), r);
+    tmem_ld_wait();
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      pk[j] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(r[2 * j]), a2, -mx)) * inv,
+                          ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), a2, -mx)) * inv);
+    stage_put_bf16<P>(s, i, pk);
+  }
+  stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), p.ldd * 2,
+                        lane, rows_valid);
+}
+// ---- fused softmax backward for one unit: kPass = 0 accumulates dot += sum_n P * dP; kPass = 1 writes
+// dS = alpha * P * (dP - dot). P (aux) is fetched through the staging tile both times (DRAM, then L2).
+template <int P, int kPass>
+__device__ __forceinline__ float softmax_bwd_unit(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
+                                                  int rows_valid, int col0, float dot, const StageAddr& s) {
+  uint32_t ex[P * 4];
+  load_rows_via_stage<P>(s, reinterpret_cast<const uint8_t*>(p.aux + row_base_off + col0), p.ldd * 2, lane, rows_valid, ex);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < P / 2; ++i) {
+    uint32_t r[16];
+    tmem_ld_32x16(taddr + (uint32_t)(16 * i), r);
+    tmem_ld_wait();
+    if (kPass == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 f = unpack_bf16x2(ex[8 * i + j]);
+        acc = fmaf(f.x, __uint_as_float(r[2 * j]), acc);
+        acc = fmaf(f.y, __uint_as_float(r[2 * j + 1]), acc);
+      }
+    } else {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 f = unpack_bf16x2(ex[8 * i + j]);
+        pk[j] = pack_bf16x2(p.alpha * f.x * (__uint_as_float(r[2 * j]) - dot),
+                            p.alpha * f.y * (__uint_as_float(r[2 * j + 1]) - dot));
+      }
+      stage_put_bf16<P>(s, i, pk);
+    }
+  }
+  if (kPass == 1)
+    stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), p.ldd * 2,
+                          lane, rows_valid);
+  return acc;
+}
+
+template <int kEpi, bool kOutF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const KParams p) {
+                    const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -297,18 +510,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full_bar) + 256;   // 8 x 4 KB per-warp store staging tiles
+  uint64_t* tempty_bar = tfull_bar + MAX_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + MAX_ACC);
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full_bar) + 256;   // 16 x 4 KB per-warp staging tiles
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < MAX_ACC; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one elected lane per warp of the owning epilogue group
+      mbar_init(&tempty_bar[a], NUM_EPI_WARPS / 2);  // one elected lane per warp of the owning epilogue group
     }
     fence_barrier_init();
   }
@@ -323,144 +536,211 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.batch1 * p.batch2 * p.split_k * p.num_m_blocks * p.num_n_blocks;
+  const int acc_mask = p.num_acc - 1;                 // num_acc is 2 or 4
+  const int acc_shift = (p.num_acc == 4) ? 2 : 1;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
-        const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * p.block_n;
-        const int kb0 = tc.split * p.kb_per_split;
-        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          const int k0 = kb * BLOCK_K;
-          if (!p.a_mn) {
-            tma_load_4d(sa, &tmA, &full_bar[stage], k0, m0, tc.b2 * p.a_b2, tc.b1 * p.a_b1);
-          } else {
+  if (warp < FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          const TileCoord tc = decode_tile(p, t);
+          const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * p.block_n;
+          const int kb0 = tc.split * p.kb_per_split;
+          const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            const int k0 = kb * BLOCK_K;
+            if (!p.a_mn) {
+              tma_load_4d(sa, &tmA, &full_bar[stage], k0, m0, tc.b2 * p.a_b2, tc.b1 * p.a_b1);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_4d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, k0, tc.b2 * p.a_b2,
-                          tc.b1 * p.a_b1);
-          }
-          if (!p.b_mn) {
-            tma_load_4d(sb, &tmB, &full_bar[stage], k0, n0, tc.b2 * p.b_b2, tc.b1 * p.b_b1);
-          } else {
-            for (int j = 0; j < p.block_n / 64; ++j)
-              tma_load_4d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, k0, tc.b2 * p.b_b2,
-                          tc.b1 * p.b_b1);
-          }
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_4d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, k0, tc.b2 * p.a_b2, tc.b1 * p.a_b1);
+            }
+            if (!p.b_mn) {
+              tma_load_4d(sb, &tmB, &full_bar[stage], k0, n0, tc.b2 * p.b_b2, tc.b1 * p.b_b1);
+            } else {
+              for (int j = 0; j < p.block_n / 64; ++j)
+                tma_load_4d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, k0, tc.b2 * p.b_b2, tc.b1 * p.b_b1);
+            }
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(p.block_n, p.a_mn, p.b_mn);
-      // K-major: 8-row groups are 1024 B apart (SBO); the single 128 B swizzle atom along K makes LBO unused.
-      // MN-major: 64(mn) x 8(k) atoms; SBO = 1024 B between k-groups, LBO = 8192 B between 64-wide mn groups.
-      const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
-      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
-        const int kb0 = tc.split * p.kb_per_split;
-        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        const uint32_t idesc = make_instr_desc(p.block_n, p.a_mn, p.b_mn);
+        // K-major: 8-row groups are 1024 B apart (SBO); the single 128 B swizzle atom along K makes LBO unused.
+        // MN-major: 64(mn) x 8(k) atoms; SBO = 1024 B between k-groups, LBO = 8192 B between 64-wide mn groups.
+        const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
+        const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+        int stage = 0;
+        uint32_t phase = 0;
+        int local = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+          const TileCoord tc = decode_tile(p, t);
+          const int kb0 = tc.split * p.kb_per_split;
+          const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+          const int acc = local & acc_mask;
+          const uint32_t acc_phase = (uint32_t)(local >> acc_shift) & 1u;
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024u);
-            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024u);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024u);
+              const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024u);
+              umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+          umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPILOGUE_REGS));
     // ===================== epilogue warps =====================
-    // Two groups of four warps (one warp per TMEM lane quarter). Group g drains accumulator buffer g, i.e. every
-    // second tile of this CTA, so the (latency-bound) epilogues of consecutive tiles overlap each other as well as
-    // the mainloop. Residual / aux operands of a chunk are fetched one chunk ahead (and, for the first chunk,
-    // before waiting for the MMA).
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int group = (warp - 2) >> 2;     // accumulator buffer / tile parity owned by this warp
-    constexpr bool has_extra = kHasExtra;
-    uint32_t phase = 0;
-    int local = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-      if ((local & 1) != group) continue;
+    // 16 warps = 2 tile parities x 4 TMEM lane quarters x 2 column halves. The warps of parity g drain every second
+    // tile of this CTA, so the epilogues of consecutive tiles overlap each other as well as the mainloop. A warp
+    // walks its column range in "units" of one staging tile: 64 bf16 / 32 fp32 columns (128-byte row segments), a
+    // 32-column bf16 unit for an odd remainder, and a predicated tail path for ragged N.
+    const int ew = warp - FIRST_EPI_WARP;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int group = (ew >> 2) & 1;       // tile parity owned by this warp
+    const int half = ew >> 3;              // column half of the tile
+    const int nchunks = p.block_n >> 5;    // 32-column chunks per tile
+    const int split = (nchunks + 1) >> 1;
+    const int c_begin = half ? split : 0;
+    const int c_end = half ? nchunks : split;
+    const uint32_t stage = smem_u32(stage_base) + (uint32_t)ew * 4096u;
+    const uint32_t partner_stage = smem_u32(stage_base) + (uint32_t)(ew ^ 8) * 4096u;
+    const StageAddr sa = make_stage_addr(stage, lane);
+    const int pair_bar = 1 + group * 4 + quarter;   // named barriers 1..8 (0 is __syncthreads)
+    const bool ld_aligned = (p.ldd & 7) == 0;
+    for (int local = group, t = blockIdx.x + group * gridDim.x; t < total_tiles; t += 2 * gridDim.x, local += 2) {
       const TileCoord tc = decode_tile(p, t);
-      const int row = tc.m_blk * BLOCK_M + quarter * 32 + lane;
       const int n0 = tc.n_blk * p.block_n;
-      const bool row_ok = row < p.M;
       const int row_base = tc.m_blk * BLOCK_M + quarter * 32;
       const int rows_valid = min(32, p.M - row_base);          // <= 0 when the whole warp is past the M tail
       const long long batch_off = (long long)tc.b1 * p.sD1 + (long long)tc.b2 * p.sD2;
       const long long row_base_off = batch_off + (long long)row_base * p.ldd;
-      const long long row_off = row_base_off + (long long)lane * p.ldd;
       float rs = 1.f;
-      if (p.rowscale != nullptr && row_ok) rs = p.rowscale[row / p.rows_per_scale];
-      const bool aligned = ((p.ldd & 7) == 0) && ((batch_off & 7) == 0);
-      uint8_t* stage = stage_base + (warp - 2) * 4096;
+      if (p.rowscale != nullptr && lane < rows_valid) rs = p.rowscale[(row_base + lane) / p.rows_per_scale];
+      const bool aligned = ld_aligned && ((batch_off & 7) == 0);
+      const int acc = local & acc_mask;
 
-      uint32_t exA[32], exB[32];
-      if (kHasExtra) issue_extra(p, row_off, n0, row_ok && chunk_vec_ok(p, n0, aligned), exA);
-      mbar_wait(&tfull_bar[group], phase);
+      mbar_wait(&tfull_bar[acc], (uint32_t)(local >> acc_shift) & 1u);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * p.block_n);
-      for (int c = 0; c < p.block_n; c += 64) {
-        uint32_t r[32];
-        {
-          tmem_ld_32x32(taddr0 + (uint32_t)c, r);
-          const int cn = n0 + c + 32;
-          if (kHasExtra && c + 32 < p.block_n) issue_extra(p, row_off, cn, row_ok && chunk_vec_ok(p, cn, aligned), exB);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n);
+      if constexpr (kEpi == EPI_SOFTMAX) {
+        // ---- fused row softmax (whole row in this tile): pass 1 = this warp's partial (max, sum) over its column
+        // half, exchanged with the partner warp; pass 2 = normalise + store. The accumulator is read twice from TMEM.
+        const float a2 = p.alpha * 1.4426950408889634f;   // exp(alpha*x) = exp2(a2*x)
+        float mx = -INFINITY, sum = 0.f;
+        for (int ci = c_begin; ci < c_end; ++ci) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr0 + (uint32_t)(ci * 32), r);
           tmem_ld_wait();
-          const int col0 = n0 + c;
-          if (rows_valid > 0 && col0 < p.N) epilogue_chunk<kHasExtra>(p, r, exA, row_base_off, lane, rows_valid, col0, rs, aligned, stage);
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(r[j]) * a2);
+          const float mn = fmaxf(mx, cm);
+          float cs = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cs += ex2_approx(fmaf(__uint_as_float(r[j]), a2, -mn));
+          sum = fmaf(sum, ex2_approx(mx - mn), cs);
+          mx = mn;
         }
-        if (c + 32 < p.block_n) {
-          tmem_ld_32x32(taddr0 + (uint32_t)(c + 32), r);
-          const int cn = n0 + c + 64;
-          if (kHasExtra && c + 64 < p.block_n) issue_extra(p, row_off, cn, row_ok && chunk_vec_ok(p, cn, aligned), exA);
-          tmem_ld_wait();
-          const int col0 = n0 + c + 32;
-          if (rows_valid > 0 && col0 < p.N) epilogue_chunk<kHasExtra>(p, r, exB, row_base_off, lane, rows_valid, col0, rs, aligned, stage);
+        {
+          const float2 o = pair_exchange(stage, partner_stage, pair_bar, lane, make_float2(mx, sum));
+          const float mn = fmaxf(mx, o.x);
+          // a warp without columns (block_n = 32) contributes (-inf, 0): guard the inf - inf
+          const float s_me = (sum > 0.f) ? sum * ex2_approx(mx - mn) : 0.f;
+          const float s_ot = (o.y > 0.f) ? o.y * ex2_approx(o.x - mn) : 0.f;
+          sum = s_me + s_ot;
+          mx = mn;
+        }
+        const float inv = 1.f / sum;
+        if (rows_valid > 0) {
+          for (int ci = c_begin; ci < c_end;) {
+            if (ci + 2 <= c_end) {
+              softmax_unit<8>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, a2, mx, inv, sa);
+              ci += 2;
+            } else {
+              softmax_unit<4>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, a2, mx, inv, sa);
+              ci += 1;
+            }
+          }
+        }
+      } else if constexpr (kEpi == EPI_SOFTMAX_BWD) {
+        // ---- fused softmax backward: dS = alpha * P * (dP - sum_n P*dP)
+        float dot = 0.f;
+        for (int ci = c_begin; ci < c_end;) {
+          if (ci + 2 <= c_end) {
+            dot += softmax_bwd_unit<8, 0>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, 0.f, sa);
+            ci += 2;
+          } else {
+            dot += softmax_bwd_unit<4, 0>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, 0.f, sa);
+            ci += 1;
+          }
+        }
+        dot += pair_exchange(stage, partner_stage, pair_bar, lane, make_float2(dot, 0.f)).x;
+        for (int ci = c_begin; ci < c_end;) {
+          if (ci + 2 <= c_end) {
+            softmax_bwd_unit<8, 1>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, dot, sa);
+            ci += 2;
+          } else {
+            softmax_bwd_unit<4, 1>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, dot, sa);
+            ci += 1;
+          }
+        }
+      } else if (rows_valid > 0) {
+        for (int ci = c_begin; ci < c_end;) {
+          const int col0 = n0 + ci * 32;
+          const uint32_t taddr = taddr0 + (uint32_t)(ci * 32);
+          if (col0 >= p.N) break;
+          if (!aligned || col0 + 32 > p.N) {
+            epilogue_chunk_tail(p, taddr, row_base_off, lane, rows_valid, col0, rs);
+            ci += 1;
+          } else if constexpr (kOutF32) {
+            epilogue_unit_vec<kEpi, true, 8>(p, taddr, row_base_off, lane, rows_valid, col0, rs, sa);
+            ci += 1;
+          } else {
+            if (ci + 2 <= c_end && col0 + 64 <= p.N) {
+              epilogue_unit_vec<kEpi, false, 8>(p, taddr, row_base_off, lane, rows_valid, col0, rs, sa);
+              ci += 2;
+            } else {
+              epilogue_unit_vec<kEpi, false, 4>(p, taddr, row_base_off, lane, rows_valid, col0, rs, sa);
+              ci += 1;
+            }
+          }
         }
       }
       // all of this warp's TMEM reads are complete (wait::ld above): release the accumulator buffer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[group]);
-      phase ^= 1;
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
 
@@ -594,6 +874,42 @@ int make_operand_map(CUtensorMap* out, const void* base, int rows, int K, int mn
   return get_tensor_map(out, base, dims, str, box);
 }
 
+FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.m = 0;
+  f.sh = 0;
+  if (d > 1) {
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                      // l = ceil(log2 d) >= 1
+    f.m = (uint32_t)((((unsigned long long)1 << (31 + l)) + d - 1) / d);   // ceil(2^(31+l) / d) < 2^32 ... <= 2^32 - 1 for d > 2^(l-1)
+    f.sh = l - 1;
+  }
+  return f;
+}
+
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
+struct KernelVariant {
+  GemmKernelFn fn;
+  const char* name;
+};
+const KernelVariant kVariants[] = {
+    {gemm_tcgen05_kernel<EPI_PLAIN, false>, "plain/bf16"},       {gemm_tcgen05_kernel<EPI_PLAIN, true>, "plain/f32"},
+    {gemm_tcgen05_kernel<EPI_GELU, false>, "gelu/bf16"},         {gemm_tcgen05_kernel<EPI_AUX, false>, "aux/bf16"},
+    {gemm_tcgen05_kernel<EPI_RESID, true>, "residual/f32"},      {gemm_tcgen05_kernel<EPI_SOFTMAX, false>, "softmax/bf16"},
+    {gemm_tcgen05_kernel<EPI_SOFTMAX_BWD, false>, "softmax_bwd/bf16"},
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+int pick_variant(const mvlt_gemm_desc* g) {
+  if (g->act == MVLT_ACT_SOFTMAX) return 5;
+  if (g->act == MVLT_ACT_SOFTMAX_BWD) return 6;
+  if (g->residual != nullptr) return 4;
+  if (g->aux != nullptr) return 3;
+  if (!g->out_f32 && (g->act == MVLT_ACT_GELU || g->act == MVLT_ACT_GELU_SAVE_GRAD)) return 2;
+  return g->out_f32 ? 1 : 0;
+}
+
 int pick_block_n(const mvlt_gemm_desc* g) {
   const int N = g->N;
   const int step = g->b_mn ? 64 : 32;
@@ -618,17 +934,34 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   MVLT_CHECK_ARG(g->A && g->B && g->D, "mvlt_gemm: null operand");
   MVLT_CHECK_ARG(!(g->atomic_add && !g->out_f32), "mvlt_gemm: atomic_add needs an fp32 output");
   MVLT_CHECK_ARG(!(g->split_k > 1 && !g->atomic_add), "mvlt_gemm: split_k > 1 needs atomic_add");
-  MVLT_CHECK_ARG(!((g->act == MVLT_ACT_DGELU || g->act == MVLT_ACT_MUL_AUX) && g->aux == nullptr),
+  MVLT_CHECK_ARG(!((g->act == MVLT_ACT_DGELU || g->act == MVLT_ACT_MUL_AUX || g->act == MVLT_ACT_SOFTMAX_BWD) && g->aux == nullptr),
                  "mvlt_gemm: dgelu / mul_aux epilogue needs aux");
   MVLT_CHECK_ARG(!(g->act == MVLT_ACT_GELU_SAVE_GRAD && g->D2 == nullptr), "mvlt_gemm: gelu_save_grad needs D2");
+  if (g->act == MVLT_ACT_SOFTMAX || g->act == MVLT_ACT_SOFTMAX_BWD) {
+    MVLT_CHECK_ARG(g->N <= 256 && g->N % 32 == 0 && !g->out_f32 && !g->atomic_add && !g->bias && !g->residual &&
+                       !g->rowscale && (g->ldd % 8) == 0 && (g->sD1 % 8) == 0 && (g->sD2 % 8) == 0 &&
+                       (g->block_n == 0 || g->block_n == g->N) && (g->b_mn == 0 || g->N % 64 == 0),
+                   "mvlt_gemm: row softmax epilogues need N <= 256, N %% 32 == 0, bf16 output, 16-byte aligned rows");
+    MVLT_CHECK_ARG((g->act == MVLT_ACT_SOFTMAX) == (g->aux == nullptr), "mvlt_gemm: softmax_bwd needs aux = P, softmax none");
+  }
   MVLT_CHECK_ARG(!((g->act == MVLT_ACT_GELU || g->act == MVLT_ACT_GELU_SAVE_GRAD) && (g->residual || g->aux)),
                  "mvlt_gemm: the GELU epilogues do not combine with residual / aux operands");
+  // the epilogue streams residual / aux / D2 through the same staging-tile geometry as D
+  MVLT_CHECK_ARG(!(g->residual && !g->out_f32), "mvlt_gemm: residual (fp32) needs an fp32 output");
+  MVLT_CHECK_ARG(!(g->residual && g->aux), "mvlt_gemm: residual and aux are mutually exclusive");
+  MVLT_CHECK_ARG(!(g->aux && g->out_f32), "mvlt_gemm: aux (bf16) needs a bf16 output");
+  MVLT_CHECK_ARG(!(g->D2 && g->out_f32), "mvlt_gemm: D2 (bf16) needs a bf16 output");
+  MVLT_CHECK_ARG(!(g->act == MVLT_ACT_GELU_SAVE_GRAD && g->out_f32), "mvlt_gemm: gelu_save_grad needs a bf16 output");
+  MVLT_CHECK_ARG(!(g->atomic_add && (g->residual || g->aux || g->act != MVLT_ACT_NONE)),
+                 "mvlt_gemm: atomic_add only combines with alpha / bias / rowscale");
+  MVLT_CHECK_ARG(!(g->aux && g->act != MVLT_ACT_MUL_AUX && g->act != MVLT_ACT_DGELU && g->act != MVLT_ACT_SOFTMAX_BWD),
+                 "mvlt_gemm: aux is only consumed by the mul_aux / dgelu / softmax_bwd epilogues");
   MVLT_CHECK_ARG(!(g->rowscale && g->rows_per_scale <= 0), "mvlt_gemm: rowscale needs rows_per_scale");
 
   KParams p;
   memset(&p, 0, sizeof(p));
   p.M = g->M; p.N = g->N; p.K = g->K;
-  p.block_n = pick_block_n(g);
+  p.block_n = (g->act == MVLT_ACT_SOFTMAX || g->act == MVLT_ACT_SOFTMAX_BWD) ? g->N : pick_block_n(g);
   MVLT_CHECK_ARG(p.block_n >= 32 && p.block_n <= 256 && p.block_n % (g->b_mn ? 64 : 32) == 0,
                  "mvlt_gemm: unsupported block_n %d", p.block_n);
   const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
@@ -642,6 +975,11 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   p.kb_per_split = (p.num_k_blocks + split - 1) / split;
   p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   p.batch1 = g->batch1; p.batch2 = g->batch2;
+  p.num_acc = (p.block_n <= 128) ? 4 : 2;
+  p.div_n = make_fastdiv((uint32_t)p.num_n_blocks);
+  p.div_m = make_fastdiv((uint32_t)p.num_m_blocks);
+  p.div_s = make_fastdiv((uint32_t)p.split_k);
+  p.div_b2 = make_fastdiv((uint32_t)p.batch2);
   p.a_mn = g->a_mn ? 1 : 0; p.b_mn = g->b_mn ? 1 : 0;
   p.D = g->D; p.D2 = g->D2; p.bias = g->bias;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(g->aux);
@@ -663,17 +1001,22 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
   if (smem < 120 * 1024) smem = 120 * 1024;
   static std::once_flag attr_once;
+  static int launch_regs_ok = 1;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (int v = 0; v < kNumVariants; ++v) {
+      cudaFuncSetAttribute(kVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      // the setmaxnreg budget assumes the launch allocation; a smaller one would make setmaxnreg.inc block forever
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, kVariants[v].fn) != cudaSuccess || fa.numRegs != LAUNCH_REGS) launch_regs_ok = 0;
+    }
   });
+  MVLT_CHECK_ARG(launch_regs_ok, "mvlt_gemm: a kernel variant was not built with exactly %d registers per thread", LAUNCH_REGS);
   const long long total_tiles =
       (long long)p.batch1 * p.batch2 * p.split_k * p.num_m_blocks * p.num_n_blocks;
   MVLT_CHECK_ARG(total_tiles < (1ll << 31), "mvlt_gemm: too many tiles");
   int grid = mvlt_num_sms();
   if (total_tiles < grid) grid = (int)total_tiles;
-  if (p.residual != nullptr || p.aux != nullptr) gemm_tcgen05_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
-  else gemm_tcgen05_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  kVariants[pick_variant(g)].fn<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -176,16 +176,15 @@ class PVLTEngine:
         else:
             Nk = N
             kvin = xn
-        if Nk % 64 != 0 or Nk > 512:
-            raise MvltError(f"K/V length {Nk} unsupported by the softmax kernel (need a multiple of 64, <= 512)")
+        if Nk % 32 != 0 or Nk > 256:
+            raise MvltError(f"K/V length {Nk} unsupported by the fused softmax epilogue (need a multiple of 32, <= 256)")
         kv = _empty((B * Nk, 2 * C), BF16, dev)
         k.gemm(kvin, Wb[pfx + ".attn.kv.weight"], kv, bias=P[pfx + ".attn.kv.bias"])
         q4 = q.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3)
         kv5 = kv.view(B, Nk, 2, heads, HEAD_DIM)
         k4, v4 = kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3)
         Pm = _empty((B, heads, N, Nk), BF16, dev)
-        k.gemm(q4, k4, Pm, alpha=HEAD_DIM ** -0.5)
-        k.softmax_fwd(Pm, B * heads * N, Nk)
+        k.gemm(q4, k4, Pm, alpha=HEAD_DIM ** -0.5, act=k.ACT_SOFTMAX)   # softmax fused into the QK^T epilogue
         o = _empty((M, C), BF16, dev)
         k.gemm(Pm, v4.transpose(-1, -2), o.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3))
         X1 = _empty((B, N, C), F32, dev)
@@ -246,8 +245,8 @@ class PVLTEngine:
         Pm = c["Pm"]
         k.gemm(Pm.transpose(-1, -2), do4.transpose(-1, -2), dv4)          # dV = P^T dO
         dS = _empty((B, heads, N, Nk), BF16, dev)
-        k.gemm(do4, v4, dS)                                               # dP = dO V^T
-        k.softmax_bwd(Pm, dS, B * heads * N, Nk, HEAD_DIM ** -0.5)        # dS (includes the qk scale)
+        # dP = dO V^T with the softmax backward (and the qk scale) fused into the epilogue: writes dS directly
+        k.gemm(do4, v4, dS, alpha=HEAD_DIM ** -0.5, act=k.ACT_SOFTMAX_BWD, aux=Pm)
         dq = dyp  # reuse
         k.gemm(dS, k4.transpose(-1, -2), dq.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3))   # dQ = dS K
         k.gemm(dS.transpose(-1, -2), q4.transpose(-1, -2), dk4)           # dK = dS^T Q

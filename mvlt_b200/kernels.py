@@ -9,8 +9,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (ACT_DGELU, ACT_GELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_NONE, GemmDesc, call, ptr,
-                   require_cuda)
+from ._lib import (ACT_DGELU, ACT_GELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_NONE, ACT_SOFTMAX, ACT_SOFTMAX_BWD,
+                   GemmDesc, call, ptr, require_cuda)
 
 BF16 = torch.bfloat16
 F32 = torch.float32

@@ -165,3 +165,85 @@ def test_gemm_vocab_shape():
     k.gemm(logits, e.t(), dh)                                      # dH = dlogits E   (K = vocab, B MN-major)
     _check(dh, logits.float() @ e.float(), V, "vocab dH", atol_scale=2.0)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("Nq,Nk", [(1000, 192), (4224, 192), (130, 32), (384, 256), (77, 96)])
+def test_gemm_fused_softmax_fwd_bwd(Nq, Nk):
+    """QK^T with the row softmax in the epilogue, and dP GEMM with the softmax backward in the epilogue."""
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(23 + Nk)
+    B, H, D = 2, 5, 64
+    C = H * D
+    q = _rand((B * Nq, C), g, 1.0)
+    kv = _rand((B * Nk, 2 * C), g, 1.0)
+    q4 = q.view(B, Nq, H, D).permute(0, 2, 1, 3)
+    k4 = kv.view(B, Nk, 2, H, D)[:, :, 0].permute(0, 2, 1, 3)
+    v4 = kv.view(B, Nk, 2, H, D)[:, :, 1].permute(0, 2, 1, 3)
+    P = torch.empty((B, H, Nq, Nk), device="cuda", dtype=BF16)
+    k.gemm(q4, k4, P, alpha=0.125, act=k.ACT_SOFTMAX)
+    ref = torch.softmax(0.125 * q4.float() @ k4.float().transpose(-1, -2), -1)
+    err = (P.float() - ref).abs().max().item()
+    assert err < 4e-3, err
+    assert (P.float().sum(-1) - 1).abs().max().item() < 2e-2
+    do4 = _rand((B * Nq, C), g, 0.5).view(B, Nq, H, D).permute(0, 2, 1, 3)
+    dS = torch.empty_like(P)
+    k.gemm(do4, v4, dS, alpha=0.125, act=k.ACT_SOFTMAX_BWD, aux=P)
+    dP = do4.float() @ v4.float().transpose(-1, -2)
+    Pf = P.float()
+    refd = 0.125 * Pf * (dP - (Pf * dP).sum(-1, keepdim=True))
+    _check(dS, refd, D, "softmax bwd epilogue", atol_scale=2.0)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 200, 96), (1000, 320, 64), (257, 96, 128), (640, 512, 64), (130, 72, 64)])
+def test_gemm_epilogue_units_and_tails(M, N, K):
+    """Every epilogue flavour on shapes that mix 64-column units, 32-column units and the ragged-N tail path."""
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a, b = _rand((M, K), g, 0.5), _rand((N, K), g, 0.3)
+    bias = torch.randn(N, generator=g, device="cuda")
+    ref = _ref(a, b) + bias
+    # fp32 + residual + rowscale (rows_per_scale = 1)
+    res = torch.randn((M, N), generator=g, device="cuda")
+    rs = torch.rand(M, generator=g, device="cuda")
+    out = torch.empty((M, N), device="cuda", dtype=F32)
+    k.gemm(a, b, out, bias=bias, residual=res, rowscale=rs, rows_per_scale=1)
+    _check(out, res + rs[:, None] * ref, K, "residual")
+    # bf16 + gelu + saved derivative
+    out = torch.empty((M, N), device="cuda", dtype=BF16)
+    dg = torch.empty((M, N), device="cuda", dtype=BF16)
+    k.gemm(a, b, out, bias=bias, act=k.ACT_GELU_SAVE_GRAD, preact_out=dg)
+    refr = ref.clone().requires_grad_(True)
+    torch.nn.functional.gelu(refr).sum().backward()
+    _check(out, torch.nn.functional.gelu(ref), K, "gelu")
+    _check(dg, refr.grad, K, "gelu'")
+    # bf16 + gelu + saved pre-activation
+    pre = torch.empty((M, N), device="cuda", dtype=BF16)
+    k.gemm(a, b, out, bias=bias, act=k.ACT_GELU, preact_out=pre)
+    _check(out, torch.nn.functional.gelu(ref), K, "gelu(2)")
+    _check(pre, ref, K, "preact")
+    # bf16 * aux, bf16 * gelu'(aux)
+    out2 = torch.empty((M, N), device="cuda", dtype=BF16)
+    k.gemm(a, b, out2, act=k.ACT_MUL_AUX, aux=dg)
+    _check(out2, _ref(a, b) * dg.float(), K, "mul_aux")
+    k.gemm(a, b, out2, act=k.ACT_DGELU, aux=pre)
+    pr = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(pr).sum().backward()
+    _check(out2, _ref(a, b) * pr.grad, K, "dgelu")
+    # fp32 atomic accumulation (vector reductions through the staging tile)
+    acc = torch.ones((M, N), device="cuda", dtype=F32)
+    k.gemm(a, b, acc, atomic_add=True)
+    _check(acc, 1.0 + _ref(a, b), K, "atomic")
+    # plain bf16 with row scale
+    k.gemm(a, b, out2, rowscale=rs, rows_per_scale=1)
+    _check(out2, rs[:, None] * _ref(a, b), K, "rowscale")
+    torch.cuda.synchronize()
+
+
+def test_gemm_rejects_mismatched_epilogue_operands():
+    from mvlt_b200 import kernels as k
+    from mvlt_b200._lib import MvltError
+    a = torch.zeros((128, 64), device="cuda", dtype=BF16)
+    b = torch.zeros((64, 64), device="cuda", dtype=BF16)
+    with pytest.raises(MvltError):
+        k.gemm(a, b, torch.empty((128, 64), device="cuda", dtype=F32), act=k.ACT_MUL_AUX,
+               aux=torch.zeros((128, 64), device="cuda", dtype=BF16))

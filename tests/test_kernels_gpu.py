@@ -294,7 +294,9 @@ def test_cross_entropy_fwd_bwd(n_cls, dtype):
     k.ce_fwd(logits, ld, labels, rows, n_cls, -1, lse, loss, 1.0 / n, total_sum=total, argmax_out=am, correct=corr)
     lr = logits.float().clone().requires_grad_(True)
     ref = F.cross_entropy(lr, labels, ignore_index=-1)
-    assert abs(loss.item() - ref.item()) < 1e-4 * max(1, abs(ref.item())) and abs(total.item() - loss.item()) < 1e-6
+    assert abs(loss.item() - ref.item()) < 1e-4 * max(1, abs(ref.item()))
+    # loss and total are accumulated by independent fp32 atomics (order differs run to run): a few ulp apart
+    assert abs(total.item() - loss.item()) < 1e-5 * max(1, abs(ref.item()))
     assert torch.equal(am.long(), logits.float().argmax(-1))
     assert int(corr.item()) == int(((logits.float().argmax(-1) == labels) & (labels != -1)).sum())
     ref.backward()
