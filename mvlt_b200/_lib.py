@@ -32,10 +32,13 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float),
         ("act", C.c_int32), ("out_f32", C.c_int32), ("atomic_add", C.c_int32),
         ("rows_per_scale", C.c_int32), ("split_k", C.c_int32), ("block_n", C.c_int32),
+        ("conv_mode", C.c_int32), ("conv_B", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32),
+        ("conv_C", C.c_int32), ("conv_pix_stride", C.c_int64), ("conv_batch_stride", C.c_int64),
     ]
 
 
 ACT_NONE, ACT_GELU, ACT_DGELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_SOFTMAX, ACT_SOFTMAX_BWD = 0, 1, 2, 3, 4, 5, 6
+CONV_NONE, CONV_A, CONV_BT = 0, 1, 2
 
 
 def lib_path() -> Path:

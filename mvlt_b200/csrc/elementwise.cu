@@ -266,6 +266,17 @@ __global__ void cast_conv_weight_kernel(const float* __restrict__ src, __nv_bflo
     dst[(long long)co * dst_ld + (long long)kk * Ci + ci] = __float2bfloat16(src[((long long)co * Ci + ci) * KK + kk]);
   }
 }
+// transposed + spatially flipped copy for the input-gradient convolution: dst[ci, t*Co + co] = src[co, ci, KK-1-t]
+__global__ void cast_conv_weight_t_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Co, int Ci,
+                                          int KK) {
+  const long long n = (long long)Co * Ci * KK;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Co);
+    const int t = (int)((i / Co) % KK);
+    const int ci = (int)(i / ((long long)Co * KK));
+    dst[i] = __float2bfloat16(src[((long long)co * Ci + ci) * KK + (KK - 1 - t)]);
+  }
+}
 // gradient of the permuted copy back to the master layout: dW[co,ci,kk] += dWp[co,kk,ci]
 __global__ void uncast_conv_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int KK,
                                          int src_ld) {
@@ -460,6 +471,12 @@ extern "C" int mvlt_cast_weight(const float* src, void* dst_bf16, long long n, v
 extern "C" int mvlt_cast_conv_weight(const float* src, void* dst_bf16, int Co, int Ci, int KK, int dst_ld, void* stream_) {
   cast_conv_weight_kernel<<<cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), Co, Ci, KK, dst_ld);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int mvlt_cast_conv_weight_t(const float* src, void* dst_bf16, int Co, int Ci, int KK, void* stream_) {
+  cast_conv_weight_t_kernel<<<cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), Co, Ci, KK);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

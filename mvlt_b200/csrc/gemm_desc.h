@@ -8,6 +8,12 @@
 //   MN-major (x_mn = 1): element (r,k) at  base + k*ld + r      (a transposed view, no copy)
 // so the three GEMMs of a Linear layer (y = x W^T, dx = dy W, dW = dy^T x) and the four batched
 // products of attention all map onto this one descriptor without materialising a transpose.
+//
+// Implicit 3x3 convolution (stride 1, zero padding 1) over an NHWC bf16 tensor X[b, y, x, c] (conv_* fields): the
+// im2col matrix col[(b,y,x), tap*C + c] = X[b, y + tap/3 - 1, x + tap%3 - 1, c] is never materialised; TMA fetches
+// shifted boxes of X (out-of-bounds = the zero padding) straight into the swizzled operand tiles.
+//   conv_mode = MVLT_CONV_A : A := col    (M = B*H*W, K = 9*C, a_mn = 0)   forward / input-gradient convolutions
+//   conv_mode = MVLT_CONV_BT: B := col^T  (N = 9*C, K = B*H*W, b_mn = 1)   weight-gradient GEMM dW = dY^T col
 #pragma once
 #include <stdint.h>
 
@@ -25,6 +31,8 @@ enum {
   MVLT_ACT_SOFTMAX = 5,         // D = softmax_n(alpha * acc)                        (attention probabilities)
   MVLT_ACT_SOFTMAX_BWD = 6,     // D = alpha * aux * (acc - sum_n aux * acc)         (aux = P; acc = dP -> dS)
 };
+
+enum { MVLT_CONV_NONE = 0, MVLT_CONV_A = 1, MVLT_CONV_BT = 2 };
 
 typedef struct mvlt_gemm_desc {
   const void* A;  // bf16
@@ -47,6 +55,10 @@ typedef struct mvlt_gemm_desc {
   int32_t rows_per_scale;  // rows of D per rowscale entry
   int32_t split_k;         // 0/1 = no split; >1 requires atomic_add
   int32_t block_n;         // 0 = auto
+  // implicit 3x3 convolution operand (see above); the replaced operand pointer (A or B) is the NHWC base
+  int32_t conv_mode;
+  int32_t conv_B, conv_H, conv_W, conv_C;           // C % 64 == 0; W <= 64 and 64 % W == 0; (H*W) % 64 == 0
+  int64_t conv_pix_stride, conv_batch_stride;       // element strides of X (x -> x+1, b -> b+1); y stride = W * pix_stride
 } mvlt_gemm_desc;
 
 #ifdef __cplusplus

@@ -76,6 +76,9 @@ struct KParams {
   long long ldd, sD1, sD2;
   float alpha;
   int act, out_f32, atomic_add, rows_per_scale;
+  // implicit 3x3 convolution operand (gemm_desc.h): tile/k-block index -> (b, y) pixel coordinates and (tap, c0)
+  int conv_mode, conv_W, conv_C;
+  FastDiv div_hw, div_w, div_cb, div_c;   // pixels / (H*W), / W; k-block / (C/64); column / C
 };
 
 // ---- UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp, restated) -----------------------------
@@ -557,14 +560,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint8_t* sb = sa + A_STAGE_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
             const int k0 = kb * BLOCK_K;
-            if (!p.a_mn) {
+            if (p.conv_mode == MVLT_CONV_A) {
+              // A tile = 128 consecutive pixels x 64 channels of tap (kb / (C/64)): one shifted NHWC box
+              uint32_t tap, cb, b0, rem, y0, xr;
+              fast_divmod(p.div_cb, (uint32_t)kb, tap, cb);
+              fast_divmod(p.div_hw, (uint32_t)m0, b0, rem);
+              fast_divmod(p.div_w, rem, y0, xr);
+              const int ty = (int)tap / 3;
+              tma_load_4d(sa, &tmA, &full_bar[stage], (int)cb * 64, (int)tap - 3 * ty - 1, (int)y0 + ty - 1, (int)b0);
+            } else if (!p.a_mn) {
               tma_load_4d(sa, &tmA, &full_bar[stage], k0, m0, tc.b2 * p.a_b2, tc.b1 * p.a_b1);
             } else {
 #pragma unroll
               for (int j = 0; j < BLOCK_M / 64; ++j)
                 tma_load_4d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, k0, tc.b2 * p.a_b2, tc.b1 * p.a_b1);
             }
-            if (!p.b_mn) {
+            if (p.conv_mode == MVLT_CONV_BT) {
+              // B tile (MN-major) = 64 consecutive pixels (k) x 64 channels of tap (n / C) per 64-column atom
+              uint32_t b0, rem, y0, xr;
+              fast_divmod(p.div_hw, (uint32_t)k0, b0, rem);
+              fast_divmod(p.div_w, rem, y0, xr);
+              for (int j = 0; j < p.block_n / 64; ++j) {
+                uint32_t tap, c0;
+                fast_divmod(p.div_c, (uint32_t)(n0 + j * 64), tap, c0);
+                const int ty = (int)tap / 3;
+                if (tap < 9u)
+                  tma_load_4d(sb + j * 8192, &tmB, &full_bar[stage], (int)c0, (int)tap - 3 * ty - 1, (int)y0 + ty - 1, (int)b0);
+                else   // columns past 9*C (N tail of the last block): any in-bounds-free box = zeros, keeps the tx count
+                  tma_load_4d(sb + j * 8192, &tmB, &full_bar[stage], 0, 0, 0, 0x40000000);
+              }
+            } else if (!p.b_mn) {
               tma_load_4d(sb, &tmB, &full_bar[stage], k0, n0, tc.b2 * p.b_b2, tc.b1 * p.b_b1);
             } else {
               for (int j = 0; j < p.block_n / 64; ++j)
@@ -901,6 +926,22 @@ const KernelVariant kVariants[] = {
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
+// NHWC bf16 tensor X[b, y, x, c] as a 4-D map (c, x, y, b) whose box covers `pixels` consecutive pixels x 64 channels
+int make_conv_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base, int pixels) {
+  const int W = g->conv_W, H = g->conv_H;
+  if (((uintptr_t)base & 15) != 0 || (g->conv_pix_stride % 8) != 0 || (g->conv_batch_stride % 8) != 0) {
+    mvlt_set_error("conv operand: base / strides must be 16-byte aligned (base=%p pix_stride=%lld batch_stride=%lld)", base,
+                   (long long)g->conv_pix_stride, (long long)g->conv_batch_stride);
+    return MVLT_ERR_ALIGN;
+  }
+  const int by = (pixels / W < H) ? pixels / W : H;   // rows of one image in the box
+  const int bb = pixels / (W * by);                    // images in the box (small feature maps)
+  uint64_t dims[4] = {(uint64_t)g->conv_C, (uint64_t)W, (uint64_t)H, (uint64_t)g->conv_B};
+  uint64_t str[3] = {(uint64_t)g->conv_pix_stride * 2, (uint64_t)g->conv_pix_stride * 2 * W, (uint64_t)g->conv_batch_stride * 2};
+  uint32_t box[4] = {64, (uint32_t)W, (uint32_t)by, (uint32_t)bb};
+  return get_tensor_map(out, base, dims, str, box);
+}
+
 int pick_variant(const mvlt_gemm_desc* g) {
   if (g->act == MVLT_ACT_SOFTMAX) return 5;
   if (g->act == MVLT_ACT_SOFTMAX_BWD) return 6;
@@ -990,11 +1031,32 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   p.rows_per_scale = g->rows_per_scale > 0 ? g->rows_per_scale : 1;
 
   CUtensorMap tmA, tmB;
-  int rc = make_operand_map(&tmA, g->A, g->M, g->K, p.a_mn, g->lda, g->batch1, g->batch2, g->sA1, g->sA2, BLOCK_M,
-                            &p.a_b1, &p.a_b2);
+  int rc = 0;
+  p.conv_mode = g->conv_mode;
+  if (g->conv_mode != MVLT_CONV_NONE) {
+    const long long HW = (long long)g->conv_H * g->conv_W, pix = HW * g->conv_B;
+    MVLT_CHECK_ARG(g->conv_mode == MVLT_CONV_A || g->conv_mode == MVLT_CONV_BT, "mvlt_gemm: bad conv_mode %d", g->conv_mode);
+    MVLT_CHECK_ARG(g->batch1 == 1 && g->batch2 == 1, "mvlt_gemm: implicit convolution is not batched");
+    MVLT_CHECK_ARG(g->conv_B > 0 && g->conv_H > 0 && g->conv_W > 0 && g->conv_C > 0 && g->conv_C % 64 == 0 &&
+                       g->conv_W <= 64 && 64 % g->conv_W == 0 && HW % 64 == 0 && (HW >= 128 ? HW % 128 == 0 : 128 % HW == 0),
+                   "mvlt_gemm: unsupported conv geometry B=%d H=%d W=%d C=%d", g->conv_B, g->conv_H, g->conv_W, g->conv_C);
+    p.conv_W = g->conv_W;
+    p.conv_C = g->conv_C;
+    p.div_hw = make_fastdiv((uint32_t)HW);
+    p.div_w = make_fastdiv((uint32_t)g->conv_W);
+    p.div_cb = make_fastdiv((uint32_t)(g->conv_C / 64));
+    p.div_c = make_fastdiv((uint32_t)g->conv_C);
+    if (g->conv_mode == MVLT_CONV_A)
+      MVLT_CHECK_ARG(g->M == pix && g->K == 9 * g->conv_C && !g->a_mn, "mvlt_gemm: conv A needs M = B*H*W, K = 9*C, K-major");
+    else
+      MVLT_CHECK_ARG(g->K == pix && g->N == 9 * g->conv_C && g->b_mn && p.block_n % 64 == 0,
+                     "mvlt_gemm: conv B^T needs K = B*H*W, N = 9*C, MN-major");
+  }
+  if (g->conv_mode == MVLT_CONV_A) rc = make_conv_map(&tmA, g, g->A, BLOCK_M);
+  else rc = make_operand_map(&tmA, g->A, g->M, g->K, p.a_mn, g->lda, g->batch1, g->batch2, g->sA1, g->sA2, BLOCK_M, &p.a_b1, &p.a_b2);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, g->B, g->N, g->K, p.b_mn, g->ldb, g->batch1, g->batch2, g->sB1, g->sB2, p.block_n,
-                        &p.b_b1, &p.b_b2);
+  if (g->conv_mode == MVLT_CONV_BT) rc = make_conv_map(&tmB, g, g->B, 64);
+  else rc = make_operand_map(&tmB, g->B, g->N, g->K, p.b_mn, g->ldb, g->batch1, g->batch2, g->sB1, g->sB2, p.block_n, &p.b_b1, &p.b_b2);
   if (rc) return rc;
 
   // > half of the SM's shared memory so two CTAs (each wanting all 512 TMEM columns) never share an SM

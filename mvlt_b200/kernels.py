@@ -9,8 +9,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (ACT_DGELU, ACT_GELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_NONE, ACT_SOFTMAX, ACT_SOFTMAX_BWD,
-                   GemmDesc, call, ptr, require_cuda)
+from ._lib import (ACT_DGELU, ACT_GELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_NONE, ACT_SOFTMAX, ACT_SOFTMAX_BWD, CONV_A,
+                   CONV_BT, GemmDesc, call, ptr, require_cuda)
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -108,6 +108,67 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
     return out
 
 
+def _conv_fields(d, x, B, H, W, Cdim, pix_stride, batch_stride, mode):
+    if x.dtype != BF16:
+        raise _lib.MvltError("implicit convolution needs a bf16 NHWC operand")
+    d.conv_mode, d.conv_B, d.conv_H, d.conv_W, d.conv_C = mode, B, H, W, Cdim
+    d.conv_pix_stride, d.conv_batch_stride = pix_stride, batch_stride
+
+
+def conv3x3_gemm(x, B, H, W, Cdim, pix_stride, batch_stride, w, out, *, residual=None, block_n: int = 0):
+    """out[(b,y,x), n] = sum_{tap,c} X[b, y+tap//3-1, x+tap%3-1, c] * w[n, tap*C + c]  (3x3, stride 1, zero pad 1).
+
+    ``x``: bf16 NHWC storage addressed by (batch_stride, W*pix_stride, pix_stride, 1); the im2col matrix is never
+    materialised (csrc/gemm_desc.h, MVLT_CONV_A). ``w``: bf16 [N, 9*C] K-major. ``out``: [B*H*W, N] bf16 / fp32.
+    """
+    require_cuda(x, w, out)
+    M, N, K = B * H * W, w.shape[0], 9 * Cdim
+    if w.shape[1] != K or w.stride(1) != 1 or out.shape[0] != M or out.shape[1] != N or out.stride(1) != 1:
+        raise _lib.MvltError(f"conv3x3_gemm shape mismatch: w {tuple(w.shape)} out {tuple(out.shape)} M={M} K={K}")
+    d = GemmDesc()
+    d.A, d.B, d.D = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.M, d.N, d.K = M, N, K
+    d.a_mn, d.b_mn = 0, 0
+    d.lda, d.ldb, d.ldd = K, w.stride(0), out.stride(0)
+    d.batch1 = d.batch2 = 1
+    d.alpha = 1.0
+    d.out_f32 = 1 if out.dtype == F32 else 0
+    d.block_n = block_n
+    _conv_fields(d, x, B, H, W, Cdim, pix_stride, batch_stride, CONV_A)
+    if residual is not None and (residual.dtype != F32 or residual.stride() != out.stride()):
+        raise _lib.MvltError("conv3x3_gemm residual must be fp32 with out's strides")
+    if _lib.PROFILE is not None:
+        _lib.GEMM_FLOPS += 2.0 * M * N * K
+    call("gemm", C.byref(d))
+    return out
+
+
+def conv3x3_wgrad(dy, x, B, H, W, Cdim, pix_stride, batch_stride, out, *, split_k: int = 0):
+    """out[co, tap*C + c] += sum_{b,y,x} dy[(b,y,x), co] * X[b, y+tap//3-1, x+tap%3-1, c]  (fp32 atomic accumulation).
+
+    ``dy``: bf16 [B*H*W, Co] contiguous rows; ``x`` as in conv3x3_gemm (MVLT_CONV_BT: col^T is the MN-major B operand).
+    """
+    require_cuda(dy, x, out)
+    Kp, Co, N = B * H * W, dy.shape[1], 9 * Cdim
+    if dy.shape[0] != Kp or dy.stride(1) != 1 or out.shape[0] != Co or out.shape[1] != N or out.dtype != F32:
+        raise _lib.MvltError(f"conv3x3_wgrad shape mismatch: dy {tuple(dy.shape)} out {tuple(out.shape)}")
+    d = GemmDesc()
+    d.A, d.B, d.D = dy.data_ptr(), x.data_ptr(), out.data_ptr()
+    d.M, d.N, d.K = Co, N, Kp
+    d.a_mn, d.b_mn = 1, 1
+    d.lda, d.ldb, d.ldd = dy.stride(0), N, out.stride(0)
+    d.batch1 = d.batch2 = 1
+    d.alpha = 1.0
+    d.out_f32, d.atomic_add = 1, 1
+    d.split_k = split_k
+    _conv_fields(d, x, B, H, W, Cdim, pix_stride, batch_stride, CONV_BT)
+    if _lib.PROFILE is not None:
+        _lib.GEMM_FLOPS += 2.0 * Co * N * Kp
+    call("gemm", C.byref(d))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------
 # Non-GEMM kernels
 # ------------------------------------------------------------------------------------------------------
@@ -199,6 +260,10 @@ def cast_weight(src, dst):
 
 def cast_conv_weight(src, dst, Co, Ci, KK, dst_ld):
     call("cast_conv_weight", ptr(src), ptr(dst), C.c_int(Co), C.c_int(Ci), C.c_int(KK), C.c_int(dst_ld))
+
+
+def cast_conv_weight_t(src, dst, Co, Ci, KK):
+    call("cast_conv_weight_t", ptr(src), ptr(dst), C.c_int(Co), C.c_int(Ci), C.c_int(KK))
 
 
 def uncast_conv_wgrad(dwp, dw, Co, Ci, KK, src_ld):

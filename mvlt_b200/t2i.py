@@ -1,5 +1,6 @@
 """MVM / text-to-image head (the reference's ITGHead, /root/reference/libs/vl_heads.py:107-165) scheduled
-by hand on the C-ABI kernels: im2col + tcgen05 GEMM for the eleven 3x3 convolutions, train-mode BatchNorm,
+by hand on the C-ABI kernels: implicit-GEMM 3x3 convolutions (TMA-shifted NHWC boxes feeding the tcgen05 GEMM; no
+im2col / col2im buffers) for the eleven conv+BN units, forward, input-gradient and weight-gradient, train-mode BatchNorm,
 x2 bilinear upsampling, elementwise products written into channel slices of the concat buffers, the 1x1 score
 conv, and the x8 upsample fused with the SmoothL1 loss (engine_grid_masking.py:101).
 
@@ -46,6 +47,10 @@ class T2IHead:
             if name not in self.W:
                 self.W[name] = torch.empty((w.shape[0], 9 * w.shape[1]), dtype=BF16, device=w.device)
             k.cast_conv_weight(w, self.W[name], w.shape[0], w.shape[1], 9, 9 * w.shape[1])
+            tname = name + "^T"             # flipped + transposed copy for the input-gradient convolution
+            if tname not in self.W:
+                self.W[tname] = torch.empty((w.shape[1], 9 * w.shape[0]), dtype=BF16, device=w.device)
+            k.cast_conv_weight_t(w, self.W[tname], w.shape[0], w.shape[1], 9)
 
     # ---- conv3x3 (no bias) + BatchNorm ----------------------------------------------------------------
     def _convbn_fwd(self, u, src, batch_stride, pix_stride, B, H, W, Ci, training, out=None, out_ld=None, out_coff=0):
@@ -55,10 +60,12 @@ class T2IHead:
         Co = Wp.shape[0]
         rows = B * H * W
         dev = Wp.device
-        col = torch.empty((rows, 9 * Ci), dtype=BF16, device=dev)
-        k.im2col3x3(src, batch_stride, pix_stride, col, B, H, W, Ci)
+        if src.dtype != BF16:   # encoder token buffers are fp32: one bf16 NHWC copy of the image rows (kept for the weight gradient)
+            xb = torch.empty((rows, Ci), dtype=BF16, device=dev)
+            k.copy_rows(src, xb, rows, Ci, smap=(H * W, batch_stride // pix_stride, 0), lds=pix_stride)
+            src, batch_stride, pix_stride = xb, H * W * Ci, Ci
         y = torch.empty((rows, Co), dtype=BF16, device=dev)
-        k.gemm(col, Wp, y)
+        k.conv3x3_gemm(src, B, H, W, Ci, pix_stride, batch_stride, Wp, y)
         st = k.zeros((2, Co), F32, dev)
         if training:
             k.bn_stats(y, rows, Co, st[0], st[1])
@@ -71,7 +78,7 @@ class T2IHead:
             out = torch.empty((rows, Co), dtype=BF16, device=dev)
             out_ld = Co
         k.bn_apply(y, aff[0], aff[1], out, out_ld, out_coff, rows, Co)
-        return out, dict(col=col, y=y, aff=aff, B=B, H=H, W=W, Ci=Ci, Co=Co, training=training)
+        return out, dict(x=src, xs=(batch_stride, pix_stride), y=y, aff=aff, B=B, H=H, W=W, Ci=Ci, Co=Co, training=training)
 
     def _convbn_bwd(self, u, dout, c, G, dst, dst_batch_stride, dst_pix_stride, accumulate=False):
         """dout: contiguous bf16 [rows, Co]. Writes/accumulates the input gradient into ``dst`` (NHWC, fp32 or bf16)."""
@@ -90,11 +97,19 @@ class T2IHead:
         key = "__perm__" + pfx + ".0.weight"
         if key not in G:
             G[key] = k.zeros(tuple(Wp.shape), F32, dev)
-        k.gemm(dy.t(), c["col"].t(), G[key], atomic_add=True, split_k=_split_k(Co, 9 * Ci, rows))
+        k.conv3x3_wgrad(dy, c["x"], B, H, W, Ci, c["xs"][1], c["xs"][0], G[key], split_k=_split_k(Co, 9 * Ci, rows))
         if dst is not None:
-            dcol = torch.empty((rows, 9 * Ci), dtype=BF16, device=dev)
-            k.gemm(dy, Wp.t(), dcol)
-            k.col2im3x3(dcol, dst, dst_batch_stride, dst_pix_stride, B, H, W, Ci, accumulate)
+            Wt = self.W[pfx + ".0.weight^T"]
+            linear = dst_pix_stride == Ci and dst_batch_stride == H * W * Ci
+            if linear and dst.dtype == F32:
+                k.conv3x3_gemm(dy, B, H, W, Co, Co, H * W * Co, Wt, dst.view(rows, Ci), residual=dst.view(rows, Ci) if accumulate else None)
+            elif linear and not accumulate:
+                k.conv3x3_gemm(dy, B, H, W, Co, Co, H * W * Co, Wt, dst.view(rows, Ci))
+            else:   # bf16 accumulation, or rows scattered in a token buffer: one temporary + a strided (accumulating) copy
+                tmp = torch.empty((rows, Ci), dtype=BF16 if dst.dtype == BF16 else F32, device=dev)
+                k.conv3x3_gemm(dy, B, H, W, Co, Co, H * W * Co, Wt, tmp)
+                k.copy_rows(tmp, dst, rows, Ci, dmap=(H * W, dst_batch_stride // dst_pix_stride, 0), ldd=dst_pix_stride,
+                            accumulate=accumulate)
 
     def _slice(self, t, ld, coff, rows, Cdim):
         out = torch.empty((rows, Cdim), dtype=t.dtype, device=t.device)

@@ -247,3 +247,45 @@ def test_gemm_rejects_mismatched_epilogue_operands():
     with pytest.raises(MvltError):
         k.gemm(a, b, torch.empty((128, 64), device="cuda", dtype=F32), act=k.ACT_MUL_AUX,
                aux=torch.zeros((128, 64), device="cuda", dtype=BF16))
+
+
+@pytest.mark.parametrize("B,H,W,C,Co,pad_c", [(3, 32, 32, 64, 64, 0), (4, 16, 16, 128, 192, 64), (6, 8, 8, 320, 64, 0),
+                                              (5, 8, 8, 64, 64, 0), (2, 32, 32, 192, 192, 0)])
+def test_implicit_conv3x3_fwd_dgrad_wgrad(B, H, W, C, Co, pad_c):
+    """3x3 convolutions as implicit GEMMs (TMA-shifted NHWC boxes, no im2col) vs torch.nn.functional.conv2d."""
+    import torch.nn.functional as F
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + C)
+    pix = C + pad_c                                                     # channel slice of a wider NHWC buffer
+    store = _rand((B, H * W + 3, pix), g, 0.5)                          # + 3 trailing rows per sample (token-buffer style)
+    x = store[:, :H * W, :C]                                            # logical [B, HW, C] view
+    w = (torch.randn((Co, C, 3, 3), generator=g, device="cuda") * 0.05)
+    wp = torch.empty((Co, 9 * C), device="cuda", dtype=BF16)
+    k.cast_conv_weight(w, wp, Co, C, 9, 9 * C)
+    out = torch.empty((B * H * W, Co), device="cuda", dtype=BF16)
+    k.conv3x3_gemm(store, B, H, W, C, pix, (H * W + 3) * pix, wp, out)
+    xn = x.float().reshape(B, H, W, C).permute(0, 3, 1, 2)
+    wq = wp.float().view(Co, 3, 3, C).permute(0, 3, 1, 2)
+    ref = F.conv2d(xn, wq, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, Co)
+    _check(out, ref, 9 * C, "conv fwd")
+    # input gradient = convolution of dy with the flipped, transposed weights; accumulate into an fp32 buffer
+    dy = _rand((B * H * W, Co), g, 0.3)
+    wt = torch.empty((C, 9 * Co), device="cuda", dtype=BF16)
+    k.cast_conv_weight_t(w, wt, Co, C, 9)
+    dx = torch.randn((B * H * W, C), generator=g, device="cuda")
+    dx0 = dx.clone()
+    k.conv3x3_gemm(dy, B, H, W, Co, Co, H * W * Co, wt, dx, residual=dx)
+    dyn = dy.float().view(B, H, W, Co).permute(0, 3, 1, 2)
+    wtq = wt.float().view(C, 3, 3, Co)                                  # [ci, ty, tx, co]
+    refdx = F.conv2d(dyn, wtq.permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1).reshape(B * H * W, C)
+    # cross-check the flipped/transposed weights against autograd's conv_transpose semantics
+    refdx2 = torch.nn.grad.conv2d_input(xn.shape, w.to(BF16).float(), dyn, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, C)
+    assert (refdx - refdx2).abs().max().item() < 2e-3 * refdx2.abs().max().item() + 1e-4
+    _check(dx, dx0 + refdx, 9 * Co, "conv dgrad")
+    # weight gradient with split-K atomics
+    dw = torch.ones((Co, 9 * C), device="cuda", dtype=F32)
+    k.conv3x3_wgrad(dy, store, B, H, W, C, pix, (H * W + 3) * pix, dw, split_k=7)
+    refdw = torch.nn.grad.conv2d_weight(xn, w.shape, dyn, padding=1)    # [Co, C, 3, 3]
+    refdw = refdw.permute(0, 2, 3, 1).reshape(Co, 9 * C)
+    _check(dw, 1.0 + refdw, B * H * W, "conv wgrad")
+    torch.cuda.synchronize()
