@@ -83,6 +83,16 @@ def require_cuda(*tensors):
 
 LAUNCHES = 0          # number of C-ABI kernel entry points invoked (bench.py's gpu_launches)
 GEMM_FLOPS = 0.0      # executed GEMM flops accumulated while PROFILE is active
+GEMM_BYTES = 0.0      # algorithmic (compulsory) operand + result bytes of the same launches
+GEMM_LOG = None       # when a list: one (flops, bytes) tuple per GEMM launch, in launch order
+
+
+def account_gemm(flops: float, nbytes: float):
+    global GEMM_FLOPS, GEMM_BYTES
+    GEMM_FLOPS += flops
+    GEMM_BYTES += nbytes
+    if GEMM_LOG is not None:
+        GEMM_LOG.append((flops, nbytes))
 PROFILE = None        # when a dict: name -> list of (start_event, end_event) recorded around every call
 
 

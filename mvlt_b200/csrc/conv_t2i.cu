@@ -267,14 +267,37 @@ __device__ __forceinline__ void ac_index(int dst, int in_size, int out_size, int
   l1 = s - (float)i0;
 }
 
+__device__ __forceinline__ void load8f(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8f(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void store8f(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// 8 channels (one 16-byte vector) per thread
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict__ src, long long batch_stride, int pix_stride,
                                                              __nv_bfloat16* __restrict__ dst, int B, int h, int w, int C) {
-  const int H = 2 * h, W = 2 * w, c2n = C / 2;
-  const long long total = (long long)B * H * W * c2n;
+  const int H = 2 * h, W = 2 * w, c8n = C / 8;
+  const long long total = (long long)B * H * W * c8n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c2n) * 2;
-    long long t = i / c2n;
+    const int c = (int)(i % c8n) * 8;
+    long long t = i / c8n;
     const int X = (int)(t % W); t /= W;
     const int Y = (int)(t % H);
     const int b = (int)(t / H);
@@ -283,65 +306,76 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict
     ac_index(Y, h, H, y0, y1, ly);
     ac_index(X, w, W, x0, x1, lx);
     const T* sb = src + (long long)b * batch_stride + c;
-    auto ld = [&](int yy, int xx) -> float2 {
-      const T* p = sb + ((long long)yy * w + xx) * pix_stride;
-      if constexpr (sizeof(T) == 2) return unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p));
-      else return *reinterpret_cast<const float2*>(p);
-    };
-    const float2 v00 = ld(y0, x0), v01 = ld(y0, x1), v10 = ld(y1, x0), v11 = ld(y1, x1);
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    load8f(sb + ((long long)y0 * w + x0) * pix_stride, v00);
+    load8f(sb + ((long long)y0 * w + x1) * pix_stride, v01);
+    load8f(sb + ((long long)y1 * w + x0) * pix_stride, v10);
+    load8f(sb + ((long long)y1 * w + x1) * pix_stride, v11);
     const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    *reinterpret_cast<uint32_t*>(dst + (((long long)b * H + Y) * W + X) * C + c) =
-        pack_bf16x2(w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x,
-                    w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = w00 * v00[j] + w01 * v01[j] + w10 * v10[j] + w11 * v11[j];
+    store8f(dst + (((long long)b * H + Y) * W + X) * C + c, o);
   }
 }
 
-// gather form of the transposed operator: dx[b,i,j,c] (+)= sum over the <= 5x5 output pixels that read (i,j)
+// gather form of the transposed operator: dx[b,i,j,c] (+)= sum over the <= 5x5 output pixels that read (i,j);
+// 8 channels per thread, the (tiny) weight search is amortised over them
 template <typename TD>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, TD* __restrict__ dx,
                                                              long long batch_stride, int pix_stride, int B, int h, int w, int C,
                                                              int accumulate) {
-  const int H = 2 * h, W = 2 * w, c2n = C / 2;
-  const long long total = (long long)B * h * w * c2n;
+  const int H = 2 * h, W = 2 * w, c8n = C / 8;
+  const long long total = (long long)B * h * w * c8n;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % c2n) * 2;
-    long long t = idx / c2n;
+    const int c = (int)(idx % c8n) * 8;
+    long long t = idx / c8n;
     const int j = (int)(t % w); t /= w;
     const int i = (int)(t % h);
     const int b = (int)(t / h);
-    float a0 = 0.f, a1 = 0.f;
-    for (int Y = max(0, 2 * i - 3); Y <= min(H - 1, 2 * i + 3); ++Y) {
-      int y0, y1;
-      float ly;
-      ac_index(Y, h, H, y0, y1, ly);
-      float wy = 0.f;
-      if (y0 == i) wy += 1.f - ly;
-      if (y1 == i) wy += ly;
-      if (wy == 0.f) continue;
-      for (int X = max(0, 2 * j - 3); X <= min(W - 1, 2 * j + 3); ++X) {
-        int x0, x1;
-        float lx;
-        ac_index(X, w, W, x0, x1, lx);
-        float wx = 0.f;
-        if (x0 == j) wx += 1.f - lx;
-        if (x1 == j) wx += lx;
-        if (wx == 0.f) continue;
-        const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + (((long long)b * H + Y) * W + X) * C + c));
-        a0 += wy * wx * g.x;
-        a1 += wy * wx * g.y;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // per-axis weights of the <= 7 candidate output coordinates
+    float wys[7], wxs[7];
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      const int Y = 2 * i - 3 + u, X = 2 * j - 3 + u;
+      int a0, a1;
+      float l;
+      wys[u] = 0.f;
+      wxs[u] = 0.f;
+      if (Y >= 0 && Y < H) {
+        ac_index(Y, h, H, a0, a1, l);
+        if (a0 == i) wys[u] += 1.f - l;
+        if (a1 == i) wys[u] += l;
+      }
+      if (X >= 0 && X < W) {
+        ac_index(X, w, W, a0, a1, l);
+        if (a0 == j) wxs[u] += 1.f - l;
+        if (a1 == j) wxs[u] += l;
+      }
+    }
+#pragma unroll
+    for (int uy = 0; uy < 7; ++uy) {
+      if (wys[uy] == 0.f) continue;
+      const int Y = 2 * i - 3 + uy;
+#pragma unroll
+      for (int ux = 0; ux < 7; ++ux) {
+        if (wxs[ux] == 0.f) continue;
+        const int X = 2 * j - 3 + ux;
+        float g[8];
+        load8f(dy + (((long long)b * H + Y) * W + X) * C + c, g);
+        const float wgt = wys[uy] * wxs[ux];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += wgt * g[q];
       }
     }
     TD* d = dx + (long long)b * batch_stride + ((long long)i * w + j) * pix_stride + c;
-    if constexpr (sizeof(TD) == 2) {
-      if (accumulate) {
-        const float2 o = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(d));
-        a0 += o.x; a1 += o.y;
-      }
-      *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(a0, a1);
-    } else {
-      if (accumulate) { a0 += d[0]; a1 += d[1]; }
-      *reinterpret_cast<float2*>(d) = make_float2(a0, a1);
+    if (accumulate) {
+      float o[8];
+      load8f(d, o);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += o[q];
     }
+    store8f(d, acc);
   }
 }
 
@@ -420,40 +454,40 @@ __global__ void __launch_bounds__(256) upsample8_fwd_kernel(const float* __restr
   }
 }
 
-// One block per (b, c, output-row band). mode 0: g = dpred (given);  mode 1: g = d SmoothL1(pred - target) * scale * gscale
-// and the loss itself is accumulated. dscore (fp32 NHWC [B,h,w,3]) receives the transposed-interpolation of g via
-// atomics on a tiny L2-resident buffer, after a block-local reduction over the band.
+// One block per (b, c, output-row band of S rows). mode 0: g = dpred (given); mode 1: g = d SmoothL1(pred - target) *
+// scale * gscale and the loss itself is accumulated. dscore (fp32 NHWC [B,h,w,3]) receives the transposed interpolation
+// of g, computed separably inside the block without shared-memory atomics:
+//   phase 1: g[S][W] -> shared;  phase 2: gx[Y][x] = sum_X g[Y][X] * wx(X -> x);  phase 3: rows (<= 3 score rows touched by
+//   the band) = sum_Y gx[Y][x] * wy(Y -> row), then one global atomic per touched score cell.
 __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restrict__ score, const float* __restrict__ target,
                                                            const float* __restrict__ dpred, float* __restrict__ dscore,
                                                            float* __restrict__ loss_sum, float* __restrict__ total_sum,
                                                            float loss_scale, float grad_scale, const float* __restrict__ gscale,
                                                            int B, int h, int w, int S, int mode, int want_grad) {
-  extern __shared__ float sh[];  // [2][w] partial dscore rows + 32 for reductions
+  extern __shared__ float sh[];  // g[S][W] | gx[S][w] | 32 for reductions
   const int H = h * S, W = w * S;
-  const int bands = H / S;  // one band = S output rows => touches at most score rows (y0, y0+1)
+  const int bands = H / S;  // one band = S output rows => touches at most score rows ybase .. ybase+2
   const int band = blockIdx.x % bands;
   const int c = (blockIdx.x / bands) % 3;
   const int b = blockIdx.x / (bands * 3);
-  float* acc = sh;            // [rows_touched(<=3)][w]
-  float* red = sh + 3 * w;
-  for (int i = threadIdx.x; i < 3 * w; i += blockDim.x) acc[i] = 0.f;
-  __syncthreads();
+  float* gs = sh;             // [S][W]
+  float* gx = sh + S * W;     // [S][w]
+  float* red = gx + S * w;
   const float* sb = score + (long long)b * h * w * 3 + c;
   const float g_mul = grad_scale * (gscale ? *gscale : 1.f);
-  // the first score row any output row of this band can touch
   int ybase, ytmp;
   float ltmp;
   ac_index(band * S, h, H, ybase, ytmp, ltmp);
   float lsum = 0.f;
   for (int e = threadIdx.x; e < S * W; e += blockDim.x) {
     const int Y = band * S + e / W, X = e % W;
-    int y0, y1, x0, x1;
-    float ly, lx;
-    ac_index(Y, h, H, y0, y1, ly);
-    ac_index(X, w, W, x0, x1, lx);
     const long long off = (((long long)b * 3 + c) * H + Y) * W + X;
     float g;
     if (mode == 1) {
+      int y0, y1, x0, x1;
+      float ly, lx;
+      ac_index(Y, h, H, y0, y1, ly);
+      ac_index(X, w, W, x0, x1, lx);
       const float v00 = sb[(y0 * w + x0) * 3], v01 = sb[(y0 * w + x1) * 3], v10 = sb[(y1 * w + x0) * 3], v11 = sb[(y1 * w + x1) * 3];
       const float pred = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
       const float d = pred - target[off];
@@ -463,13 +497,7 @@ __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restri
     } else {
       g = dpred[off];
     }
-    if (want_grad) {
-      const int ry0 = y0 - ybase, ry1 = y1 - ybase;  // in {0,1,2}
-      atomicAdd(&acc[ry0 * w + x0], g * (1.f - ly) * (1.f - lx));
-      atomicAdd(&acc[ry0 * w + x1], g * (1.f - ly) * lx);
-      atomicAdd(&acc[ry1 * w + x0], g * ly * (1.f - lx));
-      atomicAdd(&acc[ry1 * w + x1], g * ly * lx);
-    }
+    gs[e] = g;
   }
   if (mode == 1 && loss_sum != nullptr) {
     lsum = block_sum(lsum, red);
@@ -478,13 +506,44 @@ __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restri
       if (total_sum) atomicAdd(total_sum, lsum * loss_scale);
     }
   }
+  if (!want_grad) return;
   __syncthreads();
-  if (want_grad) {
-    for (int i = threadIdx.x; i < 3 * w; i += blockDim.x) {
-      const int ry = i / w, x = i % w;
-      const int y = ybase + ry;
-      if (y < h && acc[i] != 0.f) atomicAdd(dscore + ((long long)b * h * w + (long long)y * w + x) * 3 + c, acc[i]);
+  // phase 2: along X. Output column X reads score columns x0(X), x0(X)+1; column x is read by X in ((x-1)/r, (x+1)/r), r = (w-1)/(W-1)
+  const float inv_r = (w > 1) ? (float)(W - 1) / (float)(w - 1) : 0.f;
+  for (int e = threadIdx.x; e < S * w; e += blockDim.x) {
+    const int yy = e / w, x = e % w;
+    int Xlo = (int)floorf((float)(x - 1) * inv_r) - 1, Xhi = (int)ceilf((float)(x + 1) * inv_r) + 1;
+    Xlo = max(Xlo, 0);
+    Xhi = min(Xhi, W - 1);
+    float a = 0.f;
+    for (int X = Xlo; X <= Xhi; ++X) {
+      int x0, x1;
+      float lx;
+      ac_index(X, w, W, x0, x1, lx);
+      float wx = 0.f;
+      if (x0 == x) wx += 1.f - lx;
+      if (x1 == x) wx += lx;
+      a = fmaf(wx, gs[yy * W + X], a);
     }
+    gx[e] = a;
+  }
+  __syncthreads();
+  // phase 3: along Y, then the global accumulation (score rows ybase .. ybase+2)
+  for (int e = threadIdx.x; e < 3 * w; e += blockDim.x) {
+    const int ry = e / w, x = e % w;
+    const int y = ybase + ry;
+    if (y >= h) continue;
+    float a = 0.f;
+    for (int yy = 0; yy < S; ++yy) {
+      int y0, y1;
+      float ly;
+      ac_index(band * S + yy, h, H, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == y) wy += 1.f - ly;
+      if (y1 == y) wy += ly;
+      a = fmaf(wy, gx[yy * w + x], a);
+    }
+    if (a != 0.f) atomicAdd(dscore + ((long long)b * h * w + (long long)y * w + x) * 3 + c, a);
   }
 }
 
@@ -593,9 +652,9 @@ extern "C" int mvlt_ew_mul(const void* a, int a_f32, int a_ld, int a_coff, const
 
 extern "C" int mvlt_upsample2x_fwd(const void* src, int src_f32, long long batch_stride, int pix_stride, void* dst_bf16, int B,
                                    int h, int w, int C, void* stream_) {
-  MVLT_CHECK_ARG(C % 2 == 0, "upsample2x_fwd: C must be even");
+  MVLT_CHECK_ARG(C % 8 == 0 && pix_stride % 8 == 0 && batch_stride % 8 == 0, "upsample2x_fwd: C / strides must be multiples of 8");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  const long long total = (long long)B * 4 * h * w * (C / 2);
+  const long long total = (long long)B * 4 * h * w * (C / 8);
   if (src_f32)
     upsample2x_fwd_kernel<float><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(src), batch_stride, pix_stride,
                                                                        reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, h, w, C);
@@ -608,9 +667,9 @@ extern "C" int mvlt_upsample2x_fwd(const void* src, int src_f32, long long batch
 
 extern "C" int mvlt_upsample2x_bwd(const void* dy_bf16, void* dx, int dx_f32, long long batch_stride, int pix_stride, int B, int h,
                                    int w, int C, int accumulate, void* stream_) {
-  MVLT_CHECK_ARG(C % 2 == 0, "upsample2x_bwd: C must be even");
+  MVLT_CHECK_ARG(C % 8 == 0 && pix_stride % 8 == 0 && batch_stride % 8 == 0, "upsample2x_bwd: C / strides must be multiples of 8");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  const long long total = (long long)B * h * w * (C / 2);
+  const long long total = (long long)B * h * w * (C / 8);
   if (dx_f32)
     upsample2x_bwd_kernel<float><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
                                                                        reinterpret_cast<float*>(dx), batch_stride, pix_stride, B, h, w, C, accumulate);
@@ -653,9 +712,9 @@ extern "C" int mvlt_upsample8_fwd(const float* score, float* out, int B, int h, 
 extern "C" int mvlt_t2i_up_loss(const float* score, const float* target, const float* dpred, float* dscore, float* loss_sum,
                                 float* total_sum, float loss_scale, float grad_scale, const float* gscale_dev, int B, int h, int w,
                                 int S, int mode, int want_grad, void* stream_) {
-  MVLT_CHECK_ARG(S >= 2 && w <= 1024, "t2i_up_loss: bad geometry");
+  MVLT_CHECK_ARG(S >= 2 && (size_t)(S * w * S + S * w + 32) * sizeof(float) <= 48 * 1024, "t2i_up_loss: bad geometry");
   const int blocks = B * 3 * h;
-  const size_t smem = (3 * w + 32) * sizeof(float);
+  const size_t smem = (size_t)(S * w * S + S * w + 32) * sizeof(float);
   t2i_up8_loss_kernel<<<blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(
       score, target, dpred, dscore, loss_sum, total_sum, loss_scale, grad_scale, gscale_dev, B, h, w, S, mode, want_grad);
   MVLT_CHECK_LAUNCH();

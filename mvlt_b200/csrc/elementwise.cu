@@ -129,19 +129,27 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __
 // flattening), zero padded to Kpad
 __global__ void __launch_bounds__(256) patchify_nchw_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ dst,
                                                             int B, int Cin, int H, int W, int P, int Kpad) {
+  // One block per (b, oy) row of patches: the Cin*P image rows it needs are read as whole rows (coalesced), transposed
+  // through shared memory into [ow][Kpad] bf16 (zero padded) and written out as one contiguous ow*Kpad*2-byte run.
+  extern __shared__ __align__(16) unsigned char patch_sh[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(patch_sh);
   const int ow = W / P, oh = H / P;
-  const long long total = (long long)B * oh * ow * Cin * P;  // one thread per (patch, ci, ky): P contiguous pixels
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    // ox fastest so that consecutive threads read consecutive image columns
-    const int ox = (int)(i % ow);
-    long long t = i / ow;
-    const int ky = (int)(t % P); t /= P;
-    const int ci = (int)(t % Cin); t /= Cin;
-    const int oy = (int)(t % oh);
-    const int b = (int)(t / oh);
-    const float* s = img + (((long long)b * Cin + ci) * H + (oy * P + ky)) * W + ox * P;
-    __nv_bfloat16* d = dst + (((long long)b * oh + oy) * ow + ox) * Kpad + (ci * P + ky) * P;
-    for (int kx = 0; kx < P; ++kx) d[kx] = __float2bfloat16(s[kx]);
+  const int K = Cin * P * P;
+  for (int blk = blockIdx.x; blk < B * oh; blk += gridDim.x) {
+    const int oy = blk % oh, b = blk / oh;
+    __syncthreads();
+    if (Kpad > K)
+      for (int i = threadIdx.x; i < ow * (Kpad - K); i += blockDim.x) tile[(i / (Kpad - K)) * Kpad + K + i % (Kpad - K)] = __float2bfloat16(0.f);
+    for (int i = threadIdx.x; i < Cin * P * W; i += blockDim.x) {
+      const int x = i % W, r = i / W;            // r = ci*P + ky
+      const int ci = r / P, ky = r % P;
+      const float v = img[(((long long)b * Cin + ci) * H + (oy * P + ky)) * W + x];
+      tile[(x / P) * Kpad + r * P + x % P] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    uint4* out = reinterpret_cast<uint4*>(dst + (long long)blk * ow * Kpad);
+    const uint4* tin = reinterpret_cast<const uint4*>(tile);
+    for (int i = threadIdx.x; i < ow * Kpad / 8; i += blockDim.x) out[i] = tin[i];
   }
 }
 
@@ -191,19 +199,35 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const TI* __restrict__ s
 
 // ---- out[r, c] (+)= sum_b x[b*batch_stride + r*C + c]  (position-embedding gradients) -------------------------
 __global__ void __launch_bounds__(256) batch_reduce_kernel(const float* __restrict__ x, long long batch_stride, int B,
-                                                           long long n4, float* __restrict__ out, int accumulate) {
+                                                           long long n4, float* __restrict__ out, int accumulate, int bchunk) {
+  // blockIdx.y owns samples [y*bchunk, (y+1)*bchunk); with more than one chunk the partial sums meet in `out` through
+  // vector atomics (the caller zeroes `out` first when it is not accumulating).
+  const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b = 0; b < B; ++b) {
-      const float4 v = *reinterpret_cast<const float4*>(x + (long long)b * batch_stride + i * 4);
+    const float* xi = x + i * 4;
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(xi + (long long)(b + u) * batch_stride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; b < b1; ++b) {
+      const float4 v = *reinterpret_cast<const float4*>(xi + (long long)b * batch_stride);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    float4* o = reinterpret_cast<float4*>(out + i * 4);
-    if (accumulate) {
-      const float4 p = *o;
-      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    float* o = out + i * 4;
+    if (gridDim.y > 1) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+    } else {
+      if (accumulate) {
+        const float4 p = *reinterpret_cast<const float4*>(o);
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+      }
+      *reinterpret_cast<float4*>(o) = acc;
     }
-    *o = acc;
   }
 }
 
@@ -409,10 +433,18 @@ extern "C" int mvlt_patchify_nchw(const float* img, void* dst_bf16, int B, int C
                                   void* stream_) {
   MVLT_CHECK_ARG(H % P == 0 && W % P == 0 && Kpad >= Cin * P * P, "patchify_nchw: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  if (Kpad > Cin * P * P) cudaMemsetAsync(dst_bf16, 0, (size_t)B * (H / P) * (W / P) * Kpad * 2, st);
-  const long long total = (long long)B * (H / P) * (W / P) * Cin * P;
-  patchify_nchw_kernel<<<cap_grid(total, 256), 256, 0, st>>>(img, reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, Cin, H,
-                                                             W, P, Kpad);
+  MVLT_CHECK_ARG(Kpad % 8 == 0 && Kpad >= Cin * P * P && W % P == 0 && H % P == 0 && (W / P) * Kpad * 2 <= 96 * 1024,
+                 "patchify_nchw: unsupported geometry (W=%d P=%d Kpad=%d)", W, P, Kpad);
+  const size_t smem = (size_t)(W / P) * Kpad * 2;
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaFuncSetAttribute(patchify_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  int grid = B * (H / P);
+  const int cap = mvlt_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  patchify_nchw_kernel<<<grid, 256, smem, st>>>(img, reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, Cin, H, W, P, Kpad);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -443,8 +475,16 @@ extern "C" int mvlt_copy_rows(const void* src, int src_f32, const int* smap, lon
 extern "C" int mvlt_batch_reduce(const float* x, long long batch_stride, int B, long long n, float* out, int accumulate,
                                  void* stream_) {
   MVLT_CHECK_ARG(n % 4 == 0 && batch_stride % 4 == 0, "batch_reduce: n must be a multiple of 4");
-  batch_reduce_kernel<<<cap_grid(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, batch_stride, B,
-                                                                                                n / 4, out, accumulate);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  // enough (column-block x batch-chunk) CTAs to fill the machine: split the batch when the row is short
+  const long long xblocks = (n / 4 + 255) / 256;
+  int chunks = 1;
+  while (xblocks * chunks < 4LL * mvlt_num_sms() && chunks * 16 <= B) chunks *= 2;
+  const int bchunk = (B + chunks - 1) / chunks;
+  chunks = (B + bchunk - 1) / bchunk;
+  if (chunks > 1 && !accumulate) cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), st);
+  dim3 grid((unsigned)(xblocks < 65535 ? xblocks : 65535), (unsigned)chunks);
+  batch_reduce_kernel<<<grid, 256, 0, st>>>(x, batch_stride, B, n / 4, out, accumulate, bchunk);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -54,66 +54,76 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <typename TI, typename TO, int G, int NV>
+// RU = row groups a warp normalises per loop iteration: all their loads are issued before the first reduction, so a
+// warp keeps RU * NV 16-byte loads per lane in flight (one row per warp is latency-bound, not bandwidth-bound).
+template <typename TI, typename TO, int G, int NV, int RU>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, RowMap xm, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, TO* __restrict__ y, RowMap ym,
                                                      const float* __restrict__ post_add, float* __restrict__ mean_out,
                                                      float* __restrict__ rstd_out, int rows, int C, float eps) {
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, sub = lane % G;
-  const int rows_per_block = (blockDim.x >> 5) * RPW;
+  const int warps = blockDim.x >> 5;
+  const int rows_per_block = warps * RPW * RU;
   const int nvec = (C + 4 * G - 1) / (4 * G);
   const float inv_c = 1.f / (float)C;
   for (int r0 = blockIdx.x * rows_per_block; r0 < rows; r0 += gridDim.x * rows_per_block) {
-    const int r = r0 + (threadIdx.x >> 5) * RPW + lane / G;
-    const bool ok = r < rows;
-    const TI* xr = x + (ok ? map_row(xm, r) : 0) * C;
-    float4 v[NV];
-    float s = 0.f;
+    float4 v[RU][NV];
+    int rr[RU];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = i * 4 * G + sub * 4;
-      if (ok && i < nvec && c < C) {
-        v[i] = load4<TI>(xr + c);
-        s += v[i].x + v[i].y + v[i].z + v[i].w;
-      } else {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < RU; ++u) {
+      const int r = r0 + (u * warps + (threadIdx.x >> 5)) * RPW + lane / G;
+      rr[u] = r;
+      const bool ok = r < rows;
+      const TI* xr = x + (ok ? map_row(xm, r) : 0) * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = i * 4 * G + sub * 4;
+        v[u][i] = (ok && i < nvec && c < C) ? load4<TI>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    const float mean = group_sum<G>(s) * inv_c;
-    float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = i * 4 * G + sub * 4;
-      if (i < nvec && c < C) {
-        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-        q += a * a + b * b + cc * cc + d * d;
-      }
-    }
-    const float rstd = rsqrtf(group_sum<G>(q) * inv_c + eps);
-    if (!ok) continue;
-    if (sub == 0 && mean_out != nullptr) {
-      mean_out[r] = mean;
-      rstd_out[r] = rstd;
-    }
-    TO* yr = y + map_row(ym, r) * C;
-    const float* pa = post_add ? post_add + (long long)(r % ym.group) * C : nullptr;
+    for (int u = 0; u < RU; ++u) {
+      const int r = rr[u];
+      const bool ok = r < rows;
+      float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = i * 4 * G + sub * 4;
-      if (i < nvec && c < C) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-        float4 o;
-        o.x = (v[i].x - mean) * rstd * g.x + b.x;
-        o.y = (v[i].y - mean) * rstd * g.y + b.y;
-        o.z = (v[i].z - mean) * rstd * g.z + b.z;
-        o.w = (v[i].w - mean) * rstd * g.w + b.w;
-        if (pa) {
-          const float4 p4 = __ldg(reinterpret_cast<const float4*>(pa + c));
-          o.x += p4.x; o.y += p4.y; o.z += p4.z; o.w += p4.w;
+      for (int i = 0; i < NV; ++i) s += v[u][i].x + v[u][i].y + v[u][i].z + v[u][i].w;
+      const float mean = group_sum<G>(s) * inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = i * 4 * G + sub * 4;
+        if (i < nvec && c < C) {
+          const float a = v[u][i].x - mean, b = v[u][i].y - mean, cc = v[u][i].z - mean, d = v[u][i].w - mean;
+          q += a * a + b * b + cc * cc + d * d;
         }
-        store4<TO>(yr + c, o);
+      }
+      const float rstd = rsqrtf(group_sum<G>(q) * inv_c + eps);
+      if (!ok) continue;
+      if (sub == 0 && mean_out != nullptr) {
+        mean_out[r] = mean;
+        rstd_out[r] = rstd;
+      }
+      TO* yr = y + map_row(ym, r) * C;
+      const float* pa = post_add ? post_add + (long long)(r % ym.group) * C : nullptr;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = i * 4 * G + sub * 4;
+        if (i < nvec && c < C) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+          float4 o;
+          o.x = (v[u][i].x - mean) * rstd * g.x + b.x;
+          o.y = (v[u][i].y - mean) * rstd * g.y + b.y;
+          o.z = (v[u][i].z - mean) * rstd * g.z + b.z;
+          o.w = (v[u][i].w - mean) * rstd * g.w + b.w;
+          if (pa) {
+            const float4 p4 = __ldg(reinterpret_cast<const float4*>(pa + c));
+            o.x += p4.x; o.y += p4.y; o.z += p4.z; o.w += p4.w;
+          }
+          store4<TO>(yr + c, o);
+        }
       }
     }
   }
@@ -287,17 +297,19 @@ extern "C" int mvlt_layernorm_fwd(const void* x, int x_f32, const int* xmap, con
   MVLT_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && C <= 128 * LN_MAX_VEC, "layernorm_fwd: unsupported C=%d", C);
   RowMap xm{xmap && xmap[0] > 0 ? xmap[0] : rows, xmap && xmap[0] > 0 ? xmap[1] : rows, xmap && xmap[0] > 0 ? xmap[2] : 0};
   RowMap ym{ymap && ymap[0] > 0 ? ymap[0] : rows, ymap && ymap[0] > 0 ? ymap[1] : rows, ymap && ymap[0] > 0 ? ymap[2] : 0};
-  const int grid = ln_grid(rows, C <= 64 ? 16 : 8);
-#define LN_FWD_CALL(TI, TO, G, NV)                                                                              \
-  ln_fwd_kernel<TI, TO, G, NV><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,               \
-                                                     reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps)
-#define LAUNCH(TI, TO)                                 \
-  do {                                                 \
-    if (C <= 64) LN_FWD_CALL(TI, TO, 16, 1);           \
-    else if (C <= 128) LN_FWD_CALL(TI, TO, 32, 1);     \
-    else if (C <= 384) LN_FWD_CALL(TI, TO, 32, 3);     \
-    else if (C <= 512) LN_FWD_CALL(TI, TO, 32, 4);     \
-    else LN_FWD_CALL(TI, TO, 32, 6);                   \
+  // rows per block = 8 warps x (32 / G) x RU
+  const int rpb = C <= 64 ? 64 : (C <= 128 ? 32 : (C <= 512 ? 16 : 8));
+  const int grid = ln_grid(rows, rpb);
+#define LN_FWD_CALL(TI, TO, G, NV, RU)                                                                          \
+  ln_fwd_kernel<TI, TO, G, NV, RU><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,           \
+                                                         reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps)
+#define LAUNCH(TI, TO)                                    \
+  do {                                                    \
+    if (C <= 64) LN_FWD_CALL(TI, TO, 16, 1, 4);           \
+    else if (C <= 128) LN_FWD_CALL(TI, TO, 32, 1, 4);     \
+    else if (C <= 384) LN_FWD_CALL(TI, TO, 32, 3, 2);     \
+    else if (C <= 512) LN_FWD_CALL(TI, TO, 32, 4, 2);     \
+    else LN_FWD_CALL(TI, TO, 32, 6, 1);                   \
   } while (0)
   if (x_f32 && y_f32) LAUNCH(float, float);
   else if (x_f32 && !y_f32) LAUNCH(float, __nv_bfloat16);

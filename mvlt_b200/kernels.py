@@ -103,7 +103,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
         if t is not None and (t.dtype != BF16 or t.stride() != out.stride()):
             raise _lib.MvltError("gemm aux/preact must be bf16 with out's strides")
     if _lib.PROFILE is not None:
-        _lib.GEMM_FLOPS += 2.0 * M * N * K * b1 * b2
+        nb = b1 * b2
+        extra = sum(M * N * nb * t.element_size() for t in (aux, preact_out, residual) if t is not None)
+        _lib.account_gemm(2.0 * M * N * K * nb, (M * K + N * K) * 2.0 * nb + M * N * nb * out.element_size() + extra)
     call("gemm" if impl == "tcgen05" else "gemm_ref", C.byref(d))
     return out
 
@@ -138,8 +140,8 @@ def conv3x3_gemm(x, B, H, W, Cdim, pix_stride, batch_stride, w, out, *, residual
     _conv_fields(d, x, B, H, W, Cdim, pix_stride, batch_stride, CONV_A)
     if residual is not None and (residual.dtype != F32 or residual.stride() != out.stride()):
         raise _lib.MvltError("conv3x3_gemm residual must be fp32 with out's strides")
-    if _lib.PROFILE is not None:
-        _lib.GEMM_FLOPS += 2.0 * M * N * K
+    if _lib.PROFILE is not None:   # algorithmic bytes: X once (not the 9x im2col matrix) + weights + output (+ residual)
+        _lib.account_gemm(2.0 * M * N * K, (M * Cdim + N * K) * 2.0 + M * N * out.element_size() * (2 if residual is not None else 1))
     call("gemm", C.byref(d))
     return out
 
@@ -164,7 +166,7 @@ def conv3x3_wgrad(dy, x, B, H, W, Cdim, pix_stride, batch_stride, out, *, split_
     d.split_k = split_k
     _conv_fields(d, x, B, H, W, Cdim, pix_stride, batch_stride, CONV_BT)
     if _lib.PROFILE is not None:
-        _lib.GEMM_FLOPS += 2.0 * Co * N * Kp
+        _lib.account_gemm(2.0 * Co * N * Kp, (Kp * Co + Kp * Cdim) * 2.0 + Co * N * 4.0)
     call("gemm", C.byref(d))
     return out
 

@@ -371,3 +371,27 @@ def test_bert_embed_fwd_bwd():
     assert torch.equal(o1, o2)
     keep = float((o1 != 0).float().mean())
     assert abs(keep - 0.9) < 0.01
+
+
+@pytest.mark.parametrize("B,n,stride_pad,acc", [(128, 64 * 512, 128 * 512, False), (128, 4096 * 64, 128 * 64, True),
+                                                (5, 1024, 0, False), (33, 8192, 64, True)])
+def test_batch_reduce_chunked(B, n, stride_pad, acc):
+    """Position-embedding gradient reduction: batch split across CTAs with vector atomics when the row is short."""
+    from mvlt_b200 import kernels as k
+    stride = n + stride_pad
+    x = torch.randn((B, stride), generator=_g(B + n), device="cuda")
+    out = torch.randn(n, generator=_g(3), device="cuda")
+    ref = x[:, :n].double().sum(0).float() + (out if acc else 0)
+    k.batch_reduce(x, stride, B, n, out, accumulate=acc)
+    _close(out, ref, 1e-5, 1e-4, "batch_reduce")
+
+
+def test_patchify_nchw_full_image():
+    from mvlt_b200 import kernels as k
+    B, P, Kp = 3, 4, 64
+    img = torch.rand((B, 3, 256, 256), generator=_g(11), device="cuda")
+    pat = torch.full((B * 4096, Kp), 7.0, dtype=BF16, device="cuda")
+    k.patchify_nchw(img, pat, B, 3, 256, 256, P, Kp)
+    ref = F.unfold(img, P, stride=P).permute(0, 2, 1).reshape(B * 4096, 48)
+    assert torch.equal(pat[:, :48], ref.to(BF16))
+    assert float(pat[:, 48:].abs().max()) == 0.0

@@ -26,6 +26,15 @@ def load(path):
 
 def main():
     L = load(sys.argv[1])
+    if "--gemm-traffic" in sys.argv:      # dram bytes per launch of the dominant kernel, for bench.py's roofline.traffic
+        import json
+        G = [d for d in L if d["name"].startswith("gemm_tcgen05_kernel")]
+        tb = sum(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0) for d in G)
+        tt = sum(d.get("gpu__time_duration.sum", 0.0) for d in G)
+        out = {"kernel": "gemm_tcgen05_kernel", "launches": len(G), "dram_bytes_per_launch": round(tb / max(len(G), 1)),
+               "dram_bytes_total": round(tb), "gpu_time_us_total": round(tt, 1), "source": sys.argv[1],
+               "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over all GEMM launches of one training step"}
+        json.dump(out, open(sys.argv[sys.argv.index("--gemm-traffic") + 1], "w"), indent=1)
     agg = defaultdict(lambda: [0, 0.0, 0.0])
     for d in L:
         a = agg[d["name"]]
