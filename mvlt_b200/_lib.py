@@ -22,7 +22,7 @@ class MvltError(RuntimeError):
 class GemmDesc(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("B", C.c_void_p), ("D", C.c_void_p), ("D2", C.c_void_p),
-        ("bias", C.c_void_p), ("aux", C.c_void_p), ("residual", C.c_void_p), ("rowscale", C.c_void_p),
+        ("bias", C.c_void_p), ("aux", C.c_void_p), ("residual", C.c_void_p), ("rowscale", C.c_void_p), ("rowsum", C.c_void_p),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("a_mn", C.c_int32), ("b_mn", C.c_int32),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldd", C.c_int64),

@@ -43,6 +43,8 @@ typedef struct mvlt_gemm_desc {
   const void* aux;        // bf16 [.., M, N] with D's strides, for MVLT_ACT_DGELU
   const float* residual;  // fp32 with D's strides or NULL:  D = residual + rowscale * v
   const float* rowscale;  // fp32 [ceil(M / rows_per_scale)] or NULL (drop-path keep/scale per sample)
+  float* rowsum;          // fp32 [M] or NULL: rowsum[m] += alpha * sum_k A[m,k] (atomic), computed on the tensor core by one
+                          // extra N=16 MMA against a tile of ones: the bias gradient db = dY^T 1 rides on the dW = dY^T X GEMM
   int32_t M, N, K;
   int32_t a_mn, b_mn;
   int64_t lda, ldb, ldd;  // leading dimensions in ELEMENTS

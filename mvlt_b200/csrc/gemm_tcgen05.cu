@@ -24,6 +24,8 @@
 #include "common.cuh"
 #include "gemm_desc.h"
 
+extern "C" int mvlt_colsum(const void* x, int x_f32, long long rows, int C, long long ld, float* out, void* stream_);
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -44,7 +46,9 @@ static_assert(128 * PRODUCER_REGS + (NUM_THREADS - 128) * EPILOGUE_REGS <= NUM_T
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_ACC = 4;
-constexpr int SMEM_BUDGET = 160 * 1024;  // pipeline stages; + 64 KB epilogue staging + barriers <= 227 KB
+constexpr int SMEM_BUDGET = 160 * 1024;  // pipeline stages; + 1 KB ones tile + barriers + 64 KB epilogue staging <= 227 KB
+constexpr int ONES_BYTES = 1024;         // 8 rows x 64 bf16 of 1.0: B operand of the row-sum MMA (both 8-row groups alias it)
+constexpr int ONES_N = 16;
 constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096;
 
 // epilogue kinds the kernel is specialised on
@@ -73,6 +77,7 @@ struct KParams {
   const __nv_bfloat16* aux;
   const float* residual;
   const float* rowscale;
+  float* rowsum;
   long long ldd, sD1, sD2;
   float alpha;
   int act, out_f32, atomic_add, rows_per_scale;
@@ -510,7 +515,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int b_stage_bytes = p.block_n * BLOCK_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* ones_tile = smem + (size_t)p.stages * stage_bytes;   // 1024-byte aligned (stage sizes are multiples of 4 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones_tile + ONES_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + MAX_ACC;
@@ -531,6 +537,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+  }
+  if (p.rowsum != nullptr) {   // bf16 1.0 everywhere: layout / swizzle of this operand tile is irrelevant
+    if (threadIdx.x < ONES_BYTES / 4) reinterpret_cast<uint32_t*>(ones_tile)[threadIdx.x] = 0x3F803F80u;
+    fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -606,6 +616,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ===================== MMA issuer =====================
       if (lane == 0) {
         const uint32_t idesc = make_instr_desc(p.block_n, p.a_mn, p.b_mn);
+        const uint32_t idesc_ones = make_instr_desc(ONES_N, p.a_mn, 0);
+        const uint64_t ones_desc = make_smem_desc(smem_u32(ones_tile), 0u, 0u);   // SBO = 0: rows 8..15 re-read rows 0..7
         // K-major: 8-row groups are 1024 B apart (SBO); the single 128 B swizzle atom along K makes LBO unused.
         // MN-major: 64(mn) x 8(k) atoms; SBO = 1024 B between k-groups, LBO = 8192 B between 64-wide mn groups.
         const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
@@ -622,6 +634,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
+          const bool do_rowsum = (p.rowsum != nullptr) && tc.n_blk == 0;
+          const uint32_t tmem_ones = tmem_base + (uint32_t)(p.num_acc * p.block_n + acc * ONES_N);
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
@@ -632,6 +646,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024u);
               const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024u);
               umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (do_rowsum)   // row sums of the A tile: 128 x 16 x 16 MMA against the ones tile
+                umma_bf16(tmem_ones, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
             if (++stage == p.stages) {
@@ -760,6 +776,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ci += 1;
             }
           }
+        }
+      }
+      if constexpr (kEpi == EPI_PLAIN && kOutF32) {
+        if (p.rowsum != nullptr && tc.n_blk == 0 && half == 0) {   // row sums of A (bias gradient), once per (m, k-split)
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p.num_acc * p.block_n + acc * ONES_N), r);
+          tmem_ld_wait();
+          if (lane < rows_valid) atomicAdd(p.rowsum + row_base + lane, __uint_as_float(r[0]) * p.alpha);
         }
       }
       // all of this warp's TMEM reads are complete (wait::ld above): release the accumulator buffer
@@ -1017,6 +1041,21 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   p.batch1 = g->batch1; p.batch2 = g->batch2;
   p.num_acc = (p.block_n <= 128) ? 4 : 2;
+  p.rowsum = g->rowsum;
+  if (g->rowsum != nullptr) {
+    MVLT_CHECK_ARG(g->out_f32 && !g->residual && !g->aux && g->act == MVLT_ACT_NONE && g->batch1 == 1 && g->batch2 == 1,
+                   "mvlt_gemm: rowsum needs a plain fp32 (atomic) output and no batch");
+    if (p.block_n > 240) {
+      // 2 x 256 accumulator columns fill TMEM: no room for the row-sum columns. Narrower tiles would cost more than
+      // the fusion saves on these (tensor-bound) shapes, so the sums come from the column-sum kernel instead.
+      MVLT_CHECK_ARG(g->a_mn && g->alpha == 1.0f, "mvlt_gemm: rowsum with 256-wide tiles needs an MN-major A and alpha = 1");
+      const int rc2 = mvlt_colsum(g->A, 0, g->K, g->M, g->lda, g->rowsum, stream_);
+      if (rc2) return rc2;
+      p.rowsum = nullptr;
+    } else {
+      p.num_acc = 2;   // TMEM: 2 x block_n accumulator columns + 2 x 16 row-sum columns <= 512
+    }
+  }
   p.div_n = make_fastdiv((uint32_t)p.num_n_blocks);
   p.div_m = make_fastdiv((uint32_t)p.num_m_blocks);
   p.div_s = make_fastdiv((uint32_t)p.split_k);
@@ -1060,7 +1099,7 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   if (rc) return rc;
 
   // > half of the SM's shared memory so two CTAs (each wanting all 512 TMEM columns) never share an SM
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + ONES_BYTES + 256 /*barriers*/ + STAGING_BYTES;
   if (smem < 120 * 1024) smem = 120 * 1024;
   static std::once_flag attr_once;
   static int launch_regs_ok = 1;

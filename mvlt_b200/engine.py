@@ -116,13 +116,13 @@ class PVLTEngine:
     # helpers
     # ------------------------------------------------------------------------------------------------
     def _lin_param_grads(self, G, wname, bname, dy, x, wgrad=None):
-        """dW += dy^T x (split-K, fp32 atomics straight into the gradient buffer); db += column sums of dy."""
+        """dW += dy^T x (split-K, fp32 atomics straight into the gradient buffer); db += column sums of dy (same launch)."""
         rows, co = dy.shape
         ci = x.shape[1]
         tgt = wgrad if wgrad is not None else G[wname].view(co, -1)
-        k.gemm(dy.t(), x.t(), tgt, atomic_add=True, split_k=_split_k(co, ci, rows))
-        if bname is not None:
-            k.colsum(dy, rows, co, dy.stride(0), G[bname])
+        # the bias gradient db = dy^T 1 rides on the same GEMM (one extra N=16 MMA per k-step against a tile of ones)
+        k.gemm(dy.t(), x.t(), tgt, atomic_add=True, split_k=_split_k(co, ci, rows),
+               rowsum=G[bname] if bname is not None else None)
 
     def _pos(self, stage, H, W, dev):
         """pvlt.py:291-297,341-344: bilinear resize of the position table (cached per weight version)."""

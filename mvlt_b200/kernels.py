@@ -42,7 +42,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, preact_out: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          rowscale: Optional[torch.Tensor] = None, rows_per_scale: int = 0, atomic_add: bool = False,
-         split_k: int = 0, block_n: int = 0, impl: str = "tcgen05") -> torch.Tensor:
+         split_k: int = 0, block_n: int = 0, rowsum: Optional[torch.Tensor] = None,
+         impl: str = "tcgen05") -> torch.Tensor:
     """out[..., M, N] = epilogue(alpha * a[..., M, K] @ b[..., N, K]^T)   (see csrc/gemm_desc.h).
 
     ``a``/``b`` may be arbitrary 2-4 D views with one unit stride among the last two dims (K-major or
@@ -76,6 +77,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
     d.aux = aux.data_ptr() if aux is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
     d.rowscale = rowscale.data_ptr() if rowscale is not None else None
+    if rowsum is not None:      # rowsum[m] += alpha * sum_k a[m, k]  (fp32 atomics; the bias gradient of a dW GEMM)
+        if rowsum.dtype != F32 or rowsum.numel() != M or not rowsum.is_contiguous():
+            raise _lib.MvltError("gemm rowsum must be contiguous fp32 [M]")
+        d.rowsum = rowsum.data_ptr()
     d.M, d.N, d.K = M, N, K
     d.a_mn, d.b_mn = a_mn, b_mn
     d.lda, d.ldb, d.ldd = lda, ldb, out.stride(-2) if M > 1 else max(out.stride(-2), N)

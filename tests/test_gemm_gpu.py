@@ -289,3 +289,22 @@ def test_implicit_conv3x3_fwd_dgrad_wgrad(B, H, W, C, Co, pad_c):
     refdw = refdw.permute(0, 2, 3, 1).reshape(Co, 9 * C)
     _check(dw, 1.0 + refdw, B * H * W, "conv wgrad")
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("Ntok,Co,Ci,split", [(20000, 512, 64, 37), (4224 * 3, 64, 64, 50), (3000, 320, 1280, 4),
+                                              (777, 130, 96, 1), (24576, 2048, 512, 10)])
+def test_gemm_wgrad_with_fused_bias_rowsum(Ntok, Co, Ci, split):
+    """dW = dy^T x (split-K atomics) with db = column sums of dy produced by the same launch (ones-MMA row sums)."""
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(Ntok + Co)
+    ldy = (Co + 7) // 8 * 8
+    dy = _rand((Ntok, ldy), g, 0.1)[:, :Co]
+    x = _rand((Ntok, Ci), g, 0.1)
+    dw = torch.ones((Co, Ci), device="cuda", dtype=F32)
+    db = torch.full((Co,), 2.0, device="cuda", dtype=F32)
+    k.gemm(dy.t(), x.t(), dw, atomic_add=True, split_k=split, rowsum=db)
+    torch.cuda.synchronize()
+    _check(dw, 1.0 + dy.float().t() @ x.float(), Ntok, "dW")
+    refb = 2.0 + dy.float().sum(0)
+    err = (db - refb).abs().max().item()
+    assert err <= 2e-3 * refb.abs().max().item() + 1e-3, err
