@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                      TDX* __restrict__ dx, RowMap dxm, const float* __restrict__ dx_add,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
-                                                     int C) {
+                                                     int C, __nv_bfloat16* __restrict__ dx16, const float* __restrict__ rowscale,
+                                                     int rows_per_scale) {
   extern __shared__ float sh[];  // [2][warps * RPW][C]
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % G;
@@ -192,6 +193,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
         store4<TDX>(dx + drow + c, o);
+        if (dx16 != nullptr) {   // bf16 copy (x drop-path scale) = the A operand of the next backward GEMMs
+          const float sc = rowscale ? rowscale[r / rows_per_scale] : 1.f;
+          store4<__nv_bfloat16>(dx16 + drow + c, make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc));
+        }
       }
     }
   }
@@ -323,7 +328,8 @@ extern "C" int mvlt_layernorm_fwd(const void* x, int x_f32, const int* xmap, con
 extern "C" int mvlt_layernorm_bwd(const void* dy, int dy_f32, const int* dymap, const void* x, int x_f32,
                                   const int* xmap, const float* mean, const float* rstd, const float* gamma,
                                   void* dx, int dx_f32, const int* dxmap, const float* dx_add, float* dgamma,
-                                  float* dbeta, int rows, int C, void* stream_) {
+                                  float* dbeta, int rows, int C, void* dx_bf16_scaled, const float* rowscale,
+                                  int rows_per_scale, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   MVLT_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && C <= 128 * LN_MAX_VEC, "layernorm_bwd: unsupported C=%d", C);
   auto mk = [&](const int* m) {
@@ -338,7 +344,9 @@ extern "C" int mvlt_layernorm_bwd(const void* dy, int dy_f32, const int* dymap, 
 #define LN_BWD_CALL(TDY, TX, TDX, G, NV)                                                                         \
   ln_bwd_kernel<TDY, TX, TDX, G, NV><<<grid, 256, smem, st>>>(reinterpret_cast<const TDY*>(dy), dym,                 \
                                                               reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma, \
-                                                              reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta, rows, C)
+                                                              reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta, rows, C, \
+                                                              reinterpret_cast<__nv_bfloat16*>(dx_bf16_scaled), rowscale,     \
+                                                              rows_per_scale > 0 ? rows_per_scale : 1)
 #define LAUNCH(TDY, TX, TDX)                                  \
   do {                                                        \
     if (C <= 64) LN_BWD_CALL(TDY, TX, TDX, 16, 1);            \

@@ -1,0 +1,83 @@
+// Multi-tensor AdamW: one launch updates every parameter of a group (decoupled weight decay, bias correction),
+// reading p, g, m, v once and writing p, m, v once: 28 B per parameter, HBM-bound.
+//
+// Replaces the per-step optimizer work the reference delegates to timm.create_optimizer(opt='adamw') + torch.optim
+// (/root/reference/main_vl.py:308, stepped at engine_grid_masking.py:122-127 through timm's NativeScaler): same
+// update rule as torch.optim.AdamW(amsgrad=False, maximize=False):
+//   p <- p * (1 - lr * wd);  m <- b1 m + (1 - b1) g;  v <- b2 v + (1 - b2) g^2;
+//   p <- p - (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+#include "common.cuh"
+
+struct AdamTensor {      // one parameter tensor (48 bytes; mirrored by mvlt_b200/optim.py)
+  float* p;
+  float* g;
+  float* m;
+  float* v;
+  long long n;
+  float wd_mult;         // multiplies the group's weight decay (0 for bias / 1-D parameters)
+  int pad;
+};
+struct AdamChunk {       // one contiguous run of <= chunk_elems elements of tensor `t`
+  long long off;
+  int t;
+  int pad;
+};
+
+namespace {
+
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, float lr_wd, float b1, float b2, float step, float rbc2,
+                                      float eps) {
+  p -= p * lr_wd;
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  p -= step * m / (sqrtf(v) * rbc2 + eps);
+}
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __restrict__ tensors, const AdamChunk* __restrict__ chunks,
+                                                          int chunk_elems, float lr, float b1, float b2, float eps, float wd,
+                                                          float bc1, float bc2, const float* __restrict__ grad_scale, int zero_grads) {
+  const AdamChunk ch = chunks[blockIdx.x];
+  const AdamTensor t = tensors[ch.t];
+  const long long n = min((long long)chunk_elems, t.n - ch.off);
+  float* p = t.p + ch.off;
+  float* g = t.g + ch.off;
+  float* m = t.m + ch.off;
+  float* v = t.v + ch.off;
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  const float lr_wd = lr * wd * t.wd_mult, step = lr / bc1, rbc2 = rsqrtf(bc2);
+  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    adam1(p4.x, g4.x * gs, m4.x, v4.x, lr_wd, b1, b2, step, rbc2, eps);
+    adam1(p4.y, g4.y * gs, m4.y, v4.y, lr_wd, b1, b2, step, rbc2, eps);
+    adam1(p4.z, g4.z * gs, m4.z, v4.z, lr_wd, b1, b2, step, rbc2, eps);
+    adam1(p4.w, g4.w * gs, m4.w, v4.w, lr_wd, b1, b2, step, rbc2, eps);
+    reinterpret_cast<float4*>(p)[i] = p4;
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    if (zero_grads) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam1(pp, g[i] * gs, mm, vv, lr_wd, b1, b2, step, rbc2, eps);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (zero_grads) g[i] = 0.f;
+  }
+}
+
+}  // namespace
+
+// tensors: device array of AdamTensor; chunks: device array of n_chunks AdamChunk (one CTA each)
+extern "C" int mvlt_adamw_multi(const void* tensors, const void* chunks, int n_chunks, int chunk_elems, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, float bias_correction1, float bias_correction2,
+                                const float* grad_scale_dev, int zero_grads, void* stream_) {
+  MVLT_CHECK_ARG(tensors && chunks && n_chunks > 0 && chunk_elems > 0, "adamw_multi: empty tables");
+  MVLT_CHECK_ARG(bias_correction1 > 0.f && bias_correction2 > 0.f, "adamw_multi: bias corrections must be positive");
+  adamw_multi_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const AdamTensor*>(tensors), reinterpret_cast<const AdamChunk*>(chunks), chunk_elems, lr, beta1, beta2, eps,
+      weight_decay, bias_correction1, bias_correction2, grad_scale_dev, zero_grads);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}

@@ -207,7 +207,10 @@ class PVLTEngine:
                      mean2=mean2, rstd2=rstd2, act=act, hpre=hpre, dp=dp, Nk=Nk)
         return X2, c
 
-    def _block_bwd(self, dX2, c, pfx, i, B, H, W, G):
+    def _block_bwd(self, dX2, c, pfx, i, B, H, W, G, dy2=None, next_dp=None):
+        """``dy2``: bf16 copy of dX2 already scaled by this block's MLP drop-path mask (written by the LayerNorm backward
+        that produced dX2), or None. ``next_dp``: MLP drop-path mask of the block that runs next in backward order; when
+        given, its scaled bf16 copy of the returned gradient is produced here and returned as the second value."""
         P, Wb, T = self.P, self.W, self.T
         C, R, heads = EMBED_DIMS[i], SR_RATIOS[i], NUM_HEADS[i]
         HW, N = H * W, H * W + T
@@ -217,8 +220,9 @@ class PVLTEngine:
         hidden = C * MLP_RATIOS[i]
         dp = c["dp"]
         # ---- MLP branch
-        dy2 = _empty((M, C), BF16, dev)
-        k.cast_scale_bf16(dX2, dy2, M, C, rowscale=dp[1] if dp else None, rows_per_scale=N)
+        if dy2 is None:
+            dy2 = _empty((M, C), BF16, dev)
+            k.cast_scale_bf16(dX2, dy2, M, C, rowscale=dp[1] if dp else None, rows_per_scale=N)
         self._lin_param_grads(G, pfx + ".mlp.fc2.weight", pfx + ".mlp.fc2.bias", dy2, c["act"])
         dh = _empty((M, hidden), BF16, dev)
         k.gemm(dy2, Wb[pfx + ".mlp.fc2.weight"].t(), dh, act=k.ACT_MUL_AUX, aux=c["hpre"])
@@ -227,11 +231,11 @@ class PVLTEngine:
         k.gemm(dh, Wb[pfx + ".mlp.fc1.weight"].t(), dxn2)
         del dh
         dX1 = _empty((B, N, C), F32, dev)
+        # ---- attention branch: its bf16, drop-path-scaled input gradient is written by the same LayerNorm pass
+        dyp = _empty((M, C), BF16, dev)
         k.layernorm_bwd(dxn2, c["X1"], c["mean2"], c["rstd2"], P[pfx + ".norm2.weight"], dX1, M, C, dx_add=dX2,
-                        dgamma=G[pfx + ".norm2.weight"], dbeta=G[pfx + ".norm2.bias"])
-        # ---- attention branch
-        dyp = dxn2
-        k.cast_scale_bf16(dX1, dyp, M, C, rowscale=dp[0] if dp else None, rows_per_scale=N)
+                        dgamma=G[pfx + ".norm2.weight"], dbeta=G[pfx + ".norm2.bias"], dx_bf16=dyp,
+                        rowscale=dp[0] if dp else None, rows_per_scale=N)
         self._lin_param_grads(G, pfx + ".attn.proj.weight", pfx + ".attn.proj.bias", dyp, c["o"])
         do = _empty((M, C), BF16, dev)
         k.gemm(dyp, Wb[pfx + ".attn.proj.weight"].t(), do)
@@ -273,9 +277,11 @@ class PVLTEngine:
             k.gemm(dq, Wb[pfx + ".attn.q.weight"].t(), dxn, residual=dxn)
         self._lin_param_grads(G, pfx + ".attn.q.weight", pfx + ".attn.q.bias", dq, c["xn"])
         dX = _empty((B, N, C), F32, dev)
+        dy_next = _empty((M, C), BF16, dev) if next_dp is not None else None      # next_dp False = "no drop-path mask"
         k.layernorm_bwd(dxn, c["X"], c["mean1"], c["rstd1"], P[pfx + ".norm1.weight"], dX, M, C, dx_add=dX1,
-                        dgamma=G[pfx + ".norm1.weight"], dbeta=G[pfx + ".norm1.bias"])
-        return dX
+                        dgamma=G[pfx + ".norm1.weight"], dbeta=G[pfx + ".norm1.bias"], dx_bf16=dy_next,
+                        rowscale=next_dp if torch.is_tensor(next_dp) else None, rows_per_scale=N)
+        return dX, dy_next
 
     def _conv_wgrad(self, G, name):
         """fp32 gradient buffer in the permuted [Co, kh*kw*Ci] layout; folded back into the master layout at the end."""
@@ -375,8 +381,12 @@ class PVLTEngine:
             HW, N = H * W, H * W + T
             if dX is None:
                 dX = torch.zeros((B, N, C), dtype=F32, device=dev)
+            dy2 = None
             for j in reversed(range(self.depths[i])):
-                dX = self._block_bwd(dX, sc["blocks"][j], f"block{s}.{j}", i, B, H, W, G)
+                # the block that runs next (j-1) needs bf16(dX * its MLP drop-path mask): produced by this block's last pass
+                nxt = sc["blocks"][j - 1]["dp"] if j > 0 else None
+                next_dp = None if j == 0 else (nxt[1] if nxt else False)
+                dX, dy2 = self._block_bwd(dX, sc["blocks"][j], f"block{s}.{j}", i, B, H, W, G, dy2=dy2, next_dp=next_dp)
             # position embeddings (pvlt.py:341-346): batch-sum of the token grads, image part through the
             # transposed bilinear resize
             pe_tab = P[f"pos_embed{s}"]

@@ -204,11 +204,13 @@ def layernorm_fwd(x, gamma, beta, y, eps, rows, Cdim, xmap=None, ymap=None, post
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, rows, Cdim, dymap=None, xmap=None, dxmap=None, dx_add=None,
-                  dgamma=None, dbeta=None):
+                  dgamma=None, dbeta=None, dx_bf16=None, rowscale=None, rows_per_scale=0):
+    """``dx_bf16`` (optional, dx's row layout): bf16 copy of dx times rowscale[row // rows_per_scale] (drop-path), i.e.
+    the A operand of the backward GEMMs that consume dx next, written by the same pass."""
     require_cuda(dy, x, dx)
     call("layernorm_bwd", ptr(dy), _f32(dy), _map(dymap), ptr(x), _f32(x), _map(xmap), ptr(mean), ptr(rstd),
          ptr(gamma), ptr(dx), _f32(dx), _map(dxmap), ptr(dx_add), ptr(dgamma), ptr(dbeta), C.c_int(rows),
-         C.c_int(Cdim))
+         C.c_int(Cdim), ptr(dx_bf16), ptr(rowscale), C.c_int(rows_per_scale))
 
 
 def softmax_fwd(s, rows, nk):

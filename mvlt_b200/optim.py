@@ -1,0 +1,95 @@
+"""Multi-tensor AdamW on the hand-written sm_100a kernel (csrc/optim.cu): one launch per parameter group.
+
+Same update rule and constructor surface as ``torch.optim.AdamW`` (the optimizer timm's ``create_optimizer(opt='adamw')``
+builds for the reference, /root/reference/main_vl.py:308): ``param_groups`` with ``lr`` / ``weight_decay`` / ``betas`` /
+``eps`` that LR schedulers may rewrite between steps, ``state_dict`` / ``load_state_dict`` in torch's format, and
+``zero_grad(set_to_none=True)``. There is no CPU fallback: parameters must live on an sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+
+import torch
+
+from . import _lib
+from ._lib import MvltError, call, ptr
+
+CHUNK = 16384   # fp32 elements per CTA (64 KB of each of p, g, m, v)
+
+
+def param_groups_no_decay(model, weight_decay):
+    """timm ``add_weight_decay`` semantics: no weight decay on 1-D parameters and biases."""
+    decay, no_decay = [], []
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        (no_decay if p.ndim <= 1 or n.endswith(".bias") else decay).append(p)
+    return [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}]
+
+
+class AdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("invalid AdamW hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._tables = {}
+
+    def _state(self, p):
+        st = self.state[p]
+        if len(st) == 0:
+            st["step"] = 0
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
+
+    def _group_tables(self, gi, ps):
+        """Device tables of (p, g, m, v, n) per tensor and of the 64 KB chunks; rebuilt only when a pointer moved."""
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr()) for p in ps)
+        cached = self._tables.get(gi)
+        if cached is not None and cached[0] == key:
+            return cached[1], cached[2], cached[3]
+        tb, cb, nchunks = bytearray(), bytearray(), 0
+        for ti, p in enumerate(ps):
+            st = self.state[p]
+            n = p.numel()
+            tb += struct.pack("<QQQQqfi", p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), n,
+                              1.0, 0)
+            for off in range(0, n, CHUNK):
+                cb += struct.pack("<qii", off, ti, 0)
+                nchunks += 1
+        dev = ps[0].device
+        tt = torch.frombuffer(tb, dtype=torch.uint8).to(dev)
+        ct = torch.frombuffer(cb, dtype=torch.uint8).to(dev)
+        self._tables[gi] = (key, tt, ct, nchunks)
+        return tt, ct, nchunks
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=None):
+        """``grad_scale``: optional 1-element fp32 device tensor multiplied into every gradient (e.g. 1 / loss scale)."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            for p in ps:
+                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32:
+                    raise MvltError("mvlt_b200.optim.AdamW needs fp32 CUDA parameters and gradients (no CPU fallback)")
+                if not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise MvltError("mvlt_b200.optim.AdamW needs contiguous parameters and gradients")
+                self._state(p)
+            steps = {self.state[p]["step"] for p in ps}
+            if len(steps) != 1:
+                raise MvltError("parameters of one group must share their step count")
+            t = steps.pop() + 1
+            b1, b2 = group["betas"]
+            tt, ct, nchunks = self._group_tables(gi, ps)
+            call("adamw_multi", ptr(tt), ptr(ct), C.c_int(nchunks), C.c_int(CHUNK), C.c_float(group["lr"]), C.c_float(b1),
+                 C.c_float(b2), C.c_float(group["eps"]), C.c_float(group["weight_decay"]), C.c_float(1.0 - b1 ** t),
+                 C.c_float(1.0 - b2 ** t), ptr(grad_scale), C.c_int(0))
+            for p in ps:
+                self.state[p]["step"] = t
+        return loss

@@ -136,8 +136,12 @@ def test_layernorm_fwd_bwd(C, in_dtype, out_dtype):
     dx = torch.empty((rows, C), dtype=F32, device="cuda")
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     add = torch.randn((rows, C), generator=_g(5), device="cuda")
-    k.layernorm_bwd(dy, x, mean, rstd, gamma, dx, rows, C, dx_add=add, dgamma=dg, dbeta=db)
+    dx16 = torch.empty((rows, C), dtype=BF16, device="cuda")
+    rs = torch.rand((rows + 49) // 50, generator=_g(6), device="cuda")
+    k.layernorm_bwd(dy, x, mean, rstd, gamma, dx, rows, C, dx_add=add, dgamma=dg, dbeta=db, dx_bf16=dx16, rowscale=rs,
+                    rows_per_scale=50)
     _close(dx, xr.grad + add, 1e-4, 1e-4, "ln dx")
+    _close(dx16, (xr.grad + add) * rs.repeat_interleave(50)[:rows, None], 1e-2, 1e-2, "ln dx (bf16, drop-path scaled copy)")
     _close(dg, gr.grad, 1e-3, 1e-3, "ln dgamma")
     _close(db, br.grad, 1e-3, 1e-3, "ln dbeta")
 
