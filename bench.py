@@ -250,8 +250,8 @@ def run_ours(args):
         gemm_n = cnt.get("gemm", 0)
         # every launch against ITS OWN bound: max(algorithmic bytes / HBM peak, flops / tensor peak)
         gev = prof.get("gemm", [])
-        ideal_ms = sum(max(b / (hbm * 1e9), f / (tf_sus * 1e12)) for f, b in glog) * 1e3
-        hbm_bound_ms = sum(a.elapsed_time(e) for (a, e), (f, b) in zip(gev, glog) if b / (hbm * 1e9) >= f / (tf_sus * 1e12))
+        ideal_ms = sum(max(b / (hbm * 1e9), f / (tf_sus * 1e12)) for f, b, _ in glog) * 1e3
+        hbm_bound_ms = sum(a.elapsed_time(e) for (a, e), (f, b, _) in zip(gev, glog) if b / (hbm * 1e9) >= f / (tf_sus * 1e12))
         ach_gbs = nbytes / (gemm_ms / 1e3) / 1e9 if gemm_ms > 0 else 0.0
         ach_tf = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         traffic = None

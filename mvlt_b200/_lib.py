@@ -87,12 +87,12 @@ GEMM_BYTES = 0.0      # algorithmic (compulsory) operand + result bytes of the s
 GEMM_LOG = None       # when a list: one (flops, bytes) tuple per GEMM launch, in launch order
 
 
-def account_gemm(flops: float, nbytes: float):
+def account_gemm(flops: float, nbytes: float, what: str = ""):
     global GEMM_FLOPS, GEMM_BYTES
     GEMM_FLOPS += flops
     GEMM_BYTES += nbytes
     if GEMM_LOG is not None:
-        GEMM_LOG.append((flops, nbytes))
+        GEMM_LOG.append((flops, nbytes, what))
 PROFILE = None        # when a dict: name -> list of (start_event, end_event) recorded around every call
 
 

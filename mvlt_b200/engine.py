@@ -25,6 +25,7 @@ import torch
 
 from . import kernels as k
 from ._lib import MvltError
+from .engine_util import split_k as _split_k
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -42,14 +43,6 @@ HEAD_DIM = 64
 
 def _empty(shape, dtype, dev):
     return torch.empty(shape, dtype=dtype, device=dev)
-
-
-def _split_k(M, N, K):
-    """split-K factor for dW-type GEMMs (tiny M x N output, huge K): fill ~2 waves of SMs."""
-    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 256 else 1)
-    kb = (K + 63) // 64
-    want = max(1, (2 * 148 + tiles - 1) // tiles)
-    return max(1, min(want, kb // 4 if kb >= 8 else 1))
 
 
 class PVLTEngine:
@@ -528,13 +521,15 @@ class PVLTEngine:
         k.gemm(dlogits.t(), c["hl"].t(), G["text_embeddings.word_embeddings.weight"], atomic_add=True,
                split_k=_split_k(VOCAB, HIDDEN, n_rows))
         k.colsum(dlogits, n_rows, VOCAB, VOCAB_PAD, G["mlm_head.bias"])
-        dhl = _empty((n_rows, HIDDEN), BF16, dev)
-        k.gemm(dlogits, Wb["text_embeddings.word_embeddings.weight"].t(), dhl)
+        # dH = dlogits E: only ~700 labelled rows but K = 30522 -> split-K into a zeroed fp32 buffer (18 tiles otherwise)
+        dhl = k.zeros((n_rows, HIDDEN), F32, dev)
+        k.gemm(dlogits, Wb["text_embeddings.word_embeddings.weight"].t(), dhl, atomic_add=True,
+               split_k=_split_k(n_rows, HIDDEN, VOCAB))
         dha = _empty((n_rows, HIDDEN), BF16, dev)
         k.layernorm_bwd(dhl, c["ha"], c["m2"], c["r2"], P["mlm_head.transform.LayerNorm.weight"], dha, n_rows, HIDDEN,
                         dgamma=G["mlm_head.transform.LayerNorm.weight"], dbeta=G["mlm_head.transform.LayerNorm.bias"])
         # GELU backward: dpre = dha * gelu'(pre), with gelu' saved by the forward epilogue
-        dpre = dhl
+        dpre = _empty((n_rows, HIDDEN), BF16, dev)
         k.ew_mul(dha, HIDDEN, 0, dpre, HIDDEN, 0, n_rows, HIDDEN, b=c["hpre"], b_ld=HIDDEN)
         self._lin_param_grads(G, "mlm_head.transform.dense.weight", "mlm_head.transform.dense.bias", dpre, c["hn"])
         dhn = dha

@@ -107,10 +107,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
     for t in (aux, preact_out):
         if t is not None and (t.dtype != BF16 or t.stride() != out.stride()):
             raise _lib.MvltError("gemm aux/preact must be bf16 with out's strides")
-    if _lib.PROFILE is not None:
+    if _lib.PROFILE is not None or _lib.GEMM_LOG is not None:
         nb = b1 * b2
         extra = sum(M * N * nb * t.element_size() for t in (aux, preact_out, residual) if t is not None)
-        _lib.account_gemm(2.0 * M * N * K * nb, (M * K + N * K) * 2.0 * nb + M * N * nb * out.element_size() + extra)
+        _lib.account_gemm(2.0 * M * N * K * nb, (M * K + N * K) * 2.0 * nb + M * N * nb * out.element_size() + extra,
+                          f"gemm M={M} N={N} K={K} b={nb} amn={a_mn} bmn={b_mn} out={'f32' if out.dtype == F32 else 'bf16'} act={act} "
+                          f"res={int(residual is not None)} atomic={int(atomic_add)} split={split_k} rowsum={int(rowsum is not None)}")
     call("gemm" if impl == "tcgen05" else "gemm_ref", C.byref(d))
     return out
 
@@ -145,8 +147,9 @@ def conv3x3_gemm(x, B, H, W, Cdim, pix_stride, batch_stride, w, out, *, residual
     _conv_fields(d, x, B, H, W, Cdim, pix_stride, batch_stride, CONV_A)
     if residual is not None and (residual.dtype != F32 or residual.stride() != out.stride()):
         raise _lib.MvltError("conv3x3_gemm residual must be fp32 with out's strides")
-    if _lib.PROFILE is not None:   # algorithmic bytes: X once (not the 9x im2col matrix) + weights + output (+ residual)
-        _lib.account_gemm(2.0 * M * N * K, (M * Cdim + N * K) * 2.0 + M * N * out.element_size() * (2 if residual is not None else 1))
+    if _lib.PROFILE is not None or _lib.GEMM_LOG is not None:   # algorithmic bytes: X once (not the 9x im2col matrix) + weights + output (+ residual)
+        _lib.account_gemm(2.0 * M * N * K, (M * Cdim + N * K) * 2.0 + M * N * out.element_size() * (2 if residual is not None else 1),
+                          f"conv3x3 M={M} N={N} K={K} HxW={H}x{W} out={'f32' if out.dtype == F32 else 'bf16'} res={int(residual is not None)}")
     call("gemm", C.byref(d))
     return out
 
@@ -170,8 +173,9 @@ def conv3x3_wgrad(dy, x, B, H, W, Cdim, pix_stride, batch_stride, out, *, split_
     d.out_f32, d.atomic_add = 1, 1
     d.split_k = split_k
     _conv_fields(d, x, B, H, W, Cdim, pix_stride, batch_stride, CONV_BT)
-    if _lib.PROFILE is not None:
-        _lib.account_gemm(2.0 * Co * N * Kp, (Kp * Co + Kp * Cdim) * 2.0 + Co * N * 4.0)
+    if _lib.PROFILE is not None or _lib.GEMM_LOG is not None:
+        _lib.account_gemm(2.0 * Co * N * Kp, (Kp * Co + Kp * Cdim) * 2.0 + Co * N * 4.0,
+                          f"conv3x3_wgrad M={Co} N={N} K={Kp} HxW={H}x{W} split={split_k}")
     call("gemm", C.byref(d))
     return out
 

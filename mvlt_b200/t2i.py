@@ -12,18 +12,12 @@ from __future__ import annotations
 import torch
 
 from . import kernels as k
+from .engine_util import split_k as _split_k
 
 BF16, F32 = torch.bfloat16, torch.float32
 CH = 64
 UNITS = ["reduction1", "reduction2", "reduction3", "conv_upsample1", "conv_upsample2", "conv_upsample3",
          "conv_upsample4", "conv_upsample5", "conv_concat2", "conv_concat3", "conv4"]
-
-
-def _split_k(M, N, K):
-    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 256 else 1)
-    kb = (K + 63) // 64
-    want = max(1, (2 * 148 + tiles - 1) // tiles)
-    return max(1, min(want, kb // 4 if kb >= 8 else 1))
 
 
 class T2IHead:

@@ -91,7 +91,10 @@ if args.dump_gemms:
     for r in sorted(out, key=lambda r: -r["ms"])[:40]:
         print(r)
 else:
+    _lib.GEMM_LOG = []          # one (flops, bytes, description) per GEMM launch of the profiled step, in launch order
     torch.cuda.profiler.start()
     step(1)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(_lib.GEMM_LOG, open("gpurun_out/gemm_desc_log.json", "w"))
