@@ -81,6 +81,7 @@ struct KParams {
   long long ldd, sD1, sD2;
   float alpha;
   int act, out_f32, atomic_add, rows_per_scale;
+  int prefetch;   // EPI_AUX only: two staging tiles per epilogue warp, the aux unit of the next tile is fetched with cp.async
   // implicit 3x3 convolution operand (gemm_desc.h): tile/k-block index -> (b, y) pixel coordinates and (tap, c0)
   int conv_mode, conv_W, conv_C;
   FastDiv div_hw, div_w, div_cb, div_c;   // pixels / (H*W), / W; k-block / (C/64); column / C
@@ -196,20 +197,21 @@ __device__ __forceinline__ void stage_flush(const StageAddr& s, uint8_t* gbase, 
   }
   __syncwarp();
 }
-// global -> staging tile (coalesced) -> this lane's row in registers
+// global -> registers in the coalesced pattern (issue only), then staging tile -> this lane's row in registers
 template <int P>
-__device__ __forceinline__ void load_rows_via_stage(const StageAddr& s, const uint8_t* gbase, long long ld_bytes, int lane,
-                                                    int rows_valid, uint32_t (&ex)[P * 4]) {
+__device__ __forceinline__ void load_rows_issue(const uint8_t* gbase, long long ld_bytes, int lane, int rows_valid, uint4 (&t)[P]) {
   constexpr int RPI = 32 / P;
   const uint8_t* g = gbase + co_goff<P>(lane, ld_bytes);
   const int row0 = (P == 8) ? (lane >> 3) : (lane >> 2);
-  uint4 t[P];
 #pragma unroll
   for (int q = 0; q < P; ++q) {
     t[q] = make_uint4(0u, 0u, 0u, 0u);
     if (rows_valid == 32 || q * RPI + row0 < rows_valid)
       t[q] = *reinterpret_cast<const uint4*>(g + (long long)(q * RPI) * ld_bytes);
   }
+}
+template <int P>
+__device__ __forceinline__ void stage_transpose(const StageAddr& s, const uint4 (&t)[P], uint32_t (&ex)[P * 4]) {
 #pragma unroll
   for (int q = 0; q < P; ++q) st_shared_v4(co_piece<P>(s, q), t[q].x, t[q].y, t[q].z, t[q].w);
   __syncwarp();
@@ -219,6 +221,13 @@ __device__ __forceinline__ void load_rows_via_stage(const StageAddr& s, const ui
     ex[4 * q] = v.x; ex[4 * q + 1] = v.y; ex[4 * q + 2] = v.z; ex[4 * q + 3] = v.w;
   }
   __syncwarp();
+}
+template <int P>
+__device__ __forceinline__ void load_rows_via_stage(const StageAddr& s, const uint8_t* gbase, long long ld_bytes, int lane,
+                                                    int rows_valid, uint32_t (&ex)[P * 4]) {
+  uint4 t[P];
+  load_rows_issue<P>(gbase, ld_bytes, lane, rows_valid, t);
+  stage_transpose<P>(s, t, ex);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2_f2(f32x2_t v) {
   float lo, hi;
@@ -275,18 +284,13 @@ __device__ __forceinline__ void apply_aux16(int act, const uint32_t* ax, f32x2_t
 // The TMEM accumulator is read 16 columns at a time to keep the register footprint small (no spills at 112
 // registers: local memory has almost no L1 behind it in this kernel). Warp-uniform; loops fully unrolled.
 template <int kEpi, bool kOutF32, int P>
-__device__ __forceinline__ void epilogue_unit_vec(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
-                                                  int rows_valid, int col0, float rs, const StageAddr& s) {
+__device__ __forceinline__ void epilogue_unit_compute(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
+                                                      int rows_valid, int col0, float rs, const StageAddr& s,
+                                                      const uint32_t (&ex)[P * 4]) {
   constexpr int COLS = kOutF32 ? 32 : P * 8;
   constexpr int N16 = COLS / 16;
   static_assert(!kOutF32 || P == 8, "fp32 units are 32 columns = 128-byte rows");
   const long long ld_bytes = p.ldd * (kOutF32 ? 4 : 2);
-  uint32_t ex[P * 4];
-  if constexpr (kEpi == EPI_RESID || kEpi == EPI_AUX) {   // residual (fp32 out) / aux (bf16 out): geometry of the output unit
-    const uint8_t* g = (kEpi == EPI_RESID) ? reinterpret_cast<const uint8_t*>(p.residual + row_base_off + col0)
-                                           : reinterpret_cast<const uint8_t*>(p.aux + row_base_off + col0);
-    load_rows_via_stage<P>(s, g, ld_bytes, lane, rows_valid, ex);
-  }
   uint32_t d2pk[P * 4];   // second bf16 output of the GELU epilogues, flushed after D (dead otherwise)
 #pragma unroll
   for (int i = 0; i < N16; ++i) {
@@ -360,6 +364,34 @@ __device__ __forceinline__ void epilogue_unit_vec(const KParams& p, uint32_t tad
       }
     }
   }
+}
+
+template <int kEpi, bool kOutF32, int P>
+__device__ __forceinline__ void epilogue_unit_vec(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
+                                                  int rows_valid, int col0, float rs, const StageAddr& s) {
+  uint32_t ex[P * 4];
+  if constexpr (kEpi == EPI_RESID || kEpi == EPI_AUX) {   // residual (fp32 out) / aux (bf16 out): geometry of the output unit
+    const long long ld_bytes = p.ldd * (kOutF32 ? 4 : 2);
+    const uint8_t* g = (kEpi == EPI_RESID) ? reinterpret_cast<const uint8_t*>(p.residual + row_base_off + col0)
+                                           : reinterpret_cast<const uint8_t*>(p.aux + row_base_off + col0);
+    load_rows_via_stage<P>(s, g, ld_bytes, lane, rows_valid, ex);
+  }
+  epilogue_unit_compute<kEpi, kOutF32, P>(p, taddr, row_base_off, lane, rows_valid, col0, rs, s, ex);
+}
+
+// Asynchronous (register-free) fetch of a 32-row x 128-byte operand unit into a staging tile: cp.async in the
+// coalesced pattern, zero-filled past rows_valid. Completion: cp.async.wait_group + __syncwarp by the caller.
+__device__ __forceinline__ void prefetch_rows_async(const StageAddr& s, const uint8_t* gbase, long long ld_bytes, int lane,
+                                                    int rows_valid) {
+  const uint8_t* g = gbase + co_goff<8>(lane, ld_bytes);
+  const int row0 = lane >> 3;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const bool ok = q * 4 + row0 < rows_valid;
+    const uint8_t* src = ok ? g + (long long)(q * 4) * ld_bytes : gbase;   // never form an out-of-range address
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(co_piece<8>(s, q)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // Tail path (N not a multiple of 32 / unaligned rows): one 32-column chunk with per-element predicates and
@@ -674,12 +706,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int split = (nchunks + 1) >> 1;
     const int c_begin = half ? split : 0;
     const int c_end = half ? nchunks : split;
-    const uint32_t stage = smem_u32(stage_base) + (uint32_t)ew * 4096u;
+    const uint32_t stage = smem_u32(stage_base) + (uint32_t)ew * (p.prefetch ? 8192u : 4096u);
     const uint32_t partner_stage = smem_u32(stage_base) + (uint32_t)(ew ^ 8) * 4096u;
     const StageAddr sa = make_stage_addr(stage, lane);
     const int pair_bar = 1 + group * 4 + quarter;   // named barriers 1..8 (0 is __syncthreads)
     const bool ld_aligned = (p.ldd & 7) == 0;
-    for (int local = group, t = blockIdx.x + group * gridDim.x; t < total_tiles; t += 2 * gridDim.x, local += 2) {
+    bool total_tiles_done = false;
+    if constexpr (kEpi == EPI_AUX) {
+      if (p.prefetch) {
+        // ---- thin-K aux epilogues (dH = (dY W2) * gelu'): block_n = 128, so every warp owns exactly one 64-column unit
+        // per tile. The unit's aux operand is the only DRAM read on the warp's critical path: it is fetched with
+        // cp.async into a second staging tile one tile AHEAD, while the current unit is computed and stored.
+        const StageAddr se = make_stage_addr(stage + 4096u, lane);
+        const long long ld_bytes = p.ldd * 2;
+        long long rbo = 0, rbo_n = 0;
+        int rv = 0, rv_n = 0, c0 = 0, c0_n = 0, rb = 0, rb_n = 0;
+        auto coords = [&](int tt, long long& o, int& v, int& c, int& r) {
+          const TileCoord tc = decode_tile(p, tt);
+          r = tc.m_blk * BLOCK_M + quarter * 32;
+          v = min(32, p.M - r);
+          o = (long long)tc.b1 * p.sD1 + (long long)tc.b2 * p.sD2 + (long long)r * p.ldd;
+          c = tc.n_blk * p.block_n + half * 64;
+        };
+        int t = blockIdx.x + group * gridDim.x;
+        if (t < total_tiles) {
+          coords(t, rbo, rv, c0, rb);
+          prefetch_rows_async(se, reinterpret_cast<const uint8_t*>(p.aux + rbo + c0), ld_bytes, lane, rv);
+        }
+        for (int local = group; t < total_tiles; t += 2 * gridDim.x, local += 2) {
+          const int tn = t + 2 * gridDim.x;
+          if (tn < total_tiles) coords(tn, rbo_n, rv_n, c0_n, rb_n);
+          float rs = 1.f;
+          if (p.rowscale != nullptr && lane < rv) rs = p.rowscale[(rb + lane) / p.rows_per_scale];
+          const int acc = local & acc_mask;
+          mbar_wait(&tfull_bar[acc], (uint32_t)(local >> acc_shift) & 1u);
+          tc_fence_after();
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          uint32_t ex[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint4 v = ld_shared_v4(own_piece<8>(se, q));
+            ex[4 * q] = v.x; ex[4 * q + 1] = v.y; ex[4 * q + 2] = v.z; ex[4 * q + 3] = v.w;
+          }
+          __syncwarp();
+          if (tn < total_tiles)
+            prefetch_rows_async(se, reinterpret_cast<const uint8_t*>(p.aux + rbo_n + c0_n), ld_bytes, lane, rv_n);
+          if (rv > 0) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n + half * 64);
+            epilogue_unit_compute<EPI_AUX, false, 8>(p, taddr, rbo, lane, rv, c0, rs, sa, ex);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          rbo = rbo_n; rv = rv_n; c0 = c0_n; rb = rb_n;
+        }
+        total_tiles_done = true;
+      }
+    }
+    for (int local = group, t = blockIdx.x + group * gridDim.x; !total_tiles_done && t < total_tiles; t += 2 * gridDim.x, local += 2) {
       const TileCoord tc = decode_tile(p, t);
       const int n0 = tc.n_blk * p.block_n;
       const int row_base = tc.m_blk * BLOCK_M + quarter * 32;
@@ -1029,8 +1114,13 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   p.block_n = (g->act == MVLT_ACT_SOFTMAX || g->act == MVLT_ACT_SOFTMAX_BWD) ? g->N : pick_block_n(g);
   MVLT_CHECK_ARG(p.block_n >= 32 && p.block_n <= 256 && p.block_n % (g->b_mn ? 64 : 32) == 0,
                  "mvlt_gemm: unsupported block_n %d", p.block_n);
+  // thin-K aux epilogues: 128-wide tiles, a second staging tile per epilogue warp (cp.async prefetch of the aux operand)
+  const bool aux_kind = g->aux != nullptr && (g->act == MVLT_ACT_MUL_AUX || g->act == MVLT_ACT_DGELU);
+  p.prefetch = (aux_kind && g->K <= 2 * BLOCK_K && g->N % 128 == 0 && (g->ldd % 8) == 0 && (g->sD1 % 8) == 0 && (g->sD2 % 8) == 0 &&
+                (g->block_n == 0 || g->block_n == 128)) ? 1 : 0;
+  if (p.prefetch) p.block_n = 128;
   const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
-  p.stages = SMEM_BUDGET / stage_bytes;
+  p.stages = (p.prefetch ? SMEM_BUDGET - STAGING_BYTES : SMEM_BUDGET) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.num_m_blocks = (g->M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_blocks = (g->N + p.block_n - 1) / p.block_n;
@@ -1099,7 +1189,7 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   if (rc) return rc;
 
   // > half of the SM's shared memory so two CTAs (each wanting all 512 TMEM columns) never share an SM
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + ONES_BYTES + 256 /*barriers*/ + STAGING_BYTES;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + ONES_BYTES + 256 /*barriers*/ + STAGING_BYTES * (p.prefetch ? 2 : 1);
   if (smem < 120 * 1024) smem = 120 * 1024;
   static std::once_flag attr_once;
   static int launch_regs_ok = 1;

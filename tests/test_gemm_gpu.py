@@ -194,7 +194,8 @@ def test_gemm_fused_softmax_fwd_bwd(Nq, Nk):
     _check(dS, refd, D, "softmax bwd epilogue", atol_scale=2.0)
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 200, 96), (1000, 320, 64), (257, 96, 128), (640, 512, 64), (130, 72, 64)])
+@pytest.mark.parametrize("M,N,K", [(300, 200, 96), (1000, 320, 64), (257, 96, 128), (640, 512, 64), (130, 72, 64),
+                                   (1000, 256, 128), (20000, 1024, 64), (77, 128, 64)])
 def test_gemm_epilogue_units_and_tails(M, N, K):
     """Every epilogue flavour on shapes that mix 64-column units, 32-column units and the ragged-N tail path."""
     from mvlt_b200 import kernels as k
