@@ -121,8 +121,11 @@ def run_ours(args):
     model.train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
-                                                        gradient_as_bucket_view=True)
+        if args.ddp:     # the reference's wrapper (main_vl.py:297): works unchanged, pays DDP's bucket copies
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
+                                                            gradient_as_bucket_view=True)
+        else:            # one NCCL all-reduce over the step's single flat gradient buffer
+            model.enable_grad_sync(True)
     opt = make_optimizer(model, lr=2.5e-4 * B * world / 512.0)
 
     host = [synth_batch(B, seed=100 * rank + i) for i in range(2)]
@@ -228,16 +231,24 @@ def run_ours(args):
 
     run_e2e(2)
     ms_e2e = timed(run_e2e, K, whole_loop=True)
+    # host-side cost of enqueueing one step (Python + ctypes + allocator), measured from an idle GPU without synchronising:
+    # as long as it stays below ms_per_step the device, not the launch path, bounds the step
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step(0, devb[0])
+    host_ms = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
     e2e_value = B * world * K / (ms_e2e / 1e3)
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in ("images", "input_ids", "itm_labels", "mlm_labels"))
 
     # ---- per-kernel breakdown (instrumented pass, NOT the reported value) -> roofline of the dominant kernel
     roof, breakdown = None, None
+    model.enable_grad_sync(None)      # the instrumented pass below runs on rank 0 alone: no collectives from here on
     if rank == 0:
         _lib.PROFILE, _lib.GEMM_FLOPS, _lib.GEMM_BYTES, _lib.GEMM_LOG = {}, 0.0, 0.0, []
         nprof = 2
         for i in range(nprof):
-            step(i, devb[i % 2], fwd=model)      # the bare module: rank 0 alone must not enter DDP's collectives
+            step(i, devb[i % 2], fwd=model)      # the bare module: rank 0 alone must not enter the gradient collectives
         torch.cuda.synchronize()
         prof, flops, nbytes, glog = _lib.PROFILE, _lib.GEMM_FLOPS, _lib.GEMM_BYTES, _lib.GEMM_LOG
         _lib.PROFILE, _lib.GEMM_LOG = None, None
@@ -296,7 +307,7 @@ def run_ours(args):
                        "mlm_rows": "MLM head evaluated on labelled rows only (identical loss/gradients)"},
             "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / K, 3)},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": round(host_ms, 3),
             "clocks": clocks,
             "model_tflops": round(value * GF_PER_SAMPLE_TRAIN / 1e3, 2),
             "model_flops_frac_of_bf16_peak": round(value * GF_PER_SAMPLE_TRAIN / 1e3 / tf_sus, 4),
@@ -370,6 +381,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--retrieval-queries", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ddp", action="store_true", help="wrap the model in torch DistributedDataParallel instead of the flat-buffer all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

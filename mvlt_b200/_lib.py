@@ -65,7 +65,13 @@ def check(rc: int, what: str = ""):
         raise MvltError(f"{what} failed (rc={rc}): {msg}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> C.c_void_p:
+    """cudaStream_t of torch's current stream on the current device (the fast private accessor when torch has it)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -96,13 +102,20 @@ def account_gemm(flops: float, nbytes: float, what: str = ""):
 PROFILE = None        # when a dict: name -> list of (start_event, end_event) recorded around every call
 
 
+_FN = {}
+
+
 def call(name: str, *args, tag: str = None):
     """Call ``int mvlt_<name>(..., void* stream)`` with the current torch stream appended."""
     global LAUNCHES
-    fn = getattr(load(), "mvlt_" + name)
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(load(), "mvlt_" + name)
     LAUNCHES += 1
     if PROFILE is None:
-        check(fn(*args, stream_ptr()), "mvlt_" + name)
+        rc = fn(*args, stream_ptr())
+        if rc != 0:
+            check(rc, "mvlt_" + name)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

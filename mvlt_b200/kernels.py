@@ -38,18 +38,9 @@ def _operand(t: torch.Tensor, name: str):
     return mn, ld, bs, st
 
 
-def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 1.0,
-         bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, preact_out: Optional[torch.Tensor] = None,
-         aux: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-         rowscale: Optional[torch.Tensor] = None, rows_per_scale: int = 0, atomic_add: bool = False,
-         split_k: int = 0, block_n: int = 0, rowsum: Optional[torch.Tensor] = None,
-         impl: str = "tcgen05") -> torch.Tensor:
-    """out[..., M, N] = epilogue(alpha * a[..., M, K] @ b[..., N, K]^T)   (see csrc/gemm_desc.h).
-
-    ``a``/``b`` may be arbitrary 2-4 D views with one unit stride among the last two dims (K-major or
-    MN-major); leading dims are batch dims (broadcast with stride 0 / size 1 allowed).
-    """
-    require_cuda(a, b, out)
+def _build_gemm_desc(a, b, out, alpha, bias, act, preact_out, aux, residual, rowscale, rows_per_scale, atomic_add, split_k,
+                     block_n, rowsum):
+    """Validate one GEMM signature and build its descriptor (everything except the device pointers)."""
     a_mn, lda, abs_, ast = _operand(a, "a")
     b_mn, ldb, bbs, bst = _operand(b, "b")
     M, K = a.shape[-2], a.shape[-1]
@@ -70,17 +61,18 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
                 if bs[i] != 1:
                     raise _lib.MvltError(f"gemm batch mismatch on {nm}: {bs} vs out {obs}")
                 st[i] = 0
+    if rowsum is not None and (rowsum.dtype != F32 or rowsum.numel() != M or not rowsum.is_contiguous()):
+        raise _lib.MvltError("gemm rowsum must be contiguous fp32 [M]")
+    if out.dtype not in (F32, BF16):
+        raise _lib.MvltError(f"gemm out dtype {out.dtype} unsupported")
+    if bias is not None and (bias.dtype != F32 or bias.numel() != N):
+        raise _lib.MvltError("gemm bias must be fp32 [N]")
+    if residual is not None and (residual.dtype != F32 or residual.stride() != out.stride()):
+        raise _lib.MvltError("gemm residual must be fp32 with out's strides")
+    for t in (aux, preact_out):
+        if t is not None and (t.dtype != BF16 or t.stride() != out.stride()):
+            raise _lib.MvltError("gemm aux/preact must be bf16 with out's strides")
     d = GemmDesc()
-    d.A, d.B, d.D = a.data_ptr(), b.data_ptr(), out.data_ptr()
-    d.D2 = preact_out.data_ptr() if preact_out is not None else None
-    d.bias = bias.data_ptr() if bias is not None else None
-    d.aux = aux.data_ptr() if aux is not None else None
-    d.residual = residual.data_ptr() if residual is not None else None
-    d.rowscale = rowscale.data_ptr() if rowscale is not None else None
-    if rowsum is not None:      # rowsum[m] += alpha * sum_k a[m, k]  (fp32 atomics; the bias gradient of a dW GEMM)
-        if rowsum.dtype != F32 or rowsum.numel() != M or not rowsum.is_contiguous():
-            raise _lib.MvltError("gemm rowsum must be contiguous fp32 [M]")
-        d.rowsum = rowsum.data_ptr()
     d.M, d.N, d.K = M, N, K
     d.a_mn, d.b_mn = a_mn, b_mn
     d.lda, d.ldb, d.ldd = lda, ldb, out.stride(-2) if M > 1 else max(out.stride(-2), N)
@@ -90,30 +82,67 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
     d.sD1, d.sD2 = ost
     d.alpha = alpha
     d.act = act
-    if out.dtype == F32:
-        d.out_f32 = 1
-    elif out.dtype == BF16:
-        d.out_f32 = 0
-    else:
-        raise _lib.MvltError(f"gemm out dtype {out.dtype} unsupported")
+    d.out_f32 = 1 if out.dtype == F32 else 0
     d.atomic_add = 1 if atomic_add else 0
     d.rows_per_scale = rows_per_scale
     d.split_k = split_k
     d.block_n = block_n
-    if bias is not None and (bias.dtype != F32 or bias.numel() != N):
-        raise _lib.MvltError("gemm bias must be fp32 [N]")
-    if residual is not None and (residual.dtype != F32 or residual.stride() != out.stride()):
-        raise _lib.MvltError("gemm residual must be fp32 with out's strides")
-    for t in (aux, preact_out):
-        if t is not None and (t.dtype != BF16 or t.stride() != out.stride()):
-            raise _lib.MvltError("gemm aux/preact must be bf16 with out's strides")
+    nb = b1 * b2
+    extra = sum(M * N * nb * t.element_size() for t in (aux, preact_out, residual) if t is not None)
+    acct = (2.0 * M * N * K * nb, (M * K + N * K) * 2.0 * nb + M * N * nb * out.element_size() + extra,
+            f"gemm M={M} N={N} K={K} b={nb} amn={a_mn} bmn={b_mn} out={'f32' if out.dtype == F32 else 'bf16'} act={act} "
+            f"res={int(residual is not None)} atomic={int(atomic_add)} split={split_k} rowsum={int(rowsum is not None)}")
+    return d, C.byref(d), acct
+
+
+_GEMM_CACHE = {}
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 1.0,
+         bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, preact_out: Optional[torch.Tensor] = None,
+         aux: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         rowscale: Optional[torch.Tensor] = None, rows_per_scale: int = 0, atomic_add: bool = False,
+         split_k: int = 0, block_n: int = 0, rowsum: Optional[torch.Tensor] = None,
+         impl: str = "tcgen05") -> torch.Tensor:
+    """out[..., M, N] = epilogue(alpha * a[..., M, K] @ b[..., N, K]^T)   (see csrc/gemm_desc.h).
+
+    ``a``/``b`` may be arbitrary 2-4 D views with one unit stride among the last two dims (K-major or
+    MN-major); leading dims are batch dims (broadcast with stride 0 / size 1 allowed).
+
+    A training step repeats the same ~250 GEMM signatures every iteration: the validated descriptor of each signature
+    (geometry, strides, dtypes, epilogue options) is cached and only its device pointers are refreshed per call, which
+    keeps the host-side cost of a launch to a few microseconds.
+    """
+    if not (a.is_cuda and b.is_cuda and out.is_cuda):
+        raise _lib.MvltError("mvlt_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
+    key = (a.shape, a.stride(), b.shape, b.stride(), out.shape, out.stride(), a.dtype, b.dtype, out.dtype, alpha, act,
+           rows_per_scale, atomic_add, split_k, block_n,
+           None if bias is None else (bias.dtype, bias.shape), None if preact_out is None else (preact_out.dtype, preact_out.stride()),
+           None if aux is None else (aux.dtype, aux.stride()), None if residual is None else (residual.dtype, residual.stride()),
+           rowscale is None, None if rowsum is None else (rowsum.dtype, rowsum.shape, rowsum.stride()))
+    ent = _GEMM_CACHE.get(key)
+    if ent is None:
+        for t in (bias, preact_out, aux, residual, rowscale, rowsum):
+            if t is not None and not t.is_cuda:
+                raise _lib.MvltError("mvlt_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
+        ent = _build_gemm_desc(a, b, out, alpha, bias, act, preact_out, aux, residual, rowscale, rows_per_scale, atomic_add,
+                               split_k, block_n, rowsum)
+        if len(_GEMM_CACHE) > 4096:
+            _GEMM_CACHE.clear()
+        _GEMM_CACHE[key] = ent
+    d, ref, acct = ent
+    d.A = a.data_ptr()
+    d.B = b.data_ptr()
+    d.D = out.data_ptr()
+    d.D2 = None if preact_out is None else preact_out.data_ptr()
+    d.bias = None if bias is None else bias.data_ptr()
+    d.aux = None if aux is None else aux.data_ptr()
+    d.residual = None if residual is None else residual.data_ptr()
+    d.rowscale = None if rowscale is None else rowscale.data_ptr()
+    d.rowsum = None if rowsum is None else rowsum.data_ptr()
     if _lib.PROFILE is not None or _lib.GEMM_LOG is not None:
-        nb = b1 * b2
-        extra = sum(M * N * nb * t.element_size() for t in (aux, preact_out, residual) if t is not None)
-        _lib.account_gemm(2.0 * M * N * K * nb, (M * K + N * K) * 2.0 * nb + M * N * nb * out.element_size() + extra,
-                          f"gemm M={M} N={N} K={K} b={nb} amn={a_mn} bmn={b_mn} out={'f32' if out.dtype == F32 else 'bf16'} act={act} "
-                          f"res={int(residual is not None)} atomic={int(atomic_add)} split={split_k} rowsum={int(rowsum is not None)}")
-    call("gemm" if impl == "tcgen05" else "gemm_ref", C.byref(d))
+        _lib.account_gemm(*acct)
+    call("gemm" if impl == "tcgen05" else "gemm_ref", ref)
     return out
 
 

@@ -115,8 +115,29 @@ class _PVLTFunction(torch.autograd.Function):
         else:
             eng_backward_losses(eng, saved, gouts[0], G)
         ctx.saved = None
+        sync = model.__dict__.get("_grad_sync")
+        if sync is not None:
+            # data parallelism without DistributedDataParallel's bucket copies: every gradient of the step already lives
+            # in ONE flat fp32 buffer, so the whole exchange is a single NCCL all-reduce (average) over NVLink
+            allreduce_flat_(G["__flat__"], sync)
         names = model._param_names
         return (None, None, None, None, None) + tuple(G[n] for n in names)
+
+
+def allreduce_flat_(flat, group=None):
+    """In-place average of a flat gradient buffer over the data-parallel group (the role DDP's reducer plays at
+    /root/reference/main_vl.py:297-299)."""
+    import torch.distributed as dist
+    grp = None if group is True else group
+    world = dist.get_world_size(grp)
+    if world == 1:
+        return flat
+    if dist.get_backend(grp) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=grp)
+    else:   # gloo (CPU tests) has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp)
+        flat.div_(world)
+    return flat
 
 
 def _heads_common_fwd(eng, enc, B):
@@ -340,6 +361,7 @@ class PyramidVisionLanguageTransformer(nn.Module):
             self.t2i_head = ITGHead(embed_dims=embed_dims, channel=64)
         self.apply(self._init_weights)
         self.__dict__["_eng"] = None
+        self.__dict__["_grad_sync"] = None
 
     def _init_weights(self, m):   # pvlt.py:282-289
         if isinstance(m, nn.Linear):
@@ -365,6 +387,19 @@ class PyramidVisionLanguageTransformer(nn.Module):
             self.__dict__["_eng"] = eng
             self.__dict__["_param_names"] = list(params.keys())
         return eng
+
+    def enable_grad_sync(self, group=True, broadcast_from: Optional[int] = 0):
+        """Data-parallel training without a DistributedDataParallel wrapper: the backward pass all-reduces (averages) its
+        single flat gradient buffer over ``group`` (``True`` = the default process group) before handing the per-parameter
+        views to autograd. ``broadcast_from``: rank whose parameters / buffers are copied to every rank first (DDP's
+        construction-time broadcast); ``None`` skips it. ``enable_grad_sync(None)`` turns the exchange off."""
+        import torch.distributed as dist
+        self.__dict__["_grad_sync"] = group
+        if group is not None and broadcast_from is not None:
+            grp = None if group is True else group
+            for t in list(self.parameters()) + list(self.buffers()):
+                dist.broadcast(t.data, src=broadcast_from, group=grp)
+        return self
 
     def state_dict(self, *args, **kwargs):
         eng = self.__dict__.get("_eng")

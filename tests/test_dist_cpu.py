@@ -71,3 +71,36 @@ def test_shard_bounds_cover(world):
         assert hi - lo <= per
         seen += list(range(lo, hi))
     assert seen == list(range(n))
+
+
+def _sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mvlt_b200.libs.pvlt import allreduce_flat_
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)      # this rank's "flat gradient buffer"
+        views = [flat[:4].view(2, 2), flat[4:]]                         # per-parameter views handed to autograd
+        allreduce_flat_(flat, True)
+        q.put((rank, flat.tolist(), views[0].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    """The data-parallel exchange of the training step: ONE all-reduce (average) over the flat gradient buffer; the
+    per-parameter views alias it, so they see the reduced values."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [1.5 * i for i in range(10)]
+    for _, flat, v0 in res:
+        assert flat == pytest.approx(want)
+        assert v0 == [[0.0, 1.5], [3.0, 4.5]]
