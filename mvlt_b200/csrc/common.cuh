@@ -164,7 +164,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 // gelu_erf(x) and gelu_erf'(x) for two values at once. Same Abramowitz-Stegun 7.1.26 erfc tail as gelu_and_grad
 // (|error| <= 1.5e-7) but evaluated with packed fp32x2 FMAs and approximate MUFU ex2 / rcp:
-// 14 packed FP ops + 4 MUFU + ~8 ALU per PAIR instead of ~38 instructions per ELEMENT.
+// 15 packed FP ops + 4 MUFU + 2 LOP3 per PAIR instead of ~38 instructions per ELEMENT.
 __device__ __forceinline__ void gelu_and_grad2(f32x2_t x, f32x2_t& g, f32x2_t& dg) {
   float x0, x1;
   f2_unpack(x, x0, x1);
@@ -183,11 +183,13 @@ __device__ __forceinline__ void gelu_and_grad2(f32x2_t x, f32x2_t& g, f32x2_t& d
   poly = f2_fma(poly, t, f2_splat(-0.142248368f));
   poly = f2_fma(poly, t, f2_splat(0.127414796f));
   const f32x2_t h = f2_mul(f2_mul(poly, t), e);                                  // 0.5 * erfc(|x|/sqrt(2))
-  const f32x2_t omh = f2_fma(h, f2_splat(-1.0f), f2_splat(1.0f));                // 1 - h
-  float h0, h1, m0, m1;
-  f2_unpack(h, h0, h1);
-  f2_unpack(omh, m0, m1);
-  const f32x2_t cdf = f2_pack(x0 >= 0.f ? m0 : h0, x1 >= 0.f ? m1 : h1);
+  // Phi(x) = 0.5 + sign(x) * (0.5 - h): the sign is OR-ed in (0.5 - h >= 0), no compare / select, no register shuffling
+  const f32x2_t q = f2_fma(h, f2_splat(-1.0f), f2_splat(0.5f));
+  float q0, q1;
+  f2_unpack(q, q0, q1);
+  q0 = __uint_as_float(__float_as_uint(q0) | (__float_as_uint(x0) & 0x80000000u));
+  q1 = __uint_as_float(__float_as_uint(q1) | (__float_as_uint(x1) & 0x80000000u));
+  const f32x2_t cdf = f2_add(f2_pack(q0, q1), f2_splat(0.5f));
   g = f2_mul(x, cdf);
   dg = f2_fma(f2_mul(x, e), f2_splat(0.39894228040143267794f), cdf);
 }
