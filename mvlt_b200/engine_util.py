@@ -1,4 +1,5 @@
 """Launch heuristics shared by the hand-scheduled engine modules."""
+from functools import lru_cache
 
 
 def pick_block_n(N, b_mn=True):
@@ -16,6 +17,7 @@ def pick_block_n(N, b_mn=True):
     return 128 if b_mn else 256
 
 
+@lru_cache(maxsize=4096)
 def split_k(M, N, K, b_mn=True):
     """split-K factor for GEMMs with a small M x N output and a long K (dW = dy^T x, the vocabulary dH): the persistent
     grid runs ceil(tiles * s / 148) waves of ceil(kb / s) k-blocks each (+ ~8 k-blocks worth of per-tile prologue /

@@ -373,17 +373,46 @@ class PyramidVisionLanguageTransformer(nn.Module):
             nn.init.constant_(m.weight, 1.0)
 
     # -- engine plumbing
+    def _params_list(self):
+        """Parameters in named_parameters() order. Walking the module tree costs ~1 ms of host time per call, so the list
+        is cached and revalidated against the modules' own parameter dicts only when a parameter object was replaced
+        (``_apply`` / ``load_state_dict(assign=True)`` / re-registration bump this through ``_eng = None`` or identity)."""
+        cached = self.__dict__.get("_plist")
+        if cached is not None:
+            owners, names, plist = cached
+            ok = True
+            for (mod, key), p in zip(owners, plist):
+                if mod._parameters.get(key) is not p:
+                    ok = False
+                    break
+            if ok:
+                return names, plist
+        owners, names, plist, seen = [], [], [], set()
+        for mname, mod in self.named_modules():
+            for key, p in mod._parameters.items():
+                if p is None or id(p) in seen:
+                    continue
+                seen.add(id(p))
+                owners.append((mod, key))
+                names.append((mname + "." if mname else "") + key)
+                plist.append(p)
+        assert names == [n for n, _ in self.named_parameters()]
+        self.__dict__["_plist"] = (owners, names, plist)
+        return names, plist
+
     def _engine(self) -> PVLTEngine:
         eng = self.__dict__.get("_eng")
-        params = dict(self.named_parameters())
-        dev = next(iter(params.values())).device
-        if eng is None or eng._device != dev or any(eng.P[n] is not p for n, p in params.items()):
+        names, plist = self._params_list()
+        dev = plist[0].device
+        if eng is None or eng._device != dev or eng._plist_id is not plist:
+            params = dict(zip(names, plist))
             if dev.type != "cuda":
                 raise MvltError("mvlt_b200 runs on CUDA (sm_100a) only: move the model with .to('cuda'); "
                                 "there is no CPU fallback")
             eng = PVLTEngine(params, dict(self.named_buffers()), self.depths, self.loss_type, self.T_num,
                              self.drop_path_rate, self.text_embeddings.dropout.p)
             eng._device = dev
+            eng._plist_id = plist
             self.__dict__["_eng"] = eng
             self.__dict__["_param_names"] = list(params.keys())
         return eng
@@ -409,6 +438,7 @@ class PyramidVisionLanguageTransformer(nn.Module):
 
     def _apply(self, fn, *a, **kw):
         self.__dict__["_eng"] = None
+        self.__dict__["_plist"] = None
         return super()._apply(fn, *a, **kw)
 
     # -- public API
@@ -421,7 +451,7 @@ class PyramidVisionLanguageTransformer(nn.Module):
         if fused:
             return self.forward_losses(input_images, input_ids, **fused)
         self._engine()
-        params = [p for _, p in self.named_parameters()]
+        params = self._params_list()[1]
         mlm, itm, sup, sub, t2i = _PVLTFunction.apply(self, ("logits", torch.is_grad_enabled()), None, input_images,
                                                             input_ids, *params)
         lt = self.loss_type
@@ -448,7 +478,7 @@ class PyramidVisionLanguageTransformer(nn.Module):
                        mlm_count: Optional[int] = None, only=None):
         """Fused step: heads + losses of engine_grid_masking.py:81-102. Returns (total_loss, stats[8])."""
         self._engine()
-        params = [p for _, p in self.named_parameters()]
+        params = self._params_list()[1]
         batch = dict(mlm_labels=mlm_labels, itm_labels=itm_labels, sup_cls_labels=sup_cls_labels,
                      sub_cls_labels=sub_cls_labels, target_images=target_images, weights=weights or {},
                      mlm_count=mlm_count, only=only)
