@@ -3,6 +3,11 @@
 // sliding-window quirk at :246) and :176-177 (masked_fill_ with 1e-6). Integer kernel: numpy's legacy
 // np.random.seed(int) + list shuffle (= Fisher-Yates from the top with masked-rejection random_interval)
 // are restated here; one warp per sample keeps the 624-word generator state in shared memory.
+//
+// BERT token masking (15 % of the word pieces: 80 % -> [MASK], 10 % -> random vocabulary entry, 10 % kept; labels = the
+// original ids, -1 elsewhere) is the same kind of integer kernel: /root/reference/mcloader/fashion_gen.py:383-409
+// (random_masking_features) drives CPython's `random` module, i.e. MT19937 seeded through init_by_array, random() as a
+// 53-bit double from two draws and choice() as getrandbits rejection sampling; restated bit for bit per sample seed.
 #include "common.cuh"
 
 namespace {
@@ -43,6 +48,66 @@ __device__ void mt_shuffle(MT& s, uint8_t* v, int n) {
   for (int i = n - 1; i >= 1; --i) {
     const uint32_t j = mt_interval(s, (uint32_t)i);
     const uint8_t t = v[i]; v[i] = v[j]; v[j] = t;
+  }
+}
+
+// CPython random.seed(int) for 0 <= seed < 2^32: init_by_array(key = [seed])  (Modules/_randommodule.c)
+__device__ void mt_seed_py(MT& s, uint32_t seed) {
+  mt_seed(s, 19650218u);
+  uint32_t* mt = s.mt;
+  int i = 1;
+  for (int k = 624; k; --k) {           // key_length = 1: init_key[j] + j == seed + 0 every round
+    mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + seed;
+    if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+  }
+  for (int k = 623; k; --k) {
+    mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+    if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+  }
+  mt[0] = 0x80000000u;
+  s.idx = 624;
+}
+// random.random(): 53-bit double from two 32-bit draws
+__device__ double mt_random_py(MT& s) {
+  const uint32_t a = mt_next(s) >> 5, b = mt_next(s) >> 6;
+  return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+// random.choice(seq) index: _randbelow(n) = getrandbits(n.bit_length()) with rejection
+__device__ uint32_t mt_randbelow_py(MT& s, uint32_t n) {
+  const int k = 32 - __clz(n);
+  uint32_t r = mt_next(s) >> (32 - k);
+  while (r >= n) r = mt_next(s) >> (32 - k);
+  return r;
+}
+
+// one warp per sample; lane 0 walks the generator over the word pieces between [CLS] and [SEP]
+__global__ void __launch_bounds__(32) token_mask_kernel(const uint32_t* __restrict__ seeds, const long long* __restrict__ ori,
+                                                        long long* __restrict__ ids, long long* __restrict__ labels, int B, int T,
+                                                        int sep_id, int mask_id, int vocab, double rate) {
+  __shared__ uint32_t state[624];
+  const int b = blockIdx.x;
+  const long long* o = ori + (long long)b * T;
+  long long* x = ids + (long long)b * T;
+  long long* l = labels + (long long)b * T;
+  for (int i = threadIdx.x; i < T; i += 32) {
+    x[i] = o[i];
+    l[i] = -1;
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    MT s{state, 624};
+    mt_seed_py(s, seeds[b]);
+    for (int i = 1; i < T; ++i) {
+      const long long tok = o[i];
+      if (tok == sep_id) break;                       // word pieces are positions 1 .. (first [SEP]) - 1
+      double prob = mt_random_py(s);
+      if (prob < rate) {
+        prob /= rate;
+        if (prob < 0.8) x[i] = mask_id;
+        else if (prob < 0.9) x[i] = (long long)mt_randbelow_py(s, (uint32_t)vocab);   // vocab.items() is in id order
+        l[i] = tok;
+      }
+    }
   }
 }
 
@@ -107,6 +172,16 @@ extern "C" int mvlt_grid_mask(const uint32_t* seeds_dev, uint8_t* grid_out, int 
   MVLT_CHECK_ARG(nw * nh <= MAX_PATCHES && nw <= MAX_NW, "grid_mask: too many patches");
   const int n_mask = (int)(mask_ratio * (double)(nw * nh));
   grid_mask_kernel<<<B, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(seeds_dev, grid_out, B, nw, nh, n_mask);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+// ori_ids / input_ids / labels: int64 [B, T]; row = [CLS] pieces... [SEP] [PAD]...; seeds: one CPython random.seed(int) per sample
+extern "C" int mvlt_token_mask(const uint32_t* seeds_dev, const long long* ori_ids, long long* input_ids, long long* labels, int B,
+                               int T, int sep_id, int mask_id, int vocab_size, double mask_rate, void* stream_) {
+  MVLT_CHECK_ARG(B > 0 && T > 1 && vocab_size > 0 && mask_rate > 0.0 && mask_rate <= 1.0, "token_mask: bad arguments");
+  token_mask_kernel<<<B, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(seeds_dev, ori_ids, input_ids, labels, B, T, sep_id,
+                                                                           mask_id, vocab_size, mask_rate);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

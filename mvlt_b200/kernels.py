@@ -369,6 +369,11 @@ def grid_mask(seeds_u32, grid_out, B, size_w, size_h, patch, ratio):
          C.c_double(ratio))
 
 
+def token_mask(seeds_u32, ori_ids, input_ids, labels, B, T, sep_id, mask_id, vocab_size, rate):
+    call("token_mask", ptr(seeds_u32), ptr(ori_ids), ptr(input_ids), ptr(labels), C.c_int(B), C.c_int(T), C.c_int(sep_id),
+         C.c_int(mask_id), C.c_int(vocab_size), C.c_double(rate))
+
+
 def masked_fill(img, grid, out, mask_out, B, Cc, H, W, patch, fill=1e-6):
     call("masked_fill", ptr(img), ptr(grid), ptr(out), ptr(mask_out), C.c_int(B), C.c_int(Cc), C.c_int(H),
          C.c_int(W), C.c_int(patch), C.c_float(fill))

@@ -1,4 +1,5 @@
-"""Random grid masking on the GPU, bit-exact against the reference's host implementation for a given seed.
+"""Random grid masking and BERT token masking on the GPU, bit-exact against the reference's host implementations for a
+given per-sample seed.
 
 Reference: /root/reference/mcloader/fashion_gen.py:225-254 (``generate_grid_mask``; note the sliding-window quirk at
 :246) and :176-177 (``masked_fill_`` with 1e-6). The reference draws from numpy's process-global legacy RNG inside
@@ -55,3 +56,29 @@ def generate_grid_mask(input_size=(352, 352), mask_ratio=0.75, patch_size=16, se
         seed = int(np.random.randint(0, 2 ** 32, dtype=np.uint64))
     grid = grid_mask_batch([seed], input_size, mask_ratio, patch_size)[0].cpu().numpy()
     return np.kron(grid, np.ones((patch_size, patch_size)))[None].astype(np.float64)
+
+
+def _seeds_u32(seeds, device):
+    if torch.is_tensor(seeds):
+        s = seeds.to(device=device, dtype=torch.int64)
+    else:
+        s = torch.tensor([int(v) & 0xFFFFFFFF for v in seeds], dtype=torch.int64, device=device)
+    return ((s & 0xFFFFFFFF).to(torch.uint32) if hasattr(torch, "uint32") else s.to(torch.int32)).contiguous()
+
+
+def mask_tokens_batch(seeds, ori_input_ids: torch.Tensor, mask_rate=0.15, sep_id=102, mask_id=103, vocab_size=30522):
+    """BERT word-piece masking of the reference's text pipeline on the device (mcloader/fashion_gen.py:383-409, called
+    from text_process :334): every word piece between [CLS] and [SEP] is selected with probability ``mask_rate``; a
+    selected piece becomes [MASK] (80 %), a uniformly random vocabulary id (10 %) or stays (10 %) and its original id is
+    the MLM label, all other positions get label -1. Sample b reproduces ``random.seed(seeds[b])`` followed by the
+    reference loop bit for bit (CPython MT19937 / random() / choice()).
+
+    ori_input_ids: int64 [B, T] rows ``[CLS] pieces... [SEP] [PAD]...``. Returns (input_ids, mlm_labels), int64 [B, T]."""
+    if not ori_input_ids.is_cuda or ori_input_ids.dtype != torch.int64 or ori_input_ids.dim() != 2:
+        raise MvltError("mask_tokens_batch expects a CUDA int64 [B, T] tensor")
+    ori = ori_input_ids.contiguous()
+    B, T = ori.shape
+    ids = torch.empty_like(ori)
+    labels = torch.empty_like(ori)
+    k.token_mask(_seeds_u32(seeds, ori.device), ori, ids, labels, B, T, sep_id, mask_id, vocab_size, float(mask_rate))
+    return ids, labels

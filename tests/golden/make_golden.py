@@ -5,6 +5,7 @@ Run in the build container only (the GPU box has no /root/reference):
 
 Writes
   tests/golden/grid_mask_golden.npz   reference generate_grid_mask under np.random.seed(s) for many seeds
+  tests/golden/token_mask_golden.npz  reference random_masking_features (BERT word-piece masking) under random.seed(s)
   tests/golden/pvlt_tiny_golden.npz   reference PVLT-tiny (libs/pvlt.py) outputs, losses and gradient summaries
                                       for oracle.make_state_dict(seed) weights and oracle.make_inputs batches
 
@@ -149,6 +150,48 @@ def golden_pvlt():
     np.savez_compressed(os.path.join(HERE, "pvlt_tiny_golden.npz"), **out)
 
 
+def golden_token_masks():
+    """Runs the reference's own ``random_masking_features`` (fashion_gen.py:383-409) on word-piece STRINGS with the
+    vendored BERT vocabulary under ``random.seed(s)``; records ids so that the fixture does not depend on the tokenizer."""
+    import collections
+    import random
+    src = open(os.path.join(REF, "mcloader", "fashion_gen.py")).read()
+    start = src.index("    def random_masking_features")
+    end = src.index("    def rgb_loader")
+    ns = {"random": random}
+    exec("class _Holder:\n" + src[start:end], ns)          # executes the reference text in place, nothing copied
+    fn = ns["_Holder"].random_masking_features
+    vocab = collections.OrderedDict()
+    with open(os.path.join(REF, "preweights", "bert-base-uncased-vocab.txt"), encoding="utf-8") as f:
+        for i, line in enumerate(f):
+            vocab[line.rstrip("\n")] = i
+    inv = list(vocab.keys())
+    assert len(vocab) == 30522 and vocab["[MASK]"] == 103 and vocab["[SEP]"] == 102 and vocab["[CLS]"] == 101
+
+    class _Tok:
+        pass
+    holder = types.SimpleNamespace(word_mask_rate=0.15, tokenizer=_Tok())
+    holder.tokenizer.vocab = vocab
+    T = 128
+    rs = np.random.RandomState(7)
+    seeds, ori, ids, labels = [], [], [], []
+    for s in list(range(48)) + [12345, 2 ** 31 - 1, 2 ** 32 - 1, 1000003 * 9 + 1]:
+        L = int(rs.randint(3, T - 1))                          # number of word pieces (max T - 2, text_process :326-328)
+        pieces = rs.randint(1000, 30522, size=L)
+        toks = [inv[i] for i in pieces]
+        random.seed(s)
+        out_toks, lab = fn(holder, list(toks))
+        row_ori = [101] + [int(i) for i in pieces] + [102] + [0] * (T - L - 2)
+        row_ids = [101] + [vocab[t] for t in out_toks] + [102] + [0] * (T - L - 2)
+        row_lab = [-1] + [int(v) for v in lab] + [-1] + [-1] * (T - L - 2)
+        seeds.append(s); ori.append(row_ori); ids.append(row_ids); labels.append(row_lab)
+    np.savez_compressed(os.path.join(HERE, "token_mask_golden.npz"), seeds=np.array(seeds, dtype=np.uint64),
+                        ori=np.array(ori, dtype=np.int64), ids=np.array(ids, dtype=np.int64),
+                        labels=np.array(labels, dtype=np.int64))
+    print("token_mask_golden.npz:", len(seeds), "samples,", int((np.array(labels) != -1).sum()), "labelled pieces")
+
+
 if __name__ == "__main__":
     golden_grid_masks()
+    golden_token_masks()
     golden_pvlt()

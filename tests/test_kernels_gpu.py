@@ -399,3 +399,30 @@ def test_patchify_nchw_full_image():
     ref = F.unfold(img, P, stride=P).permute(0, 2, 1).reshape(B * 4096, 48)
     assert torch.equal(pat[:, :48], ref.to(BF16))
     assert float(pat[:, 48:].abs().max()) == 0.0
+
+
+def test_token_mask_bit_exact_vs_oracle_and_reference_golden():
+    """Device BERT word-piece masking == CPython random-driven reference loop, per sample seed (integer path: bit-exact)."""
+    import os
+    import numpy as np
+    from mvlt_b200 import masking
+    from oracle import token_mask as tm
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "token_mask_golden.npz"))
+    ori = torch.from_numpy(g["ori"]).cuda()
+    ids, labels = masking.mask_tokens_batch([int(s) for s in g["seeds"]], ori)
+    assert torch.equal(ids.cpu(), torch.from_numpy(g["ids"])) and torch.equal(labels.cpu(), torch.from_numpy(g["labels"]))
+    # a full-size batch against the oracle: 512 samples, ragged lengths incl. the extremes (1 piece, 126 pieces)
+    rs = np.random.RandomState(3)
+    B, T = 512, 128
+    rows = np.zeros((B, T), dtype=np.int64)
+    for b in range(B):
+        L = [1, T - 2][b] if b < 2 else int(rs.randint(1, T - 1))
+        rows[b, 0], rows[b, 1:1 + L], rows[b, 1 + L] = 101, rs.randint(1000, 30522, size=L), 102
+    seeds = [masking.sample_seed(5, b) for b in range(B)]
+    ids, labels = masking.mask_tokens_batch(seeds, torch.from_numpy(rows).cuda())
+    ids, labels = ids.cpu().numpy(), labels.cpu().numpy()
+    for b in range(B):
+        i2, l2 = tm.mask_tokens(seeds[b], rows[b])
+        assert (ids[b] == i2).all() and (labels[b] == l2).all(), b
+    frac = (labels != -1).sum() / (rows[:, 1:] > 102).sum()
+    assert 0.13 < frac < 0.17

@@ -92,3 +92,17 @@ def test_scores_and_rank():
     lg[0, 2, 5] = 1
     assert O.compute_mlm_score(lg, torch.tensor([[-1, 3, 4, -1]])) == 0.5
     assert O.compute_psnr(torch.zeros(2, 2), torch.zeros(2, 2)) == 100
+
+
+def test_token_mask_oracle_matches_reference_golden():
+    """BERT word-piece masking (fashion_gen.py:383-409): oracle restatement on ids vs the reference method's own output."""
+    from oracle import token_mask as tm
+    g = np.load(os.path.join(GOLD, "token_mask_golden.npz"))
+    n_random = 0
+    for seed, ori, ids, labels in zip(g["seeds"], g["ori"], g["ids"], g["labels"]):
+        i2, l2 = tm.mask_tokens(int(seed), ori)
+        assert (i2 == ids).all() and (l2 == labels).all(), f"oracle differs at seed {seed}"
+        n_random += int(((ids != ori) & (ids != 103)).sum())
+    assert n_random > 10                                  # the random.choice branch is exercised by the fixture
+    lab = g["labels"]
+    assert (lab[:, 0] == -1).all() and ((lab == -1) | (lab == g["ori"])).all()
