@@ -37,11 +37,16 @@ class _Args:
     eval_retrieval_itr = False
 
 
-def test_train_and_eval_loops_run_and_learn():
+@pytest.mark.parametrize("own_optimizer", [False, True])
+def test_train_and_eval_loops_run_and_learn(own_optimizer):
     import engine_grid_masking as E
     m = _model(PRE, drop_path=0.0)
     m.text_embeddings.dropout.p = 0.0
-    opt = torch.optim.AdamW(m.parameters(), lr=2e-4)
+    if own_optimizer:     # the multi-tensor sm_100a AdamW with timm's no-decay grouping (main_vl.py:308)
+        from mvlt_b200.optim import AdamW, param_groups_no_decay
+        opt = AdamW(param_groups_no_decay(m, 0.01), lr=2e-4)
+    else:
+        opt = torch.optim.AdamW(m.parameters(), lr=2e-4)
     data = _loader(2, 8) * 6                        # 12 steps over two fixed batches: the loss must go down
     s0 = E.train_one_epoch_vl(m, None, data[:2], opt, torch.device("cuda"), 0, None, args=_Args())
     for ep in range(1, 5):
