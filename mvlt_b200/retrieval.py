@@ -61,7 +61,7 @@ def accuracy_at(ranks, ks=(1, 5, 10)):
     return {kk: float((r < kk).sum()) / max(r.numel(), 1) for kk in ks}
 
 
-def bench_sweep(dev, rank, world, n_query=1000, n_cand=101, queries_per_step=4, warmup=1, pool=512):
+def bench_sweep(dev, rank, world, n_query=1000, n_cand=101, queries_per_step=8, warmup=1, pool=512):
     """Synthetic TIR protocol: per query one id row repeated n_cand times against n_cand images drawn
     from a device-resident pool. Returns the JSON sub-object bench.py prints."""
     import mvlt_b200
