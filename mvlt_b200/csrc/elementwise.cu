@@ -4,6 +4,7 @@
 //
 // Reference ops replaced: the permute/reshape/contiguous copies around /root/reference/libs/pvlt.py:102-104,168,
 // 350-352, F.interpolate at :295-297, torch.cat/split at :107,:346 and autograd's bias/broadcast reductions.
+#include <string.h>
 #include "common.cuh"
 
 namespace {
@@ -517,6 +518,44 @@ extern "C" int mvlt_cast_conv_weight(const float* src, void* dst_bf16, int Co, i
 extern "C" int mvlt_cast_conv_weight_t(const float* src, void* dst_bf16, int Co, int Ci, int KK, void* stream_) {
   cast_conv_weight_t_kernel<<<cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), Co, Ci, KK);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+// ---- the same fold for up to 24 convolution weights in one launch (blockIdx.y = tensor) --------------------------
+struct UncastEntry {
+  const float* dwp;
+  float* dw;
+  int Co, Ci, KK, src_ld;
+};
+struct UncastBatch {
+  int n;
+  int pad;
+  UncastEntry t[24];
+};
+__global__ void uncast_conv_wgrad_multi_kernel(const UncastBatch b) {
+  const UncastEntry e = b.t[blockIdx.y];
+  const long long n = (long long)e.Co * e.Ci * e.KK;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % e.KK);
+    const int ci = (int)((i / e.KK) % e.Ci);
+    const int co = (int)(i / ((long long)e.Ci * e.KK));
+    e.dw[i] += e.dwp[(long long)co * e.src_ld + (long long)kk * e.Ci + ci];
+  }
+}
+// entries: host array of n records {const float* dwp; float* dw; int Co, Ci, KK, src_ld;} (32 bytes each), n <= 24
+extern "C" int mvlt_uncast_conv_wgrad_multi(const void* entries, int n, void* stream_) {
+  MVLT_CHECK_ARG(entries != nullptr && n > 0 && n <= 24, "uncast_conv_wgrad_multi: 1..24 tensors per launch");
+  UncastBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n = n;
+  memcpy(b.t, entries, (size_t)n * sizeof(UncastEntry));
+  long long mx = 0;
+  for (int i = 0; i < n; ++i) {
+    const long long e = (long long)b.t[i].Co * b.t[i].Ci * b.t[i].KK;
+    if (e > mx) mx = e;
+  }
+  dim3 grid((unsigned)cap_grid(mx, 256, 2), (unsigned)n);
+  uncast_conv_wgrad_multi_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(b);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -278,11 +278,7 @@ class PVLTEngine:
 
     def _conv_wgrad(self, G, name):
         """fp32 gradient buffer in the permuted [Co, kh*kw*Ci] layout; folded back into the master layout at the end."""
-        key = "__perm__" + name
-        if key not in G:
-            w = self.W[name]
-            G[key] = torch.zeros(w.shape, dtype=F32, device=w.device)
-        return G[key]
+        return G["__perm__" + name]
 
     # ------------------------------------------------------------------------------------------------
     # encoder
@@ -429,14 +425,11 @@ class PVLTEngine:
                                  G["text_embeddings.position_embeddings.weight"],
                                  G["text_embeddings.token_type_embeddings.weight"], G["text_embeddings.LayerNorm.weight"],
                                  G["text_embeddings.LayerNorm.bias"], B * T, T, ctx["p_drop"], ctx["seed"])
-        # fold the permuted conv-weight gradients back into the master [Co, Ci, kh, kw] layout
-        for key in [kk for kk in G if kk.startswith("__perm__")]:
-            name = key[len("__perm__"):]
-            if name.startswith("t2i_head."):
-                continue
-            w = P[name]
-            KK = w.shape[2] * w.shape[3]
-            k.uncast_conv_wgrad(G[key], G[name], w.shape[0], w.shape[1], KK, G[key].shape[1])
+        # fold the permuted conv-weight gradients back into the master [Co, Ci, kh, kw] layout (one launch)
+        items = [(G[key], G[key[len("__perm__"):]]) for key in G
+                 if key.startswith("__perm__") and not key.startswith("__perm__t2i_head.")]
+        if items:
+            k.uncast_conv_wgrad_multi(items)
 
     # ------------------------------------------------------------------------------------------------
     # heads (pvlt.py:365-397)
@@ -553,4 +546,15 @@ class PVLTEngine:
             G[name] = flat[off:off + p.numel()].view(p.shape)
             off += (p.numel() + 3) // 4 * 4
         G["__flat__"] = flat
+        # convolution weights accumulate their gradient in the GEMM-friendly permuted layout [Co, kh*kw*Ci]: one zeroed
+        # arena for all of them, folded back into the master [Co, Ci, kh, kw] views by one launch per head / encoder
+        convs = [(name, p) for name, p in self.P.items() if p.dim() == 4]
+        ptotal = sum((p.numel() + 3) // 4 * 4 for _, p in convs)
+        if ptotal:
+            arena = torch.zeros(ptotal, dtype=F32, device=dev)
+            off = 0
+            for name, p in convs:
+                co, ci, kh, kw = p.shape
+                G["__perm__" + name] = arena[off:off + p.numel()].view(co, kh * kw * ci)
+                off += (p.numel() + 3) // 4 * 4
         return G

@@ -312,6 +312,22 @@ def uncast_conv_wgrad(dwp, dw, Co, Ci, KK, src_ld):
     call("uncast_conv_wgrad", ptr(dwp), ptr(dw), C.c_int(Co), C.c_int(Ci), C.c_int(KK), C.c_int(src_ld))
 
 
+def uncast_conv_wgrad_multi(items):
+    """items: [(dwp fp32 [Co, KK*Ci], dw fp32 [Co, Ci, kh, kw]), ...]: dw[co,ci,kk] += dwp[co,kk,ci] for every pair, one
+    launch per 24 tensors."""
+    import struct
+    for i in range(0, len(items), 24):
+        chunk = items[i:i + 24]
+        buf = bytearray()
+        for dwp, dw in chunk:
+            Co, Ci = dw.shape[0], dw.shape[1]
+            KK = dw.shape[2] * dw.shape[3]
+            if dwp.dtype != F32 or dw.dtype != F32 or dwp.shape != (Co, KK * Ci) or not dw.is_contiguous() or dwp.stride(1) != 1:
+                raise _lib.MvltError("uncast_conv_wgrad_multi: bad gradient buffers")
+            buf += struct.pack("<QQiiii", dwp.data_ptr(), dw.data_ptr(), Co, Ci, KK, dwp.stride(0))
+        call("uncast_conv_wgrad_multi", (C.c_char * len(buf)).from_buffer(buf), C.c_int(len(chunk)))
+
+
 def bert_embed_fwd(ids, word, pos, typ, gamma, beta, out, mean, rstd, rows, T, eps, p_drop, seed):
     call("bert_embed_fwd", ptr(ids), ptr(word), ptr(pos), ptr(typ), ptr(gamma), ptr(beta), ptr(out), ptr(mean),
          ptr(rstd), C.c_int(rows), C.c_int(T), C.c_float(eps), C.c_float(p_drop), C.c_ulonglong(seed))

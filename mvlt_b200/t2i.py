@@ -25,6 +25,16 @@ class T2IHead:
         self.e = engine
         self.W = {}
         self.nbt_pending = {}
+        self._arena, self._arena_used = None, 0
+
+    def _scratch(self, dev):
+        """[2, 192] fp32 zeros for one unit's BatchNorm sums, carved from an arena that is zeroed once per pass."""
+        if self._arena is None or self._arena_used >= self._arena.shape[0]:
+            self._arena = k.zeros((len(UNITS), 2, 3 * CH), F32, dev)
+            self._arena_used = 0
+        t = self._arena[self._arena_used]
+        self._arena_used += 1
+        return t
 
     def sync_buffers(self):
         """BatchNorm's num_batches_tracked is bookkeeping only (momentum is fixed): counted on the host and written
@@ -60,7 +70,7 @@ class T2IHead:
             src, batch_stride, pix_stride = xb, H * W * Ci, Ci
         y = torch.empty((rows, Co), dtype=BF16, device=dev)
         k.conv3x3_gemm(src, B, H, W, Ci, pix_stride, batch_stride, Wp, y)
-        st = k.zeros((2, Co), F32, dev)
+        st = self._scratch(dev)
         if training:
             k.bn_stats(y, rows, Co, st[0], st[1])
         aff = torch.empty((4, Co), dtype=F32, device=dev)  # scale, shift, mean, invstd
@@ -83,14 +93,12 @@ class T2IHead:
         dev = dout.device
         aff = c["aff"]
         dy = torch.empty((rows, Co), dtype=BF16, device=dev)
-        red = k.zeros((2, Co), F32, dev)
+        red = self._scratch(dev)
         # aff[0] = gamma * invstd is exactly the leading factor of the BatchNorm backward formula
         k.bn_bwd(dout, c["y"], aff[0], aff[2], aff[3], red[0], red[1], dy, rows, Co, c["training"])
         k.copy_rows(red[0:1], G[pfx + ".1.bias"].view(1, Co), 1, Co, accumulate=True)
         k.copy_rows(red[1:2], G[pfx + ".1.weight"].view(1, Co), 1, Co, accumulate=True)
         key = "__perm__" + pfx + ".0.weight"
-        if key not in G:
-            G[key] = k.zeros(tuple(Wp.shape), F32, dev)
         k.conv3x3_wgrad(dy, c["x"], B, H, W, Ci, c["xs"][1], c["xs"][0], G[key], split_k=_split_k(Co, 9 * Ci, rows))
         if dst is not None:
             Wt = self.W[pfx + ".0.weight^T"]
@@ -208,9 +216,6 @@ class T2IHead:
         self._convbn_bwd("reduction2", g_mid, c["r2"], G, dfeat3, Hm * Wm * Cm, Cm)
         dfeat2 = torch.empty((B, Hl * Wl, Cl), dtype=F32, device=dev)
         self._convbn_bwd("reduction1", g_low, c["r1"], G, dfeat2, Hl * Wl * Cl, Cl)
-        # fold the permuted 3x3 weight gradients back to [Co, Ci, 3, 3]
-        for u in UNITS:
-            name = f"t2i_head.{u}.0.weight"
-            w = P[name]
-            k.uncast_conv_wgrad(G["__perm__" + name], G[name], w.shape[0], w.shape[1], 9, 9 * w.shape[1])
+        # fold the permuted 3x3 weight gradients back to [Co, Ci, 3, 3] (one launch for the eleven units)
+        k.uncast_conv_wgrad_multi([(G["__perm__t2i_head.%s.0.weight" % u], G["t2i_head.%s.0.weight" % u]) for u in UNITS])
         return dfeat2, dfeat3
