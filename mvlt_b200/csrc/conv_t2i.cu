@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restri
                                                            float* __restrict__ loss_sum, float* __restrict__ total_sum,
                                                            float loss_scale, float grad_scale, const float* __restrict__ gscale,
                                                            int B, int h, int w, int S, int mode, int want_grad) {
-  extern __shared__ float sh[];  // g[S][W] | gx[S][w] | 32 for reductions
+  extern __shared__ float sh[];  // g[S][W] | gx[S][w] | 32 for reductions | lx[W] | ly[S] | x0[W] (int) | y0[S] (int)
   const int H = h * S, W = w * S;
   const int bands = H / S;  // one band = S output rows => touches at most score rows ybase .. ybase+2
   const int band = blockIdx.x % bands;
@@ -472,22 +472,40 @@ __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restri
   const int b = blockIdx.x / (bands * 3);
   float* gs = sh;             // [S][W]
   float* gx = sh + S * W;     // [S][w]
-  float* red = gx + S * w;
+  float* red = gx + S * w;    // [32]
+  float* lxs = red + 32;      // [W]  interpolation weight of output column X
+  float* lys = lxs + W;       // [S]
+  int* x0s = reinterpret_cast<int*>(lys + S);   // [W]  left source column of output column X
+  int* y0s = x0s + W;                           // [S]
+  // the source index / weight of every output column and of the band's rows, computed once per block
+  for (int X = threadIdx.x; X < W; X += blockDim.x) {
+    int x0, x1;
+    float lx;
+    ac_index(X, w, W, x0, x1, lx);
+    x0s[X] = x0;
+    lxs[X] = lx;
+  }
+  for (int yy = threadIdx.x; yy < S; yy += blockDim.x) {
+    int y0, y1;
+    float ly;
+    ac_index(band * S + yy, h, H, y0, y1, ly);
+    y0s[yy] = y0;
+    lys[yy] = ly;
+  }
+  __syncthreads();
   const float* sb = score + (long long)b * h * w * 3 + c;
   const float g_mul = grad_scale * (gscale ? *gscale : 1.f);
-  int ybase, ytmp;
-  float ltmp;
-  ac_index(band * S, h, H, ybase, ytmp, ltmp);
+  const int ybase = y0s[0];
   float lsum = 0.f;
   for (int e = threadIdx.x; e < S * W; e += blockDim.x) {
-    const int Y = band * S + e / W, X = e % W;
+    const int yy = e / W, X = e % W;
+    const int Y = band * S + yy;
     const long long off = (((long long)b * 3 + c) * H + Y) * W + X;
     float g;
     if (mode == 1) {
-      int y0, y1, x0, x1;
-      float ly, lx;
-      ac_index(Y, h, H, y0, y1, ly);
-      ac_index(X, w, W, x0, x1, lx);
+      const int y0 = y0s[yy], x0 = x0s[X];
+      const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+      const float ly = lys[yy], lx = lxs[X];
       const float v00 = sb[(y0 * w + x0) * 3], v01 = sb[(y0 * w + x1) * 3], v10 = sb[(y1 * w + x0) * 3], v11 = sb[(y1 * w + x1) * 3];
       const float pred = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
       const float d = pred - target[off];
@@ -517,9 +535,9 @@ __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restri
     Xhi = min(Xhi, W - 1);
     float a = 0.f;
     for (int X = Xlo; X <= Xhi; ++X) {
-      int x0, x1;
-      float lx;
-      ac_index(X, w, W, x0, x1, lx);
+      const int x0 = x0s[X];
+      const int x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+      const float lx = lxs[X];
       float wx = 0.f;
       if (x0 == x) wx += 1.f - lx;
       if (x1 == x) wx += lx;
@@ -535,9 +553,9 @@ __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restri
     if (y >= h) continue;
     float a = 0.f;
     for (int yy = 0; yy < S; ++yy) {
-      int y0, y1;
-      float ly;
-      ac_index(band * S + yy, h, H, y0, y1, ly);
+      const int y0 = y0s[yy];
+      const int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
+      const float ly = lys[yy];
       float wy = 0.f;
       if (y0 == y) wy += 1.f - ly;
       if (y1 == y) wy += ly;
@@ -712,9 +730,9 @@ extern "C" int mvlt_upsample8_fwd(const float* score, float* out, int B, int h, 
 extern "C" int mvlt_t2i_up_loss(const float* score, const float* target, const float* dpred, float* dscore, float* loss_sum,
                                 float* total_sum, float loss_scale, float grad_scale, const float* gscale_dev, int B, int h, int w,
                                 int S, int mode, int want_grad, void* stream_) {
-  MVLT_CHECK_ARG(S >= 2 && (size_t)(S * w * S + S * w + 32) * sizeof(float) <= 48 * 1024, "t2i_up_loss: bad geometry");
+  const size_t smem = (size_t)(S * w * S + S * w + 32 + 2 * (w * S + S)) * sizeof(float);
+  MVLT_CHECK_ARG(S >= 2 && smem <= 48 * 1024, "t2i_up_loss: bad geometry");
   const int blocks = B * 3 * h;
-  const size_t smem = (size_t)(S * w * S + S * w + 32) * sizeof(float);
   t2i_up8_loss_kernel<<<blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(
       score, target, dpred, dscore, loss_sum, total_sum, loss_scale, grad_scale, gscale_dev, B, h, w, S, mode, want_grad);
   MVLT_CHECK_LAUNCH();

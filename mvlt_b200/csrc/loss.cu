@@ -113,7 +113,20 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logit
   const T* row = logits + (long long)r * ld;
   float m = -INFINITY;
   int am = 0;
-  for (int c = threadIdx.x; c < n_cls; c += blockDim.x) {
+  // bf16 rows with a 16-byte aligned pitch (the 30522-wide vocabulary logits): 8 logits per 16-byte load
+  const bool vec8 = (sizeof(T) == 2) && ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int n8 = vec8 ? (n_cls >> 3) : 0;
+  for (int i = threadIdx.x; i < n8; i += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + 8 * i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      if (f.x > m) { m = f.x; am = 8 * i + 2 * j; }
+      if (f.y > m) { m = f.y; am = 8 * i + 2 * j + 1; }
+    }
+  }
+  for (int c = 8 * n8 + threadIdx.x; c < n_cls; c += blockDim.x) {
     const float v = ldf(row + c);
     if (v > m) { m = v; am = c; }
   }
@@ -143,7 +156,16 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logit
   am = shi[0];
   __syncthreads();
   float s = 0.f;
-  for (int c = threadIdx.x; c < n_cls; c += blockDim.x) s += __expf(ldf(row + c) - m);
+  for (int i = threadIdx.x; i < n8; i += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + 8 * i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      s += __expf(f.x - m) + __expf(f.y - m);
+    }
+  }
+  for (int c = 8 * n8 + threadIdx.x; c < n_cls; c += blockDim.x) s += __expf(ldf(row + c) - m);
   s = block_sum(s, sh);
   if (threadIdx.x == 0) {
     const float lse = m + logf(s);
@@ -171,7 +193,25 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ logit
   const float l = lse[r];
   const T* row = logits + (long long)r * ld;
   T* drow = dlogits + (long long)r * ldd;
-  for (int c = threadIdx.x; c < n_cls; c += blockDim.x) {
+  const bool vec8 = (sizeof(T) == 2) && ((ld & 7) == 0) && ((ldd & 7) == 0) &&
+                    (((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0);
+  const int n8 = vec8 ? (n_cls >> 3) : 0;
+  for (int i = threadIdx.x; i < n8; i += blockDim.x) {
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (lab != ignore) {
+      u = *reinterpret_cast<const uint4*>(row + 8 * i);
+      uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        const int c = 8 * i + 2 * j;
+        w[j] = pack_bf16x2((__expf(f.x - l) - (c == lab ? 1.f : 0.f)) * g, (__expf(f.y - l) - (c + 1 == lab ? 1.f : 0.f)) * g);
+      }
+      u = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(drow + 8 * i) = u;
+  }
+  for (int c = 8 * n8 + threadIdx.x; c < n_cls; c += blockDim.x) {
     float v = 0.f;
     if (lab != ignore) v = (__expf(ldf(row + c) - l) - (c == lab ? 1.f : 0.f)) * g;
     if constexpr (sizeof(T) == 2) drow[c] = __float2bfloat16(v);
