@@ -10,6 +10,11 @@
 namespace {
 
 inline int cap_grid(long long work_items, int threads, int per_sm = 8) {
+  // the kernels decompose their linear work index with 32-bit arithmetic: refuse (grid 0 -> launch error) beyond that
+  if (work_items >= (1ll << 32)) {
+    mvlt_set_error("work size %lld exceeds the 32-bit index range of the elementwise kernels", work_items);
+    return 0;
+  }
   long long b = (work_items + threads - 1) / threads;
   const long long cap = (long long)mvlt_num_sms() * per_sm;
   if (b < 1) b = 1;
@@ -37,8 +42,8 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const T* __restrict__ sr
   const int c8n = C / 8;
   const long long total = (long long)B * H * W * 9 * c8n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % c8n);
-    long long t = i / c8n;
+    const int c8 = (int)((unsigned int)i % (unsigned int)c8n);
+    unsigned int t = (unsigned int)i / (unsigned int)c8n;
     const int tap = (int)(t % 9); t /= 9;
     const int x = (int)(t % W); t /= W;
     const int y = (int)(t % H);
@@ -59,8 +64,8 @@ __global__ void __launch_bounds__(256) col2im3x3_kernel(const __nv_bfloat16* __r
   const int c8n = C / 8;
   const long long total = (long long)B * H * W * c8n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % c8n);
-    long long t = i / c8n;
+    const int c8 = (int)((unsigned int)i % (unsigned int)c8n);
+    unsigned int t = (unsigned int)i / (unsigned int)c8n;
     const int x = (int)(t % W); t /= W;
     const int y = (int)(t % H);
     const int b = (int)(t / H);
@@ -178,8 +183,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
   const int c2n = C / 2;
   const long long total = rows * c2n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c2n) * 2;
-    const long long r = i / c2n;
+    const int c = (int)((unsigned int)i % (unsigned int)c2n) * 2;
+    const long long r = (long long)((unsigned int)i / (unsigned int)c2n);
     float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * C + c));
     v.x = v.x * scale[c] + shift[c];
     v.y = v.y * scale[c + 1] + shift[c + 1];
@@ -205,8 +210,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   const long long total = rows * c2n;
   const float inv_rows = 1.f / (float)rows;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c2n) * 2;
-    const long long r = i / c2n;
+    const int c = (int)((unsigned int)i % (unsigned int)c2n) * 2;
+    const long long r = (long long)((unsigned int)i / (unsigned int)c2n);
     const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + r * C + c));
     float o0, o1;
     if (training) {
@@ -230,8 +235,8 @@ __global__ void __launch_bounds__(256) ew_mul_kernel(const TA* __restrict__ a, i
   const int c2n = C / 2;
   const long long total = rows * c2n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c2n) * 2;
-    const long long r = i / c2n;
+    const int c = (int)((unsigned int)i % (unsigned int)c2n) * 2;
+    const long long r = (long long)((unsigned int)i / (unsigned int)c2n);
     float2 v;
     if constexpr (sizeof(TA) == 2) v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a + r * a_ld + a_coff + c));
     else v = *reinterpret_cast<const float2*>(a + r * a_ld + a_coff + c);
@@ -296,8 +301,8 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict
   const int H = 2 * h, W = 2 * w, c8n = C / 8;
   const long long total = (long long)B * H * W * c8n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c8n) * 8;
-    long long t = i / c8n;
+    const int c = (int)((unsigned int)i % (unsigned int)c8n) * 8;
+    unsigned int t = (unsigned int)i / (unsigned int)c8n;
     const int X = (int)(t % W); t /= W;
     const int Y = (int)(t % H);
     const int b = (int)(t / H);
@@ -327,8 +332,8 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
   const int H = 2 * h, W = 2 * w, c8n = C / 8;
   const long long total = (long long)B * h * w * c8n;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % c8n) * 8;
-    long long t = idx / c8n;
+    const int c = (int)((unsigned int)idx % (unsigned int)c8n) * 8;
+    unsigned int t = (unsigned int)idx / (unsigned int)c8n;
     const int j = (int)(t % w); t /= w;
     const int i = (int)(t % h);
     const int b = (int)(t / h);
@@ -439,8 +444,8 @@ __global__ void __launch_bounds__(256) upsample8_fwd_kernel(const float* __restr
   const int H = h * S, W = w * S;
   const long long total = (long long)B * 3 * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int X = (int)(i % W);
-    long long t = i / W;
+    const int X = (int)((unsigned int)i % (unsigned int)W);
+    unsigned int t = (unsigned int)i / (unsigned int)W;
     const int Y = (int)(t % H); t /= H;
     const int c = (int)(t % 3);
     const int b = (int)(t / 3);

@@ -10,6 +10,11 @@
 namespace {
 
 inline int cap_grid(long long work_items, int threads, int per_sm = 8) {
+  // the kernels decompose their linear work index with 32-bit arithmetic: refuse (grid 0 -> launch error) beyond that
+  if (work_items >= (1ll << 32)) {
+    mvlt_set_error("work size %lld exceeds the 32-bit index range of the elementwise kernels", work_items);
+    return 0;
+  }
   long long b = (work_items + threads - 1) / threads;
   const long long cap = (long long)mvlt_num_sms() * per_sm;
   if (b < 1) b = 1;
@@ -83,8 +88,8 @@ __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ src
   const long long total = (long long)B * H * W * c8n;
   const int ow = W / R, oh = H / R;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % c8n);
-    long long t = i / c8n;
+    const int c8 = (int)((unsigned int)i % (unsigned int)c8n);
+    unsigned int t = (unsigned int)i / (unsigned int)c8n;
     const int xw = (int)(t % W); t /= W;
     const int yh = (int)(t % H);
     const int b = (int)(t / H);
@@ -111,8 +116,8 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __
   const long long total = (long long)B * H * W * c8n;
   const int ow = W / R, oh = H / R;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % c8n);
-    long long t = i / c8n;
+    const int c8 = (int)((unsigned int)i % (unsigned int)c8n);
+    unsigned int t = (unsigned int)i / (unsigned int)c8n;
     const int xw = (int)(t % W); t /= W;
     const int yh = (int)(t % H);
     const int b = (int)(t / H);
@@ -157,7 +162,9 @@ __global__ void __launch_bounds__(256) patchify_nchw_kernel(const float* __restr
 // ---- generic strided row copy with dtype conversion ----------------------------------------------------------
 struct RowMap2 { int group, stride, offset; };
 __device__ __forceinline__ long long map_row2(const RowMap2& m, long long r) {
-  return (r / m.group) * m.stride + m.offset + (r % m.group);
+  if (m.stride == m.group && m.offset == 0) return r;   // identity map: no 64-bit division per element
+  const long long q = r / m.group;
+  return q * m.stride + m.offset + (r - q * m.group);
 }
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) copy_rows_kernel(const TI* __restrict__ src, RowMap2 sm, long long lds,
@@ -166,8 +173,8 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const TI* __restrict__ s
   const int c4n = C / 4;
   const long long total = rows * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c4n) * 4;
-    const long long r = i / c4n;
+    const int c = (int)((unsigned int)i % (unsigned int)c4n) * 4;
+    const long long r = (long long)((unsigned int)i / (unsigned int)c4n);
     const TI* s = src + map_row2(sm, r) * lds + c;
     TO* d = dst + map_row2(dm, r) * ldd + c;
     float4 v;

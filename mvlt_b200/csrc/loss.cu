@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   const int c4n = C / 4;
   const long long total = (long long)n_idx * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c4n) * 4;
-    const int r = (int)(i / c4n);
+    const int c = (int)((unsigned int)i % (unsigned int)c4n) * 4;
+    const int r = (int)((unsigned int)i / (unsigned int)c4n);
     const float4 v = *reinterpret_cast<const float4*>(src + map_row3(sm, idx[r]) * lds + c);
     if constexpr (sizeof(TO) == 2) {
       uint2 u;
@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const TI* __restrict_
   const int c4n = C / 4;
   const long long total = (long long)n_idx * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c4n) * 4;
-    const int r = (int)(i / c4n);
+    const int c = (int)((unsigned int)i % (unsigned int)c4n) * 4;
+    const int r = (int)((unsigned int)i / (unsigned int)c4n);
     float4 v;
     if constexpr (sizeof(TI) == 2) {
       const uint2 u = *reinterpret_cast<const uint2*>(src + (long long)r * C + c);
@@ -300,6 +300,11 @@ __global__ void __launch_bounds__(256) sq_diff_sum_kernel(const float* __restric
 }
 
 inline int cap_grid(long long work_items, int threads, int per_sm = 8) {
+  // the kernels decompose their linear work index with 32-bit arithmetic: refuse (grid 0 -> launch error) beyond that
+  if (work_items >= (1ll << 32)) {
+    mvlt_set_error("work size %lld exceeds the 32-bit index range of the elementwise kernels", work_items);
+    return 0;
+  }
   long long b = (work_items + threads - 1) / threads;
   const long long cap = (long long)mvlt_num_sms() * per_sm;
   if (b < 1) b = 1;

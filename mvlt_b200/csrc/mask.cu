@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(256) masked_fill_kernel(const float* __restric
   const long long total = (long long)B * Cc * H * w4;
   const int nw = W / P;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % w4) * 4;
-    long long t = i / w4;
+    const int x = (int)((unsigned int)i % (unsigned int)w4) * 4;
+    unsigned int t = (unsigned int)i / (unsigned int)w4;
     const int y = (int)(t % H); t /= H;
     const int c = (int)(t % Cc);
     const int b = (int)(t / Cc);
@@ -190,6 +190,7 @@ extern "C" int mvlt_masked_fill(const float* img, const uint8_t* grid, float* ou
                                 int W, int patch, float fill, void* stream_) {
   MVLT_CHECK_ARG(W % 4 == 0 && patch % 4 == 0 && H % patch == 0 && W % patch == 0, "masked_fill: bad geometry");
   const long long total = (long long)B * C * H * (W / 4);
+  MVLT_CHECK_ARG(total < (1ll << 32), "masked_fill: tensor too large for the 32-bit index decomposition");
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)mvlt_num_sms() * 16;
   if (blocks > cap) blocks = cap;

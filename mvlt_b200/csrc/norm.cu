@@ -13,7 +13,9 @@ struct RowMap {  // physical_row(r) = (r / group) * stride + offset + (r % group
   int group, stride, offset;
 };
 __device__ __forceinline__ long long map_row(const RowMap& m, int r) {
-  return (long long)(r / m.group) * m.stride + m.offset + (r % m.group);
+  if (m.stride == m.group && m.offset == 0) return r;   // identity map (the common case): no integer division per row
+  const int q = r / m.group;
+  return (long long)q * m.stride + m.offset + (r - q * m.group);
 }
 
 namespace {
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, R
         rstd_out[r] = rstd;
       }
       TO* yr = y + map_row(ym, r) * C;
-      const float* pa = post_add ? post_add + (long long)(r % ym.group) * C : nullptr;
+      const float* pa = post_add ? post_add + (long long)(r % ym.group) * C : nullptr;   // (only the patch-embed launches)
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = i * 4 * G + sub * 4;
