@@ -21,6 +21,7 @@
 #include <unordered_map>
 #include <string>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_desc.h"
 
@@ -81,6 +82,7 @@ struct KParams {
   long long ldd, sD1, sD2;
   float alpha;
   int act, out_f32, atomic_add, rows_per_scale;
+  int tma_store;  // D (and D2) leave the staging tiles through TMA bulk stores (tmD / tmD2) instead of LDS + STG
   int prefetch;   // EPI_AUX only: two staging tiles per epilogue warp, the aux unit of the next tile is fetched with cp.async
   // implicit 3x3 convolution operand (gemm_desc.h): tile/k-block index -> (b, y) pixel coordinates and (tap, c0)
   int conv_mode, conv_W, conv_C;
@@ -283,10 +285,29 @@ __device__ __forceinline__ void apply_aux16(int act, const uint32_t* ax, f32x2_t
 // i.e. one staging tile with P pieces per row. All columns of the unit are inside N and 16-byte aligned.
 // The TMEM accumulator is read 16 columns at a time to keep the register footprint small (no spills at 112
 // registers: local memory has almost no L1 behind it in this kernel). Warp-uniform; loops fully unrolled.
+// The staging tile of a 128-byte-row unit has exactly the SWIZZLE_128B layout of a [32 rows x 128 B] TMA box, so the
+// unit leaves shared memory with ONE bulk tensor store issued by one lane (rows past M are clipped by the tensor map)
+// instead of 8 x (LDS + predicated STG) per lane; the warp only waits until the TMA engine has read the tile.
+struct StoreCtx {
+  const CUtensorMap* tmD;
+  const CUtensorMap* tmD2;
+  int row, b2, b1;    // tile-row coordinate of this warp's first row and the batch coordinates
+};
+__device__ __forceinline__ void tma_flush(const CUtensorMap* tm, uint32_t tile_s, int col0, const StoreCtx& sc, int lane) {
+  fence_proxy_async();          // this lane's st.shared writes -> visible to the async proxy
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_4d(tm, tile_s, col0, sc.row, sc.b2, sc.b1);
+    tma_store_commit();
+    tma_store_wait_read();
+  }
+  __syncwarp();
+}
+
 template <int kEpi, bool kOutF32, int P>
 __device__ __forceinline__ void epilogue_unit_compute(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
                                                       int rows_valid, int col0, float rs, const StageAddr& s,
-                                                      const uint32_t (&ex)[P * 4]) {
+                                                      const uint32_t (&ex)[P * 4], const StoreCtx& sc) {
   constexpr int COLS = kOutF32 ? 32 : P * 8;
   constexpr int N16 = COLS / 16;
   static_assert(!kOutF32 || P == 8, "fp32 units are 32 columns = 128-byte rows");
@@ -346,8 +367,11 @@ __device__ __forceinline__ void epilogue_unit_compute(const KParams& p, uint32_t
   if constexpr (kOutF32) {
     uint8_t* g = reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(p.D) + row_base_off + col0);
     if (kEpi == EPI_PLAIN && p.atomic_add) stage_flush<8, true>(s, g, ld_bytes, lane, rows_valid);
+    else if (p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
     else stage_flush<8, false>(s, g, ld_bytes, lane, rows_valid);
   } else {
+    if (P == 8 && p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+    else
     stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), ld_bytes,
                           lane, rows_valid);
     if constexpr (kEpi == EPI_GELU) {
@@ -359,6 +383,8 @@ __device__ __forceinline__ void epilogue_unit_compute(const KParams& p, uint32_t
           for (int j = 0; j < 8; ++j) pk[j] = d2pk[8 * i + j];
           stage_put_bf16<P>(s, i, pk);
         }
+        if (P == 8 && p.tma_store) tma_flush(sc.tmD2, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+        else
         stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D2) + row_base_off + col0),
                               ld_bytes, lane, rows_valid);
       }
@@ -368,7 +394,7 @@ __device__ __forceinline__ void epilogue_unit_compute(const KParams& p, uint32_t
 
 template <int kEpi, bool kOutF32, int P>
 __device__ __forceinline__ void epilogue_unit_vec(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
-                                                  int rows_valid, int col0, float rs, const StageAddr& s) {
+                                                  int rows_valid, int col0, float rs, const StageAddr& s, const StoreCtx& sc) {
   uint32_t ex[P * 4];
   if constexpr (kEpi == EPI_RESID || kEpi == EPI_AUX) {   // residual (fp32 out) / aux (bf16 out): geometry of the output unit
     const long long ld_bytes = p.ldd * (kOutF32 ? 4 : 2);
@@ -376,7 +402,7 @@ __device__ __forceinline__ void epilogue_unit_vec(const KParams& p, uint32_t tad
                                            : reinterpret_cast<const uint8_t*>(p.aux + row_base_off + col0);
     load_rows_via_stage<P>(s, g, ld_bytes, lane, rows_valid, ex);
   }
-  epilogue_unit_compute<kEpi, kOutF32, P>(p, taddr, row_base_off, lane, rows_valid, col0, rs, s, ex);
+  epilogue_unit_compute<kEpi, kOutF32, P>(p, taddr, row_base_off, lane, rows_valid, col0, rs, s, ex, sc);
 }
 
 // Asynchronous (register-free) fetch of a 32-row x 128-byte operand unit into a staging tile: cp.async in the
@@ -482,7 +508,7 @@ __device__ __forceinline__ float2 pair_exchange(uint32_t my_stage_s, uint32_t pa
 // ---- fused row softmax (forward): pass 2 for one unit of P*8 bf16 columns: P = exp2(a2 * acc - mx) * inv
 template <int P>
 __device__ __forceinline__ void softmax_unit(const KParams& p, uint32_t taddr, long long row_base_off, int lane, int rows_valid,
-                                             int col0, float a2, float mx, float inv, const StageAddr& s) {
+                                             int col0, float a2, float mx, float inv, const StageAddr& s, const StoreCtx& sc) {
 #pragma unroll
   for (int i = 0; i < P / 2; ++i) {
     uint32_t r[16];
@@ -495,6 +521,8 @@ __device__ __forceinline__ void softmax_unit(const KParams& p, uint32_t taddr, l
                           ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), a2, -mx)) * inv);
     stage_put_bf16<P>(s, i, pk);
   }
+  if (P == 8 && p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+  else
   stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), p.ldd * 2,
                         lane, rows_valid);
 }
@@ -502,7 +530,7 @@ __device__ __forceinline__ void softmax_unit(const KParams& p, uint32_t taddr, l
 // dS = alpha * P * (dP - dot). P (aux) is fetched through the staging tile both times (DRAM, then L2).
 template <int P, int kPass>
 __device__ __forceinline__ float softmax_bwd_unit(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
-                                                  int rows_valid, int col0, float dot, const StageAddr& s) {
+                                                  int rows_valid, int col0, float dot, const StageAddr& s, const StoreCtx& sc) {
   uint32_t ex[P * 4];
   load_rows_via_stage<P>(s, reinterpret_cast<const uint8_t*>(p.aux + row_base_off + col0), p.ldd * 2, lane, rows_valid, ex);
   float acc = 0.f;
@@ -529,15 +557,19 @@ __device__ __forceinline__ float softmax_bwd_unit(const KParams& p, uint32_t tad
       stage_put_bf16<P>(s, i, pk);
     }
   }
-  if (kPass == 1)
-    stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), p.ldd * 2,
-                          lane, rows_valid);
+  if (kPass == 1) {
+    if (P == 8 && p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+    else
+      stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), p.ldd * 2,
+                            lane, rows_valid);
+  }
   return acc;
 }
 
 template <int kEpi, bool kOutF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                     const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -553,7 +585,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + MAX_ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + MAX_ACC);
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full_bar) + 256;   // 16 x 4 KB per-warp staging tiles
+  uint8_t* stage_base = ones_tile + 2048;   // 16 x 4 KB per-warp staging tiles, 1024-byte aligned (TMA 128B-swizzle atoms)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -569,6 +601,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) {
+      tma_prefetch_desc(&tmD);
+      if (p.D2 != nullptr) tma_prefetch_desc(&tmD2);
+    }
   }
   if (p.rowsum != nullptr) {   // bf16 1.0 everywhere: layout / swizzle of this operand tile is irrelevant
     if (threadIdx.x < ONES_BYTES / 4) reinterpret_cast<uint32_t*>(ones_tile)[threadIdx.x] = 0x3F803F80u;
@@ -720,9 +756,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const StageAddr se = make_stage_addr(stage + 4096u, lane);
         const long long ld_bytes = p.ldd * 2;
         long long rbo = 0, rbo_n = 0;
-        int rv = 0, rv_n = 0, c0 = 0, c0_n = 0, rb = 0, rb_n = 0;
-        auto coords = [&](int tt, long long& o, int& v, int& c, int& r) {
+        int rv = 0, rv_n = 0, c0 = 0, c0_n = 0, rb = 0, rb_n = 0, tb1 = 0, tb2 = 0, tb1_n = 0, tb2_n = 0;
+        auto coords = [&](int tt, long long& o, int& v, int& c, int& r, int& cb1, int& cb2) {
           const TileCoord tc = decode_tile(p, tt);
+          cb1 = tc.b1;
+          cb2 = tc.b2;
           r = tc.m_blk * BLOCK_M + quarter * 32;
           v = min(32, p.M - r);
           o = (long long)tc.b1 * p.sD1 + (long long)tc.b2 * p.sD2 + (long long)r * p.ldd;
@@ -730,12 +768,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         };
         int t = blockIdx.x + group * gridDim.x;
         if (t < total_tiles) {
-          coords(t, rbo, rv, c0, rb);
+          coords(t, rbo, rv, c0, rb, tb1, tb2);
           prefetch_rows_async(se, reinterpret_cast<const uint8_t*>(p.aux + rbo + c0), ld_bytes, lane, rv);
         }
         for (int local = group; t < total_tiles; t += 2 * gridDim.x, local += 2) {
           const int tn = t + 2 * gridDim.x;
-          if (tn < total_tiles) coords(tn, rbo_n, rv_n, c0_n, rb_n);
+          if (tn < total_tiles) coords(tn, rbo_n, rv_n, c0_n, rb_n, tb1_n, tb2_n);
           float rs = 1.f;
           if (p.rowscale != nullptr && lane < rv) rs = p.rowscale[(rb + lane) / p.rows_per_scale];
           const int acc = local & acc_mask;
@@ -754,12 +792,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             prefetch_rows_async(se, reinterpret_cast<const uint8_t*>(p.aux + rbo_n + c0_n), ld_bytes, lane, rv_n);
           if (rv > 0) {
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n + half * 64);
-            epilogue_unit_compute<EPI_AUX, false, 8>(p, taddr, rbo, lane, rv, c0, rs, sa, ex);
+            const StoreCtx sc{&tmD, &tmD2, rb, tb2, tb1};
+            epilogue_unit_compute<EPI_AUX, false, 8>(p, taddr, rbo, lane, rv, c0, rs, sa, ex, sc);
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-          rbo = rbo_n; rv = rv_n; c0 = c0_n; rb = rb_n;
+          rbo = rbo_n; rv = rv_n; c0 = c0_n; rb = rb_n; tb1 = tb1_n; tb2 = tb2_n;
         }
         total_tiles_done = true;
       }
@@ -779,6 +818,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[acc], (uint32_t)(local >> acc_shift) & 1u);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n);
+      const StoreCtx ssc{&tmD, &tmD2, row_base, tc.b2, tc.b1};
       if constexpr (kEpi == EPI_SOFTMAX) {
         // ---- fused row softmax (whole row in this tile): pass 1 = this warp's partial (max, sum) over its column
         // half, exchanged with the partner warp; pass 2 = normalise + store. The accumulator is read twice from TMEM.
@@ -811,10 +851,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (rows_valid > 0) {
           for (int ci = c_begin; ci < c_end;) {
             if (ci + 2 <= c_end) {
-              softmax_unit<8>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, a2, mx, inv, sa);
+              softmax_unit<8>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, a2, mx, inv, sa, ssc);
               ci += 2;
             } else {
-              softmax_unit<4>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, a2, mx, inv, sa);
+              softmax_unit<4>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, a2, mx, inv, sa, ssc);
               ci += 1;
             }
           }
@@ -824,24 +864,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float dot = 0.f;
         for (int ci = c_begin; ci < c_end;) {
           if (ci + 2 <= c_end) {
-            dot += softmax_bwd_unit<8, 0>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, 0.f, sa);
+            dot += softmax_bwd_unit<8, 0>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, 0.f, sa, ssc);
             ci += 2;
           } else {
-            dot += softmax_bwd_unit<4, 0>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, 0.f, sa);
+            dot += softmax_bwd_unit<4, 0>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, 0.f, sa, ssc);
             ci += 1;
           }
         }
         dot += pair_exchange(stage, partner_stage, pair_bar, lane, make_float2(dot, 0.f)).x;
         for (int ci = c_begin; ci < c_end;) {
           if (ci + 2 <= c_end) {
-            softmax_bwd_unit<8, 1>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, dot, sa);
+            softmax_bwd_unit<8, 1>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, dot, sa, ssc);
             ci += 2;
           } else {
-            softmax_bwd_unit<4, 1>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, dot, sa);
+            softmax_bwd_unit<4, 1>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, dot, sa, ssc);
             ci += 1;
           }
         }
       } else if (rows_valid > 0) {
+        const StoreCtx sc{&tmD, &tmD2, row_base, tc.b2, tc.b1};
         for (int ci = c_begin; ci < c_end;) {
           const int col0 = n0 + ci * 32;
           const uint32_t taddr = taddr0 + (uint32_t)(ci * 32);
@@ -850,14 +891,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             epilogue_chunk_tail(p, taddr, row_base_off, lane, rows_valid, col0, rs);
             ci += 1;
           } else if constexpr (kOutF32) {
-            epilogue_unit_vec<kEpi, true, 8>(p, taddr, row_base_off, lane, rows_valid, col0, rs, sa);
+            epilogue_unit_vec<kEpi, true, 8>(p, taddr, row_base_off, lane, rows_valid, col0, rs, sa, sc);
             ci += 1;
           } else {
             if (ci + 2 <= c_end && col0 + 64 <= p.N) {
-              epilogue_unit_vec<kEpi, false, 8>(p, taddr, row_base_off, lane, rows_valid, col0, rs, sa);
+              epilogue_unit_vec<kEpi, false, 8>(p, taddr, row_base_off, lane, rows_valid, col0, rs, sa, sc);
               ci += 2;
             } else {
-              epilogue_unit_vec<kEpi, false, 4>(p, taddr, row_base_off, lane, rows_valid, col0, rs, sa);
+              epilogue_unit_vec<kEpi, false, 4>(p, taddr, row_base_off, lane, rows_valid, col0, rs, sa, sc);
               ci += 1;
             }
           }
@@ -878,6 +919,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
 
+  if (p.tma_store && warp >= FIRST_EPI_WARP && lane == 0)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this lane's bulk stores have fully completed
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -923,7 +966,7 @@ struct MapKeyHash {
 
 // Builds (or fetches) a 4-D bf16 tensor map: dims innermost-first, strides in BYTES for dims 1..3.
 int get_tensor_map(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
-                   const uint32_t box[4]) {
+                   const uint32_t box[4], int f32 = 0) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key;
@@ -931,6 +974,7 @@ int get_tensor_map(CUtensorMap* out, const void* base, const uint64_t dims[4], c
   for (int i = 0; i < 4; ++i) key.v[1 + i] = dims[i];
   for (int i = 0; i < 3; ++i) key.v[5 + i] = strides_b[i];
   for (int i = 0; i < 4; ++i) key.v[8 + i] = box[i];
+  key.v[11] |= (uint64_t)(f32 ? 1 : 0) << 32;
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -949,7 +993,7 @@ int get_tensor_map(CUtensorMap* out, const void* base, const uint64_t dims[4], c
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = fn(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1022,7 +1066,7 @@ FastDiv make_fastdiv(uint32_t d) {
   return f;
 }
 
-typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
 struct KernelVariant {
   GemmKernelFn fn;
   const char* name;
@@ -1049,6 +1093,17 @@ int make_conv_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base, i
   uint64_t str[3] = {(uint64_t)g->conv_pix_stride * 2, (uint64_t)g->conv_pix_stride * 2 * W, (uint64_t)g->conv_batch_stride * 2};
   uint32_t box[4] = {64, (uint32_t)W, (uint32_t)by, (uint32_t)bb};
   return get_tensor_map(out, base, dims, str, box);
+}
+
+// Output tensor D (or D2) as a 4-D map (n, m, batch2, batch1) whose box is one staging tile: 32 rows x 128 bytes
+int make_output_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base, int f32) {
+  const uint64_t es = f32 ? 4 : 2;
+  const int ub2 = (g->batch2 > 1) ? 1 : 0, ub1 = (g->batch1 > 1) ? 1 : 0;
+  uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->M, ub2 ? (uint64_t)g->batch2 : 1, ub1 ? (uint64_t)g->batch1 : 1};
+  const uint64_t dflt = (((uint64_t)g->M * (uint64_t)g->ldd * es + 15) / 16) * 16;
+  uint64_t str[3] = {(uint64_t)g->ldd * es, ub2 ? (uint64_t)g->sD2 * es : dflt, ub1 ? (uint64_t)g->sD1 * es : dflt};
+  uint32_t box[4] = {(uint32_t)(128 / es), 32, 1, 1};
+  return get_tensor_map(out, base, dims, str, box, f32);
 }
 
 int pick_variant(const mvlt_gemm_desc* g) {
@@ -1189,7 +1244,8 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   if (rc) return rc;
 
   // > half of the SM's shared memory so two CTAs (each wanting all 512 TMEM columns) never share an SM
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + ONES_BYTES + 256 /*barriers*/ + STAGING_BYTES * (p.prefetch ? 2 : 1);
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 2048 /*ones tile + barriers, keeps staging 1 KB aligned*/ +
+                STAGING_BYTES * (p.prefetch ? 2 : 1);
   if (smem < 120 * 1024) smem = 120 * 1024;
   static std::once_flag attr_once;
   static int launch_regs_ok = 1;
@@ -1207,7 +1263,24 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   MVLT_CHECK_ARG(total_tiles < (1ll << 31), "mvlt_gemm: too many tiles");
   int grid = mvlt_num_sms();
   if (total_tiles < grid) grid = (int)total_tiles;
-  kVariants[pick_variant(g)].fn<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  // TMA-store epilogue: 16-byte aligned output pitch / batch strides / base, non-atomic
+  CUtensorMap tmD = tmA, tmD2 = tmA;
+  {
+    const long long es = g->out_f32 ? 4 : 2;
+    const bool ok = !g->atomic_add && ((uintptr_t)g->D & 15) == 0 && (g->ldd * es) % 16 == 0 && (g->sD1 * es) % 16 == 0 && (g->sD2 * es) % 16 == 0 &&
+                    (g->batch1 == 1 || g->sD1 != 0) && (g->batch2 == 1 || g->sD2 != 0) &&
+                    (g->D2 == nullptr || ((uintptr_t)g->D2 & 15) == 0);
+    if (ok) {
+      rc = make_output_map(&tmD, g, g->D, g->out_f32);
+      if (rc) return rc;
+      if (g->D2 != nullptr) {
+        rc = make_output_map(&tmD2, g, g->D2, 0);
+        if (rc) return rc;
+      }
+      p.tma_store = 1;
+    }
+  }
+  kVariants[pick_variant(g)].fn<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmD, tmD2, p);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
