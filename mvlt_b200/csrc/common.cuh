@@ -290,6 +290,12 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src
                "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// same, as an element-wise fp32 add into global memory (the tensor map's data type selects the arithmetic)
+__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the TMA engine has finished READING the shared-memory source of all committed bulk stores
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -289,15 +289,19 @@ __device__ __forceinline__ void apply_aux16(int act, const uint32_t* ax, f32x2_t
 // unit leaves shared memory with ONE bulk tensor store issued by one lane (rows past M are clipped by the tensor map)
 // instead of 8 x (LDS + predicated STG) per lane; the warp only waits until the TMA engine has read the tile.
 struct StoreCtx {
-  const CUtensorMap* tmD;
+  const CUtensorMap* tmD;     // 128-byte-row boxes (64 bf16 / 32 fp32 columns)
   const CUtensorMap* tmD2;
+  const CUtensorMap* tmDh;    // 64-byte-row boxes (32 bf16 columns), SWIZZLE_64B == the P = 4 staging layout
+  const CUtensorMap* tmD2h;
   int row, b2, b1;    // tile-row coordinate of this warp's first row and the batch coordinates
 };
+template <bool kAdd = false>
 __device__ __forceinline__ void tma_flush(const CUtensorMap* tm, uint32_t tile_s, int col0, const StoreCtx& sc, int lane) {
   fence_proxy_async();          // this lane's st.shared writes -> visible to the async proxy
   __syncwarp();
   if (lane == 0) {
-    tma_store_4d(tm, tile_s, col0, sc.row, sc.b2, sc.b1);
+    if (kAdd) tma_reduce_add_4d(tm, tile_s, col0, sc.row, sc.b2, sc.b1);   // split-K / gradient accumulation (fp32)
+    else tma_store_4d(tm, tile_s, col0, sc.row, sc.b2, sc.b1);
     tma_store_commit();
     tma_store_wait_read();
   }
@@ -366,11 +370,13 @@ __device__ __forceinline__ void epilogue_unit_compute(const KParams& p, uint32_t
   }
   if constexpr (kOutF32) {
     uint8_t* g = reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(p.D) + row_base_off + col0);
-    if (kEpi == EPI_PLAIN && p.atomic_add) stage_flush<8, true>(s, g, ld_bytes, lane, rows_valid);
-    else if (p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+    if (kEpi == EPI_PLAIN && p.atomic_add) {
+      if (p.tma_store) tma_flush<true>(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+      else stage_flush<8, true>(s, g, ld_bytes, lane, rows_valid);
+    } else if (p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
     else stage_flush<8, false>(s, g, ld_bytes, lane, rows_valid);
   } else {
-    if (P == 8 && p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+    if (p.tma_store) tma_flush(P == 8 ? sc.tmD : sc.tmDh, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
     else
     stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), ld_bytes,
                           lane, rows_valid);
@@ -383,7 +389,7 @@ __device__ __forceinline__ void epilogue_unit_compute(const KParams& p, uint32_t
           for (int j = 0; j < 8; ++j) pk[j] = d2pk[8 * i + j];
           stage_put_bf16<P>(s, i, pk);
         }
-        if (P == 8 && p.tma_store) tma_flush(sc.tmD2, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+        if (p.tma_store) tma_flush(P == 8 ? sc.tmD2 : sc.tmD2h, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
         else
         stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D2) + row_base_off + col0),
                               ld_bytes, lane, rows_valid);
@@ -521,7 +527,7 @@ __device__ __forceinline__ void softmax_unit(const KParams& p, uint32_t taddr, l
                           ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), a2, -mx)) * inv);
     stage_put_bf16<P>(s, i, pk);
   }
-  if (P == 8 && p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+  if (p.tma_store) tma_flush(P == 8 ? sc.tmD : sc.tmDh, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
   else
   stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), p.ldd * 2,
                         lane, rows_valid);
@@ -558,7 +564,7 @@ __device__ __forceinline__ float softmax_bwd_unit(const KParams& p, uint32_t tad
     }
   }
   if (kPass == 1) {
-    if (P == 8 && p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+    if (p.tma_store) tma_flush(P == 8 ? sc.tmD : sc.tmDh, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
     else
       stage_flush<P, false>(s, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.D) + row_base_off + col0), p.ldd * 2,
                             lane, rows_valid);
@@ -570,6 +576,7 @@ template <int kEpi, bool kOutF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
+                    const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmD2h,
                     const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -792,7 +799,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             prefetch_rows_async(se, reinterpret_cast<const uint8_t*>(p.aux + rbo_n + c0_n), ld_bytes, lane, rv_n);
           if (rv > 0) {
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n + half * 64);
-            const StoreCtx sc{&tmD, &tmD2, rb, tb2, tb1};
+            const StoreCtx sc{&tmD, &tmD2, &tmDh, &tmD2h, rb, tb2, tb1};
             epilogue_unit_compute<EPI_AUX, false, 8>(p, taddr, rbo, lane, rv, c0, rs, sa, ex, sc);
           }
           tc_fence_before();
@@ -818,7 +825,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[acc], (uint32_t)(local >> acc_shift) & 1u);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n);
-      const StoreCtx ssc{&tmD, &tmD2, row_base, tc.b2, tc.b1};
+      const StoreCtx ssc{&tmD, &tmD2, &tmDh, &tmD2h, row_base, tc.b2, tc.b1};
       if constexpr (kEpi == EPI_SOFTMAX) {
         // ---- fused row softmax (whole row in this tile): pass 1 = this warp's partial (max, sum) over its column
         // half, exchanged with the partner warp; pass 2 = normalise + store. The accumulator is read twice from TMEM.
@@ -882,7 +889,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       } else if (rows_valid > 0) {
-        const StoreCtx sc{&tmD, &tmD2, row_base, tc.b2, tc.b1};
+        const StoreCtx sc{&tmD, &tmD2, &tmDh, &tmD2h, row_base, tc.b2, tc.b1};
         for (int ci = c_begin; ci < c_end;) {
           const int col0 = n0 + ci * 32;
           const uint32_t taddr = taddr0 + (uint32_t)(ci * 32);
@@ -966,7 +973,7 @@ struct MapKeyHash {
 
 // Builds (or fetches) a 4-D bf16 tensor map: dims innermost-first, strides in BYTES for dims 1..3.
 int get_tensor_map(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
-                   const uint32_t box[4], int f32 = 0) {
+                   const uint32_t box[4], int f32 = 0, int swizzle64 = 0) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key;
@@ -974,7 +981,7 @@ int get_tensor_map(CUtensorMap* out, const void* base, const uint64_t dims[4], c
   for (int i = 0; i < 4; ++i) key.v[1 + i] = dims[i];
   for (int i = 0; i < 3; ++i) key.v[5 + i] = strides_b[i];
   for (int i = 0; i < 4; ++i) key.v[8 + i] = box[i];
-  key.v[11] |= (uint64_t)(f32 ? 1 : 0) << 32;
+  key.v[11] |= (uint64_t)((f32 ? 1 : 0) | (swizzle64 ? 2 : 0)) << 32;
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -994,7 +1001,8 @@ int get_tensor_map(CUtensorMap* out, const void* base, const uint64_t dims[4], c
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUtensorMap m;
   CUresult r = fn(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     mvlt_set_error("cuTensorMapEncodeTiled failed (%d): base=%p dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] "
@@ -1066,7 +1074,8 @@ FastDiv make_fastdiv(uint32_t d) {
   return f;
 }
 
-typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const CUtensorMap, const KParams);
 struct KernelVariant {
   GemmKernelFn fn;
   const char* name;
@@ -1096,14 +1105,15 @@ int make_conv_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base, i
 }
 
 // Output tensor D (or D2) as a 4-D map (n, m, batch2, batch1) whose box is one staging tile: 32 rows x 128 bytes
-int make_output_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base, int f32) {
+// (SWIZZLE_128B), or 32 rows x 64 bytes (SWIZZLE_64B) for the 32-column bf16 remainder units
+int make_output_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base, int f32, int row_bytes = 128) {
   const uint64_t es = f32 ? 4 : 2;
   const int ub2 = (g->batch2 > 1) ? 1 : 0, ub1 = (g->batch1 > 1) ? 1 : 0;
   uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->M, ub2 ? (uint64_t)g->batch2 : 1, ub1 ? (uint64_t)g->batch1 : 1};
   const uint64_t dflt = (((uint64_t)g->M * (uint64_t)g->ldd * es + 15) / 16) * 16;
   uint64_t str[3] = {(uint64_t)g->ldd * es, ub2 ? (uint64_t)g->sD2 * es : dflt, ub1 ? (uint64_t)g->sD1 * es : dflt};
-  uint32_t box[4] = {(uint32_t)(128 / es), 32, 1, 1};
-  return get_tensor_map(out, base, dims, str, box, f32);
+  uint32_t box[4] = {(uint32_t)(row_bytes / es), 32, 1, 1};
+  return get_tensor_map(out, base, dims, str, box, f32, row_bytes == 64);
 }
 
 int pick_variant(const mvlt_gemm_desc* g) {
@@ -1263,11 +1273,12 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   MVLT_CHECK_ARG(total_tiles < (1ll << 31), "mvlt_gemm: too many tiles");
   int grid = mvlt_num_sms();
   if (total_tiles < grid) grid = (int)total_tiles;
-  // TMA-store epilogue: 16-byte aligned output pitch / batch strides / base, non-atomic
-  CUtensorMap tmD = tmA, tmD2 = tmA;
+  // TMA-store epilogue (bulk tensor stores, or bulk tensor fp32 reductions for atomic_add): 16-byte aligned output pitch /
+  // batch strides / base
+  CUtensorMap tmD = tmA, tmD2 = tmA, tmDh = tmA, tmD2h = tmA;
   {
     const long long es = g->out_f32 ? 4 : 2;
-    const bool ok = !g->atomic_add && ((uintptr_t)g->D & 15) == 0 && (g->ldd * es) % 16 == 0 && (g->sD1 * es) % 16 == 0 && (g->sD2 * es) % 16 == 0 &&
+    const bool ok = ((uintptr_t)g->D & 15) == 0 && (g->ldd * es) % 16 == 0 && (g->sD1 * es) % 16 == 0 && (g->sD2 * es) % 16 == 0 &&
                     (g->batch1 == 1 || g->sD1 != 0) && (g->batch2 == 1 || g->sD2 != 0) &&
                     (g->D2 == nullptr || ((uintptr_t)g->D2 & 15) == 0);
     if (ok) {
@@ -1277,10 +1288,18 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
         rc = make_output_map(&tmD2, g, g->D2, 0);
         if (rc) return rc;
       }
+      if (!g->out_f32) {   // 32-column remainder units of bf16 outputs
+        rc = make_output_map(&tmDh, g, g->D, 0, 64);
+        if (rc) return rc;
+        if (g->D2 != nullptr) {
+          rc = make_output_map(&tmD2h, g, g->D2, 0, 64);
+          if (rc) return rc;
+        }
+      }
       p.tma_store = 1;
     }
   }
-  kVariants[pick_variant(g)].fn<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmD, tmD2, p);
+  kVariants[pick_variant(g)].fn<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmD, tmD2, tmDh, tmD2h, p);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
