@@ -68,13 +68,11 @@ class MLMHead(nn.Module):
         self.transform = BertHeadTransform(config)
         self.hidden_size = config['hidden_size']
         self.vocab_size = config['vocab_size']
-        assert self.hidden_size == bert_model_embedding_weights.size(1), \
-            '>>> hidden size: {} is not equal to bert embedding setting: {}'.format(
-                self.hidden_size, bert_model_embedding_weights.size(1))
-        assert self.vocab_size == bert_model_embedding_weights.size(0), \
-            '>>> vocab size: {} is not equal to bert embedding setting: {}'.format(
-                self.vocab_size, bert_model_embedding_weights.size(0))
-        self.mlm_decoder = nn.Linear(bert_model_embedding_weights.size(1), bert_model_embedding_weights.size(0), bias=False)
+        rows, cols = bert_model_embedding_weights.shape
+        if (rows, cols) != (self.vocab_size, self.hidden_size):   # same two checks as vl_heads.py:50-55
+            raise MvltError(f"tied word-embedding table is {rows}x{cols}, the head was configured for "
+                            f"{self.vocab_size}x{self.hidden_size}")
+        self.mlm_decoder = nn.Linear(cols, rows, bias=False)
         self.mlm_decoder.weight = bert_model_embedding_weights
         self.bias = nn.Parameter(torch.zeros(self.vocab_size))
 
