@@ -377,7 +377,7 @@ def train_step_grads(sd, batch, loss_type, model="pvlt_tiny", masked_images=None
     ls = losses(out, batch, batch["images"])
     ls["total"].backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
-    return {k: float(v) for k, v in ls.items()}, grads, out
+    return {k: float(v.detach()) for k, v in ls.items()}, grads, out
 
 
 # --------------------------------------------------------------------------------------------------------
