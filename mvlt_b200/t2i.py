@@ -93,11 +93,10 @@ class T2IHead:
         dev = dout.device
         aff = c["aff"]
         dy = torch.empty((rows, Co), dtype=BF16, device=dev)
-        red = self._scratch(dev)
-        # aff[0] = gamma * invstd is exactly the leading factor of the BatchNorm backward formula
-        k.bn_bwd(dout, c["y"], aff[0], aff[2], aff[3], red[0], red[1], dy, rows, Co, c["training"])
-        k.copy_rows(red[0:1], G[pfx + ".1.bias"].view(1, Co), 1, Co, accumulate=True)
-        k.copy_rows(red[1:2], G[pfx + ".1.weight"].view(1, Co), 1, Co, accumulate=True)
+        # aff[0] = gamma * invstd is exactly the leading factor of the BatchNorm backward formula. The two column sums the
+        # backward needs (sum dy, sum dy*xhat) ARE dbeta and dgamma: they are reduced straight into the (zero-initialised,
+        # written once per step) gradient views, no scratch buffers and no copies.
+        k.bn_bwd(dout, c["y"], aff[0], aff[2], aff[3], G[pfx + ".1.bias"], G[pfx + ".1.weight"], dy, rows, Co, c["training"])
         key = "__perm__" + pfx + ".0.weight"
         k.conv3x3_wgrad(dy, c["x"], B, H, W, Ci, c["xs"][1], c["xs"][0], G[key], split_k=_split_k(Co, 9 * Ci, rows))
         if dst is not None:
