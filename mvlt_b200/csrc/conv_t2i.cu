@@ -602,6 +602,86 @@ extern "C" int mvlt_col2im3x3(const void* dcol, void* dst, int dst_f32, long lon
   return 0;
 }
 
+// 8 channels (one 16-byte vector) per thread; requires C, leading dimensions and column offsets to be multiples of 8
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void load8p(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__global__ void __launch_bounds__(256) bn_apply8_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, const __nv_bfloat16* __restrict__ m1,
+                                                        int m1_ld, const __nv_bfloat16* __restrict__ m2, int m2_ld,
+                                                        __nv_bfloat16* __restrict__ out, int out_ld, int out_coff,
+                                                        long long rows, int C) {
+  const unsigned int c8n = (unsigned int)(C / 8);
+  const long long total = rows * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((unsigned int)i % c8n) * 8;
+    const long long r = (long long)((unsigned int)i / c8n);
+    float v[8], sc[8], sh[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + r * C + c), v);
+    load8p(scale + c, sc);
+    load8p(shift + c, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    if (m1) {
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(m1 + r * m1_ld + c), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= a[j];
+    }
+    if (m2) {
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(m2 + r * m2_ld + c), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= a[j];
+    }
+    *reinterpret_cast<uint4*>(out + r * out_ld + out_coff + c) = pack8(v);
+  }
+}
+__global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                            const float* __restrict__ scale, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, const float* __restrict__ sum_dy,
+                                                            const float* __restrict__ sum_dy_xhat, __nv_bfloat16* __restrict__ dx,
+                                                            long long rows, int C, int training) {
+  const unsigned int c8n = (unsigned int)(C / 8);
+  const long long total = rows * c8n;
+  const float inv_rows = 1.f / (float)rows;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((unsigned int)i % c8n) * 8;
+    const long long r = (long long)((unsigned int)i / c8n);
+    float d[8], sc[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + r * C + c), d);
+    load8p(scale + c, sc);
+    if (training) {
+      float xv[8], mu[8], is[8], s1[8], s2[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + r * C + c), xv);
+      load8p(mean + c, mu);
+      load8p(invstd + c, is);
+      load8p(sum_dy + c, s1);
+      load8p(sum_dy_xhat + c, s2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mu[j]) * is[j];
+        o[j] = sc[j] * (d[j] - s1[j] * inv_rows - xh * s2[j] * inv_rows);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = sc[j] * d[j];
+    }
+    *reinterpret_cast<uint4*>(dx + r * C + c) = pack8(o);
+  }
+}
+
 static void bn_reduce_launch(const void* x, const void* dy, const float* mean, const float* invstd, long long rows, int C,
                              float* o0, float* o1, cudaStream_t st) {
   const int gx = (C + 63) / 64;
@@ -634,6 +714,14 @@ extern "C" int mvlt_bn_finalize(const float* sum, const float* sumsq, long long 
 extern "C" int mvlt_bn_apply(const void* x_bf16, const float* scale, const float* shift, const void* m1, int m1_ld, const void* m2,
                              int m2_ld, void* out_bf16, int out_ld, int out_coff, long long rows, int C, void* stream_) {
   MVLT_CHECK_ARG(C % 2 == 0 && out_ld % 2 == 0 && out_coff % 2 == 0, "bn_apply: even sizes required");
+  const bool vec8 = (C % 8 == 0) && (out_ld % 8 == 0) && (out_coff % 8 == 0) && (m1 == nullptr || m1_ld % 8 == 0) &&
+                    (m2 == nullptr || m2_ld % 8 == 0) &&
+                    ((((uintptr_t)x_bf16 | (uintptr_t)out_bf16 | (uintptr_t)m1 | (uintptr_t)m2 | (uintptr_t)scale | (uintptr_t)shift) & 15) == 0);
+  if (vec8)
+    bn_apply8_kernel<<<cap_grid(rows * (C / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, shift, reinterpret_cast<const __nv_bfloat16*>(m1), m1_ld,
+        reinterpret_cast<const __nv_bfloat16*>(m2), m2_ld, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_ld, out_coff, rows, C);
+  else
   bn_apply_kernel<<<cap_grid(rows * (C / 2), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, shift, reinterpret_cast<const __nv_bfloat16*>(m1), m1_ld,
       reinterpret_cast<const __nv_bfloat16*>(m2), m2_ld, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_ld, out_coff, rows, C);
@@ -647,6 +735,13 @@ extern "C" int mvlt_bn_bwd(const void* dy_bf16, const void* x_bf16, const float*
   MVLT_CHECK_ARG(C % 2 == 0, "bn_bwd: C must be even");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   bn_reduce_launch(x_bf16, dy_bf16, mean, invstd, rows, C, sum_dy, sum_dy_xhat, st);
+  const bool vec8 = (C % 8 == 0) && ((((uintptr_t)dy_bf16 | (uintptr_t)x_bf16 | (uintptr_t)dx_bf16 | (uintptr_t)scale | (uintptr_t)mean |
+                                        (uintptr_t)invstd | (uintptr_t)sum_dy | (uintptr_t)sum_dy_xhat) & 15) == 0);
+  if (vec8)
+    bn_bwd_apply8_kernel<<<cap_grid(rows * (C / 8), 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, mean, invstd,
+        sum_dy, sum_dy_xhat, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows, C, training);
+  else
   bn_bwd_apply_kernel<<<cap_grid(rows * (C / 2), 256), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, mean, invstd,
       sum_dy, sum_dy_xhat, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows, C, training);
