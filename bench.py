@@ -29,7 +29,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PRE = {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0}
+CLS = {"itm": 0, "mlm": 0, "t2i": 0, "cls": 1}   # recognition fine-tune (BASELINE configs[3], dws_mvlt_ft_exp48.py:11)
 GF_PER_SAMPLE_TRAIN = 50.35   # dense model FLOPs fwd+bwd, PVLT-tiny, MLM+ITM+t2i
+# SURVEY §8d [probe]: (model, heads) -> dense fwd+bwd GFLOP per sample; the default line is ("pvlt_tiny", "pretrain")
+GF_TABLE = {("pvlt_tiny", "pretrain"): 50.35, ("pvlt_tiny", "recognition"): 24.97, ("pvlt_small", "pretrain"): 73.98}
+WORKLOADS = {
+    "pretrain": "pretraining step (grid masking on odd steps + MLM/ITM/t2i losses + backward + AdamW), 256x256 images, "
+                "128 BERT tokens",
+    "recognition": "recognition fine-tune step (M-CR 48-way + S-CR 122-way classification heads, cls losses + backward + "
+                   "AdamW), 256x256 images, 128 BERT tokens",
+}
 GF_PER_PAIR_RETR = 8.33       # encoder + ITM head forward
 
 
@@ -115,8 +124,10 @@ def run_ours(args):
     hbm, tf_burst, tf_sus, peak_src = _peaks()
 
     torch.manual_seed(1234)
-    model = mvlt_b200.create_model("pvlt_tiny", pretrained=True, num_classes=1000, drop_rate=0.0, drop_path_rate=0.1,
-                                   drop_block_rate=None, token_hidden_size=768, num_text_tokens=128, loss_type=dict(PRE),
+    heads = dict(PRE if args.workload == "pretrain" else CLS)
+    gf_per_sample = GF_TABLE.get((args.model, args.workload))
+    model = mvlt_b200.create_model(args.model, pretrained=True, num_classes=1000, drop_rate=0.0, drop_path_rate=0.1,
+                                   drop_block_rate=None, token_hidden_size=768, num_text_tokens=128, loss_type=heads,
                                    pretrained_pth="").to(dev)
     model.train()
     net = model
@@ -137,13 +148,16 @@ def run_ours(args):
     def step(i, b, fwd=None):
         fwd = fwd or net
         img = b["images"]
-        if i % 2 == 1:   # engine_grid_masking.py:72-78: odd steps feed the grid-masked image
+        if i % 2 == 1 and heads["t2i"]:   # engine_grid_masking.py:72-78: odd steps feed the grid-masked image
             grid = masking.grid_mask_batch(seeds + i * B, (img.shape[3], img.shape[2]), 0.5, 16, device=dev)
             x = masking.apply_grid_mask(img, grid, 16)
         else:
             x = img
-        total, stats = fwd(x, b["input_ids"], mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=img,
-                           mlm_count=b["mlm_count"])
+        if heads["cls"]:
+            total, stats = fwd(x, b["input_ids"], sup_cls_labels=b["sup_cls_labels"], sub_cls_labels=b["sub_cls_labels"])
+        else:
+            total, stats = fwd(x, b["input_ids"], mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=img,
+                               mlm_count=b["mlm_count"])
         total.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
@@ -153,7 +167,8 @@ def run_ours(args):
     # The copies are double-buffered on a side stream so that the H2D of step i+1 overlaps the compute of step i, and
     # the loss of step i is read (pinned buffer + event) while step i+1 is already enqueued: all K input copies and all
     # K loss reads happen inside the timed region.
-    E2E_KEYS = ("images", "input_ids", "itm_labels", "mlm_labels")
+    E2E_KEYS = ("images", "input_ids", "sup_cls_labels", "sub_cls_labels") if heads["cls"] else \
+        ("images", "input_ids", "itm_labels", "mlm_labels")
     copy_stream = torch.cuda.Stream(device=dev)
     stage_bufs = [{k: torch.empty_like(host[0][k], device=dev) for k in E2E_KEYS} for _ in range(2)]
     loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -239,7 +254,7 @@ def run_ours(args):
     host_ms = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
     e2e_value = B * world * K / (ms_e2e / 1e3)
-    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in ("images", "input_ids", "itm_labels", "mlm_labels"))
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in E2E_KEYS)
 
     # ---- per-kernel breakdown (instrumented pass, NOT the reported value) -> roofline of the dominant kernel
     roof, breakdown = None, None
@@ -286,11 +301,12 @@ def run_ours(args):
 
     # ---- retrieval sweep (configs[2]): 1000 queries x 101 candidates, candidates sharded across ranks
     retr = None
-    try:
-        from mvlt_b200 import retrieval
-        retr = retrieval.bench_sweep(dev, rank, world, n_query=args.retrieval_queries, n_cand=101, warmup=1)
-    except Exception as ex:   # the training number must still be reported
-        retr = {"error": repr(ex)[:200]}
+    if args.retrieval_queries > 0:
+        try:
+            from mvlt_b200 import retrieval
+            retr = retrieval.bench_sweep(dev, rank, world, n_query=args.retrieval_queries, n_cand=101, warmup=1)
+        except Exception as ex:   # the training number must still be reported
+            retr = {"error": repr(ex)[:200]}
 
     cpu = cpu_baseline(args) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
@@ -299,18 +315,19 @@ def run_ours(args):
             "metric": "train_samples_per_s", "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": K,
             "warmup": max(Wm, 3), "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "PVLT-tiny pretraining step (grid masking on odd steps + MLM/ITM/t2i losses + backward "
-                                   "+ AdamW), 256x256 images, 128 BERT tokens, BASELINE configs[1]",
+            "config": {"workload": f"{args.model} {WORKLOADS[args.workload]}, BASELINE configs["
+                                   f"{1 if (args.model, args.workload) == ('pvlt_tiny', 'pretrain') else 3 if args.workload == 'recognition' else 4}]",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "inputs and activations (>2 GB/step) exceed the 126 MB L2",
                        "optimizer": "mvlt_b200.optim.AdamW (own multi-tensor kernel, one launch per parameter group)",
-                       "mlm_rows": "MLM head evaluated on labelled rows only (identical loss/gradients)"},
+                       "mlm_rows": "MLM head evaluated on labelled rows only (identical loss/gradients)",
+                       "fused_attention": bool(__import__("mvlt_b200.engine", fromlist=["x"]).FUSED_ATTENTION)},
             "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / K, 3)},
             "gpu_launches": launches, "host_enqueue_ms_per_step": round(host_ms, 3),
             "clocks": clocks,
-            "model_tflops": round(value * GF_PER_SAMPLE_TRAIN / 1e3, 2),
-            "model_flops_frac_of_bf16_peak": round(value * GF_PER_SAMPLE_TRAIN / 1e3 / tf_sus, 4),
+            "model_tflops": round(value * gf_per_sample / 1e3, 2) if gf_per_sample else None,
+            "model_flops_frac_of_bf16_peak": round(value * gf_per_sample / 1e3 / tf_sus, 4) if gf_per_sample else None,
             "roofline": roof, "kernel_breakdown": breakdown, "retrieval": retr, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -381,6 +398,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--retrieval-queries", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--model", default="pvlt_tiny", choices=["pvlt_tiny", "pvlt_small", "pvlt_medium", "pvlt_large"],
+                    help="default pvlt_tiny = BASELINE configs[1]; pvlt_small = the configs[4] stand-in (SURVEY H9)")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "recognition"],
+                    help="pretrain = MLM+ITM+t2i heads (configs[1]); recognition = cls-only fine-tune step (configs[3])")
     ap.add_argument("--ddp", action="store_true", help="wrap the model in torch DistributedDataParallel instead of the flat-buffer all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1141,6 +1141,12 @@ int pick_block_n(const mvlt_gemm_desc* g) {
 
 }  // namespace
 
+// tensor-map cache shared with attn_tcgen05.cu (C++ linkage: not part of the C-ABI)
+int mvlt_tensor_map_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
+                       const uint32_t box[4], int f32, int swizzle64) {
+  return get_tensor_map(out, base, dims, strides_b, box, f32, swizzle64);
+}
+
 extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MVLT_CHECK_ARG(g != nullptr, "mvlt_gemm: null descriptor");

@@ -19,6 +19,7 @@ residual stream, LayerNorm / softmax / losses in fp32, bf16 GEMM operands with f
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -39,6 +40,9 @@ DEPTHS = {"pvlt_tiny": [2, 2, 2, 2], "pvlt_small": [3, 4, 6, 3], "pvlt_medium": 
 VOCAB, HIDDEN = 30522, 768
 VOCAB_PAD = 30528  # leading dimension of logits buffers (TMA needs 16-byte row strides)
 HEAD_DIM = 64
+# fused SR-attention forward (csrc/attn_tcgen05.cu); MVLT_FUSED_ATTN=0 keeps the two-GEMM path (QK^T + softmax epilogue, PV)
+# for A/B measurements -- both are sm_100a tcgen05 kernels
+FUSED_ATTENTION = os.environ.get("MVLT_FUSED_ATTN", "1") != "0"
 
 
 def _empty(shape, dtype, dev):
@@ -176,10 +180,16 @@ class PVLTEngine:
         q4 = q.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3)
         kv5 = kv.view(B, Nk, 2, heads, HEAD_DIM)
         k4, v4 = kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3)
-        Pm = _empty((B, heads, N, Nk), BF16, dev)
-        k.gemm(q4, k4, Pm, alpha=HEAD_DIM ** -0.5, act=k.ACT_SOFTMAX)   # softmax fused into the QK^T epilogue
         o = _empty((M, C), BF16, dev)
-        k.gemm(Pm, v4.transpose(-1, -2), o.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3))
+        if FUSED_ATTENTION and Nk <= k.SR_ATTENTION_MAX_NK:
+            # one kernel: S = QK^T in TMEM, softmax in registers, P staged in shared memory as the A operand of PV;
+            # the probabilities reach HBM only when the backward needs them
+            Pm = _empty((B, heads, N, Nk), BF16, dev) if save else None
+            k.sr_attention_fwd(q, kv, o, Pm, B, N, Nk, heads, HEAD_DIM ** -0.5)
+        else:
+            Pm = _empty((B, heads, N, Nk), BF16, dev)
+            k.gemm(q4, k4, Pm, alpha=HEAD_DIM ** -0.5, act=k.ACT_SOFTMAX)   # softmax fused into the QK^T epilogue
+            k.gemm(Pm, v4.transpose(-1, -2), o.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3))
         X1 = _empty((B, N, C), F32, dev)
         k.gemm(o, Wb[pfx + ".attn.proj.weight"], X1.view(M, C), bias=P[pfx + ".attn.proj.bias"],
                residual=X.view(M, C), rowscale=dp[0] if dp else None, rows_per_scale=N)

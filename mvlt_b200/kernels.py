@@ -246,6 +246,24 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, rows, Cdim, dymap=None, xmap=Non
          C.c_int(Cdim), ptr(dx_bf16), ptr(rowscale), C.c_int(rows_per_scale))
 
 
+SR_ATTENTION_MAX_NK = 192
+
+
+def sr_attention_fwd(q, kv, o, p_out, B, N, Nk, heads, scale):
+    """o[B*N, C] = merge_heads(softmax(scale * q_h k_h^T) v_h) in one tcgen05 kernel (csrc/attn_tcgen05.cu); kv = [B*Nk, 2C]
+    (K | V column halves). ``p_out`` ([B, heads, N, Nk] bf16) receives the probabilities when given (training)."""
+    require_cuda(q, kv, o, p_out)
+    C_ = heads * 64
+    if q.dtype != BF16 or kv.dtype != BF16 or o.dtype != BF16 or (p_out is not None and p_out.dtype != BF16):
+        raise _lib.MvltError("sr_attention_fwd: bf16 operands required")
+    if (not q.is_contiguous() or not kv.is_contiguous() or not o.is_contiguous() or q.numel() != B * N * C_
+            or kv.numel() != B * Nk * 2 * C_ or o.numel() != B * N * C_
+            or (p_out is not None and (not p_out.is_contiguous() or p_out.numel() != B * heads * N * Nk))):
+        raise _lib.MvltError("sr_attention_fwd: contiguous q [B*N, C], kv [B*Nk, 2C], o [B*N, C], p [B, h, N, Nk] required")
+    call("sr_attention_fwd", ptr(q), ptr(kv), ptr(o), ptr(p_out), C.c_int(B), C.c_int(N), C.c_int(Nk), C.c_int(heads),
+         C.c_float(scale))
+
+
 def softmax_fwd(s, rows, nk):
     call("softmax_fwd", ptr(s), C.c_longlong(rows), C.c_int(nk))
 

@@ -8,6 +8,7 @@ Writes
   tests/golden/token_mask_golden.npz  reference random_masking_features (BERT word-piece masking) under random.seed(s)
   tests/golden/pvlt_tiny_golden.npz   reference PVLT-tiny (libs/pvlt.py) outputs, losses and gradient summaries
                                       for oracle.make_state_dict(seed) weights and oracle.make_inputs batches
+  tests/golden/pvlt_small_golden.npz  the same for pvlt_small (depths [3,4,6,3]; BASELINE configs[4] stand-in), batch 1
 
 Third-party gaps papered over exactly as SURVEY 8c describes: a ~30-line timm stub and
 BertConfig.from_pretrained -> BertConfig() (defaults == bert-base-uncased).
@@ -93,16 +94,19 @@ def golden_grid_masks():
     print("grid masks:", len(seeds), "seeds; masked fraction mean", float(np.mean(grids)))
 
 
-def golden_pvlt():
+TINY_CASES = (("pre", {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0}, 2), ("cls", {"itm": 0, "mlm": 0, "t2i": 0, "cls": 1}, 2))
+SMALL_CASES = (("pre", {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0}, 1),)    # BASELINE configs[4] stand-in
+
+
+def golden_pvlt(model="pvlt_tiny", cases=TINY_CASES):
     ref_pvlt = import_reference()
     from oracle import pvlt_oracle as O
     out = {}
-    for tag, loss_type, B in (("pre", {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0}, 2),
-                              ("cls", {"itm": 0, "mlm": 0, "t2i": 0, "cls": 1}, 2)):
+    for tag, loss_type, B in cases:
         torch.manual_seed(0)
-        m = ref_pvlt.pvlt_tiny(pretrained=True, token_hidden_size=768, num_text_tokens=128, loss_type=loss_type,
+        m = getattr(ref_pvlt, model)(pretrained=True, token_hidden_size=768, num_text_tokens=128, loss_type=loss_type,
                                pretrained_pth="", num_classes=1000, in_chans=3, drop_rate=0.0, drop_path_rate=0.0)
-        sd = O.make_state_dict("pvlt_tiny", loss_type, seed=0)
+        sd = O.make_state_dict(model, loss_type, seed=0)
         ref_keys = set(m.state_dict().keys())
         assert ref_keys == set(sd.keys()), (sorted(ref_keys - set(sd)), sorted(set(sd) - ref_keys))
         for k, v in m.state_dict().items():
@@ -147,7 +151,7 @@ def golden_pvlt():
         if oe["t2i_logits"] is not None:
             out[f"{tag}_eval_t2i_logits_sub"] = oe["t2i_logits"][:, :, ::16, ::16].numpy()
         print(tag, {k: float(v) for k, v in ls.items()})
-    np.savez_compressed(os.path.join(HERE, "pvlt_tiny_golden.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, f"{model}_golden.npz"), **out)
 
 
 def golden_token_masks():
@@ -192,6 +196,8 @@ def golden_token_masks():
 
 
 if __name__ == "__main__":
-    golden_grid_masks()
-    golden_token_masks()
-    golden_pvlt()
+    if "--small-only" not in sys.argv:
+        golden_grid_masks()
+        golden_token_masks()
+        golden_pvlt()
+    golden_pvlt("pvlt_small", SMALL_CASES)

@@ -20,13 +20,13 @@ CLS = {"itm": 0, "mlm": 0, "t2i": 0, "cls": 1}
 ENC = {"itm": 1, "mlm": 1, "t2i": 0, "cls": 1}
 
 
-def _model(loss_type, seed=0, drop_path=0.0):
+def _model(loss_type, seed=0, drop_path=0.0, name="pvlt_tiny"):
     import mvlt_b200
     from oracle import pvlt_oracle as O
-    m = mvlt_b200.create_model("pvlt_tiny", pretrained=True, num_classes=1000, drop_rate=0.0, drop_path_rate=drop_path,
+    m = mvlt_b200.create_model(name, pretrained=True, num_classes=1000, drop_rate=0.0, drop_path_rate=drop_path,
                                drop_block_rate=None, token_hidden_size=768, num_text_tokens=128,
                                loss_type=dict(loss_type), pretrained_pth="")
-    sd = O.make_state_dict("pvlt_tiny", loss_type, seed=seed)
+    sd = O.make_state_dict(name, loss_type, seed=seed)
     m.load_state_dict(sd)
     m.text_embeddings.dropout.p = 0.0
     return m.cuda(), sd
@@ -64,14 +64,18 @@ def test_forward_logits_match_oracle(loss_type, tag):
         assert e <= 2e-2, (key, e, errs)
 
 
-@pytest.mark.parametrize("loss_type,tag", [(ENC, "enc"), (PRE, "pre"), (CLS, "cls")])
-@pytest.mark.parametrize("path", ["fused", "dict"])
-def test_train_step_losses_and_grads_match_oracle(loss_type, tag, path):
+CASES = [(ENC, "enc", "fused", "pvlt_tiny"), (ENC, "enc", "dict", "pvlt_tiny"), (PRE, "pre", "fused", "pvlt_tiny"),
+         (PRE, "pre", "dict", "pvlt_tiny"), (CLS, "cls", "fused", "pvlt_tiny"), (CLS, "cls", "dict", "pvlt_tiny"),
+         (PRE, "pre", "fused", "pvlt_small")]      # pvlt_small: BASELINE configs[4] stand-in (depths [3,4,6,3])
+
+
+@pytest.mark.parametrize("loss_type,tag,path,arch", CASES, ids=[f"{c[3]}-{c[1]}-{c[2]}" for c in CASES])
+def test_train_step_losses_and_grads_match_oracle(loss_type, tag, path, arch):
     from oracle import pvlt_oracle as O
-    m, sd = _model(loss_type)
+    m, sd = _model(loss_type, name=arch)
     batch = O.make_inputs(2, seed=1)
     m.train()
-    ref_losses, ref_grads, _ = O.train_step_grads(sd, batch, loss_type)
+    ref_losses, ref_grads, _ = O.train_step_grads(sd, batch, loss_type, model=arch)
     img, ids = batch["images"].cuda(), batch["input_ids"].cuda()
     if path == "fused":
         total, stats = m(img, ids, mlm_labels=batch["mlm_labels"], itm_labels=batch["itm_labels"],
@@ -100,7 +104,7 @@ def test_train_step_losses_and_grads_match_oracle(loss_type, tag, path):
         num += float((p.grad.detach().float().cpu() - r).norm()) ** 2
         den += float(r.norm()) ** 2
     glob = (num / den) ** 0.5
-    _report(f"grads_{tag}_{path}.json", {"losses": got, "ref_losses": ref_losses, "global_rel": glob, "per_param": rows})
+    _report(f"grads_{arch}_{tag}_{path}.json" if arch != "pvlt_tiny" else f"grads_{tag}_{path}.json", {"losses": got, "ref_losses": ref_losses, "global_rel": glob, "per_param": rows})
     bad = {n: v for n, v in rows.items() if v[0] > (6e-2 if v[1] > 1e-3 * gmax else 0.15)}
     assert not bad, (len(bad), dict(list(bad.items())[:12]))
     assert glob <= 3e-2, glob

@@ -36,13 +36,14 @@ def test_masked_fill_semantics():
     assert (out[:, m[0] == 1] == np.float32(1e-6)).all() and (out[:, m[0] == 0] == img[:, m[0] == 0]).all()
 
 
-@pytest.mark.parametrize("tag,loss_type", [("pre", {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0}),
-                                           ("cls", {"itm": 0, "mlm": 0, "t2i": 0, "cls": 1})])
-def test_pvlt_oracle_matches_reference_golden(tag, loss_type):
-    g = np.load(os.path.join(GOLD, "pvlt_tiny_golden.npz"))
-    sd = O.make_state_dict("pvlt_tiny", loss_type, seed=0)
-    batch = O.make_inputs(2, seed=0)
-    ls, grads, out = O.train_step_grads(sd, batch, loss_type)
+@pytest.mark.parametrize("model,B,tag,loss_type", [("pvlt_tiny", 2, "pre", {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0}),
+                                                   ("pvlt_tiny", 2, "cls", {"itm": 0, "mlm": 0, "t2i": 0, "cls": 1}),
+                                                   ("pvlt_small", 1, "pre", {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0})])
+def test_pvlt_oracle_matches_reference_golden(model, B, tag, loss_type):
+    g = np.load(os.path.join(GOLD, f"{model}_golden.npz"))
+    sd = O.make_state_dict(model, loss_type, seed=0)
+    batch = O.make_inputs(B, seed=0)
+    ls, grads, out = O.train_step_grads(sd, batch, loss_type, model=model)
     for k in ("mlm", "itm", "t2i", "sup_cls", "sub_cls", "total"):
         if f"{tag}_loss_{k}" in g:
             assert abs(ls[k] - float(g[f"{tag}_loss_{k}"])) < 2e-5 * max(1.0, abs(ls[k])), k
@@ -71,11 +72,11 @@ def test_pvlt_oracle_matches_reference_golden(tag, loss_type):
     #  momentum-0.1 update; replay that update through the oracle's bn_stats hook)
     with torch.no_grad():
         stats = {}
-        O.forward(sd, batch["images"], batch["input_ids"], loss_type, training=True, bn_stats=stats)
+        O.forward(sd, batch["images"], batch["input_ids"], loss_type, model=model, training=True, bn_stats=stats)
         sde = dict(sd)
         for p, (rm, rv) in stats.items():
             sde[p + ".1.running_mean"], sde[p + ".1.running_var"] = rm, rv
-        oe = O.forward(sde, batch["images"], batch["input_ids"], loss_type, training=False)
+        oe = O.forward(sde, batch["images"], batch["input_ids"], loss_type, model=model, training=False)
     if loss_type["itm"]:
         cmp(oe["itm_logits"], g[f"{tag}_eval_itm_logits"], 2e-5)
     if loss_type["t2i"]:

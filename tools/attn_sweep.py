@@ -40,6 +40,12 @@ for (H, N) in [(1, 4224), (2, 1152), (5, 384), (8, 192)]:
     print(f"H={H} N={N:5d}  QK^T+softmax   {t*1e3:7.1f} us  {(pb + qb)/t/1e6:6.0f} GB/s")
     t = bench(lambda: k.gemm(P, v4.transpose(-1, -2), o4))
     print(f"H={H} N={N:5d}  PV             {t*1e3:7.1f} us  {(pb + qb)/t/1e6:6.0f} GB/s")
+    kvb = kv.numel() * 2
+    if "--fused" in sys.argv:   # one-kernel forward (csrc/attn_tcgen05.cu): with / without the probability store
+        t = bench(lambda: k.sr_attention_fwd(q, kv, o, P, B, N, Nk, H, 0.125))
+        print(f"H={H} N={N:5d}  fused fwd (+P) {t*1e3:7.1f} us  {(pb + 2 * qb + kvb)/t/1e6:6.0f} GB/s")
+        t = bench(lambda: k.sr_attention_fwd(q, kv, o, None, B, N, Nk, H, 0.125))
+        print(f"H={H} N={N:5d}  fused fwd      {t*1e3:7.1f} us  {(2 * qb + kvb)/t/1e6:6.0f} GB/s")
     t = bench(lambda: k.gemm(do4, v4, dS, alpha=0.125, act=k.ACT_SOFTMAX_BWD, aux=P))
     print(f"H={H} N={N:5d}  dP+softmax_bwd {t*1e3:7.1f} us  {(2 * pb + qb)/t/1e6:6.0f} GB/s")
     t = bench(lambda: k.gemm(dS, k4.transpose(-1, -2), o4))
