@@ -14,6 +14,9 @@ void mvlt_set_error(const char* fmt, ...);
 #define MVLT_ERR_ARG (-1)
 #define MVLT_ERR_ALIGN (-2)
 #define MVLT_ERR_DRIVER (-3)
+#ifndef MVLT_PDL_DEFAULT
+#define MVLT_PDL_DEFAULT 0
+#endif
 
 #define MVLT_CHECK_ARG(cond, ...)                 \
   do {                                            \
@@ -45,9 +48,52 @@ static inline int mvlt_num_sms() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Kernel launch with programmatic dependent launch (PDL). Every kernel of this library starts with
+// pdl_prologue() (or pdl_trigger() ... pdl_wait() around a prologue that touches no global memory):
+//   griddepcontrol.launch_dependents  - the NEXT kernel of the stream may be scheduled as soon as every CTA of this
+//                                       grid has started, i.e. its CTAs fill the SMs this grid's tail leaves idle;
+//   griddepcontrol.wait               - blocks until the PREVIOUS kernel has completed and its writes are visible;
+//                                       no global memory is read or written before it.
+// Launch latency, CTA scheduling and (GEMM / attention) barrier + TMEM set-up of kernel i+1 thus overlap the tail of
+// kernel i. Both instructions are no-ops when the launch attribute is absent (MVLT_PDL=0).
+// ---------------------------------------------------------------------------------------------
+#include <stdlib.h>
+static inline bool mvlt_pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MVLT_PDL");
+    return e == nullptr ? (MVLT_PDL_DEFAULT != 0) : (e[0] != '0');
+  }();
+  return on;
+}
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mvlt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mvlt_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // Small device utilities
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_trigger();
+  pdl_wait();
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -39,6 +39,7 @@ __device__ __forceinline__ uint4 load8_as_bf16(const T* p) {
 template <typename T>
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const T* __restrict__ src, long long batch_stride, int pix_stride,
                                                         __nv_bfloat16* __restrict__ col, int B, int H, int W, int C) {
+  pdl_prologue();
   const int c8n = C / 8;
   const long long total = (long long)B * H * W * 9 * c8n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -61,6 +62,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) col2im3x3_kernel(const __nv_bfloat16* __restrict__ dcol, T* __restrict__ dst,
                                                         long long batch_stride, int pix_stride, int B, int H, int W, int C,
                                                         int accumulate) {
+  pdl_prologue();
   const int c8n = C / 8;
   const long long total = (long long)B * H * W * c8n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         long long rows, int C, float* __restrict__ out0,
                                                         float* __restrict__ out1, long long rows_per_block) {
+  pdl_prologue();
   __shared__ float sh0[8][64], sh1[8][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + tx * 2;
@@ -151,6 +154,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, int training, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, var;
@@ -180,6 +184,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                        int m1_ld, const __nv_bfloat16* __restrict__ m2, int m2_ld,
                                                        __nv_bfloat16* __restrict__ out, int out_ld, int out_coff,
                                                        long long rows, int C) {
+  pdl_prologue();
   const int c2n = C / 2;
   const long long total = rows * c2n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ invstd, const float* __restrict__ sum_dy,
                                                            const float* __restrict__ sum_dy_xhat, __nv_bfloat16* __restrict__ dx,
                                                            long long rows, int C, int training) {
+  pdl_prologue();
   const int c2n = C / 2;
   const long long total = rows * c2n;
   const float inv_rows = 1.f / (float)rows;
@@ -232,6 +238,7 @@ template <typename TA, typename TD>
 __global__ void __launch_bounds__(256) ew_mul_kernel(const TA* __restrict__ a, int a_ld, int a_coff, const __nv_bfloat16* __restrict__ b,
                                                      int b_ld, const __nv_bfloat16* __restrict__ c2, int c2_ld, TD* __restrict__ dst,
                                                      int d_ld, int d_coff, long long rows, int C, int accumulate) {
+  pdl_prologue();
   const int c2n = C / 2;
   const long long total = rows * c2n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -298,6 +305,7 @@ __device__ __forceinline__ void store8f(float* p, const float (&v)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict__ src, long long batch_stride, int pix_stride,
                                                              __nv_bfloat16* __restrict__ dst, int B, int h, int w, int C) {
+  pdl_prologue();
   const int H = 2 * h, W = 2 * w, c8n = C / 8;
   const long long total = (long long)B * H * W * c8n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -329,6 +337,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, TD* __restrict__ dx,
                                                              long long batch_stride, int pix_stride, int B, int h, int w, int C,
                                                              int accumulate) {
+  pdl_prologue();
   const int H = 2 * h, W = 2 * w, c8n = C / 8;
   const long long total = (long long)B * h * w * c8n;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -388,6 +397,7 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
 __global__ void __launch_bounds__(256) score_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ W,
                                                         const float* __restrict__ bias, float* __restrict__ out, long long rows,
                                                         int Cin) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long wid = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= rows) return;
@@ -410,6 +420,7 @@ __global__ void __launch_bounds__(256) score_bwd_kernel(const float* __restrict_
                                                         const float* __restrict__ W, __nv_bfloat16* __restrict__ dx,
                                                         float* __restrict__ dW, float* __restrict__ db, long long rows, int Cin,
                                                         long long rows_per_block) {
+  pdl_prologue();
   extern __shared__ float shw[];  // [3*Cin] partial dW + [3] db
   for (int i = threadIdx.x; i < 3 * Cin + 3; i += blockDim.x) shw[i] = 0.f;
   __syncthreads();
@@ -441,6 +452,7 @@ __global__ void __launch_bounds__(256) score_bwd_kernel(const float* __restrict_
 // ---- x8 bilinear upsample (align_corners=True) of the NHWC score map to NCHW, and SmoothL1 fused with it ----------
 __global__ void __launch_bounds__(256) upsample8_fwd_kernel(const float* __restrict__ score, float* __restrict__ out, int B, int h,
                                                             int w, int S) {
+  pdl_prologue();
   const int H = h * S, W = w * S;
   const long long total = (long long)B * 3 * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -469,6 +481,7 @@ __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restri
                                                            float* __restrict__ loss_sum, float* __restrict__ total_sum,
                                                            float loss_scale, float grad_scale, const float* __restrict__ gscale,
                                                            int B, int h, int w, int S, int mode, int want_grad) {
+  pdl_prologue();
   extern __shared__ float sh[];  // g[S][W] | gx[S][w] | 32 for reductions | lx[W] | ly[S] | x0[W] (int) | y0[S] (int)
   const int H = h * S, W = w * S;
   const int bands = H / S;  // one band = S output rows => touches at most score rows ybase .. ybase+2
@@ -578,10 +591,10 @@ extern "C" int mvlt_im2col3x3(const void* src, int src_f32, long long batch_stri
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = (long long)B * H * W * 9 * (C / 8);
   if (src_f32)
-    im2col3x3_kernel<float><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(src), batch_stride, pix_stride,
+    mvlt_launch(im2col3x3_kernel<float>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const float*>(src), batch_stride, pix_stride,
                                                                   reinterpret_cast<__nv_bfloat16*>(col), B, H, W, C);
   else
-    im2col3x3_kernel<__nv_bfloat16><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), batch_stride,
+    mvlt_launch(im2col3x3_kernel<__nv_bfloat16>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(src), batch_stride,
                                                                           pix_stride, reinterpret_cast<__nv_bfloat16*>(col), B, H, W, C);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -593,10 +606,10 @@ extern "C" int mvlt_col2im3x3(const void* dcol, void* dst, int dst_f32, long lon
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = (long long)B * H * W * (C / 8);
   if (dst_f32)
-    col2im3x3_kernel<float><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dcol),
+    mvlt_launch(col2im3x3_kernel<float>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(dcol),
                                                                   reinterpret_cast<float*>(dst), batch_stride, pix_stride, B, H, W, C, accumulate);
   else
-    col2im3x3_kernel<__nv_bfloat16><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dcol),
+    mvlt_launch(col2im3x3_kernel<__nv_bfloat16>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(dcol),
                                                                           reinterpret_cast<__nv_bfloat16*>(dst), batch_stride, pix_stride, B, H, W, C, accumulate);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -622,6 +635,7 @@ __global__ void __launch_bounds__(256) bn_apply8_kernel(const __nv_bfloat16* __r
                                                         int m1_ld, const __nv_bfloat16* __restrict__ m2, int m2_ld,
                                                         __nv_bfloat16* __restrict__ out, int out_ld, int out_coff,
                                                         long long rows, int C) {
+  pdl_prologue();
   const unsigned int c8n = (unsigned int)(C / 8);
   const long long total = rows * c8n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -653,6 +667,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ invstd, const float* __restrict__ sum_dy,
                                                             const float* __restrict__ sum_dy_xhat, __nv_bfloat16* __restrict__ dx,
                                                             long long rows, int C, int training) {
+  pdl_prologue();
   const unsigned int c8n = (unsigned int)(C / 8);
   const long long total = rows * c8n;
   const float inv_rows = 1.f / (float)rows;
@@ -690,7 +705,7 @@ static void bn_reduce_launch(const void* x, const void* dy, const float* mean, c
   long long rpb = (rows + gy - 1) / gy;
   if (rpb < 64) rpb = 64;
   gy = (rows + rpb - 1) / rpb;
-  bn_reduce_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  mvlt_launch(bn_reduce_kernel, dim3(gx, (unsigned)gy), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x),
                                                            reinterpret_cast<const __nv_bfloat16*>(dy), mean, invstd, rows, C, o0, o1, rpb);
 }
 
@@ -705,8 +720,7 @@ extern "C" int mvlt_bn_stats(const void* x_bf16, long long rows, int C, float* s
 extern "C" int mvlt_bn_finalize(const float* sum, const float* sumsq, long long rows, const float* gamma, const float* beta,
                                 float* running_mean, float* running_var, float momentum, float eps, int training, float* scale,
                                 float* shift, float* mean_out, float* invstd_out, int C, void* stream_) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      sum, sumsq, rows, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift, mean_out, invstd_out, C);
+  mvlt_launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream_), sum, sumsq, rows, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift, mean_out, invstd_out, C);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -718,12 +732,10 @@ extern "C" int mvlt_bn_apply(const void* x_bf16, const float* scale, const float
                     (m2 == nullptr || m2_ld % 8 == 0) &&
                     ((((uintptr_t)x_bf16 | (uintptr_t)out_bf16 | (uintptr_t)m1 | (uintptr_t)m2 | (uintptr_t)scale | (uintptr_t)shift) & 15) == 0);
   if (vec8)
-    bn_apply8_kernel<<<cap_grid(rows * (C / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, shift, reinterpret_cast<const __nv_bfloat16*>(m1), m1_ld,
+    mvlt_launch(bn_apply8_kernel, cap_grid(rows * (C / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, shift, reinterpret_cast<const __nv_bfloat16*>(m1), m1_ld,
         reinterpret_cast<const __nv_bfloat16*>(m2), m2_ld, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_ld, out_coff, rows, C);
   else
-  bn_apply_kernel<<<cap_grid(rows * (C / 2), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, shift, reinterpret_cast<const __nv_bfloat16*>(m1), m1_ld,
+  mvlt_launch(bn_apply_kernel, cap_grid(rows * (C / 2), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, shift, reinterpret_cast<const __nv_bfloat16*>(m1), m1_ld,
       reinterpret_cast<const __nv_bfloat16*>(m2), m2_ld, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_ld, out_coff, rows, C);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -738,12 +750,10 @@ extern "C" int mvlt_bn_bwd(const void* dy_bf16, const void* x_bf16, const float*
   const bool vec8 = (C % 8 == 0) && ((((uintptr_t)dy_bf16 | (uintptr_t)x_bf16 | (uintptr_t)dx_bf16 | (uintptr_t)scale | (uintptr_t)mean |
                                         (uintptr_t)invstd | (uintptr_t)sum_dy | (uintptr_t)sum_dy_xhat) & 15) == 0);
   if (vec8)
-    bn_bwd_apply8_kernel<<<cap_grid(rows * (C / 8), 256), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, mean, invstd,
+    mvlt_launch(bn_bwd_apply8_kernel, cap_grid(rows * (C / 8), 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, mean, invstd,
         sum_dy, sum_dy_xhat, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows, C, training);
   else
-  bn_bwd_apply_kernel<<<cap_grid(rows * (C / 2), 256), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, mean, invstd,
+  mvlt_launch(bn_bwd_apply_kernel, cap_grid(rows * (C / 2), 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), scale, mean, invstd,
       sum_dy, sum_dy_xhat, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows, C, training);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -757,7 +767,7 @@ extern "C" int mvlt_ew_mul(const void* a, int a_f32, int a_ld, int a_coff, const
   const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b);
   const __nv_bfloat16* cc = reinterpret_cast<const __nv_bfloat16*>(c2);
 #define LAUNCH(TA, TD)                                                                                                   \
-  ew_mul_kernel<TA, TD><<<grid, 256, 0, st>>>(reinterpret_cast<const TA*>(a), a_ld, a_coff, bb, b_ld, cc, c2_ld,          \
+  mvlt_launch(ew_mul_kernel<TA, TD>, grid, 256, 0, st, reinterpret_cast<const TA*>(a), a_ld, a_coff, bb, b_ld, cc, c2_ld,          \
                                               reinterpret_cast<TD*>(dst), d_ld, d_coff, rows, C, accumulate)
   if (a_f32 && dst_f32) LAUNCH(float, float);
   else if (a_f32) LAUNCH(float, __nv_bfloat16);
@@ -774,10 +784,10 @@ extern "C" int mvlt_upsample2x_fwd(const void* src, int src_f32, long long batch
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = (long long)B * 4 * h * w * (C / 8);
   if (src_f32)
-    upsample2x_fwd_kernel<float><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(src), batch_stride, pix_stride,
+    mvlt_launch(upsample2x_fwd_kernel<float>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const float*>(src), batch_stride, pix_stride,
                                                                        reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, h, w, C);
   else
-    upsample2x_fwd_kernel<__nv_bfloat16><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), batch_stride,
+    mvlt_launch(upsample2x_fwd_kernel<__nv_bfloat16>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(src), batch_stride,
                                                                                pix_stride, reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, h, w, C);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -789,10 +799,10 @@ extern "C" int mvlt_upsample2x_bwd(const void* dy_bf16, void* dx, int dx_f32, lo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = (long long)B * h * w * (C / 8);
   if (dx_f32)
-    upsample2x_bwd_kernel<float><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
+    mvlt_launch(upsample2x_bwd_kernel<float>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
                                                                        reinterpret_cast<float*>(dx), batch_stride, pix_stride, B, h, w, C, accumulate);
   else
-    upsample2x_bwd_kernel<__nv_bfloat16><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
+    mvlt_launch(upsample2x_bwd_kernel<__nv_bfloat16>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
                                                                                reinterpret_cast<__nv_bfloat16*>(dx), batch_stride, pix_stride, B, h, w, C, accumulate);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -800,8 +810,7 @@ extern "C" int mvlt_upsample2x_bwd(const void* dy_bf16, void* dx, int dx_f32, lo
 
 extern "C" int mvlt_score_fwd(const void* x_bf16, const float* W, const float* bias, float* out, long long rows, int Cin, void* stream_) {
   MVLT_CHECK_ARG(Cin % 2 == 0, "score_fwd: Cin must be even");
-  score_fwd_kernel<<<(int)((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x_bf16), W, bias, out, rows, Cin);
+  mvlt_launch(score_fwd_kernel, (int)((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(x_bf16), W, bias, out, rows, Cin);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -813,15 +822,14 @@ extern "C" int mvlt_score_bwd(const float* dscore, const void* x_bf16, const flo
   long long rpb = (rows + blocks - 1) / blocks;
   if (rpb < 16) rpb = 16;
   blocks = (rows + rpb - 1) / rpb;
-  score_bwd_kernel<<<(int)blocks, 256, (3 * Cin + 3) * sizeof(float), reinterpret_cast<cudaStream_t>(stream_)>>>(
-      dscore, reinterpret_cast<const __nv_bfloat16*>(x_bf16), W, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dW, db, rows, Cin, rpb);
+  mvlt_launch(score_bwd_kernel, (int)blocks, 256, (3 * Cin + 3) * sizeof(float), reinterpret_cast<cudaStream_t>(stream_), dscore, reinterpret_cast<const __nv_bfloat16*>(x_bf16), W, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dW, db, rows, Cin, rpb);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int mvlt_upsample8_fwd(const float* score, float* out, int B, int h, int w, int S, void* stream_) {
   const long long total = (long long)B * 3 * h * S * w * S;
-  upsample8_fwd_kernel<<<cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(score, out, B, h, w, S);
+  mvlt_launch(upsample8_fwd_kernel, cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), score, out, B, h, w, S);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -833,8 +841,7 @@ extern "C" int mvlt_t2i_up_loss(const float* score, const float* target, const f
   const size_t smem = (size_t)(S * w * S + S * w + 32 + 2 * (w * S + S)) * sizeof(float);
   MVLT_CHECK_ARG(S >= 2 && smem <= 48 * 1024, "t2i_up_loss: bad geometry");
   const int blocks = B * 3 * h;
-  t2i_up8_loss_kernel<<<blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      score, target, dpred, dscore, loss_sum, total_sum, loss_scale, grad_scale, gscale_dev, B, h, w, S, mode, want_grad);
+  mvlt_launch(t2i_up8_loss_kernel, blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream_), score, target, dpred, dscore, loss_sum, total_sum, loss_scale, grad_scale, gscale_dev, B, h, w, S, mode, want_grad);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -25,6 +25,7 @@ inline int cap_grid(long long work_items, int threads, int per_sm = 8) {
 __global__ void __launch_bounds__(256) cast_scale_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                          long long n8, int C, const float* __restrict__ rowscale,
                                                          int rows_per_scale, float alpha) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 8;
     float s = alpha;
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(256) cast_scale_kernel(const float* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int C, long long ld,
                                                      float* __restrict__ out, long long rows_per_block, int tx_n) {
+  pdl_prologue();
   __shared__ float sh[256 * 8];
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
   const int ry = blockDim.x / tx_n;
@@ -84,6 +86,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ src, long long src_batch_stride,
                                                        __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C,
                                                        int R) {
+  pdl_prologue();
   const int c8n = C / 8;
   const long long total = (long long)B * H * W * c8n;
   const int ow = W / R, oh = H / R;
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ src
 // inverse: dpatch bf16 [B*oh*ow, R*R*C] -> dst fp32 NHWC rows (writes, does not accumulate)
 __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
                                                          long long dst_batch_stride, int B, int H, int W, int C, int R) {
+  pdl_prologue();
   const int c8n = C / 8;
   const long long total = (long long)B * H * W * c8n;
   const int ow = W / R, oh = H / R;
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __
 // flattening), zero padded to Kpad
 __global__ void __launch_bounds__(256) patchify_nchw_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ dst,
                                                             int B, int Cin, int H, int W, int P, int Kpad) {
+  pdl_prologue();
   // One block per (b, oy) row of patches: the Cin*P image rows it needs are read as whole rows (coalesced), transposed
   // through shared memory into [ow][Kpad] bf16 (zero padded) and written out as one contiguous ow*Kpad*2-byte run.
   extern __shared__ __align__(16) unsigned char patch_sh[];
@@ -170,6 +175,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) copy_rows_kernel(const TI* __restrict__ src, RowMap2 sm, long long lds,
                                                         TO* __restrict__ dst, RowMap2 dm, long long ldd, long long rows,
                                                         int C, int accumulate) {
+  pdl_prologue();
   const int c4n = C / 4;
   const long long total = rows * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -208,6 +214,7 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const TI* __restrict__ s
 // ---- out[r, c] (+)= sum_b x[b*batch_stride + r*C + c]  (position-embedding gradients) -------------------------
 __global__ void __launch_bounds__(256) batch_reduce_kernel(const float* __restrict__ x, long long batch_stride, int B,
                                                            long long n4, float* __restrict__ out, int accumulate, int bchunk) {
+  pdl_prologue();
   // blockIdx.y owns samples [y*bchunk, (y+1)*bchunk); with more than one chunk the partial sums meet in `out` through
   // vector atomics (the caller zeroes `out` first when it is not accumulating).
   const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
@@ -250,6 +257,7 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
 }
 __global__ void pos_resize_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst, int h, int w, int H, int W,
                                       int C) {
+  pdl_prologue();
   const long long total = (long long)H * W * C;
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -266,6 +274,7 @@ __global__ void pos_resize_fwd_kernel(const float* __restrict__ src, float* __re
 }
 __global__ void pos_resize_bwd_kernel(const float* __restrict__ dsrc_resized, float* __restrict__ dtable, int h, int w,
                                       int H, int W, int C) {
+  pdl_prologue();
   const long long total = (long long)H * W * C;
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -285,11 +294,13 @@ __global__ void pos_resize_bwd_kernel(const float* __restrict__ dsrc_resized, fl
 
 // ---- weight preparation: fp32 master -> bf16 compute copy, optionally permuting conv [Co,Ci,kh,kw] -> [Co,kh,kw,Ci]
 __global__ void cast_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16(src[i]);
 }
 __global__ void cast_conv_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Co, int Ci,
                                         int KK, int dst_ld) {
+  pdl_prologue();
   const long long n = (long long)Co * Ci * KK;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Ci);
@@ -301,6 +312,7 @@ __global__ void cast_conv_weight_kernel(const float* __restrict__ src, __nv_bflo
 // transposed + spatially flipped copy for the input-gradient convolution: dst[ci, t*Co + co] = src[co, ci, KK-1-t]
 __global__ void cast_conv_weight_t_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Co, int Ci,
                                           int KK) {
+  pdl_prologue();
   const long long n = (long long)Co * Ci * KK;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i % Co);
@@ -312,6 +324,7 @@ __global__ void cast_conv_weight_t_kernel(const float* __restrict__ src, __nv_bf
 // gradient of the permuted copy back to the master layout: dW[co,ci,kk] += dWp[co,kk,ci]
 __global__ void uncast_conv_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int KK,
                                          int src_ld) {
+  pdl_prologue();
   const long long n = (long long)Co * Ci * KK;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int kk = (int)(i % KK);
@@ -324,6 +337,7 @@ __global__ void uncast_conv_wgrad_kernel(const float* __restrict__ dwp, float* _
 // ---- out = dy * gelu_erf'(pre), all bf16 -----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pre,
                                                        __nv_bfloat16* __restrict__ out, long long n2) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const float2 d = unpack_bf16x2(reinterpret_cast<const uint32_t*>(dy)[i]);
     const float2 x = unpack_bf16x2(reinterpret_cast<const uint32_t*>(pre)[i]);
@@ -335,6 +349,7 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __re
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) cast2d_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst,
                                                      long long ldd, long long rows, int C, float alpha) {
+  pdl_prologue();
   const long long total = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / C;
@@ -352,8 +367,7 @@ __global__ void __launch_bounds__(256) cast2d_kernel(const TI* __restrict__ src,
 
 extern "C" int mvlt_gelu_bwd(const void* dy_bf16, const void* pre_bf16, void* out_bf16, long long n, void* stream_) {
   MVLT_CHECK_ARG(n % 2 == 0, "gelu_bwd: n must be even");
-  gelu_bwd_kernel<<<cap_grid(n / 2, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(pre_bf16),
+  mvlt_launch(gelu_bwd_kernel, cap_grid(n / 2, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(pre_bf16),
       reinterpret_cast<__nv_bfloat16*>(out_bf16), n / 2);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -363,7 +377,7 @@ extern "C" int mvlt_cast2d(const void* src, int src_f32, long long lds, void* ds
                            long long rows, int C, float alpha, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const int grid = cap_grid(rows * C, 256);
-#define LAUNCH(TI, TO) cast2d_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(src), lds, reinterpret_cast<TO*>(dst), ldd, rows, C, alpha)
+#define LAUNCH(TI, TO) mvlt_launch(cast2d_kernel<TI, TO>, grid, 256, 0, st, reinterpret_cast<const TI*>(src), lds, reinterpret_cast<TO*>(dst), ldd, rows, C, alpha)
   if (src_f32 && dst_f32) LAUNCH(float, float);
   else if (src_f32) LAUNCH(float, __nv_bfloat16);
   else if (dst_f32) LAUNCH(__nv_bfloat16, float);
@@ -386,8 +400,7 @@ extern "C" int mvlt_cast_scale_bf16(const float* src, void* dst, long long rows,
                                     int rows_per_scale, float alpha, void* stream_) {
   MVLT_CHECK_ARG(C % 8 == 0, "cast_scale: C=%d must be a multiple of 8", C);
   const long long n8 = rows * C / 8;
-  cast_scale_kernel<<<cap_grid(n8, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst), n8, C, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, alpha);
+  mvlt_launch(cast_scale_kernel, cap_grid(n8, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), src, reinterpret_cast<__nv_bfloat16*>(dst), n8, C, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, alpha);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -406,8 +419,8 @@ extern "C" int mvlt_colsum(const void* x, int x_f32, long long rows, int C, long
   gy = (rows + rpb - 1) / rpb;
   dim3 grid(gx, (unsigned)gy);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  if (x_f32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), rows, C, ld, out, rpb, tx_n);
-  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, ld, out, rpb, tx_n);
+  if (x_f32) mvlt_launch(colsum_kernel<float>, grid, 256, 0, st, reinterpret_cast<const float*>(x), rows, C, ld, out, rpb, tx_n);
+  else mvlt_launch(colsum_kernel<__nv_bfloat16>, grid, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x), rows, C, ld, out, rpb, tx_n);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -418,11 +431,10 @@ extern "C" int mvlt_patchify(const void* src, int src_f32, long long src_batch_s
   const long long total = (long long)B * H * W * (C / 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (src_f32)
-    patchify_kernel<float><<<cap_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(src), src_batch_stride,
+    mvlt_launch(patchify_kernel<float>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const float*>(src), src_batch_stride,
                                                                  reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C, R);
   else
-    patchify_kernel<__nv_bfloat16><<<cap_grid(total, 256), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(src), src_batch_stride, reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C, R);
+    mvlt_launch(patchify_kernel<__nv_bfloat16>, cap_grid(total, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(src), src_batch_stride, reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C, R);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -431,8 +443,7 @@ extern "C" int mvlt_unpatchify(const void* src_bf16, float* dst, long long dst_b
                                int R, void* stream_) {
   MVLT_CHECK_ARG(C % 8 == 0 && H % R == 0 && W % R == 0, "unpatchify: bad shape");
   const long long total = (long long)B * H * W * (C / 8);
-  unpatchify_kernel<<<cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src_bf16), dst, dst_batch_stride, B, H, W, C, R);
+  mvlt_launch(unpatchify_kernel, cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(src_bf16), dst, dst_batch_stride, B, H, W, C, R);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -452,7 +463,7 @@ extern "C" int mvlt_patchify_nchw(const float* img, void* dst_bf16, int B, int C
   int grid = B * (H / P);
   const int cap = mvlt_num_sms() * 8;
   if (grid > cap) grid = cap;
-  patchify_nchw_kernel<<<grid, 256, smem, st>>>(img, reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, Cin, H, W, P, Kpad);
+  mvlt_launch(patchify_nchw_kernel, grid, 256, smem, st, img, reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, Cin, H, W, P, Kpad);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -469,7 +480,7 @@ extern "C" int mvlt_copy_rows(const void* src, int src_f32, const int* smap, lon
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const int grid = cap_grid(total, 256);
 #define LAUNCH(TI, TO)                                                                                          \
-  copy_rows_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(src), sm, lds,                     \
+  mvlt_launch(copy_rows_kernel<TI, TO>, grid, 256, 0, st, reinterpret_cast<const TI*>(src), sm, lds,                     \
                                                  reinterpret_cast<TO*>(dst), dm, ldd, rows, C, accumulate)
   if (src_f32 && dst_f32) LAUNCH(float, float);
   else if (src_f32) LAUNCH(float, __nv_bfloat16);
@@ -492,39 +503,36 @@ extern "C" int mvlt_batch_reduce(const float* x, long long batch_stride, int B, 
   chunks = (B + bchunk - 1) / bchunk;
   if (chunks > 1 && !accumulate) cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), st);
   dim3 grid((unsigned)(xblocks < 65535 ? xblocks : 65535), (unsigned)chunks);
-  batch_reduce_kernel<<<grid, 256, 0, st>>>(x, batch_stride, B, n / 4, out, accumulate, bchunk);
+  mvlt_launch(batch_reduce_kernel, grid, 256, 0, st, x, batch_stride, B, n / 4, out, accumulate, bchunk);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int mvlt_pos_resize_fwd(const float* table, float* out, int h, int w, int H, int W, int C, void* stream_) {
   const long long total = (long long)H * W * C;
-  pos_resize_fwd_kernel<<<cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(table, out, h, w, H, W, C);
+  mvlt_launch(pos_resize_fwd_kernel, cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), table, out, h, w, H, W, C);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 extern "C" int mvlt_pos_resize_bwd(const float* dout, float* dtable, int h, int w, int H, int W, int C, void* stream_) {
   const long long total = (long long)H * W * C;
-  pos_resize_bwd_kernel<<<cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(dout, dtable, h, w, H, W, C);
+  mvlt_launch(pos_resize_bwd_kernel, cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), dout, dtable, h, w, H, W, C);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int mvlt_cast_weight(const float* src, void* dst_bf16, long long n, void* stream_) {
-  cast_weight_kernel<<<cap_grid(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
+  mvlt_launch(cast_weight_kernel, cap_grid(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 extern "C" int mvlt_cast_conv_weight(const float* src, void* dst_bf16, int Co, int Ci, int KK, int dst_ld, void* stream_) {
-  cast_conv_weight_kernel<<<cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), Co, Ci, KK, dst_ld);
+  mvlt_launch(cast_conv_weight_kernel, cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), Co, Ci, KK, dst_ld);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 extern "C" int mvlt_cast_conv_weight_t(const float* src, void* dst_bf16, int Co, int Ci, int KK, void* stream_) {
-  cast_conv_weight_t_kernel<<<cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), Co, Ci, KK);
+  mvlt_launch(cast_conv_weight_t_kernel, cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), Co, Ci, KK);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -540,6 +548,7 @@ struct UncastBatch {
   UncastEntry t[24];
 };
 __global__ void uncast_conv_wgrad_multi_kernel(const UncastBatch b) {
+  pdl_prologue();
   const UncastEntry e = b.t[blockIdx.y];
   const long long n = (long long)e.Co * e.Ci * e.KK;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -562,13 +571,12 @@ extern "C" int mvlt_uncast_conv_wgrad_multi(const void* entries, int n, void* st
     if (e > mx) mx = e;
   }
   dim3 grid((unsigned)cap_grid(mx, 256, 2), (unsigned)n);
-  uncast_conv_wgrad_multi_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(b);
+  mvlt_launch(uncast_conv_wgrad_multi_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_), b);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 extern "C" int mvlt_uncast_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KK, int src_ld, void* stream_) {
-  uncast_conv_wgrad_kernel<<<cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      dwp, dw, Co, Ci, KK, src_ld);
+  mvlt_launch(uncast_conv_wgrad_kernel, cap_grid((long long)Co * Ci * KK, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), dwp, dw, Co, Ci, KK, src_ld);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) bert_embed_fwd_kernel(const long long* __
                                                              __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out,
                                                              float* __restrict__ rstd_out, int rows, int T, float eps,
                                                              float p_drop, unsigned long long seed) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) bert_embed_bwd_kernel(const __nv_bfloat16
                                                              float* __restrict__ dtype_, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, int rows, int T, float p_drop,
                                                              unsigned long long seed, int pad_id) {
+  pdl_prologue();
   __shared__ float shg[8][HID];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -150,8 +152,7 @@ extern "C" int mvlt_bert_embed_fwd(const long long* ids, const float* word, cons
   int grid = (rows + 7) / 8;
   const int cap = mvlt_num_sms() * 8;
   if (grid > cap) grid = cap;
-  bert_embed_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      ids, word, pos, type, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), mean, rstd, rows, T, eps, p_drop, seed);
+  mvlt_launch(bert_embed_fwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_), ids, word, pos, type, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), mean, rstd, rows, T, eps, p_drop, seed);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -165,8 +166,7 @@ extern "C" int mvlt_bert_embed_bwd(const void* dy_bf16, const long long* ids, co
   const int cap = mvlt_num_sms() * 2;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  bert_embed_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), ids, word, pos, type, gamma, mean, rstd, dword, dpos, dtype_,
+  mvlt_launch(bert_embed_bwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(dy_bf16), ids, word, pos, type, gamma, mean, rstd, dword, dpos, dtype_,
       dgamma, dbeta, rows, T, p_drop, seed, pad_id);
   MVLT_CHECK_LAUNCH();
   return 0;

@@ -7,6 +7,7 @@
 namespace {
 
 __global__ void gemm_ref_kernel(const mvlt_gemm_desc g) {
+  pdl_prologue();
   const long long total = (long long)g.batch1 * g.batch2 * g.M * g.N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -58,7 +59,7 @@ extern "C" int mvlt_gemm_ref(const mvlt_gemm_desc* g, void* stream) {
   const long long total = (long long)g->batch1 * g->batch2 * g->M * g->N;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  gemm_ref_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*g);
+  mvlt_launch(gemm_ref_kernel, (int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), *g);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -580,6 +580,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  pdl_trigger();   // the next kernel of the stream may be scheduled behind this grid's tail (common.cuh)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -622,6 +623,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // barrier / TMEM set-up above overlapped the previous kernel; global memory is only touched below
 
   const int total_tiles = p.batch1 * p.batch2 * p.split_k * p.num_m_blocks * p.num_n_blocks;
   const int acc_mask = p.num_acc - 1;                 // num_acc is 2 or 4
@@ -1305,7 +1307,7 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
       p.tma_store = 1;
     }
   }
-  kVariants[pick_variant(g)].fn<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmD, tmD2, tmDh, tmD2h, p);
+  mvlt_launch(kVariants[pick_variant(g)].fn, grid, NUM_THREADS, smem, stream, tmA, tmB, tmD, tmD2, tmDh, tmD2h, p);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -13,6 +13,7 @@ namespace {
 __global__ void __launch_bounds__(1024) compact_labels_kernel(const long long* __restrict__ labels, int n, long long ignore,
                                                               int* __restrict__ idx, long long* __restrict__ lab_out,
                                                               int* __restrict__ count) {
+  pdl_prologue();
   __shared__ int warp_tot[32];
   __shared__ int base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -52,6 +53,7 @@ __device__ __forceinline__ long long map_row3(const RowMap3& m, long long r) {
 template <typename TO>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, RowMap3 sm, long long lds,
                                                           const int* __restrict__ idx, int n_idx, TO* __restrict__ dst, int C) {
+  pdl_prologue();
   const int c4n = C / 4;
   const long long total = (long long)n_idx * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -73,6 +75,7 @@ template <typename TI>
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const TI* __restrict__ src, const int* __restrict__ idx, int n_idx,
                                                            float* __restrict__ dst, RowMap3 dm, long long ldd, int C,
                                                            int accumulate) {
+  pdl_prologue();
   const int c4n = C / 4;
   const long long total = (long long)n_idx * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logit
                                                      int n_cls, long long ignore, float* __restrict__ lse_out,
                                                      float* __restrict__ loss_sum, float* __restrict__ total_sum, float scale,
                                                      int* __restrict__ argmax_out, float* __restrict__ correct) {
+  pdl_prologue();
   __shared__ float sh[32];
   __shared__ int shi[32];
   const int r = blockIdx.x;
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ logit
                                                      int n_cls, long long ignore, const float* __restrict__ lse,
                                                      T* __restrict__ dlogits, long long ldd, float scale,
                                                      const float* __restrict__ gscale) {
+  pdl_prologue();
   const int r = blockIdx.x;
   const long long lab = labels[r];
   const float g = scale * (gscale ? *gscale : 1.f);
@@ -223,6 +228,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ logit
 __global__ void __launch_bounds__(256) small_linear_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ W,
                                                                const float* __restrict__ b1, const float* __restrict__ b2,
                                                                float* __restrict__ out, int M, int n, int K) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= M * n) return;
@@ -241,6 +247,7 @@ __global__ void __launch_bounds__(256) small_linear_bwd_kernel(const float* __re
                                                                const float* __restrict__ W, __nv_bfloat16* __restrict__ dh,
                                                                float* __restrict__ dW, float* __restrict__ db1,
                                                                float* __restrict__ db2, int M, int n, int K) {
+  pdl_prologue();
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long n_dh = (long long)M * K, n_dw = (long long)n * K;
   if (tid < n_dh) {
@@ -266,6 +273,7 @@ __global__ void __launch_bounds__(256) small_linear_bwd_kernel(const float* __re
 // ---- retrieval: rank of candidate 0 under descending p(match) -------------------------------------------------
 __global__ void itm_rank_kernel(const float* __restrict__ logits, int n_query, int n_cand, int* __restrict__ rank_out,
                                 float* __restrict__ prob_out) {
+  pdl_prologue();
   __shared__ float sh[32];
   const int q = blockIdx.x;
   const float* lq = logits + (long long)q * n_cand * 2;
@@ -289,6 +297,7 @@ __global__ void itm_rank_kernel(const float* __restrict__ logits, int n_query, i
 // sum of squared differences (compute_psnr, vl_scores.py:54-63)
 __global__ void __launch_bounds__(256) sq_diff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
                                                           float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float sh[32];
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -316,7 +325,7 @@ inline int cap_grid(long long work_items, int threads, int per_sm = 8) {
 extern "C" int mvlt_compact_labels(const long long* labels, int n, long long ignore, int* idx_out, long long* labels_out,
                                    int* count_out, void* stream_) {
   MVLT_CHECK_ARG(n > 0, "compact_labels: n must be positive");
-  compact_labels_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(labels, n, ignore, idx_out, labels_out,
+  mvlt_launch(compact_labels_kernel, 1, 1024, 0, reinterpret_cast<cudaStream_t>(stream_), labels, n, ignore, idx_out, labels_out,
                                                                                  count_out);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -329,8 +338,8 @@ extern "C" int mvlt_gather_rows(const float* src, const int* smap, long long lds
   RowMap3 sm{smap && smap[0] > 0 ? smap[0] : big, smap && smap[0] > 0 ? smap[1] : big, smap && smap[0] > 0 ? smap[2] : 0};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const int grid = cap_grid((long long)n_idx * (C / 4), 256);
-  if (dst_f32) gather_rows_kernel<float><<<grid, 256, 0, st>>>(src, sm, lds, idx, n_idx, reinterpret_cast<float*>(dst), C);
-  else gather_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, sm, lds, idx, n_idx, reinterpret_cast<__nv_bfloat16*>(dst), C);
+  if (dst_f32) mvlt_launch(gather_rows_kernel<float>, grid, 256, 0, st, src, sm, lds, idx, n_idx, reinterpret_cast<float*>(dst), C);
+  else mvlt_launch(gather_rows_kernel<__nv_bfloat16>, grid, 256, 0, st, src, sm, lds, idx, n_idx, reinterpret_cast<__nv_bfloat16*>(dst), C);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -342,8 +351,8 @@ extern "C" int mvlt_scatter_rows(const void* src, int src_f32, const int* idx, i
   RowMap3 dm{dmap && dmap[0] > 0 ? dmap[0] : big, dmap && dmap[0] > 0 ? dmap[1] : big, dmap && dmap[0] > 0 ? dmap[2] : 0};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const int grid = cap_grid((long long)n_idx * (C / 4), 256);
-  if (src_f32) scatter_rows_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), idx, n_idx, dst, dm, ldd, C, accumulate);
-  else scatter_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), idx, n_idx, dst, dm, ldd, C, accumulate);
+  if (src_f32) mvlt_launch(scatter_rows_kernel<float>, grid, 256, 0, st, reinterpret_cast<const float*>(src), idx, n_idx, dst, dm, ldd, C, accumulate);
+  else mvlt_launch(scatter_rows_kernel<__nv_bfloat16>, grid, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(src), idx, n_idx, dst, dm, ldd, C, accumulate);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -354,10 +363,10 @@ extern "C" int mvlt_ce_fwd(const void* logits, int logits_f32, long long ld, con
   MVLT_CHECK_ARG(rows > 0 && n_cls > 0, "ce_fwd: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (logits_f32)
-    ce_fwd_kernel<float><<<rows, 256, 0, st>>>(reinterpret_cast<const float*>(logits), ld, labels, n_cls, ignore, lse,
+    mvlt_launch(ce_fwd_kernel<float>, rows, 256, 0, st, reinterpret_cast<const float*>(logits), ld, labels, n_cls, ignore, lse,
                                                loss_sum, total_sum, scale, argmax_out, correct);
   else
-    ce_fwd_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, labels, n_cls,
+    mvlt_launch(ce_fwd_kernel<__nv_bfloat16>, rows, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(logits), ld, labels, n_cls,
                                                        ignore, lse, loss_sum, total_sum, scale, argmax_out, correct);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -369,10 +378,10 @@ extern "C" int mvlt_ce_bwd(const void* logits, int logits_f32, long long ld, con
   MVLT_CHECK_ARG(rows > 0 && n_cls > 0, "ce_bwd: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (logits_f32)
-    ce_bwd_kernel<float><<<rows, 256, 0, st>>>(reinterpret_cast<const float*>(logits), ld, labels, n_cls, ignore, lse,
+    mvlt_launch(ce_bwd_kernel<float>, rows, 256, 0, st, reinterpret_cast<const float*>(logits), ld, labels, n_cls, ignore, lse,
                                                reinterpret_cast<float*>(dlogits), ldd, scale, gscale_dev);
   else
-    ce_bwd_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, labels, n_cls,
+    mvlt_launch(ce_bwd_kernel<__nv_bfloat16>, rows, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(logits), ld, labels, n_cls,
                                                        ignore, lse, reinterpret_cast<__nv_bfloat16*>(dlogits), ldd, scale,
                                                        gscale_dev);
   MVLT_CHECK_LAUNCH();
@@ -383,8 +392,7 @@ extern "C" int mvlt_small_linear_fwd(const void* h_bf16, const float* W, const f
                                      int M, int n, int K, void* stream_) {
   MVLT_CHECK_ARG(K % 2 == 0 && M > 0 && n > 0, "small_linear_fwd: bad shape");
   const long long warps = (long long)M * n;
-  small_linear_fwd_kernel<<<(int)((warps + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(h_bf16), W, b1, b2, out, M, n, K);
+  mvlt_launch(small_linear_fwd_kernel, (int)((warps + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(h_bf16), W, b1, b2, out, M, n, K);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -392,8 +400,7 @@ extern "C" int mvlt_small_linear_fwd(const void* h_bf16, const float* W, const f
 extern "C" int mvlt_small_linear_bwd(const float* dlogits, const void* h_bf16, const float* W, void* dh_bf16, float* dW,
                                      float* db1, float* db2, int M, int n, int K, void* stream_) {
   const long long total = (long long)M * K + (long long)n * K + n;
-  small_linear_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      dlogits, reinterpret_cast<const __nv_bfloat16*>(h_bf16), W, reinterpret_cast<__nv_bfloat16*>(dh_bf16), dW, db1, db2,
+  mvlt_launch(small_linear_bwd_kernel, (int)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), dlogits, reinterpret_cast<const __nv_bfloat16*>(h_bf16), W, reinterpret_cast<__nv_bfloat16*>(dh_bf16), dW, db1, db2,
       M, n, K);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -401,13 +408,13 @@ extern "C" int mvlt_small_linear_bwd(const float* dlogits, const void* h_bf16, c
 
 extern "C" int mvlt_itm_rank(const float* logits, int n_query, int n_cand, int* rank_out, float* prob_out, void* stream_) {
   MVLT_CHECK_ARG(n_query > 0 && n_cand > 0, "itm_rank: bad shape");
-  itm_rank_kernel<<<n_query, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(logits, n_query, n_cand, rank_out, prob_out);
+  mvlt_launch(itm_rank_kernel, n_query, 128, 0, reinterpret_cast<cudaStream_t>(stream_), logits, n_query, n_cand, rank_out, prob_out);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int mvlt_sq_diff_sum(const float* a, const float* b, long long n, float* out, void* stream_) {
-  sq_diff_sum_kernel<<<cap_grid(n, 256, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(a, b, n, out);
+  mvlt_launch(sq_diff_sum_kernel, cap_grid(n, 256, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream_), a, b, n, out);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

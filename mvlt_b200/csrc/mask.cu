@@ -84,6 +84,7 @@ __device__ uint32_t mt_randbelow_py(MT& s, uint32_t n) {
 __global__ void __launch_bounds__(32) token_mask_kernel(const uint32_t* __restrict__ seeds, const long long* __restrict__ ori,
                                                         long long* __restrict__ ids, long long* __restrict__ labels, int B, int T,
                                                         int sep_id, int mask_id, int vocab, double rate) {
+  pdl_prologue();
   __shared__ uint32_t state[624];
   const int b = blockIdx.x;
   const long long* o = ori + (long long)b * T;
@@ -117,6 +118,7 @@ constexpr int MAX_NW = 64;
 // one warp per sample; lane 0 walks the (inherently sequential) generator
 __global__ void __launch_bounds__(32) grid_mask_kernel(const uint32_t* __restrict__ seeds, uint8_t* __restrict__ grid, int B,
                                                        int nw, int nh, int n_mask) {
+  pdl_prologue();
   __shared__ uint32_t state[624];
   __shared__ uint8_t vals[MAX_PATCHES];
   __shared__ uint8_t row[MAX_NW];
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(32) grid_mask_kernel(const uint32_t* __restric
 __global__ void __launch_bounds__(256) masked_fill_kernel(const float* __restrict__ img, const uint8_t* __restrict__ grid,
                                                           float* __restrict__ out, float* __restrict__ mask_out, int B,
                                                           int Cc, int H, int W, int P, float fill) {
+  pdl_prologue();
   const int w4 = W / 4;
   const long long total = (long long)B * Cc * H * w4;
   const int nw = W / P;
@@ -171,7 +174,7 @@ extern "C" int mvlt_grid_mask(const uint32_t* seeds_dev, uint8_t* grid_out, int 
   const int nw = size_w / patch, nh = size_h / patch;
   MVLT_CHECK_ARG(nw * nh <= MAX_PATCHES && nw <= MAX_NW, "grid_mask: too many patches");
   const int n_mask = (int)(mask_ratio * (double)(nw * nh));
-  grid_mask_kernel<<<B, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(seeds_dev, grid_out, B, nw, nh, n_mask);
+  mvlt_launch(grid_mask_kernel, B, 32, 0, reinterpret_cast<cudaStream_t>(stream_), seeds_dev, grid_out, B, nw, nh, n_mask);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -180,7 +183,7 @@ extern "C" int mvlt_grid_mask(const uint32_t* seeds_dev, uint8_t* grid_out, int 
 extern "C" int mvlt_token_mask(const uint32_t* seeds_dev, const long long* ori_ids, long long* input_ids, long long* labels, int B,
                                int T, int sep_id, int mask_id, int vocab_size, double mask_rate, void* stream_) {
   MVLT_CHECK_ARG(B > 0 && T > 1 && vocab_size > 0 && mask_rate > 0.0 && mask_rate <= 1.0, "token_mask: bad arguments");
-  token_mask_kernel<<<B, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(seeds_dev, ori_ids, input_ids, labels, B, T, sep_id,
+  mvlt_launch(token_mask_kernel, B, 32, 0, reinterpret_cast<cudaStream_t>(stream_), seeds_dev, ori_ids, input_ids, labels, B, T, sep_id,
                                                                            mask_id, vocab_size, mask_rate);
   MVLT_CHECK_LAUNCH();
   return 0;
@@ -194,7 +197,7 @@ extern "C" int mvlt_masked_fill(const float* img, const uint8_t* grid, float* ou
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)mvlt_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  masked_fill_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(img, grid, out, mask_out, B, C, H, W,
+  mvlt_launch(masked_fill_kernel, (int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_), img, grid, out, mask_out, B, C, H, W,
                                                                                      patch, fill);
   MVLT_CHECK_LAUNCH();
   return 0;

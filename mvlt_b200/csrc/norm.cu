@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, R
                                                      const float* __restrict__ beta, TO* __restrict__ y, RowMap ym,
                                                      const float* __restrict__ post_add, float* __restrict__ mean_out,
                                                      float* __restrict__ rstd_out, int rows, int C, float eps) {
+  pdl_prologue();
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, sub = lane % G;
   const int warps = blockDim.x >> 5;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
                                                      int C, __nv_bfloat16* __restrict__ dx16, const float* __restrict__ rowscale,
                                                      int rows_per_scale) {
+  pdl_prologue();
   extern __shared__ float sh[];  // [2][warps * RPW][C]
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % G;
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
 constexpr int SM_MAX_PAIRS = 8;  // Nk <= 512
 
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(__nv_bfloat16* __restrict__ s, long long rows, int nk) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int npair = nk / 64;  // each lane owns bf16x2 at column lane*2 + 64*j
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(__nv_bfloat16* __restr
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p,
                                                           __nv_bfloat16* __restrict__ dp, long long rows, int nk,
                                                           float scale) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int npair = nk / 64;
@@ -308,7 +312,7 @@ extern "C" int mvlt_layernorm_fwd(const void* x, int x_f32, const int* xmap, con
   const int rpb = C <= 64 ? 64 : (C <= 128 ? 32 : (C <= 512 ? 16 : 8));
   const int grid = ln_grid(rows, rpb);
 #define LN_FWD_CALL(TI, TO, G, NV, RU)                                                                          \
-  ln_fwd_kernel<TI, TO, G, NV, RU><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), xm, gamma, beta,           \
+  mvlt_launch(ln_fwd_kernel<TI, TO, G, NV, RU>, grid, 256, 0, st, reinterpret_cast<const TI*>(x), xm, gamma, beta,           \
                                                          reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps)
 #define LAUNCH(TI, TO)                                    \
   do {                                                    \
@@ -344,7 +348,7 @@ extern "C" int mvlt_layernorm_bwd(const void* dy, int dy_f32, const int* dymap, 
   const int grid = (int)(b < cap ? (b > 0 ? b : 1) : cap);
   const size_t smem = (size_t)2 * wpb * rpw * C * sizeof(float);
 #define LN_BWD_CALL(TDY, TX, TDX, G, NV)                                                                         \
-  ln_bwd_kernel<TDY, TX, TDX, G, NV><<<grid, 256, smem, st>>>(reinterpret_cast<const TDY*>(dy), dym,                 \
+  mvlt_launch(ln_bwd_kernel<TDY, TX, TDX, G, NV>, grid, 256, smem, st, reinterpret_cast<const TDY*>(dy), dym,                 \
                                                               reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma, \
                                                               reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta, rows, C, \
                                                               reinterpret_cast<__nv_bfloat16*>(dx_bf16_scaled), rowscale,     \
@@ -377,8 +381,7 @@ extern "C" int mvlt_softmax_fwd(void* s_bf16, long long rows, int nk, void* stre
   MVLT_CHECK_ARG(nk % 64 == 0 && nk <= 64 * SM_MAX_PAIRS, "softmax_fwd: Nk=%d must be a multiple of 64 and <= 512", nk);
   long long b = (rows + 7) / 8;
   const long long cap = (long long)mvlt_num_sms() * 16;
-  softmax_fwd_kernel<<<(int)(b < cap ? b : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      reinterpret_cast<__nv_bfloat16*>(s_bf16), rows, nk);
+  mvlt_launch(softmax_fwd_kernel, (int)(b < cap ? b : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<__nv_bfloat16*>(s_bf16), rows, nk);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -388,8 +391,7 @@ extern "C" int mvlt_softmax_bwd(const void* p_bf16, void* dp_bf16, long long row
   MVLT_CHECK_ARG(nk % 64 == 0 && nk <= 64 * SM_MAX_PAIRS, "softmax_bwd: Nk=%d must be a multiple of 64 and <= 512", nk);
   long long b = (rows + 7) / 8;
   const long long cap = (long long)mvlt_num_sms() * 16;
-  softmax_bwd_kernel<<<(int)(b < cap ? b : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(p_bf16), reinterpret_cast<__nv_bfloat16*>(dp_bf16), rows, nk, scale);
+  mvlt_launch(softmax_bwd_kernel, (int)(b < cap ? b : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(p_bf16), reinterpret_cast<__nv_bfloat16*>(dp_bf16), rows, nk, scale);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
