@@ -15,7 +15,7 @@ void mvlt_set_error(const char* fmt, ...);
 #define MVLT_ERR_ALIGN (-2)
 #define MVLT_ERR_DRIVER (-3)
 #ifndef MVLT_PDL_DEFAULT
-#define MVLT_PDL_DEFAULT 0
+#define MVLT_PDL_DEFAULT 1
 #endif
 
 #define MVLT_CHECK_ARG(cond, ...)                 \
@@ -55,7 +55,8 @@ static inline int mvlt_num_sms() {
 //   griddepcontrol.wait               - blocks until the PREVIOUS kernel has completed and its writes are visible;
 //                                       no global memory is read or written before it.
 // Launch latency, CTA scheduling and (GEMM / attention) barrier + TMEM set-up of kernel i+1 thus overlap the tail of
-// kernel i. Both instructions are no-ops when the launch attribute is absent (MVLT_PDL=0).
+// kernel i (measured: 17.17 -> 16.55 ms per training step). Both instructions are no-ops when the launch attribute is
+// absent (MVLT_PDL=0 in the environment switches it off for A/B runs).
 // ---------------------------------------------------------------------------------------------
 #include <stdlib.h>
 static inline bool mvlt_pdl_enabled() {

@@ -419,8 +419,9 @@ __global__ void __launch_bounds__(256) score_fwd_kernel(const __nv_bfloat16* __r
 __global__ void __launch_bounds__(256) score_bwd_kernel(const float* __restrict__ ds, const __nv_bfloat16* __restrict__ x,
                                                         const float* __restrict__ W, __nv_bfloat16* __restrict__ dx,
                                                         float* __restrict__ dW, float* __restrict__ db, long long rows, int Cin,
-                                                        long long rows_per_block) {
+                                                        long long rows_per_block, const float* __restrict__ gscale) {
   pdl_prologue();
+  const float gsc = gscale ? *gscale : 1.f;   // upstream gradient of the total loss (device scalar), folded in here
   extern __shared__ float shw[];  // [3*Cin] partial dW + [3] db
   for (int i = threadIdx.x; i < 3 * Cin + 3; i += blockDim.x) shw[i] = 0.f;
   __syncthreads();
@@ -432,8 +433,9 @@ __global__ void __launch_bounds__(256) score_bwd_kernel(const float* __restrict_
   if (c < Cin) {
     float w0 = W[c], w1 = W[Cin + c], w2 = W[2 * Cin + c];
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll 4
     for (long long r = r0; r < r1; ++r) {
-      const float d0 = ds[r * 3], d1 = ds[r * 3 + 1], d2 = ds[r * 3 + 2];
+      const float d0 = ds[r * 3] * gsc, d1 = ds[r * 3 + 1] * gsc, d2 = ds[r * 3 + 2] * gsc;
       const float xv = __bfloat162float(x[r * Cin + c]);
       dx[r * Cin + c] = __float2bfloat16(d0 * w0 + d1 * w1 + d2 * w2);
       g0 += d0 * xv; g1 += d1 * xv; g2 += d2 * xv;
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(256) score_bwd_kernel(const float* __restrict_
     const int j = c - Cin;
     float s = 0.f;
     for (long long r = r0; r < r1; ++r) s += ds[r * 3 + j];
-    atomicAdd(db + j, s);
+    atomicAdd(db + j, s * gsc);
   }
 }
 
@@ -473,29 +475,39 @@ __global__ void __launch_bounds__(256) upsample8_fwd_kernel(const float* __restr
 
 // One block per (b, c, output-row band of S rows). mode 0: g = dpred (given); mode 1: g = d SmoothL1(pred - target) *
 // scale * gscale and the loss itself is accumulated. dscore (fp32 NHWC [B,h,w,3]) receives the transposed interpolation
-// of g, computed separably inside the block without shared-memory atomics:
-//   phase 1: g[S][W] -> shared;  phase 2: gx[Y][x] = sum_X g[Y][X] * wx(X -> x);  phase 3: rows (<= 3 score rows touched by
-//   the band) = sum_Y gx[Y][x] * wy(Y -> row), then one global atomic per touched score cell.
+// of g. Everything is separable and lanes always walk the output columns X (coalesced global reads, conflict-free
+// shared memory):
+//   setup   : per-column source index / weight tables, the first output column of every source column (xs), the weights
+//             of the band's S rows onto the <= 3 score rows it touches (wy), and -- mode 1 -- those 3 score rows
+//             interpolated along X once per block (ri), so that a prediction is 2 shared loads + 2 FMAs;
+//   phase 1 : g[S][W] -> shared (+ loss);
+//   phase 2 : along Y first: gy[r][X] = sum_Y wy[r][Y] g[Y][X] for the 3 score rows, stored pre-multiplied by the two
+//             X weights (A = (1 - lx) gy, Bv = lx gy) at padded positions X + X/8 (the X phase reads with stride ~8.2);
+//   phase 3 : along X: dscore[r][x] += sum_{X in bin(x)} A + sum_{X in bin(x-1)} Bv, one global atomic per touched cell.
 __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restrict__ score, const float* __restrict__ target,
                                                            const float* __restrict__ dpred, float* __restrict__ dscore,
                                                            float* __restrict__ loss_sum, float* __restrict__ total_sum,
                                                            float loss_scale, float grad_scale, const float* __restrict__ gscale,
                                                            int B, int h, int w, int S, int mode, int want_grad) {
   pdl_prologue();
-  extern __shared__ float sh[];  // g[S][W] | gx[S][w] | 32 for reductions | lx[W] | ly[S] | x0[W] (int) | y0[S] (int)
+  extern __shared__ float sh[];
   const int H = h * S, W = w * S;
+  const int WP = W + (W >> 3) + 1;   // padded row length of A / Bv
   const int bands = H / S;  // one band = S output rows => touches at most score rows ybase .. ybase+2
   const int band = blockIdx.x % bands;
   const int c = (blockIdx.x / bands) % 3;
   const int b = blockIdx.x / (bands * 3);
-  float* gs = sh;             // [S][W]
-  float* gx = sh + S * W;     // [S][w]
-  float* red = gx + S * w;    // [32]
-  float* lxs = red + 32;      // [W]  interpolation weight of output column X
-  float* lys = lxs + W;       // [S]
-  int* x0s = reinterpret_cast<int*>(lys + S);   // [W]  left source column of output column X
-  int* y0s = x0s + W;                           // [S]
-  // the source index / weight of every output column and of the band's rows, computed once per block
+  float* gs = sh;               // [S][W]
+  float* red = gs + S * W;      // [32]
+  float* lxs = red + 32;        // [W]  interpolation weight of output column X
+  float* lys = lxs + W;         // [S]
+  float* wys = lys + S;         // [3][S] weight of band row yy onto score row ybase + r
+  float* ri = wys + 3 * S;      // [3][W] score rows ybase .. ybase+2 interpolated along X (mode 1)
+  float* As = ri + 3 * W;       // [3][WP]
+  float* Bs = As + 3 * WP;      // [3][WP]
+  int* x0s = reinterpret_cast<int*>(Bs + 3 * WP);   // [W]  left source column of output column X
+  int* y0s = x0s + W;                               // [S]
+  int* xs = y0s + S;                                // [w + 1] first output column whose left source column is x
   for (int X = threadIdx.x; X < W; X += blockDim.x) {
     int x0, x1;
     float lx;
@@ -510,30 +522,56 @@ __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restri
     y0s[yy] = y0;
     lys[yy] = ly;
   }
+  for (int x = threadIdx.x; x <= w; x += blockDim.x) xs[x] = W;
   __syncthreads();
-  const float* sb = score + (long long)b * h * w * 3 + c;
-  const float g_mul = grad_scale * (gscale ? *gscale : 1.f);
   const int ybase = y0s[0];
-  float lsum = 0.f;
-  for (int e = threadIdx.x; e < S * W; e += blockDim.x) {
-    const int yy = e / W, X = e % W;
-    const int Y = band * S + yy;
-    const long long off = (((long long)b * 3 + c) * H + Y) * W + X;
-    float g;
-    if (mode == 1) {
-      const int y0 = y0s[yy], x0 = x0s[X];
-      const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
-      const float ly = lys[yy], lx = lxs[X];
-      const float v00 = sb[(y0 * w + x0) * 3], v01 = sb[(y0 * w + x1) * 3], v10 = sb[(y1 * w + x0) * 3], v11 = sb[(y1 * w + x1) * 3];
-      const float pred = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-      const float d = pred - target[off];
-      const float ad = fabsf(d);
-      lsum += (ad < 1.f) ? 0.5f * d * d : ad - 0.5f;
-      g = fminf(fmaxf(d, -1.f), 1.f) * g_mul;
-    } else {
-      g = dpred[off];
+  for (int X = threadIdx.x; X < W; X += blockDim.x)
+    if (X == 0 || x0s[X] != x0s[X - 1]) xs[x0s[X]] = X;     // x0 is non-decreasing in X and skips no source column
+  for (int e = threadIdx.x; e < 3 * S; e += blockDim.x) {
+    const int r = e / S, yy = e - r * S;
+    const int y0 = y0s[yy];
+    const int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
+    const float ly = lys[yy];
+    float wy = 0.f;
+    if (y0 == ybase + r) wy += 1.f - ly;
+    if (y1 == ybase + r) wy += ly;
+    wys[e] = wy;
+  }
+  const float* sb = score + (long long)b * h * w * 3 + c;
+  if (mode == 1) {
+    for (int r = 0; r < 3; ++r) {
+      const int y = min(ybase + r, h - 1);
+      for (int X = threadIdx.x; X < W; X += blockDim.x) {
+        const int x0 = x0s[X];
+        const int x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+        const float lx = lxs[X];
+        ri[r * W + X] = (1.f - lx) * sb[(y * w + x0) * 3] + lx * sb[(y * w + x1) * 3];
+      }
     }
-    gs[e] = g;
+  }
+  __syncthreads();
+  // phase 1
+  const float g_mul = grad_scale * (gscale ? *gscale : 1.f);
+  float lsum = 0.f;
+  for (int yy = 0; yy < S; ++yy) {
+    const int y0 = y0s[yy];
+    const int r0 = y0 - ybase;
+    const int r1 = min(r0 + ((y0 < h - 1) ? 1 : 0), 2);
+    const float ly = lys[yy];
+    const long long rowoff = (((long long)b * 3 + c) * H + (band * S + yy)) * W;
+    for (int X = threadIdx.x; X < W; X += blockDim.x) {
+      float g;
+      if (mode == 1) {
+        const float pred = (1.f - ly) * ri[r0 * W + X] + ly * ri[r1 * W + X];
+        const float d = pred - target[rowoff + X];
+        const float ad = fabsf(d);
+        lsum += (ad < 1.f) ? 0.5f * d * d : ad - 0.5f;
+        g = fminf(fmaxf(d, -1.f), 1.f) * g_mul;
+      } else {
+        g = dpred[rowoff + X];
+      }
+      gs[yy * W + X] = g;
+    }
   }
   if (mode == 1 && loss_sum != nullptr) {
     lsum = block_sum(lsum, red);
@@ -544,41 +582,33 @@ __global__ void __launch_bounds__(256) t2i_up8_loss_kernel(const float* __restri
   }
   if (!want_grad) return;
   __syncthreads();
-  // phase 2: along X. Output column X reads score columns x0(X), x0(X)+1; column x is read by X in ((x-1)/r, (x+1)/r), r = (w-1)/(W-1)
-  const float inv_r = (w > 1) ? (float)(W - 1) / (float)(w - 1) : 0.f;
-  for (int e = threadIdx.x; e < S * w; e += blockDim.x) {
-    const int yy = e / w, x = e % w;
-    int Xlo = (int)floorf((float)(x - 1) * inv_r) - 1, Xhi = (int)ceilf((float)(x + 1) * inv_r) + 1;
-    Xlo = max(Xlo, 0);
-    Xhi = min(Xhi, W - 1);
-    float a = 0.f;
-    for (int X = Xlo; X <= Xhi; ++X) {
-      const int x0 = x0s[X];
-      const int x1 = x0 + ((x0 < w - 1) ? 1 : 0);
-      const float lx = lxs[X];
-      float wx = 0.f;
-      if (x0 == x) wx += 1.f - lx;
-      if (x1 == x) wx += lx;
-      a = fmaf(wx, gs[yy * W + X], a);
+  // phase 2: along Y (each thread re-reads the column it wrote), pre-multiplied by the X weights
+  for (int X = threadIdx.x; X < W; X += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int yy = 0; yy < S; ++yy) {
+      const float g = gs[yy * W + X];
+      a0 = fmaf(wys[yy], g, a0);
+      a1 = fmaf(wys[S + yy], g, a1);
+      a2 = fmaf(wys[2 * S + yy], g, a2);
     }
-    gx[e] = a;
+    const float lx = lxs[X];
+    const float wl = (x0s[X] == w - 1) ? 1.f : 1.f - lx;   // the right neighbour of the last source column is itself
+    const float wr = (x0s[X] == w - 1) ? 0.f : lx;
+    const int Xp = X + (X >> 3);
+    As[Xp] = wl * a0; As[WP + Xp] = wl * a1; As[2 * WP + Xp] = wl * a2;
+    Bs[Xp] = wr * a0; Bs[WP + Xp] = wr * a1; Bs[2 * WP + Xp] = wr * a2;
   }
   __syncthreads();
-  // phase 3: along Y, then the global accumulation (score rows ybase .. ybase+2)
+  // phase 3: along X, then the global accumulation (score rows ybase .. ybase+2)
   for (int e = threadIdx.x; e < 3 * w; e += blockDim.x) {
-    const int ry = e / w, x = e % w;
-    const int y = ybase + ry;
+    const int r = e / w, x = e - r * w;
+    const int y = ybase + r;
     if (y >= h) continue;
+    const int Xa = xs[x], Xb = xs[x + 1];
     float a = 0.f;
-    for (int yy = 0; yy < S; ++yy) {
-      const int y0 = y0s[yy];
-      const int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
-      const float ly = lys[yy];
-      float wy = 0.f;
-      if (y0 == y) wy += 1.f - ly;
-      if (y1 == y) wy += ly;
-      a = fmaf(wy, gx[yy * w + x], a);
-    }
+    for (int X = Xa; X < Xb; ++X) a += As[r * WP + X + (X >> 3)];
+    if (x > 0)
+      for (int X = xs[x - 1]; X < Xa; ++X) a += Bs[r * WP + X + (X >> 3)];
     if (a != 0.f) atomicAdd(dscore + ((long long)b * h * w + (long long)y * w + x) * 3 + c, a);
   }
 }
@@ -815,14 +845,15 @@ extern "C" int mvlt_score_fwd(const void* x_bf16, const float* W, const float* b
   return 0;
 }
 
+// gscale_dev: optional device scalar multiplied into dscore (the upstream gradient of the total loss)
 extern "C" int mvlt_score_bwd(const float* dscore, const void* x_bf16, const float* W, void* dx_bf16, float* dW, float* db,
-                              long long rows, int Cin, void* stream_) {
+                              long long rows, int Cin, const float* gscale_dev, void* stream_) {
   MVLT_CHECK_ARG(Cin + 3 <= 256, "score_bwd: Cin must be <= 253");
-  long long blocks = (long long)mvlt_num_sms() * 4;
+  long long blocks = (long long)mvlt_num_sms() * 8;   // one full wave of 256-thread blocks
   long long rpb = (rows + blocks - 1) / blocks;
   if (rpb < 16) rpb = 16;
   blocks = (rows + rpb - 1) / rpb;
-  mvlt_launch(score_bwd_kernel, (int)blocks, 256, (3 * Cin + 3) * sizeof(float), reinterpret_cast<cudaStream_t>(stream_), dscore, reinterpret_cast<const __nv_bfloat16*>(x_bf16), W, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dW, db, rows, Cin, rpb);
+  mvlt_launch(score_bwd_kernel, (int)blocks, 256, (3 * Cin + 3) * sizeof(float), reinterpret_cast<cudaStream_t>(stream_), dscore, reinterpret_cast<const __nv_bfloat16*>(x_bf16), W, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dW, db, rows, Cin, rpb, gscale_dev);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -838,7 +869,8 @@ extern "C" int mvlt_upsample8_fwd(const float* score, float* out, int B, int h, 
 extern "C" int mvlt_t2i_up_loss(const float* score, const float* target, const float* dpred, float* dscore, float* loss_sum,
                                 float* total_sum, float loss_scale, float grad_scale, const float* gscale_dev, int B, int h, int w,
                                 int S, int mode, int want_grad, void* stream_) {
-  const size_t smem = (size_t)(S * w * S + S * w + 32 + 2 * (w * S + S)) * sizeof(float);
+  const int W_ = w * S, WP_ = W_ + (W_ >> 3) + 1;
+  const size_t smem = (size_t)(S * W_ + 32 + W_ + S + 3 * S + 3 * W_ + 6 * WP_ + W_ + S + (w + 1)) * sizeof(float);
   MVLT_CHECK_ARG(S >= 2 && smem <= 48 * 1024, "t2i_up_loss: bad geometry");
   const int blocks = B * 3 * h;
   mvlt_launch(t2i_up8_loss_kernel, blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream_), score, target, dpred, dscore, loss_sum, total_sum, loss_scale, grad_scale, gscale_dev, B, h, w, S, mode, want_grad);

@@ -481,8 +481,8 @@ def score_fwd(x, W, bias, out, rows, Cin):
     call("score_fwd", ptr(x), ptr(W), ptr(bias), ptr(out), C.c_longlong(rows), C.c_int(Cin))
 
 
-def score_bwd(dscore, x, W, dx, dW, db, rows, Cin):
-    call("score_bwd", ptr(dscore), ptr(x), ptr(W), ptr(dx), ptr(dW), ptr(db), C.c_longlong(rows), C.c_int(Cin))
+def score_bwd(dscore, x, W, dx, dW, db, rows, Cin, gscale=None):
+    call("score_bwd", ptr(dscore), ptr(x), ptr(W), ptr(dx), ptr(dW), ptr(db), C.c_longlong(rows), C.c_int(Cin), ptr(gscale))
 
 
 def upsample8_fwd(score, out, B, h, w, S):

@@ -264,8 +264,12 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
         target = batch["target_images"].contiguous().to(F32)
         wt = w.get("t2i", T2I_LOSS_WEIGHT)
         numel = B * 3 * h * 8 * wd * 8
-        k.t2i_up_loss(score, target, None, None, stats[5:6], stats[0:1], wt / numel, 0.0, None, B, h, wd, 8, 1, False)
-        c.update(score=score, target=target, gscale=wt / numel)
+        # training: the same launch also produces d loss / d score (for an upstream gradient of 1; the real one is a device
+        # scalar folded into the first backward kernel), so the target image is read once per step, not twice
+        dscore = k.zeros((B * h * wd, 3), F32, dev) if save else None
+        k.t2i_up_loss(score, target, None, dscore, stats[5:6], stats[0:1], wt / numel, wt / numel if save else 0.0, None, B, h, wd,
+                      8, 1, bool(save))
+        c.update(score=score, dscore=dscore)
         hc["t2i"] = c
     total = stats[0]
     saved = dict(enc=enc, hc=hc, B=B, HW4=HW4) if save else None
@@ -294,10 +298,7 @@ def eng_backward_losses(eng: PVLTEngine, saved, gtotal, G):
             eng.small_head_bwd(dl, c, name, B, HW4, dX4, G)
     if "t2i" in hc:
         c = hc["t2i"]
-        h, w = c["dims"][1], c["dims"][2]
-        dscore = k.zeros((B * h * w, 3), F32, dev)
-        k.t2i_up_loss(c["score"], c["target"], None, dscore, None, None, 0.0, c["gscale"], gs, B, h, w, 8, 1, True)
-        df2, df3 = eng.t2i.backward(dscore, c, G, dX4)
+        df2, df3 = eng.t2i.backward(c["dscore"], c, G, dX4, gscale=gs)
         dXs[1], dXs[2] = df2, df3
     eng.encoder_bwd(enc, dXs, G)
 

@@ -158,8 +158,8 @@ class T2IHead:
         return score, c
 
     # ---- backward -----------------------------------------------------------------------------------
-    def backward(self, dscore, c, G, dX4):
-        """dscore fp32 [B*Hl*Wl, 3]. Returns (dfeat2 fp32 [B,Hl*Wl,Cl], dfeat3 fp32 [B,Hm*Wm,Cm]) and accumulates the
+    def backward(self, dscore, c, G, dX4, gscale=None):
+        """dscore fp32 [B*Hl*Wl, 3] (times the device scalar ``gscale`` when given). Returns (dfeat2 fp32 [B,Hl*Wl,Cl], dfeat3 fp32 [B,Hm*Wm,Cm]) and accumulates the
         stage-4 image-row gradient into dX4 (fp32 [B, N4, C4])."""
         P = self.e.P
         T = self.e.T
@@ -170,7 +170,7 @@ class T2IHead:
         new = lambda rows, ch: torch.empty((rows, ch), dtype=BF16, device=dev)
         dr = new(rows_l, 3 * CH)
         k.score_bwd(dscore, c["r"], P["t2i_head.score.0.weight"], dr, G["t2i_head.score.0.weight"],
-                    G["t2i_head.score.0.bias"], rows_l, 3 * CH)
+                    G["t2i_head.score.0.bias"], rows_l, 3 * CH, gscale=gscale)
         d_x32 = new(rows_l, 3 * CH)
         self._convbn_bwd("conv4", dr, c["c4"], G, d_x32, Hl * Wl * 3 * CH, 3 * CH)
         d_cat3 = new(rows_l, 3 * CH)
