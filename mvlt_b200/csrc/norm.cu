@@ -7,6 +7,7 @@
 // Row maps let one launch read/write a strided sub-range of a token buffer, e.g. "rows [HW, HW+T) of every
 // sample" or "write the normalised patch rows at b*N + r and add the (resized) position embedding", which is
 // how the reference's x + pos / torch.cat (pvlt.py:346) and torch.split (:102,:350) disappear.
+#include <stdlib.h>
 #include "common.cuh"
 
 struct RowMap {  // physical_row(r) = (r / group) * stride + offset + (r % group)
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
                                                      TDX* __restrict__ dx, RowMap dxm, const float* __restrict__ dx_add,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
                                                      int C, __nv_bfloat16* __restrict__ dx16, const float* __restrict__ rowscale,
-                                                     int rows_per_scale) {
+                                                     int rows_per_scale, int vec_red) {
   pdl_prologue();
   extern __shared__ float sh[];  // [2][warps * RPW][C]
   constexpr int RPW = 32 / G;
@@ -149,9 +150,28 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
   const int rows_per_block = wpb * RPW;
   const int nvec = (C + 4 * G - 1) / (4 * G);
   const float inv_c = 1.f / (float)C;
-  float4 ag[NV], ab[NV];
+  // per-thread partial dgamma / dbeta: a thread owns the same columns in every pass. Rows wider than 128 columns keep them
+  // in shared memory (the slots the block reduction reads anyway) instead of 8 * NV registers: 107 -> ~75 registers per
+  // thread at C = 512, i.e. 3 resident blocks per SM instead of 2 for these latency-bound passes.
+  constexpr bool kSmemAcc = NV >= 3;
+  float* const shg_own = sh + (warp * RPW + lane / G) * C;
+  float* const shb_own = shg_own + wpb * RPW * C;
+  float4 ag[kSmemAcc ? 1 : NV], ab[kSmemAcc ? 1 : NV];
+  if (kSmemAcc) {
+    if (dgamma != nullptr) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < NV; ++i) {
+        const int c = i * 4 * G + sub * 4;
+        if (i < nvec && c < C) {
+          *reinterpret_cast<float4*>(shg_own + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(shb_own + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < (kSmemAcc ? 1 : NV); ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int r0 = blockIdx.x * rows_per_block; r0 < rows; r0 += gridDim.x * rows_per_block) {
     const int r = r0 + warp * RPW + lane / G;
     const bool ok = r < rows;
@@ -169,8 +189,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
         float4 xh;
         xh.x = (xv.x - mu) * rs; xh.y = (xv.y - mu) * rs; xh.z = (xv.z - mu) * rs; xh.w = (xv.w - mu) * rs;
-        ag[i].x += d.x * xh.x; ag[i].y += d.y * xh.y; ag[i].z += d.z * xh.z; ag[i].w += d.w * xh.w;
-        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        if (kSmemAcc) {
+          if (dgamma != nullptr) {
+            float4 pg = *reinterpret_cast<float4*>(shg_own + c), pb = *reinterpret_cast<float4*>(shb_own + c);
+            pg.x += d.x * xh.x; pg.y += d.y * xh.y; pg.z += d.z * xh.z; pg.w += d.w * xh.w;
+            pb.x += d.x; pb.y += d.y; pb.z += d.z; pb.w += d.w;
+            *reinterpret_cast<float4*>(shg_own + c) = pg;
+            *reinterpret_cast<float4*>(shb_own + c) = pb;
+          }
+        } else {
+          ag[i].x += d.x * xh.x; ag[i].y += d.y * xh.y; ag[i].z += d.z * xh.z; ag[i].w += d.w * xh.w;
+          ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        }
         float4 gd;
         gd.x = d.x * g.x; gd.y = d.y * g.y; gd.z = d.z * g.z; gd.w = d.w * g.w;
         s1 += gd.x + gd.y + gd.z + gd.w;
@@ -210,15 +240,30 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
   float* shg = sh;
   float* shb = sh + slots * C;
   const int slot = warp * RPW + lane / G;
+  if (!kSmemAcc) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = i * 4 * G + sub * 4;
-    if (i < nvec && c < C) {
-      *reinterpret_cast<float4*>(shg + slot * C + c) = ag[i];
-      *reinterpret_cast<float4*>(shb + slot * C + c) = ab[i];
+    for (int i = 0; i < (kSmemAcc ? 1 : NV); ++i) {
+      const int c = i * 4 * G + sub * 4;
+      if (i < nvec && c < C) {
+        *reinterpret_cast<float4*>(shg + slot * C + c) = ag[i];
+        *reinterpret_cast<float4*>(shb + slot * C + c) = ab[i];
+      }
     }
   }
   __syncthreads();
+  if (vec_red) {   // 16-byte aligned gradient rows: one vector reduction per 4 columns
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f), b = g;
+      for (int w = 0; w < slots; ++w) {
+        const float4 gv = *reinterpret_cast<const float4*>(shg + w * C + c), bv = *reinterpret_cast<const float4*>(shb + w * C + c);
+        g.x += gv.x; g.y += gv.y; g.z += gv.z; g.w += gv.w;
+        b.x += bv.x; b.y += bv.y; b.z += bv.z; b.w += bv.w;
+      }
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + c), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + c), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+    }
+    return;
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float g = 0.f, b = 0.f;
     for (int w = 0; w < slots; ++w) {
@@ -343,16 +388,23 @@ extern "C" int mvlt_layernorm_bwd(const void* dy, int dy_f32, const int* dymap, 
   };
   RowMap dym = mk(dymap), xm = mk(xmap), dxm = mk(dxmap);
   const int wpb = 8, rpw = C <= 64 ? 2 : 1;
-  long long b = ((long long)rows + wpb * rpw * 4 - 1) / (wpb * rpw * 4);  // >= 4 row passes per warp to amortise the atomics
-  const long long cap = (long long)mvlt_num_sms() * 6;
+  // tuning knobs (tools/ln_sweep.py): row passes per warp that amortise the dgamma / dbeta reductions, blocks per SM
+  static const int min_passes = [] { const char* e = getenv("MVLT_LN_BWD_PASSES"); return e ? atoi(e) : 4; }();
+  static const int bps_env = [] { const char* e = getenv("MVLT_LN_BWD_BPS"); return e ? atoi(e) : 0; }();
+  // resident 256-thread blocks per SM of the variant that will run (registers: 40-47 / 64 / 68-72 / 92-96 per thread)
+  const int blocks_per_sm = bps_env > 0 ? bps_env : (C <= 128 ? 6 : (C <= 384 ? 4 : (C <= 512 ? 3 : 2)));
+  static const int vec_red_on = [] { const char* e = getenv("MVLT_LN_BWD_VEC"); return e ? atoi(e) : 1; }();
+  long long b = ((long long)rows + wpb * rpw * min_passes - 1) / (wpb * rpw * min_passes);
+  const long long cap = (long long)mvlt_num_sms() * blocks_per_sm;
   const int grid = (int)(b < cap ? (b > 0 ? b : 1) : cap);
+  const int vec_red = (vec_red_on && dgamma != nullptr && ((((uintptr_t)dgamma) | ((uintptr_t)dbeta)) & 15) == 0) ? 1 : 0;
   const size_t smem = (size_t)2 * wpb * rpw * C * sizeof(float);
 #define LN_BWD_CALL(TDY, TX, TDX, G, NV)                                                                         \
   mvlt_launch(ln_bwd_kernel<TDY, TX, TDX, G, NV>, grid, 256, smem, st, reinterpret_cast<const TDY*>(dy), dym,                 \
                                                               reinterpret_cast<const TX*>(x), xm, mean, rstd, gamma, \
                                                               reinterpret_cast<TDX*>(dx), dxm, dx_add, dgamma, dbeta, rows, C, \
                                                               reinterpret_cast<__nv_bfloat16*>(dx_bf16_scaled), rowscale,     \
-                                                              rows_per_scale > 0 ? rows_per_scale : 1)
+                                                              rows_per_scale > 0 ? rows_per_scale : 1, vec_red)
 #define LAUNCH(TDY, TX, TDX)                                  \
   do {                                                        \
     if (C <= 64) LN_BWD_CALL(TDY, TX, TDX, 16, 1);            \
