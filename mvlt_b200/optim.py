@@ -81,7 +81,8 @@ class AdamW(torch.optim.Optimizer):
                 if not p.is_contiguous() or not p.grad.is_contiguous():
                     raise MvltError("mvlt_b200.optim.AdamW needs contiguous parameters and gradients")
                 self._state(p)
-            steps = {self.state[p]["step"] for p in ps}
+            # torch.optim.AdamW checkpoints (main_vl.py:340) carry ``step`` as a 0-dim tensor: accept both forms
+            steps = {int(self.state[p]["step"]) for p in ps}
             if len(steps) != 1:
                 raise MvltError("parameters of one group must share their step count")
             t = steps.pop() + 1

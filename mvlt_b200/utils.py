@@ -89,3 +89,35 @@ class MetricLogger:
             if print_freq and (i % print_freq == 0 or (n is not None and i == n - 1)):
                 if not is_dist() or dist.get_rank() == 0:
                     print(f"{header} [{i}{'/' + str(n) if n else ''}] {self}  elapsed {time.time() - t0:.1f}s")
+
+
+def load_checkpoint(model, checkpoint, optimizer=None, lr_scheduler=None, loss_scaler=None, strict=False):
+    """Checkpoint compatibility with the reference's files. ``checkpoint``: a path or an already loaded
+    object in any of the forms the reference writes / reads:
+      * ``{'model': state_dict, 'optimizer': ..., 'lr_scheduler': ..., 'epoch': ..., 'scaler': ...}`` (main_vl.py:327-346,
+        utils.save_on_master) or a bare ``state_dict`` (``checkpoint_retrieval.pth`` / ``checkpoint_recognition.pth``);
+      * keys optionally prefixed with ``module.`` (saved from a DistributedDataParallel wrapper);
+      * ImageNet ``head.*`` / ``head_dist.*`` classifier rows of another shape are dropped (main_vl.py:283-288).
+    Parameter names and shapes are the reference's own (Appendix A), so nothing is renamed. Returns
+    ``(missing_keys, unexpected_keys, next_epoch)``; optimizer / scheduler / scaler states are restored when both the
+    object and its entry are present (torch.optim.AdamW and mvlt_b200.optim.AdamW share the state layout)."""
+    net = model.module if hasattr(model, "module") else model
+    ck = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "__fspath__") \
+        else checkpoint
+    sd = ck["model"] if isinstance(ck, dict) and "model" in ck else ck
+    sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items()}
+    own = net.state_dict()
+    for k in ("head.weight", "head.bias", "head_dist.weight", "head_dist.bias"):
+        if k in sd and (k not in own or sd[k].shape != own[k].shape):
+            del sd[k]
+    res = net.load_state_dict(sd, strict=strict)
+    next_epoch = None
+    if isinstance(ck, dict) and "optimizer" in ck and "epoch" in ck:
+        if optimizer is not None:
+            optimizer.load_state_dict(ck["optimizer"])
+        if lr_scheduler is not None and "lr_scheduler" in ck:
+            lr_scheduler.load_state_dict(ck["lr_scheduler"])
+        if loss_scaler is not None and "scaler" in ck:
+            loss_scaler.load_state_dict(ck["scaler"])
+        next_epoch = int(ck["epoch"]) + 1
+    return list(res.missing_keys), list(res.unexpected_keys), next_epoch

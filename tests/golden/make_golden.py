@@ -8,6 +8,7 @@ Writes
   tests/golden/token_mask_golden.npz  reference random_masking_features (BERT word-piece masking) under random.seed(s)
   tests/golden/pvlt_tiny_golden.npz   reference PVLT-tiny (libs/pvlt.py) outputs, losses and gradient summaries
                                       for oracle.make_state_dict(seed) weights and oracle.make_inputs batches
+  tests/golden/text_golden.npz        reference text_process (tokenize / truncate / pad) on a few captions, vendored vocabulary
   tests/golden/pvlt_small_golden.npz  the same for pvlt_small (depths [3,4,6,3]; BASELINE configs[4] stand-in), batch 1
 
 Third-party gaps papered over exactly as SURVEY 8c describes: a ~30-line timm stub and
@@ -195,8 +196,57 @@ def golden_token_masks():
     print("token_mask_golden.npz:", len(seeds), "samples,", int((np.array(labels) != -1).sum()), "labelled pieces")
 
 
+CAPTIONS = [
+    "Long sleeve cotton poplin shirt in white. Spread collar. Button closure at front.",
+    "Slim-fit jeans in 'washed' indigo blue; fading, whiskering & distressing throughout!",
+    "Leather ankle boots in black. Almond toe. Zip closure at inner side. Tonal stitching. Approx. 1.5\" heel.",
+    "T-shirt",
+    "",
+    "Relaxed-fit hoodie " * 60,
+    "Crêpe de Chine blouse — naïve floral print, 100% silk (Made in Italy)",
+    "BOMBER JACKET IN NAVY / RIB KNIT COLLAR, CUFFS, AND HEM / TWO-WAY ZIP",
+]
+
+
+def golden_text():
+    """Runs the reference's own ``text_process`` (fashion_gen.py:321-381) with the vendored vocabulary; records the
+    RNG-independent outputs (ori_input_ids, attention_mask, segment_ids) for mvlt_b200.text.encode_captions."""
+    import random
+    from transformers import BertTokenizer
+    import inspect
+    vf = os.path.join(REF, "preweights", "bert-base-uncased-vocab.txt")
+    if "vocab" in inspect.signature(BertTokenizer.__init__).parameters:
+        with open(vf, encoding="utf-8") as f:
+            tok = BertTokenizer(vocab={line.rstrip("\n"): i for i, line in enumerate(f)}, do_lower_case=True)
+    else:
+        tok = BertTokenizer(vocab_file=vf, do_lower_case=True)
+    src = open(os.path.join(REF, "mcloader", "fashion_gen.py")).read()
+    start = src.index("    def text_process")
+    end = src.index("    def rgb_loader")
+    ns = {"random": random, "torch": torch,
+          "shift_tokens_right": lambda ids, pad_token_id, decoder_start_token_id: ids}   # BART leftover, unused output
+    exec("class _Holder:\n" + src[start:end], ns)          # executes the reference text in place, nothing copied
+    holder = types.SimpleNamespace(word_mask_rate=0.15, tokenizer=tok)
+    holder.random_masking_features = lambda toks: ns["_Holder"].random_masking_features(holder, toks)
+    ori, att, seg = [], [], []
+    for T in (128, 24):
+        for cap in CAPTIONS:
+            random.seed(0)
+            out = ns["_Holder"].text_process(holder, cap, T)
+            input_ids, attention_mask, mlm_labels, segment_ids, ori_input_ids = out[:5]
+            row = lambda t: np.pad(t.numpy(), (0, 128 - T))
+            ori.append(row(ori_input_ids)); att.append(row(attention_mask)); seg.append(row(segment_ids))
+    np.savez_compressed(os.path.join(HERE, "text_golden.npz"), captions=np.array(CAPTIONS), lengths=np.array([128, 24]),
+                        ori=np.stack(ori), att=np.stack(att), seg=np.stack(seg))
+    print("text_golden.npz:", len(ori), "rows")
+
+
 if __name__ == "__main__":
+    if "--text-only" in sys.argv:
+        golden_text()
+        sys.exit(0)
     if "--small-only" not in sys.argv:
+        golden_text()
         golden_grid_masks()
         golden_token_masks()
         golden_pvlt()
