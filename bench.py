@@ -92,6 +92,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def hbm_kernel_table(byte_counts, times_ms, launches, nprof, hbm_gbs):
+    """Per-kernel-family view of the memory-bound kernels of the instrumented pass: algorithmic bytes (counted by the
+    wrappers in mvlt_b200/kernels.py) / CUDA-event time vs the measured HBM peak."""
+    out = {}
+    for name, nbytes in sorted(byte_counts.items()):
+        ms = times_ms.get(name, 0.0)
+        if ms <= 0.0 or nbytes <= 0.0:
+            continue
+        gbs = nbytes / (ms / 1e3) / 1e9
+        out[name] = {"ms_per_step": round(ms / nprof, 4), "launches_per_step": launches.get(name, 0) / nprof,
+                     "algorithmic_gb_per_step": round(nbytes / nprof / 1e9, 4), "achieved_gbs": round(gbs, 1),
+                     "frac_of_hbm_peak": round(gbs / hbm_gbs, 4)}
+    return out
+
+
 def synth_batch(B, seed, pin=True):
     """SURVEY 8d synthetic Fashion-Gen-shaped batch, on the (pinned) host."""
     from mvlt_b200.synthetic import make_batch
@@ -257,18 +272,24 @@ def run_ours(args):
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in E2E_KEYS)
 
     # ---- per-kernel breakdown (instrumented pass, NOT the reported value) -> roofline of the dominant kernel
-    roof, breakdown = None, None
+    roof, breakdown, hbm_kernels = None, None, None
     model.enable_grad_sync(None)      # the instrumented pass below runs on rank 0 alone: no collectives from here on
     if rank == 0:
         _lib.PROFILE, _lib.GEMM_FLOPS, _lib.GEMM_BYTES, _lib.GEMM_LOG = {}, 0.0, 0.0, []
+        _lib.BYTES = {}
         nprof = 2
         for i in range(nprof):
             step(i, devb[i % 2], fwd=model)      # the bare module: rank 0 alone must not enter the gradient collectives
         torch.cuda.synchronize()
         prof, flops, nbytes, glog = _lib.PROFILE, _lib.GEMM_FLOPS, _lib.GEMM_BYTES, _lib.GEMM_LOG
         _lib.PROFILE, _lib.GEMM_LOG = None, None
+        byte_counts, _lib.BYTES = (_lib.BYTES or {}), None
         tot = {n: sum(a.elapsed_time(b) for a, b in ev) for n, ev in prof.items()}
         cnt = {n: len(ev) for n, ev in prof.items()}
+        try:
+            hbm_kernels = hbm_kernel_table(byte_counts, tot, cnt, nprof, hbm)
+        except Exception as ex:      # reporting only: never lose the bench line over it
+            hbm_kernels = {"error": repr(ex)[:200]}
         allms = sum(tot.values())
         breakdown = {n: {"ms_per_step": round(tot[n] / nprof, 4), "launches_per_step": cnt[n] / nprof,
                          "share": round(tot[n] / allms, 4)} for n in sorted(tot, key=lambda n: -tot[n])[:12]}
@@ -328,7 +349,8 @@ def run_ours(args):
             "clocks": clocks,
             "model_tflops": round(value * gf_per_sample / 1e3, 2) if gf_per_sample else None,
             "model_flops_frac_of_bf16_peak": round(value * gf_per_sample / 1e3 / tf_sus, 4) if gf_per_sample else None,
-            "roofline": roof, "kernel_breakdown": breakdown, "retrieval": retr, "cpu_baseline": cpu,
+            "roofline": roof, "kernel_breakdown": breakdown, "hbm_bound_kernels": hbm_kernels, "retrieval": retr,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -100,6 +100,14 @@ def account_gemm(flops: float, nbytes: float, what: str = ""):
     if GEMM_LOG is not None:
         GEMM_LOG.append((flops, nbytes, what))
 PROFILE = None        # when a dict: name -> list of (start_event, end_event) recorded around every call
+BYTES = None          # when a dict: name -> algorithmic (compulsory) bytes of the memory-bound kernels launched under that name
+
+
+def account_bytes(tag: str, nbytes: float):
+    """Algorithmic bytes of one launch of a memory-bound kernel (bench.py's per-kernel HBM fractions); no-op unless
+    ``BYTES`` is a dict."""
+    if BYTES is not None:
+        BYTES[tag] = BYTES.get(tag, 0.0) + float(nbytes)
 
 
 _FN = {}

@@ -232,6 +232,8 @@ def _f32(t):
 
 def layernorm_fwd(x, gamma, beta, y, eps, rows, Cdim, xmap=None, ymap=None, post_add=None, mean=None, rstd=None):
     require_cuda(x, y)
+    if _lib.BYTES is not None:
+        _lib.account_bytes("layernorm_fwd", rows * Cdim * (x.element_size() + y.element_size()))
     call("layernorm_fwd", ptr(x), _f32(x), _map(xmap), ptr(gamma), ptr(beta), ptr(y), _f32(y), _map(ymap),
          ptr(post_add), ptr(mean), ptr(rstd), C.c_int(rows), C.c_int(Cdim), C.c_float(eps))
 
@@ -241,6 +243,9 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, rows, Cdim, dymap=None, xmap=Non
     """``dx_bf16`` (optional, dx's row layout): bf16 copy of dx times rowscale[row // rows_per_scale] (drop-path), i.e.
     the A operand of the backward GEMMs that consume dx next, written by the same pass."""
     require_cuda(dy, x, dx)
+    if _lib.BYTES is not None:
+        _lib.account_bytes("layernorm_bwd", rows * Cdim * (dy.element_size() + x.element_size() + dx.element_size()
+                                                           + (4 if dx_add is not None else 0) + (2 if dx_bf16 is not None else 0)))
     call("layernorm_bwd", ptr(dy), _f32(dy), _map(dymap), ptr(x), _f32(x), _map(xmap), ptr(mean), ptr(rstd),
          ptr(gamma), ptr(dx), _f32(dx), _map(dxmap), ptr(dx_add), ptr(dgamma), ptr(dbeta), C.c_int(rows),
          C.c_int(Cdim), ptr(dx_bf16), ptr(rowscale), C.c_int(rows_per_scale))
@@ -260,6 +265,8 @@ def sr_attention_fwd(q, kv, o, p_out, B, N, Nk, heads, scale):
             or kv.numel() != B * Nk * 2 * C_ or o.numel() != B * N * C_
             or (p_out is not None and (not p_out.is_contiguous() or p_out.numel() != B * heads * N * Nk))):
         raise _lib.MvltError("sr_attention_fwd: contiguous q [B*N, C], kv [B*Nk, 2C], o [B*N, C], p [B, h, N, Nk] required")
+    if _lib.BYTES is not None:
+        _lib.account_bytes("sr_attention_fwd", 2 * (q.numel() + o.numel() + kv.numel() + (p_out.numel() if p_out is not None else 0)))
     call("sr_attention_fwd", ptr(q), ptr(kv), ptr(o), ptr(p_out), C.c_int(B), C.c_int(N), C.c_int(Nk), C.c_int(heads),
          C.c_float(scale))
 

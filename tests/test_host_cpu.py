@@ -119,3 +119,28 @@ def test_encode_captions_matches_reference_text_process_golden():
         assert (att.numpy() == g["att"][row:row + n, :L]).all()
         assert (seg.numpy() == g["seg"][row:row + n, :L]).all()
         row += n
+
+
+def test_bench_hbm_kernel_table_and_byte_accounting():
+    """bench.py's per-kernel HBM fractions: the wrappers count algorithmic bytes only while _lib.BYTES is a dict."""
+    import importlib.util
+    from mvlt_b200 import _lib
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert _lib.BYTES is None
+    _lib.account_bytes("layernorm_fwd", 10.0)          # inactive: must not create state
+    assert _lib.BYTES is None
+    _lib.BYTES = {}
+    try:
+        _lib.account_bytes("layernorm_fwd", 3.0e9)
+        _lib.account_bytes("layernorm_fwd", 3.0e9)
+        _lib.account_bytes("adamw_multi", 1.0e9)
+        tab = bench.hbm_kernel_table(_lib.BYTES, {"layernorm_fwd": 2.0, "adamw_multi": 0.0, "gemm": 5.0},
+                                     {"layernorm_fwd": 4}, 2, 6000.0)
+    finally:
+        _lib.BYTES = None
+    assert set(tab) == {"layernorm_fwd"}                # kernels without a measured time are dropped
+    row = tab["layernorm_fwd"]
+    assert row["achieved_gbs"] == 3000.0 and row["frac_of_hbm_peak"] == 0.5
+    assert row["ms_per_step"] == 1.0 and row["launches_per_step"] == 2.0 and row["algorithmic_gb_per_step"] == 3.0
