@@ -144,3 +144,39 @@ def test_bench_hbm_kernel_table_and_byte_accounting():
     row = tab["layernorm_fwd"]
     assert row["achieved_gbs"] == 3000.0 and row["frac_of_hbm_peak"] == 0.5
     assert row["ms_per_step"] == 1.0 and row["launches_per_step"] == 2.0 and row["algorithmic_gb_per_step"] == 3.0
+
+
+def test_entrypoints_register_with_timm_and_hubconf(monkeypatch):
+    """main_vl.py:16,259: ``from libs import pvlt`` registers pvlt_* with timm's registry; hubconf exports them."""
+    import importlib
+    import sys
+    import types
+    registered = {}
+    timm = types.ModuleType("timm")
+    models = types.ModuleType("timm.models")
+    registry = types.ModuleType("timm.models.registry")
+
+    def register_model(fn):
+        registered[fn.__name__] = fn
+        return fn
+    registry.register_model = register_model
+    for name, mod in (("timm", timm), ("timm.models", models), ("timm.models.registry", registry)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    import mvlt_b200.libs.pvlt as P
+    importlib.reload(P)
+    try:
+        assert set(registered) == {"pvlt_tiny", "pvlt_small", "pvlt_medium", "pvlt_large"}
+    finally:
+        for name in ("timm", "timm.models", "timm.models.registry"):
+            monkeypatch.delitem(sys.modules, name)
+        importlib.reload(P)
+    import hubconf
+    for name in ("pvlt_tiny", "pvlt_small", "pvlt_medium", "pvlt_large"):
+        assert callable(getattr(hubconf, name))
+    import mvlt_b200
+    m = mvlt_b200.create_model("pvlt_small", pretrained=False, drop_block_rate=None, token_hidden_size=768, num_text_tokens=128,
+                               loss_type={"itm": 1, "mlm": 0, "t2i": 0, "cls": 1}, pretrained_pth="", drop_path_rate=0.1)
+    assert len(m.block3) == 6      # depths [3, 4, 6, 3]
+    with pytest.raises(TypeError):      # the reference constructor has no drop_block_rate either: timm strips None values
+        mvlt_b200.create_model("pvlt_tiny", pretrained=False, drop_block_rate=0.1, token_hidden_size=768, num_text_tokens=128,
+                               loss_type=dict(PRE), pretrained_pth="")
