@@ -43,6 +43,9 @@ HEAD_DIM = 64
 # fused SR-attention forward (csrc/attn_tcgen05.cu); MVLT_FUSED_ATTN=0 keeps the two-GEMM path (QK^T + softmax epilogue, PV)
 # for A/B measurements -- both are sm_100a tcgen05 kernels
 FUSED_ATTENTION = os.environ.get("MVLT_FUSED_ATTN", "1") != "0"
+# EXPERIMENTAL fused attention backward (csrc/attn_bwd_tcgen05.cu): written after the round's GPU budget was spent and
+# not yet validated on a device, hence opt-in; the default backward is the four-GEMM path below
+FUSED_ATTENTION_BWD = os.environ.get("MVLT_FUSED_ATTN_BWD", "0") == "1"
 
 
 def _empty(shape, dtype, dev):
@@ -250,14 +253,17 @@ class PVLTEngine:
         dkv5 = dkv.view(B, Nk, 2, heads, HEAD_DIM)
         dk4, dv4 = dkv5[:, :, 0].permute(0, 2, 1, 3), dkv5[:, :, 1].permute(0, 2, 1, 3)
         Pm = c["Pm"]
-        k.gemm(Pm.transpose(-1, -2), do4.transpose(-1, -2), dv4)          # dV = P^T dO
-        dS = _empty((B, heads, N, Nk), BF16, dev)
-        # dP = dO V^T with the softmax backward (and the qk scale) fused into the epilogue: writes dS directly
-        k.gemm(do4, v4, dS, alpha=HEAD_DIM ** -0.5, act=k.ACT_SOFTMAX_BWD, aux=Pm)
         dq = dyp  # reuse
-        k.gemm(dS, k4.transpose(-1, -2), dq.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3))   # dQ = dS K
-        k.gemm(dS.transpose(-1, -2), q4.transpose(-1, -2), dk4)           # dK = dS^T Q
-        del dS
+        if FUSED_ATTENTION_BWD and Nk <= k.SR_ATTENTION_MAX_NK:
+            k.sr_attention_bwd(c["q"], c["kv"], do, Pm, dq, dkv, B, N, Nk, heads, HEAD_DIM ** -0.5)
+        else:
+            k.gemm(Pm.transpose(-1, -2), do4.transpose(-1, -2), dv4)          # dV = P^T dO
+            dS = _empty((B, heads, N, Nk), BF16, dev)
+            # dP = dO V^T with the softmax backward (and the qk scale) fused into the epilogue: writes dS directly
+            k.gemm(do4, v4, dS, alpha=HEAD_DIM ** -0.5, act=k.ACT_SOFTMAX_BWD, aux=Pm)
+            k.gemm(dS, k4.transpose(-1, -2), dq.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3))   # dQ = dS K
+            k.gemm(dS.transpose(-1, -2), q4.transpose(-1, -2), dk4)           # dK = dS^T Q
+            del dS
         self._lin_param_grads(G, pfx + ".attn.kv.weight", pfx + ".attn.kv.bias", dkv, c["kvin"])
         dxn = _empty((M, C), F32, dev)
         if R > 1:

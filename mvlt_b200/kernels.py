@@ -271,6 +271,21 @@ def sr_attention_fwd(q, kv, o, p_out, B, N, Nk, heads, scale):
          C.c_float(scale))
 
 
+def sr_attention_bwd(q, kv, do, p, dq, dkv, B, N, Nk, heads, scale):
+    """EXPERIMENTAL (csrc/attn_bwd_tcgen05.cu, not yet validated on a device; engine.py only uses it under
+    MVLT_FUSED_ATTN_BWD=1): dq [B*N, C] and dkv [B*Nk, 2C] (dK | dV) of the fused attention from the saved probabilities."""
+    require_cuda(q, kv, do, p, dq, dkv)
+    C_ = heads * 64
+    for t in (q, kv, do, p, dq, dkv):
+        if t.dtype != BF16 or not t.is_contiguous():
+            raise _lib.MvltError("sr_attention_bwd: contiguous bf16 operands required")
+    if (q.numel() != B * N * C_ or do.numel() != B * N * C_ or dq.numel() != B * N * C_ or kv.numel() != B * Nk * 2 * C_
+            or dkv.numel() != B * Nk * 2 * C_ or p.numel() != B * heads * N * Nk):
+        raise _lib.MvltError("sr_attention_bwd: q/do/dq [B*N, C], kv/dkv [B*Nk, 2C], p [B, h, N, Nk] required")
+    call("sr_attention_bwd", ptr(q), ptr(kv), ptr(do), ptr(p), ptr(dq), ptr(dkv), C.c_int(B), C.c_int(N), C.c_int(Nk),
+         C.c_int(heads), C.c_float(scale))
+
+
 def softmax_fwd(s, rows, nk):
     call("softmax_fwd", ptr(s), C.c_longlong(rows), C.c_int(nk))
 

@@ -75,3 +75,29 @@ def test_fused_attention_rejects_unsupported_lengths():
     o = torch.empty_like(q)
     with pytest.raises(MvltError):
         k.sr_attention_fwd(q, kv, o, None, 1, 128, 224, 1, 0.125)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MVLT_FUSED_ATTN_BWD", "0") != "1",
+                    reason="experimental fused attention backward: opt-in until it has been validated on a device")
+@pytest.mark.parametrize("B,N,heads,Nk", SHAPES)
+def test_fused_attention_backward_matches_fp32_autograd(B, N, heads, Nk):
+    from mvlt_b200 import kernels as k
+    q, kv = _inputs(B, N, heads, Nk, seed=3 * N + Nk)
+    C = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    do = torch.randn((B * N, C), generator=g, device="cuda").to(BF16)
+    o = torch.empty((B * N, C), device="cuda", dtype=BF16)
+    P = torch.empty((B, heads, N, Nk), device="cuda", dtype=BF16)
+    k.sr_attention_fwd(q, kv, o, P, B, N, Nk, heads, 64 ** -0.5)
+    dq = torch.full((B * N, C), float("nan"), device="cuda", dtype=BF16)
+    dkv = torch.full((B * Nk, 2 * C), float("nan"), device="cuda", dtype=BF16)
+    k.sr_attention_bwd(q, kv, do, P, dq, dkv, B, N, Nk, heads, 64 ** -0.5)
+    torch.cuda.synchronize()
+    qf = q.float().requires_grad_(True)
+    kvf = kv.float().requires_grad_(True)
+    _, Or = _reference(qf, kvf, B, N, heads, Nk)
+    Or.backward(do.float())
+    rel = lambda a, b: float((a.float() - b).norm() / (b.norm() + 1e-12))
+    assert torch.isfinite(dq.float()).all() and torch.isfinite(dkv.float()).all()
+    assert rel(dq, qf.grad) <= 2e-2, rel(dq, qf.grad)
+    assert rel(dkv, kvf.grad) <= 2e-2, rel(dkv, kvf.grad)
