@@ -402,8 +402,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train_samples_per_s", "value": round(v, 3), "unit": "samples/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": min(Wm, 2), "ms_per_step": round(dt / K * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PVLT-tiny pretraining step on the host CPU (reference algorithm, fp32 port), bounded "
-                                   "sample: batch 4 per step", "batch_per_step": B},
+            "config": {"workload": f"pvlt_tiny {WORKLOADS['pretrain']}, BASELINE configs[1]",
+                       "sample": "reference algorithm on the host CPU (fp32 oracle port), bounded sample: batch 4 per step",
+                       "batch_per_step": B},
             "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{K} steps of batch {B}, fwd + MLM/ITM/t2i losses + backward (no optimizer)"},
             "e2e": {"value": round(v, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
