@@ -180,3 +180,18 @@ def test_entrypoints_register_with_timm_and_hubconf(monkeypatch):
     with pytest.raises(TypeError):      # the reference constructor has no drop_block_rate either: timm strips None values
         mvlt_b200.create_model("pvlt_tiny", pretrained=False, drop_block_rate=0.1, token_hidden_size=768, num_text_tokens=128,
                                loss_type=dict(PRE), pretrained_pth="")
+
+
+def test_validated_defaults_are_the_ones_shipped():
+    """The switches the GPU runs of this round validated: fused attention forward on, programmatic dependent launch on,
+    the not-yet-validated fused attention backward off."""
+    import importlib
+    for var in ("MVLT_FUSED_ATTN", "MVLT_FUSED_ATTN_BWD"):
+        assert var not in os.environ or var == "MVLT_FUSED_ATTN_BWD", f"{var} is set in the test environment"
+    import mvlt_b200.engine as E
+    if "MVLT_FUSED_ATTN" not in os.environ:
+        assert E.FUSED_ATTENTION is True
+    if "MVLT_FUSED_ATTN_BWD" not in os.environ:
+        assert E.FUSED_ATTENTION_BWD is False
+    src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "mvlt_b200", "csrc", "common.cuh")).read()
+    assert "#define MVLT_PDL_DEFAULT 1" in src
