@@ -357,16 +357,34 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _cpu_train_sample(steps, B, threads):
-    """One bounded sample of the same workload on the host: oracle fp32 step (fwd + losses + backward), batch B."""
+def _cpu_stepper(B, threads):
+    """The same workload on the host: oracle fp32 fwd + MLM/ITM/t2i losses + backward (oracle/pvlt_oracle.py, the
+    reference's algorithm) followed by torch.optim.AdamW on the same parameters (main_vl.py:308). Returns step()."""
     from oracle import pvlt_oracle as O
     torch.set_num_threads(threads)
     sd = O.make_state_dict("pvlt_tiny", PRE, seed=0)
     batch = O.make_inputs(B, seed=0)
+    state = {}
+
+    def step():
+        _, grads, _ = O.train_step_grads(sd, batch, PRE)
+        if not state:
+            state["names"] = list(grads)
+            state["params"] = [torch.nn.Parameter(sd[k]) for k in state["names"]]    # shares storage with sd
+            state["opt"] = torch.optim.AdamW(state["params"], lr=1e-5, weight_decay=0.05)
+        for p, k in zip(state["params"], state["names"]):
+            p.grad = grads[k]
+        state["opt"].step()
+    return step
+
+
+def _cpu_train_sample(steps, B, threads):
+    """One bounded sample of the same workload on the host, batch B: median of ``steps`` steps after one warm-up."""
+    step = _cpu_stepper(B, threads)
     ts = []
     for i in range(steps + 1):
         t0 = time.perf_counter()
-        O.train_step_grads(sd, batch, PRE)
+        step()
         ts.append(time.perf_counter() - t0)
     ts = sorted(ts[1:])
     return B / ts[len(ts) // 2]
@@ -376,8 +394,8 @@ def cpu_baseline(args):
     threads = os.cpu_count() or 1
     v = _cpu_train_sample(steps=3, B=4, threads=threads)
     return {"value": round(v, 3), "unit": "samples/s", "cores": threads, "kind": "port",
-            "sample": "oracle/pvlt_oracle.py fp32 train step (fwd + MLM/ITM/t2i losses + backward), batch 4, median of 3 "
-                      "steps after 1 warm-up (BASELINE configs[0])"}
+            "sample": "oracle/pvlt_oracle.py fp32 train step (fwd + MLM/ITM/t2i losses + backward + torch AdamW), batch 4, "
+                      "median of 3 steps after 1 warm-up (BASELINE configs[0])"}
 
 
 def run_reference(args):
@@ -386,17 +404,14 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     K, Wm = args.steps, max(args.warmup, 1)
-    from oracle import pvlt_oracle as O
-    torch.set_num_threads(threads)
     B = 4
-    sd = O.make_state_dict("pvlt_tiny", PRE, seed=0)
-    batch = O.make_inputs(B, seed=0)
+    step = _cpu_stepper(B, threads)
     K = min(K, 8)
     for _ in range(min(Wm, 2)):
-        O.train_step_grads(sd, batch, PRE)
+        step()
     t0 = time.perf_counter()
     for _ in range(K):
-        O.train_step_grads(sd, batch, PRE)
+        step()
     dt = time.perf_counter() - t0
     v = B * K / dt
     line = {"impl": "reference", "metric": "train_samples_per_s", "value": round(v, 3), "unit": "samples/s",
@@ -406,7 +421,7 @@ def run_reference(args):
                        "sample": "reference algorithm on the host CPU (fp32 oracle port), bounded sample: batch 4 per step",
                        "batch_per_step": B},
             "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": f"{K} steps of batch {B}, fwd + MLM/ITM/t2i losses + backward (no optimizer)"},
+                             "sample": f"{K} steps of batch {B}, fwd + MLM/ITM/t2i losses + backward + torch AdamW"},
             "e2e": {"value": round(v, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
