@@ -87,6 +87,17 @@ def require_cuda(*tensors):
             raise MvltError("mvlt_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
 
 
+PARAM_EPOCH = 0       # bumped by every raw-pointer parameter write (own optimizer step, broadcasts): derived tables are stale
+WEIGHT_EPOCH = 0      # bumped when such a write could not refresh the engine's bf16 weight copies itself: recast them
+
+
+def params_written():
+    """Tell every engine that parameters were rewritten behind autograd's back (``p.data`` writes such as collectives)."""
+    global PARAM_EPOCH, WEIGHT_EPOCH
+    PARAM_EPOCH += 1
+    WEIGHT_EPOCH += 1
+
+
 LAUNCHES = 0          # number of C-ABI kernel entry points invoked (bench.py's gpu_launches)
 GEMM_FLOPS = 0.0      # executed GEMM flops accumulated while PROFILE is active
 GEMM_BYTES = 0.0      # algorithmic (compulsory) operand + result bytes of the same launches

@@ -1,9 +1,8 @@
 // Fused spatial-reduction attention BACKWARD for sm_100a (B200): dQ, dK, dV of O = softmax(scale * Q K^T) V in ONE
 // kernel, from the probabilities P the forward kernel saved (attn_tcgen05.cu).
 //
-// STATUS: EXPERIMENTAL -- written after this round's GPU budget was spent; compiled for sm_100a but NOT yet run on a
-// device. It is off by default (MVLT_FUSED_ATTN_BWD=1 selects it in engine.py; its GPU test is skipped unless that
-// variable is set). The default backward is the validated four-GEMM path (engine.py:_block_bwd).
+// Default backward of the attention core (engine.py:_block_bwd; MVLT_FUSED_ATTN_BWD=0 selects the four-GEMM path for A/B
+// runs). Validated against fp32 autograd in tests/test_attention_gpu.py and through the model parity tests.
 //
 // One CTA (128 threads, 1 per SM: it owns all 512 TMEM columns) walks the (batch, head) strips assigned to it. For a
 // strip, K and V ([Nk x 64] each) stay in shared memory and dK / dV accumulate in TMEM across the strip's 128-row query
@@ -309,7 +308,6 @@ sr_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
 // dq[B*N, C], dkv[B*Nk, 2C] (dK | dV column halves) from q [B*N, C], kv [B*Nk, 2C], do [B*N, C] and the saved
 // probabilities p [B, heads, N, Nk] (all bf16, contiguous, 16-byte aligned). Nk % 32 == 0, Nk <= 192, head dim 64.
-// EXPERIMENTAL (see the header of this file): not enabled by default.
 extern "C" int mvlt_sr_attention_bwd(const void* q_bf16, const void* kv_bf16, const void* do_bf16, const void* p_bf16,
                                      void* dq_bf16, void* dkv_bf16, int B, int N, int Nk, int heads, float scale, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -143,7 +143,35 @@ __global__ void __launch_bounds__(256) bert_embed_bwd_kernel(const __nv_bfloat16
   }
 }
 
+// ---- stochastic-depth / dropout keep factors from the counter-based hash (common.cuh) ---------------------------------
+// out[r, b] = hash_uniform(seed, r * cols + b) >= rate[r] ? 1 / (1 - rate[r]) : 0   (rate_per_row == nullptr: `rate` for all)
+__global__ void keep_scale_kernel(float* __restrict__ out, int rows, int cols, const float* __restrict__ rate_per_row, float rate,
+                                  unsigned long long seed) {
+  pdl_prologue();
+  const long long n = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float r = rate_per_row ? rate_per_row[i / cols] : rate;
+    out[i] = (r <= 0.f || hash_uniform(seed, (unsigned long long)i) >= r) ? 1.f / (1.f - r) : 0.f;
+  }
+}
+
 }  // namespace
+
+// Keep factors of timm's DropPath (per sample, libs/pvlt.py:135,141-142 with the rates of :197) for all residual branches of
+// one step in ONE launch: out fp32 [rows, cols] (rows = 2 * #blocks, cols = batch), rate_per_row fp32 [rows] on the device.
+// With rate_per_row == nullptr it writes the element-wise dropout factors bert_embed_fwd applies for (seed, rate) to a
+// [rows, cols = 768] activation (transformers BertEmbeddings.dropout) -- lets tests rebuild the mask a step drew.
+extern "C" int mvlt_keep_scale(float* out, int rows, int cols, const float* rate_per_row, float rate, unsigned long long seed,
+                               void* stream_) {
+  MVLT_CHECK_ARG(out && rows > 0 && cols > 0 && rate >= 0.f && rate < 1.f, "keep_scale: bad arguments");
+  const long long n = (long long)rows * cols;
+  int grid = (int)((n + 255) / 256);
+  const int cap = mvlt_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  mvlt_launch(keep_scale_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_), out, rows, cols, rate_per_row, rate, seed);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int mvlt_bert_embed_fwd(const long long* ids, const float* word, const float* pos, const float* type,
                                    const float* gamma, const float* beta, void* out_bf16, float* mean, float* rstd,

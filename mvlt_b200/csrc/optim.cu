@@ -8,14 +8,20 @@
 //   p <- p - (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 #include "common.cuh"
 
-struct AdamTensor {      // one parameter tensor (48 bytes; mirrored by mvlt_b200/optim.py)
+struct AdamTensor {      // one parameter tensor (88 bytes; mirrored by mvlt_b200/optim.py)
   float* p;
   float* g;
   float* m;
   float* v;
   long long n;
   float wd_mult;         // multiplies the group's weight decay (0 for bias / 1-D parameters)
-  int pad;
+  int shadow;            // bf16 compute copies the engine's GEMMs read, refreshed by this kernel (0 = none):
+                         //   1: w16[i] = bf16(p[i])                                  (Linear / embedding weights)
+                         //   2: p = [Co, Ci, KK]: w16[co * ld + kk * Ci + ci]        (convolutions as GEMMs, K = (tap, ci))
+                         //      and, when w16t != nullptr, w16t[ci, (KK-1-kk) * Co + co]  (flipped + transposed: input gradient)
+  __nv_bfloat16* w16;
+  __nv_bfloat16* w16t;
+  int Co, Ci, KK, ld;
 };
 struct AdamChunk {       // one contiguous run of <= chunk_elems elements of tensor `t`
   long long off;
@@ -24,6 +30,15 @@ struct AdamChunk {       // one contiguous run of <= chunk_elems elements of ten
 };
 
 namespace {
+
+__device__ __forceinline__ void shadow_conv(const AdamTensor& t, long long e, float val) {
+  const int kk = (int)(e % t.KK);
+  const int ci = (int)((e / t.KK) % t.Ci);
+  const int co = (int)(e / ((long long)t.Ci * t.KK));
+  const __nv_bfloat16 b = __float2bfloat16(val);
+  t.w16[(long long)co * t.ld + (long long)kk * t.Ci + ci] = b;
+  if (t.w16t) t.w16t[((long long)ci * t.KK + (t.KK - 1 - kk)) * t.Co + co] = b;
+}
 
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, float lr_wd, float b1, float b2, float step, float rbc2,
                                       float eps) {
@@ -46,7 +61,8 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __re
   float* v = t.v + ch.off;
   const float gs = grad_scale ? *grad_scale : 1.f;
   const float lr_wd = lr * wd * t.wd_mult, step = lr / bc1, rbc2 = rsqrtf(bc2);
-  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
+  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0 &&
+                   (t.shadow != 1 || (((uintptr_t)t.w16) & 7) == 0);
   const long long n4 = vec ? n / 4 : 0;
   for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
     float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
@@ -59,12 +75,25 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __re
     reinterpret_cast<float4*>(m)[i] = m4;
     reinterpret_cast<float4*>(v)[i] = v4;
     if (zero_grads) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t.shadow == 1) {          // ch.off is a multiple of 4 elements and w16 is 8-byte aligned (checked by the host)
+      uint2 o;
+      o.x = pack_bf16x2(p4.x, p4.y);
+      o.y = pack_bf16x2(p4.z, p4.w);
+      reinterpret_cast<uint2*>(t.w16 + ch.off)[i] = o;
+    } else if (t.shadow == 2) {
+      shadow_conv(t, ch.off + 4 * i, p4.x);
+      shadow_conv(t, ch.off + 4 * i + 1, p4.y);
+      shadow_conv(t, ch.off + 4 * i + 2, p4.z);
+      shadow_conv(t, ch.off + 4 * i + 3, p4.w);
+    }
   }
   for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
     float pp = p[i], mm = m[i], vv = v[i];
     adam1(pp, g[i] * gs, mm, vv, lr_wd, b1, b2, step, rbc2, eps);
     p[i] = pp; m[i] = mm; v[i] = vv;
     if (zero_grads) g[i] = 0.f;
+    if (t.shadow == 1) t.w16[ch.off + i] = __float2bfloat16(pp);
+    else if (t.shadow == 2) shadow_conv(t, ch.off + i, pp);
   }
 }
 

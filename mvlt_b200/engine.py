@@ -24,6 +24,7 @@ from typing import Dict, List, Optional
 
 import torch
 
+from . import _lib
 from . import kernels as k
 from ._lib import MvltError
 from .engine_util import split_k as _split_k
@@ -43,9 +44,9 @@ HEAD_DIM = 64
 # fused SR-attention forward (csrc/attn_tcgen05.cu); MVLT_FUSED_ATTN=0 keeps the two-GEMM path (QK^T + softmax epilogue, PV)
 # for A/B measurements -- both are sm_100a tcgen05 kernels
 FUSED_ATTENTION = os.environ.get("MVLT_FUSED_ATTN", "1") != "0"
-# EXPERIMENTAL fused attention backward (csrc/attn_bwd_tcgen05.cu): written after the round's GPU budget was spent and
-# not yet validated on a device, hence opt-in; the default backward is the four-GEMM path below
-FUSED_ATTENTION_BWD = os.environ.get("MVLT_FUSED_ATTN_BWD", "0") == "1"
+# fused attention backward (csrc/attn_bwd_tcgen05.cu: dQ, dK, dV in one kernel); MVLT_FUSED_ATTN_BWD=0 keeps the four-GEMM
+# path (dV, dP + softmax-backward epilogue, dQ, dK) for A/B measurements
+FUSED_ATTENTION_BWD = os.environ.get("MVLT_FUSED_ATTN_BWD", "1") != "0"
 
 
 def _empty(shape, dtype, dev):
@@ -55,7 +56,7 @@ def _empty(shape, dtype, dev):
 class PVLTEngine:
     def __init__(self, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor], depths: List[int],
                  loss_type: Dict[str, int], num_text_tokens: int = 128, drop_path_rate: float = 0.0,
-                 embed_dropout: float = 0.1):
+                 embed_dropout: float = 0.1, step_counter: Optional[list] = None):
         self.P = params          # name -> fp32 parameter tensor (live nn.Parameter data)
         self.Bf = buffers        # name -> buffer (BatchNorm running stats)
         self.depths = depths
@@ -67,7 +68,10 @@ class PVLTEngine:
         self.W: Dict[str, torch.Tensor] = {}   # bf16 compute copies (conv weights permuted to [Co, kh, kw, Ci])
         self._w_version = None
         self._pos_cache = {}
-        self._step = 0
+        self.step_counter = step_counter if step_counter is not None else [0]
+        self._seed_base = None
+        self._dp_rates = None
+        self.last_rng = None
         from . import t2i as _t2i
         self.t2i = _t2i.T2IHead(self) if loss_type.get("t2i") else None
 
@@ -87,7 +91,9 @@ class PVLTEngine:
 
     def prepare_weights(self):
         """fp32 master -> bf16 compute copies, refreshed only when a parameter changed (optimizer step / load)."""
-        ver = tuple(p._version for p in self.P.values())
+        # invalidation: autograd version counters (torch optimizers, load_state_dict, in-place edits) + the package epoch for
+        # writers that go through raw pointers. The own AdamW kernel refreshes the registered copies itself (optim.cu)
+        ver = (tuple(p._version for p in self.P.values()), _lib.WEIGHT_EPOCH)
         dev = next(iter(self.P.values())).device
         if self._w_version == ver and self.W:
             return
@@ -106,11 +112,36 @@ class PVLTEngine:
                 self.W[name] = _empty(shape, BF16, dev)
             if name in convs:
                 k.cast_conv_weight(p, self.W[name], p.shape[0], p.shape[1], convs[name], self.W[name].shape[1])
+                p._mvlt_shadow = (2, self.W[name], None, p.shape[0], p.shape[1], convs[name], self.W[name].shape[1])
             else:
                 k.cast_weight(p, self.W[name])
+                p._mvlt_shadow = (1, self.W[name], None, 0, 0, 0, 0)
         if self.t2i is not None:
             self.t2i.prepare_weights()
         self._w_version = ver
+
+    def _next_seeds(self):
+        """Seeds of this step's dropout / drop-path draws (counter-based hash, csrc/common.cuh). The stream is derived from
+        torch's seed (``torch.manual_seed``; main_vl.py:205-208 seeds ``args.seed + rank``) and the data-parallel rank, so
+        runs are reproducible and ranks draw different masks; the step counter lives on the model (survives engine rebuilds)."""
+        if self._seed_base is None:
+            rank = 0
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    rank = dist.get_rank()
+            except Exception:
+                rank = 0
+            self._seed_base = (torch.initial_seed() * 0x9E3779B97F4A7C15 + (rank + 1) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+        self.step_counter[0] += 1
+        z = (self._seed_base + self.step_counter[0] * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z ^= z >> 31
+        return z & 0xFFFFFFFFFFFF, (z * 0x94D049BB133111EB + 1) & 0xFFFFFFFFFFFF
+
+    def invalidate(self):
+        """Call after writing parameters behind autograd's back (``p.data`` writes, broadcasts, raw pointers)."""
+        self._w_version = None
+        self._pos_cache = {}
 
     # ------------------------------------------------------------------------------------------------
     # helpers
@@ -126,7 +157,7 @@ class PVLTEngine:
 
     def _pos(self, stage, H, W, dev):
         """pvlt.py:291-297,341-344: bilinear resize of the position table (cached per weight version)."""
-        key = (stage, H, W, self.P[f"pos_embed{stage}"]._version)
+        key = (stage, H, W, self.P[f"pos_embed{stage}"]._version, _lib.PARAM_EPOCH)
         if key in self._pos_cache:
             return self._pos_cache[key]
         pe = self.P[f"pos_embed{stage}"]
@@ -306,10 +337,9 @@ class PVLTEngine:
         if ids.shape != (B, T):
             raise MvltError(f"input_ids must be [B, {T}], got {tuple(ids.shape)}")
         ctx = {"B": B, "stages": [], "IH": IH, "IW": IW}
-        self._step += 1
         # --- BERT embeddings (pvlt.py:326)
         p_drop = self.embed_dropout if training else 0.0
-        seed = (self._step * 0x9E3779B1) & 0xFFFFFFFFFFFF
+        seed, dp_seed = self._next_seeds() if training else (0, 0)
         y768 = _empty((B * T, HIDDEN), BF16, dev)
         em, er = _empty((B * T,), F32, dev), _empty((B * T,), F32, dev)
         ids = ids.contiguous()
@@ -321,8 +351,11 @@ class PVLTEngine:
         nblk = sum(self.depths)
         dps = None
         if training and any(r > 0 for r in self.dpr):
-            keep = torch.tensor([1.0 - r for r in self.dpr for _ in (0, 1)], device=dev, dtype=F32).view(-1, 1)
-            dps = (torch.rand((2 * nblk, B), device=dev) < keep).to(F32) / keep
+            if self._dp_rates is None or self._dp_rates.device != dev:   # built once: no per-step host->device copy
+                self._dp_rates = torch.tensor([r for r in self.dpr for _ in (0, 1)], device=dev, dtype=F32)
+            dps = _empty((2 * nblk, B), F32, dev)
+            k.keep_scale(dps, 2 * nblk, B, rate_per_row=self._dp_rates, seed=dp_seed)
+        self.last_rng = dict(seed=seed, p_drop=p_drop, dp_seed=dp_seed, dps=dps)   # what this step drew (read back by the parity tests)
         Xprev, Hp, Wp = None, IH, IW
         te_in = y768
         blk = 0

@@ -272,8 +272,8 @@ def sr_attention_fwd(q, kv, o, p_out, B, N, Nk, heads, scale):
 
 
 def sr_attention_bwd(q, kv, do, p, dq, dkv, B, N, Nk, heads, scale):
-    """EXPERIMENTAL (csrc/attn_bwd_tcgen05.cu, not yet validated on a device; engine.py only uses it under
-    MVLT_FUSED_ATTN_BWD=1): dq [B*N, C] and dkv [B*Nk, 2C] (dK | dV) of the fused attention from the saved probabilities."""
+    """dq [B*N, C] and dkv [B*Nk, 2C] (dK | dV) of the fused attention from the saved probabilities, one tcgen05 kernel
+    (csrc/attn_bwd_tcgen05.cu)."""
     require_cuda(q, kv, do, p, dq, dkv)
     C_ = heads * 64
     for t in (q, kv, do, p, dq, dkv):
@@ -378,6 +378,12 @@ def bert_embed_bwd(dy, ids, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp
     call("bert_embed_bwd", ptr(dy), ptr(ids), ptr(word), ptr(pos), ptr(typ), ptr(gamma), ptr(mean), ptr(rstd),
          ptr(dword), ptr(dpos), ptr(dtype_), ptr(dgamma), ptr(dbeta), C.c_int(rows), C.c_int(T), C.c_float(p_drop),
          C.c_ulonglong(seed), C.c_int(pad_id))
+
+
+def keep_scale(out, rows, cols, rate_per_row=None, rate=0.0, seed=0):
+    """DropPath keep factors [rows, cols] (per-row rates on the device) or, with ``rate_per_row=None``, the element-wise
+    dropout factors ``bert_embed_fwd`` applies for (seed, rate) (csrc/embed.cu)."""
+    call("keep_scale", ptr(out), C.c_int(rows), C.c_int(cols), ptr(rate_per_row), C.c_float(rate), C.c_ulonglong(seed))
 
 
 def compact_labels(labels, n, ignore, idx_out, labels_out, count_out):

@@ -18,6 +18,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
+from .. import _lib
 from .. import kernels as k
 from .._lib import MvltError
 from ..engine import DEPTHS, EMBED_DIMS, HIDDEN, MLP_RATIOS, NUM_HEADS, PATCH, SR_RATIOS, VOCAB, VOCAB_PAD, PVLTEngine
@@ -411,7 +412,8 @@ class PyramidVisionLanguageTransformer(nn.Module):
                 raise MvltError("mvlt_b200 runs on CUDA (sm_100a) only: move the model with .to('cuda'); "
                                 "there is no CPU fallback")
             eng = PVLTEngine(params, dict(self.named_buffers()), self.depths, self.loss_type, self.T_num,
-                             self.drop_path_rate, self.text_embeddings.dropout.p)
+                             self.drop_path_rate, self.text_embeddings.dropout.p,
+                             self.__dict__.setdefault("_step_counter", [0]))
             eng._device = dev
             eng._plist_id = plist
             self.__dict__["_eng"] = eng
@@ -429,6 +431,7 @@ class PyramidVisionLanguageTransformer(nn.Module):
             grp = None if group is True else group
             for t in list(self.parameters()) + list(self.buffers()):
                 dist.broadcast(t.data, src=broadcast_from, group=grp)
+            _lib.params_written()   # .data writes bypass the version counters the engine's bf16 weight copies are keyed on
         return self
 
     def state_dict(self, *args, **kwargs):

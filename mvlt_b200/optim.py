@@ -45,16 +45,24 @@ class AdamW(torch.optim.Optimizer):
 
     def _group_tables(self, gi, ps):
         """Device tables of (p, g, m, v, n) per tensor and of the 64 KB chunks; rebuilt only when a pointer moved."""
-        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr()) for p in ps)
+        shadows = [getattr(p, "_mvlt_shadow", None) for p in ps]
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     None if sh is None else (sh[0], sh[1].data_ptr(), 0 if sh[2] is None else sh[2].data_ptr()))
+                    for p, sh in zip(ps, shadows))
         cached = self._tables.get(gi)
         if cached is not None and cached[0] == key:
             return cached[1], cached[2], cached[3]
         tb, cb, nchunks = bytearray(), bytearray(), 0
-        for ti, p in enumerate(ps):
+        for ti, (p, sh) in enumerate(zip(ps, shadows)):
             st = self.state[p]
             n = p.numel()
-            tb += struct.pack("<QQQQqfi", p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), n,
-                              1.0, 0)
+            # bf16 compute copies registered by the engine (engine.PVLTEngine._register_shadow): refreshed by the same launch
+            mode, w16, w16t, co, ci, kk, ld = sh if sh is not None else (0, None, None, 0, 0, 0, 0)
+            if mode and (w16.device != p.device or w16.dtype != torch.bfloat16 or w16.numel() < n):
+                raise MvltError("stale bf16 shadow registered on a parameter")
+            tb += struct.pack("<QQQQqfiQQiiii", p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(),
+                              st["exp_avg_sq"].data_ptr(), n, 1.0, mode, 0 if w16 is None else w16.data_ptr(),
+                              0 if w16t is None else w16t.data_ptr(), co, ci, kk, ld)
             for off in range(0, n, CHUNK):
                 cb += struct.pack("<qii", off, ti, 0)
                 nchunks += 1
@@ -95,4 +103,10 @@ class AdamW(torch.optim.Optimizer):
                  C.c_float(1.0 - b2 ** t), ptr(grad_scale), C.c_int(0))
             for p in ps:
                 self.state[p]["step"] = t
+        # the kernel writes through raw pointers, which autograd's version counters do not see: parameters whose bf16 compute
+        # copy this launch could not refresh (none registered yet) and cached derived tables (resized position embeddings) are
+        # invalidated through the package-wide epoch instead
+        _lib.PARAM_EPOCH += 1
+        if any(p.dim() >= 2 and getattr(p, "_mvlt_shadow", None) is None for g in self.param_groups for p in g["params"]):
+            _lib.WEIGHT_EPOCH += 1
         return loss

@@ -55,6 +55,7 @@ class T2IHead:
             if tname not in self.W:
                 self.W[tname] = torch.empty((w.shape[1], 9 * w.shape[0]), dtype=BF16, device=w.device)
             k.cast_conv_weight_t(w, self.W[tname], w.shape[0], w.shape[1], 9)
+            w._mvlt_shadow = (2, self.W[name], self.W[tname], w.shape[0], w.shape[1], 9, 9 * w.shape[1])
 
     # ---- conv3x3 (no bias) + BatchNorm ----------------------------------------------------------------
     def _convbn_fwd(self, u, src, batch_stride, pix_stride, B, H, W, Ci, training, out=None, out_ld=None, out_coff=0):

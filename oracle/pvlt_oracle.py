@@ -196,14 +196,17 @@ def _lin(x, sd, prefix):
     return F.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
 
 
-def bert_embeddings(sd, ids, p_drop=0.0, training=False):
-    """transformers BertEmbeddings.forward (absolute positions, token type 0); call site pvlt.py:326."""
+def bert_embeddings(sd, ids, p_drop=0.0, training=False, keep_scale=None):
+    """transformers BertEmbeddings.forward (absolute positions, token type 0); call site pvlt.py:326.
+    ``keep_scale`` [B, T, 768]: an explicit dropout mask (0 or 1/(1-p)) instead of torch's RNG draw."""
     T = ids.shape[1]
     # padding_idx=0 (BertConfig.pad_token_id): pad rows get no gradient from the gather (SURVEY H6)
     x = (F.embedding(ids, sd["text_embeddings.word_embeddings.weight"], padding_idx=0)
          + sd["text_embeddings.token_type_embeddings.weight"][0]
          + sd["text_embeddings.position_embeddings.weight"][:T])
     x = _ln(x, sd, "text_embeddings.LayerNorm", 1e-12)
+    if keep_scale is not None:
+        return x * keep_scale
     return F.dropout(x, p_drop, training)
 
 
@@ -255,11 +258,13 @@ def block(sd, p, x, H, W, T, heads, sr, dp_scale=None):
     return x + h
 
 
-def pyramid_features(sd, images, ids, model="pvlt_tiny", T=128):
-    """pvlt.py:322-356."""
+def pyramid_features(sd, images, ids, model="pvlt_tiny", T=128, dp_scales=None, embed_keep_scale=None):
+    """pvlt.py:322-356. ``dp_scales`` [2 * n_blocks, B]: timm DropPath factors (mask / keep_prob) of the attention and MLP
+    branch of every block in execution order (pvlt.py:141-142); ``embed_keep_scale``: BertEmbeddings dropout mask."""
     depths = ARCH[model]["depths"]
     B = images.shape[0]
-    y = bert_embeddings(sd, ids)
+    y = bert_embeddings(sd, ids, keep_scale=embed_keep_scale)
+    blk = 0
     x = images
     img_feats, text_feats = [], []
     for i in range(4):
@@ -271,7 +276,9 @@ def pyramid_features(sd, images, ids, model="pvlt_tiny", T=128):
         pe = resized_pos_embed(sd, s, H, W)
         x = torch.cat((x + pe, y + sd[f"text_pos_embed{s}"]), 1)
         for j in range(depths[i]):
-            x = block(sd, f"block{s}.{j}", x, H, W, T, NUM_HEADS[i], SR_RATIOS[i])
+            dp = None if dp_scales is None else (dp_scales[2 * blk], dp_scales[2 * blk + 1])
+            x = block(sd, f"block{s}.{j}", x, H, W, T, NUM_HEADS[i], SR_RATIOS[i], dp)
+            blk += 1
         x, y = x[:, :H * W], x[:, H * W:]
         x = x.reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
         img_feats.append(x)
@@ -324,9 +331,10 @@ def t2i_head(sd, low, mid, high, training=True, stats=None):
     return F.interpolate(r, scale_factor=8, mode="bilinear", align_corners=True)
 
 
-def forward(sd, images, ids, loss_type, model="pvlt_tiny", training=True, bn_stats=None):
+def forward(sd, images, ids, loss_type, model="pvlt_tiny", training=True, bn_stats=None, dp_scales=None,
+            embed_keep_scale=None):
     """pvlt.py:358-401: the logits dict with exactly the reference's keys."""
-    img_feats, text_feats = pyramid_features(sd, images, ids, model)
+    img_feats, text_feats = pyramid_features(sd, images, ids, model, dp_scales=dp_scales, embed_keep_scale=embed_keep_scale)
     out = dict(mlm_logits=None, itm_logits=None, sup_cls_logits=None, sub_cls_logits=None, t2i_logits=None)
     tf = text_feats[-1]
     if loss_type.get("mlm"):
@@ -363,7 +371,7 @@ def losses(out, batch, images_target):
     return res
 
 
-def train_step_grads(sd, batch, loss_type, model="pvlt_tiny", masked_images=None):
+def train_step_grads(sd, batch, loss_type, model="pvlt_tiny", masked_images=None, dp_scales=None, embed_keep_scale=None):
     """One fwd+bwd of engine_grid_masking.py:69-127 (no optimizer). Returns (losses, grads by name)."""
     names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k
              and k != "mlm_head.mlm_decoder.weight"]
@@ -373,7 +381,8 @@ def train_step_grads(sd, batch, loss_type, model="pvlt_tiny", masked_images=None
     if "mlm_head.mlm_decoder.weight" in sd:
         sdl["mlm_head.mlm_decoder.weight"] = leaf["text_embeddings.word_embeddings.weight"]
     x = masked_images if masked_images is not None else batch["images"]
-    out = forward(sdl, x, batch["input_ids"], loss_type, model, training=True)
+    out = forward(sdl, x, batch["input_ids"], loss_type, model, training=True, dp_scales=dp_scales,
+                  embed_keep_scale=embed_keep_scale)
     ls = losses(out, batch, batch["images"])
     ls["total"].backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}

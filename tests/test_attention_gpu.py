@@ -77,8 +77,6 @@ def test_fused_attention_rejects_unsupported_lengths():
         k.sr_attention_fwd(q, kv, o, None, 1, 128, 224, 1, 0.125)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MVLT_FUSED_ATTN_BWD", "0") != "1",
-                    reason="experimental fused attention backward: opt-in until it has been validated on a device")
 @pytest.mark.parametrize("B,N,heads,Nk", SHAPES)
 def test_fused_attention_backward_matches_fp32_autograd(B, N, heads, Nk):
     from mvlt_b200 import kernels as k

@@ -133,3 +133,62 @@ def test_full_batch_properties_b128():
     # repeatable up to the summation order of the fp32 atomics (loss / BatchNorm-statistic accumulators)
     assert abs(s1[1].item() - s2[1].item()) < 1e-4 and abs(s1[2].item() - s2[2].item()) < 1e-4
     assert float(g1.abs().sum()) > 0
+
+
+def test_own_adamw_keeps_bf16_weight_copies_fresh_and_tracks_torch_adamw():
+    """The own optimizer writes the fp32 masters through raw pointers (no autograd version bump): the bf16 copies the GEMMs
+    read must still follow them every step (csrc/optim.cu writes them in the same launch), for Linear weights, the k=s
+    convolutions (permuted) and the 3x3 t2i convolutions (permuted + flipped/transposed). Cross-check: the loss trajectory
+    equals the one of ``torch.optim.AdamW`` (which bumps versions and therefore takes the recast path) on a twin model."""
+    from mvlt_b200.optim import AdamW, param_groups_no_decay
+    from mvlt_b200.synthetic import make_batch
+    ma, mb = _model(PRE, drop_path=0.0, seed=3), _model(PRE, drop_path=0.0, seed=3)
+    mb.load_state_dict(ma.state_dict())
+    for m in (ma, mb):
+        m.text_embeddings.dropout.p = 0.0
+        m.train()
+    oa = AdamW(param_groups_no_decay(ma, 0.05), lr=3e-4)
+    ob = torch.optim.AdamW(param_groups_no_decay(mb, 0.05), lr=3e-4)
+    batches = [make_batch(8, seed=s) for s in (0, 1)]
+    la, lb = [], []
+    for step in range(6):
+        b = batches[step % 2]
+        img, ids = b["images"].cuda(), b["input_ids"].cuda()
+        for m, o, out in ((ma, oa, la), (mb, ob, lb)):
+            total, stats = m(img, ids, mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=img)
+            o.zero_grad()
+            total.backward()
+            o.step()
+            out.append(stats[:6].tolist())
+    eng = ma._engine()
+    P = dict(ma.named_parameters())
+    convs = eng._conv_names()
+    checked = 0
+    for name, w in eng.W.items():
+        p = P[name].detach()
+        if name in convs:
+            co, ci = p.shape[0], p.shape[1]
+            want = p.view(co, ci, -1).permute(0, 2, 1).reshape(co, -1).to(torch.bfloat16)
+        else:
+            want = p.view(w.shape).to(torch.bfloat16)
+        assert torch.equal(w, want), name
+        checked += 1
+    for name, w in eng.t2i.W.items():
+        p = P[name.replace("^T", "")].detach()
+        co, ci = p.shape[0], p.shape[1]
+        if name.endswith("^T"):
+            want = p.view(co, ci, 9).flip(-1).permute(1, 2, 0).reshape(ci, -1).to(torch.bfloat16)
+        else:
+            want = p.view(co, ci, 9).permute(0, 2, 1).reshape(co, -1).to(torch.bfloat16)
+        assert torch.equal(w, want), name
+        checked += 1
+    assert checked > 60
+    # the weights really moved, and both optimizers walked the same path (bf16 GEMMs + fp32 atomics: small run-to-run noise)
+    assert la[-2][0] < la[0][0] - 0.1 and la[-1][0] < la[1][0] - 0.1, la
+    for sa, sb in zip(la, lb):
+        for x, y in zip(sa, sb):
+            assert abs(x - y) <= 2e-2 * max(1.0, abs(y)), (la, lb)
+    pa, pb = dict(ma.named_parameters()), dict(mb.named_parameters())
+    for name in ("block1.0.mlp.fc1.weight", "block3.1.attn.kv.weight", "patch_embed2.proj.weight", "t2i_head.conv4.0.weight"):
+        d = (pa[name] - pb[name]).abs().max().item()
+        assert d <= 6 * 3e-4, (name, d)     # at most a few lr-sized steps apart (sign flips of ~zero gradients)

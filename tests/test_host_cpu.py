@@ -183,12 +183,11 @@ def test_entrypoints_register_with_timm_and_hubconf(monkeypatch):
 
 
 def test_validated_defaults_are_the_ones_shipped():
-    """The switches the GPU runs of this round validated: fused attention forward on, programmatic dependent launch on,
-    the not-yet-validated fused attention backward off."""
+    """The switches the GPU runs validated: fused attention forward and backward on, programmatic dependent launch on."""
     import mvlt_b200.engine as E
     if "MVLT_FUSED_ATTN" not in os.environ:
         assert E.FUSED_ATTENTION is True
     if "MVLT_FUSED_ATTN_BWD" not in os.environ:
-        assert E.FUSED_ATTENTION_BWD is False
+        assert E.FUSED_ATTENTION_BWD is True
     src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "mvlt_b200", "csrc", "common.cuh")).read()
     assert "#define MVLT_PDL_DEFAULT 1" in src

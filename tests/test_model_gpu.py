@@ -117,3 +117,84 @@ def test_state_dict_roundtrip_and_tied_weight():
     assert set(out.keys()) == set(sd.keys())
     for key in sd:
         assert tuple(out[key].shape) == tuple(sd[key].shape), key
+
+
+def _oracle_masks(m, B):
+    """The stochastic draws of the step that just ran (engine.last_rng), in the oracle's format: DropPath factors per
+    (branch, sample) and the BertEmbeddings dropout mask regenerated from the same counter-based hash."""
+    from mvlt_b200 import kernels as k
+    rng = m._engine().last_rng
+    dps = rng["dps"].cpu() if rng["dps"] is not None else None
+    keep = None
+    if rng["p_drop"] > 0:
+        keep = torch.empty((B * 128, 768), device="cuda")
+        k.keep_scale(keep, B * 128, 768, rate=rng["p_drop"], seed=rng["seed"])
+        keep = keep.view(B, 128, 768).cpu()
+    return dps, keep
+
+
+def _compare_step(m, sd, batch, loss_type, got, dps, keep, report, loss_tol=2e-2, arch="pvlt_tiny"):
+    from oracle import pvlt_oracle as O
+    ref_losses, ref_grads, _ = O.train_step_grads(sd, batch, loss_type, model=arch, dp_scales=dps, embed_keep_scale=keep)
+    for key, r in ref_losses.items():
+        assert abs(got[key] - r) <= loss_tol * max(1.0, abs(r)), (key, got[key], r)
+    gmax = max(float(g.norm()) for g in ref_grads.values())
+    rows, num, den = {}, 0.0, 0.0
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        r = ref_grads[name]
+        rows[name] = [_rel(p.grad, r), float(r.norm())]
+        num += float((p.grad.detach().float().cpu() - r).norm()) ** 2
+        den += float(r.norm()) ** 2
+    glob = (num / den) ** 0.5
+    _report(report, {"losses": got, "ref_losses": ref_losses, "global_rel": glob, "per_param": rows})
+    bad = {n: v for n, v in rows.items() if v[0] > (6e-2 if v[1] > 1e-3 * gmax else 0.15)}
+    assert not bad, (len(bad), dict(list(bad.items())[:12]))
+    assert glob <= 3e-2, glob
+
+
+def test_drop_path_and_embedding_dropout_step_matches_oracle():
+    """Row a10 (timm DropPath, pvlt.py:135,141-142,197) and BertEmbeddings dropout with the rates ON: the step's draws are
+    read back from the engine and handed to the oracle (``dp_scales`` / ``embed_keep_scale``), so forward scaling, the
+    drop-path-scaled operands the LayerNorm backward writes for the next GEMMs and the dropout backward are all compared.
+    Rate 0.5 (not the 0.1 default) so that a B=4 step certainly drops branches."""
+    from oracle import pvlt_oracle as O
+    torch.manual_seed(7)
+    m, sd = _model(PRE, drop_path=0.5)
+    m.text_embeddings.dropout.p = 0.1
+    m.train()
+    batch = O.make_inputs(4, seed=2)
+    img, ids = batch["images"].cuda(), batch["input_ids"].cuda()
+    total, stats = m(img, ids, mlm_labels=batch["mlm_labels"], itm_labels=batch["itm_labels"], target_images=img)
+    total.backward()
+    dps, keep = _oracle_masks(m, 4)
+    assert dps is not None and tuple(dps.shape) == (16, 4)
+    assert int((dps == 0).sum()) >= 3 and int((dps > 1).sum()) >= 3, dps      # both outcomes occur
+    assert abs(float((keep == 0).float().mean()) - 0.1) < 0.01
+    st = stats.cpu().tolist()
+    got = {"total": st[0], "mlm": st[1], "itm": st[2], "t2i": st[5]}
+    _compare_step(m, sd, batch, PRE, got, dps, keep, "grads_pre_droppath.json")
+
+
+@pytest.mark.parametrize("loss_type,tag", [(PRE, "pre"), (CLS, "cls")])
+def test_benched_configuration_b128_matches_oracle(loss_type, tag):
+    """The configuration bench.py times (BASELINE configs[1] / configs[3]): B = 128, drop_path 0.1, embedding dropout 0.1,
+    ``mlm_count`` supplied by the data pipeline -- losses and all parameter gradients vs the fp32 oracle (same tolerances as
+    the B = 2 cases; split-K factors, wave counts and tile shapes all differ from those)."""
+    from oracle import pvlt_oracle as O
+    torch.manual_seed(11)
+    m, sd = _model(loss_type, drop_path=0.1)
+    m.text_embeddings.dropout.p = 0.1
+    m.train()
+    B = 128
+    batch = O.make_inputs(B, seed=4)
+    img, ids = batch["images"].cuda(), batch["input_ids"].cuda()
+    total, stats = m(img, ids, mlm_labels=batch["mlm_labels"], itm_labels=batch["itm_labels"],
+                     sup_cls_labels=batch["sup_cls_labels"], sub_cls_labels=batch["sub_cls_labels"], target_images=img,
+                     mlm_count=int((batch["mlm_labels"] != -1).sum()))
+    total.backward()
+    torch.cuda.synchronize()
+    dps, keep = _oracle_masks(m, B)
+    st = stats.cpu().tolist()
+    got = {"total": st[0], "mlm": st[1], "itm": st[2], "sup_cls": st[3], "sub_cls": st[4], "t2i": st[5]}
+    _compare_step(m, sd, batch, loss_type, got, dps, keep, f"grads_b128_{tag}.json")

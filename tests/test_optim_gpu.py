@@ -47,3 +47,41 @@ def test_adamw_grad_scale_and_no_cpu_fallback():
     c.grad = torch.ones(4)
     with pytest.raises(MvltError):
         AdamW([c]).step()
+
+
+def test_adamw_refreshes_registered_bf16_shadows():
+    """The engine's GEMMs read bf16 copies of the fp32 masters; the own optimizer writes the masters through raw pointers
+    (no autograd version bump), so the SAME kernel must rewrite the copies: plain, conv-permuted [Co, tap, Ci] and the
+    flipped + transposed [Ci, tap', Co] layouts (csrc/optim.cu shadow modes 1 / 2)."""
+    from mvlt_b200.optim import AdamW
+    g = torch.Generator(device="cuda").manual_seed(5)
+    lin = torch.nn.Parameter(torch.randn((1031, 67), generator=g, device="cuda"))
+    conv = torch.nn.Parameter(torch.randn((24, 40, 2, 2), generator=g, device="cuda"))
+    c3 = torch.nn.Parameter(torch.randn((64, 128, 3, 3), generator=g, device="cuda"))
+    plain = torch.nn.Parameter(torch.randn((33, 5), generator=g, device="cuda"))
+    w_lin = torch.zeros((1031, 67), device="cuda", dtype=torch.bfloat16)
+    w_conv = torch.zeros((24, 4 * 40), device="cuda", dtype=torch.bfloat16)
+    w_c3 = torch.zeros((64, 9 * 128), device="cuda", dtype=torch.bfloat16)
+    w_c3t = torch.zeros((128, 9 * 64), device="cuda", dtype=torch.bfloat16)
+    lin._mvlt_shadow = (1, w_lin, None, 0, 0, 0, 0)
+    conv._mvlt_shadow = (2, w_conv, None, 24, 40, 4, 160)
+    c3._mvlt_shadow = (2, w_c3, w_c3t, 64, 128, 9, 9 * 128)
+    ps = [lin, conv, c3, plain]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    o1, o2 = AdamW(ps, lr=1e-2, weight_decay=0.05), torch.optim.AdamW(ref, lr=1e-2, weight_decay=0.05)
+    from mvlt_b200 import _lib
+    w_epoch = _lib.WEIGHT_EPOCH
+    for step in range(3):
+        for a, b in zip(ps, ref):
+            a.grad = torch.randn(a.shape, generator=g, device="cuda")
+            b.grad = a.grad.clone()
+        o1.step()
+        o2.step()
+    assert _lib.WEIGHT_EPOCH == w_epoch + 3          # `plain` has no registered copy: engines must recast
+    for a, b in zip(ps, ref):
+        assert (a - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
+    assert torch.equal(w_lin, lin.detach().to(torch.bfloat16))
+    assert torch.equal(w_conv.view(24, 4, 40), conv.detach().view(24, 40, 4).permute(0, 2, 1).to(torch.bfloat16))
+    assert torch.equal(w_c3.view(64, 9, 128), c3.detach().view(64, 128, 9).permute(0, 2, 1).to(torch.bfloat16))
+    # input-gradient layout: w16t[ci, t, co] = w[co, ci, 8 - t]
+    assert torch.equal(w_c3t.view(128, 9, 64), c3.detach().view(64, 128, 9).flip(-1).permute(1, 2, 0).to(torch.bfloat16))
