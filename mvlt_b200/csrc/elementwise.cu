@@ -345,6 +345,16 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __re
   }
 }
 
+// ---- stand-alone exact-erf GELU (libs/vl_heads.py:7-14 GELU.forward) and its backward on fp32 / bf16 arrays ---------
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_ew_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, long long n) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = (float)x[i];
+    out[i] = (T)(dy ? (float)dy[i] * dgelu_fast(v) : gelu_erf(v));
+  }
+}
+
 // ---- generic 2-D cast with arbitrary (unaligned) widths: dst[r*ldd + c] = (TO) src[r*lds + c] * alpha ----------
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) cast2d_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst,
@@ -365,6 +375,17 @@ __global__ void __launch_bounds__(256) cast2d_kernel(const TI* __restrict__ src,
 
 }  // namespace
 
+// out = gelu(x) (dy == nullptr) or out = dy * gelu'(x); f32 selects fp32 (else bf16) for all three arrays
+extern "C" int mvlt_gelu_ew(const void* x, const void* dy, void* out, long long n, int f32, void* stream_) {
+  MVLT_CHECK_ARG(x && out && n > 0, "gelu_ew: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  if (f32)
+    mvlt_launch(gelu_ew_kernel<float>, cap_grid(n, 256), 256, 0, st, reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(dy), reinterpret_cast<float*>(out), n);
+  else
+    mvlt_launch(gelu_ew_kernel<__nv_bfloat16>, cap_grid(n, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<__nv_bfloat16*>(out), n);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
 extern "C" int mvlt_gelu_bwd(const void* dy_bf16, const void* pre_bf16, void* out_bf16, long long n, void* stream_) {
   MVLT_CHECK_ARG(n % 2 == 0, "gelu_bwd: n must be even");
   mvlt_launch(gelu_bwd_kernel, cap_grid(n / 2, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(pre_bf16),

@@ -98,14 +98,20 @@ class PVLTEngine:
         if self._w_version == ver and self.W:
             return
         convs = self._conv_names()
+        no_copy = (0, None, None, 0, 0, 0, 0)   # read in fp32 by the kernels: nothing for the optimizer kernel to refresh
         for name, p in self.P.items():
             if p.dim() < 2 or name.startswith("pos_embed") or name.startswith("text_pos_embed"):
+                p._mvlt_shadow = no_copy
                 continue
             if name.startswith("t2i_head."):
+                if not name.endswith(".0.weight") or "score" in name:
+                    p._mvlt_shadow = no_copy
                 continue  # handled by the t2i module (3x3 layout)
             if name in ("text_embeddings.position_embeddings.weight", "text_embeddings.token_type_embeddings.weight"):
+                p._mvlt_shadow = no_copy
                 continue
             if name.endswith("linear.weight") and ("itm_head" in name or "cls_head" in name):
+                p._mvlt_shadow = no_copy
                 continue  # small heads read fp32 weights directly
             if name not in self.W:
                 shape = (p.shape[0], p[0].numel())

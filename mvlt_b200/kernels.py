@@ -445,6 +445,15 @@ def gelu_bwd(dy, pre, out, n):
     call("gelu_bwd", ptr(dy), ptr(pre), ptr(out), C.c_longlong(n))
 
 
+def gelu_ew(x, out, dy=None):
+    """out = gelu_erf(x), or dy * gelu_erf'(x) when ``dy`` is given; contiguous fp32 or bf16 arrays of one dtype."""
+    require_cuda(x, out, dy)
+    for t in (x, out, dy):
+        if t is not None and (t.dtype != x.dtype or not t.is_contiguous() or t.numel() != x.numel()):
+            raise _lib.MvltError("gelu_ew: contiguous arrays of one dtype and size required")
+    call("gelu_ew", ptr(x), ptr(dy), ptr(out), C.c_longlong(x.numel()), C.c_int(_f32(x)))
+
+
 def cast2d(src, lds, dst, ldd, rows, Cdim, alpha=1.0):
     call("cast2d", ptr(src), _f32(src), C.c_longlong(lds), ptr(dst), _f32(dst), C.c_longlong(ldd),
          C.c_longlong(rows), C.c_int(Cdim), C.c_float(alpha))

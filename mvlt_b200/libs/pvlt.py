@@ -502,7 +502,8 @@ def _make(name, pretrained, token_hidden_size, num_text_tokens, loss_type, pretr
         token_hidden_size=token_hidden_size, num_text_tokens=num_text_tokens, loss_type=loss_type, **kwargs)
     model.default_cfg = _cfg()
     if pretrained_pth:
-        model.load_state_dict(torch.load(pretrained_pth, map_location="cpu"), strict=False)
+        from ..utils import load_file
+        model.load_state_dict(load_file(pretrained_pth), strict=False)   # tensors only (weights_only=True)
         print('>>> load pretrained weights (backbone part) from:', pretrained_pth)
     return model
 

@@ -35,11 +35,31 @@ def _to_bf16(x):
     return out
 
 
+class _GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        xc = x.contiguous()
+        out = torch.empty_like(xc)
+        k.gelu_ew(xc, out)
+        ctx.save_for_backward(xc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        dx = torch.empty_like(xc)
+        k.gelu_ew(xc, dx, dy=g.contiguous().to(xc.dtype))
+        return dx
+
+
 class GELU(nn.Module):
-    """exact-erf GELU (vl_heads.py:7-14); fused into the producing GEMM's epilogue."""
+    """exact-erf GELU (vl_heads.py:7-14). Inside the heads it is fused into the producing GEMM's epilogue; called on its
+    own (as the reference's class can be) it runs the stand-alone sm_100a kernel (fp32 / bf16 CUDA tensors)."""
 
     def forward(self, x):
-        raise MvltError("GELU is fused into the dense GEMM epilogue (csrc/gemm_tcgen05.cu); call the owning head")
+        if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+            raise MvltError("mvlt_b200 GELU needs an fp32 / bf16 CUDA tensor (sm_100a); there is no CPU fallback")
+        return _GeluFn.apply(x)
 
 
 class BertHeadTransform(nn.Module):

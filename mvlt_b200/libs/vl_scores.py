@@ -1,5 +1,5 @@
 """Drop-in for the reference's ``libs/vl_scores.py`` (/root/reference/libs/vl_scores.py:5-63): same function
-names, arguments and return types; the reductions run in the C-ABI kernels (csrc/loss.cu, csrc/score.cu).
+names, arguments and return types; the reductions run in the C-ABI kernels (csrc/loss.cu).
 """
 from __future__ import annotations
 

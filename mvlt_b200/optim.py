@@ -47,7 +47,7 @@ class AdamW(torch.optim.Optimizer):
         """Device tables of (p, g, m, v, n) per tensor and of the 64 KB chunks; rebuilt only when a pointer moved."""
         shadows = [getattr(p, "_mvlt_shadow", None) for p in ps]
         key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
-                     None if sh is None else (sh[0], sh[1].data_ptr(), 0 if sh[2] is None else sh[2].data_ptr()))
+                     None if sh is None else (sh[0], 0 if sh[1] is None else sh[1].data_ptr(), 0 if sh[2] is None else sh[2].data_ptr()))
                     for p, sh in zip(ps, shadows))
         cached = self._tables.get(gi)
         if cached is not None and cached[0] == key:

@@ -131,3 +131,31 @@ def _rank_shard(model, images, ids, Q, n_cand, lo, hi, rank, world):
     ranks = torch.empty((Q,), dtype=torch.int32, device=dev)
     k.itm_rank(logits, Q, n_cand, ranks)
     return ranks
+
+
+def fit_planted_itm(model, steps: int = 300, batch: int = 64, lr: float = 5e-4, weight_decay: float = 0.01, n_classes=None,
+                    log=None):
+    """Fits ``model`` (ITM head enabled) on the planted matched / mismatched pairs of ``synthetic.planted_pairs`` with the
+    own AdamW: the preparation step of the planted-positive retrieval protocol (see synthetic.py). Returns the list of
+    logged (step, loss, accuracy)."""
+    from .optim import AdamW, param_groups_no_decay
+    from .synthetic import PLANTED_CLASSES, planted_pairs
+    dev = next(model.parameters()).device
+    opt = AdamW(param_groups_no_decay(model, weight_decay), lr=lr)
+    model.train()
+    hist = []
+    for step in range(steps):
+        b = planted_pairs(batch, seed=step, n_classes=n_classes or PLANTED_CLASSES, device=dev)
+        for g in opt.param_groups:          # linear warm-up over the first 20 steps
+            g["lr"] = lr * min(1.0, (step + 1) / 20.0)
+        total, stats = model(b["images"], b["input_ids"], itm_labels=b["itm_labels"], only=("itm",))
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        if step % 25 == 0 or step == steps - 1:
+            s = stats.tolist()
+            hist.append((step, s[2], s[8] / batch))
+            if log is not None:
+                log(f"planted ITM fit step {step}: loss {s[2]:.4f} acc {s[8] / batch:.3f}")
+    model.eval()
+    return hist

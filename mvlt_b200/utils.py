@@ -91,7 +91,23 @@ class MetricLogger:
                     print(f"{header} [{i}{'/' + str(n) if n else ''}] {self}  elapsed {time.time() - t0:.1f}s")
 
 
-def load_checkpoint(model, checkpoint, optimizer=None, lr_scheduler=None, loss_scaler=None, strict=False):
+def load_file(path, trust_pickle: bool = False):
+    """``torch.load`` restricted to tensors / plain containers (``weights_only=True``). The reference's full checkpoints
+    (main_vl.py:327-346) also pickle the argparse ``Namespace``: those need ``trust_pickle=True``, an explicit opt-in to
+    unpickling arbitrary objects from the file."""
+    import argparse
+    try:
+        with torch.serialization.safe_globals([argparse.Namespace]):
+            return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as ex:
+        if not trust_pickle:
+            raise RuntimeError(f"{path}: not loadable with weights_only=True ({type(ex).__name__}: {str(ex)[:200]}); pass "
+                               "trust_pickle=True only for checkpoints you trust") from ex
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def load_checkpoint(model, checkpoint, optimizer=None, lr_scheduler=None, loss_scaler=None, strict=False,
+                    trust_pickle: bool = False):
     """Checkpoint compatibility with the reference's files. ``checkpoint``: a path or an already loaded
     object in any of the forms the reference writes / reads:
       * ``{'model': state_dict, 'optimizer': ..., 'lr_scheduler': ..., 'epoch': ..., 'scaler': ...}`` (main_vl.py:327-346,
@@ -102,7 +118,7 @@ def load_checkpoint(model, checkpoint, optimizer=None, lr_scheduler=None, loss_s
     ``(missing_keys, unexpected_keys, next_epoch)``; optimizer / scheduler / scaler states are restored when both the
     object and its entry are present (torch.optim.AdamW and mvlt_b200.optim.AdamW share the state layout)."""
     net = model.module if hasattr(model, "module") else model
-    ck = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "__fspath__") \
+    ck = load_file(checkpoint, trust_pickle) if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "__fspath__") \
         else checkpoint
     sd = ck["model"] if isinstance(ck, dict) and "model" in ck else ck
     sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items()}
@@ -112,12 +128,13 @@ def load_checkpoint(model, checkpoint, optimizer=None, lr_scheduler=None, loss_s
             del sd[k]
     res = net.load_state_dict(sd, strict=strict)
     next_epoch = None
-    if isinstance(ck, dict) and "optimizer" in ck and "epoch" in ck:
-        if optimizer is not None:
+    if isinstance(ck, dict):
+        if optimizer is not None and "optimizer" in ck:
             optimizer.load_state_dict(ck["optimizer"])
         if lr_scheduler is not None and "lr_scheduler" in ck:
             lr_scheduler.load_state_dict(ck["lr_scheduler"])
         if loss_scaler is not None and "scaler" in ck:
             loss_scaler.load_state_dict(ck["scaler"])
-        next_epoch = int(ck["epoch"]) + 1
+        if "epoch" in ck:
+            next_epoch = int(ck["epoch"]) + 1
     return list(res.missing_keys), list(res.unexpected_keys), next_epoch

@@ -151,7 +151,11 @@ def test_own_adamw_keeps_bf16_weight_copies_fresh_and_tracks_torch_adamw():
     ob = torch.optim.AdamW(param_groups_no_decay(mb, 0.05), lr=3e-4)
     batches = [make_batch(8, seed=s) for s in (0, 1)]
     la, lb = [], []
+    from mvlt_b200 import _lib
+    epoch0 = None
     for step in range(6):
+        if step == 1:
+            epoch0 = _lib.WEIGHT_EPOCH      # every parameter is registered after the first forward
         b = batches[step % 2]
         img, ids = b["images"].cuda(), b["input_ids"].cuda()
         for m, o, out in ((ma, oa, la), (mb, ob, lb)):
@@ -160,6 +164,7 @@ def test_own_adamw_keeps_bf16_weight_copies_fresh_and_tracks_torch_adamw():
             total.backward()
             o.step()
             out.append(stats[:6].tolist())
+    assert _lib.WEIGHT_EPOCH == epoch0, "the own optimizer forced a full recast although every copy is registered"
     eng = ma._engine()
     P = dict(ma.named_parameters())
     convs = eng._conv_names()
