@@ -448,7 +448,10 @@ def run_ours(args):
     if args.retrieval_queries > 0:
         try:
             from mvlt_b200 import retrieval
-            retr = retrieval.bench_sweep(dev, rank, world, n_query=args.retrieval_queries, n_cand=101, warmup=1)
+            hook = None
+            if rank == 0 and world == 1:      # per-kernel view of one 808-pair ITM-only forward (instrumented, not the timed value)
+                hook = lambda run: instrumented_pass(run, 2, hbm, tf_sus, peak_src)   # noqa: E731
+            retr = retrieval.bench_sweep(dev, rank, world, n_query=args.retrieval_queries, n_cand=101, warmup=1, profile_hook=hook)
             if rank == 0 and world == 1 and not args.no_cpu:
                 retr["cpu_baseline"] = cpu_retrieval_baseline()
         except Exception as ex:   # the training number must still be reported

@@ -24,7 +24,9 @@ def _operand(t: torch.Tensor, name: str):
         raise _lib.MvltError(f"gemm operand {name} must be 2-4 D")
     R, K = t.shape[-2], t.shape[-1]
     sr, sk = t.stride(-2), t.stride(-1)
-    if sk == 1 or K == 1:
+    if K == 1 and R > 1 and sr == 1 and sk >= R:
+        mn, ld = 1, sk      # a transposed single row (dy^T of a one-sample batch): keep the MN-major reading of its strides
+    elif sk == 1 or K == 1:
         mn, ld = 0, sr if R > 1 else max(sr, K)
     elif sr == 1 or R == 1:
         mn, ld = 1, sk if K > 1 else max(sk, R)
@@ -284,6 +286,25 @@ def sr_attention_bwd(q, kv, do, p, dq, dkv, B, N, Nk, heads, scale):
         raise _lib.MvltError("sr_attention_bwd: q/do/dq [B*N, C], kv/dkv [B*Nk, 2C], p [B, h, N, Nk] required")
     call("sr_attention_bwd", ptr(q), ptr(kv), ptr(do), ptr(p), ptr(dq), ptr(dkv), C.c_int(B), C.c_int(N), C.c_int(Nk),
          C.c_int(heads), C.c_float(scale))
+
+
+def mlp_fwd(x, w1, b1, w2, b2, residual, out, rowscale=None, rows_per_scale=0):
+    """out = residual + rowscale[row // rows_per_scale] * (gelu(x @ w1^T + b1) @ w2^T + b2), the hidden activation staying
+    on-chip (csrc/mlp_tcgen05.cu). x bf16 [M, C], w1 bf16 [HD, C], w2 bf16 [C, HD], residual / out fp32 [M, C]; C in {64, 128}."""
+    require_cuda(x, w1, w2, residual, out, b1, b2, rowscale)
+    M, C_ = x.shape
+    HD = w1.shape[0]
+    if (x.dtype != BF16 or w1.dtype != BF16 or w2.dtype != BF16 or residual.dtype != F32 or out.dtype != F32
+            or b1.dtype != F32 or b2.dtype != F32 or tuple(w1.shape) != (HD, C_) or tuple(w2.shape) != (C_, HD)
+            or tuple(residual.shape) != (M, C_) or tuple(out.shape) != (M, C_) or b1.numel() != HD or b2.numel() != C_):
+        raise _lib.MvltError("mlp_fwd: x bf16 [M, C], w1 bf16 [HD, C], w2 bf16 [C, HD], b1 / b2 fp32, residual / out fp32 [M, C] required")
+    for t in (x, w1, w2, residual, out, b1, b2):
+        if not t.is_contiguous():
+            raise _lib.MvltError("mlp_fwd: contiguous operands required")
+    if _lib.BYTES is not None:
+        _lib.account_bytes("mlp_fwd", M * C_ * (2 + 4 + 4) + 4 * HD * C_)
+    call("mlp_fwd", ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(residual), ptr(out), ptr(rowscale), C.c_int(rows_per_scale),
+         C.c_int(M), C.c_int(C_), C.c_int(HD))
 
 
 def softmax_fwd(s, rows, nk):

@@ -62,9 +62,12 @@ def accuracy_at(ranks, ks=(1, 5, 10)):
     return {kk: float((r < kk).sum()) / max(r.numel(), 1) for kk in ks}
 
 
-def bench_sweep(dev, rank, world, n_query=1000, n_cand=101, queries_per_step=8, warmup=1, pool=512):
-    """Synthetic TIR protocol: per query one id row repeated n_cand times against n_cand images drawn
-    from a device-resident pool. Returns the JSON sub-object bench.py prints."""
+def bench_sweep(dev, rank, world, n_query=1000, n_cand=101, queries_per_step=8, warmup=1, pool=512, e2e=True, profile_hook=None):
+    """Synthetic TIR protocol: per query one id row repeated n_cand times against n_cand images.
+    ``value``: inputs gathered from a device-resident pool. ``e2e``: the same sweep with every step's (image, id) pairs
+    copied from pinned HOST buffers (as the reference's loader hands them over, engine_grid_masking.py:349-352) on a side
+    stream, double-buffered, and the ranks read back to the host: all copies inside the timed region.
+    Returns the JSON sub-object bench.py prints."""
     import mvlt_b200
     from .synthetic import make_batch
     torch.manual_seed(4321)
@@ -81,42 +84,97 @@ def bench_sweep(dev, rank, world, n_query=1000, n_cand=101, queries_per_step=8, 
     qps = queries_per_step * world
     n_steps = (n_query + qps - 1) // qps
     cand = torch.arange(n_cand, device=dev)
+    lo, hi, _ = shard_bounds(qps * n_cand, rank, world)
 
-    def one(step):
+    def indices(step):
         q0 = step * qps
         qs = torch.arange(q0, q0 + qps, device=dev)
         img_idx = ((qs.unsqueeze(1) * 37 + cand.unsqueeze(0) * 11) % pool).reshape(-1)
         ids_idx = (qs % pool).repeat_interleave(n_cand)
-        lo, hi, _ = shard_bounds(qps * n_cand, rank, world)
+        return img_idx[lo:hi], ids_idx[lo:hi]
+
+    def one(step):
         # only this rank's shard is materialised; rank_queries slices [lo:hi] of a virtual full tensor
-        images = img_pool[img_idx[lo:hi]]
-        ids = ids_pool[ids_idx[lo:hi]]
-        return _rank_shard(model, images, ids, qps, n_cand, lo, hi, rank, world)
+        ii, ti = indices(step)
+        return _rank_shard(model, img_pool[ii], ids_pool[ti], qps, n_cand, lo, hi, rank, world)
+
+    def timed(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     for s in range(warmup):
         one(s)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    acc1 = 0
-    for s in range(n_steps):
-        ranks = one(s)
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = timed(lambda: [one(s) for s in range(n_steps)])
     pairs = n_steps * qps * n_cand
     v = pairs / (ms / 1e3)
-    return {"metric": "itm_retrieval_pairs_per_s", "value": round(v, 1), "unit": "pairs/s", "n_query": n_steps * qps,
-            "n_cand": n_cand, "pairs": pairs, "ms_total": round(ms, 2), "scaling": "strong (candidate pairs sharded)",
-            "model_tflops": round(v * 8.33 / 1e3, 2), "config": "BASELINE configs[2], ITM-only forward, bf16 operands"}
+    out = {"metric": "itm_retrieval_pairs_per_s", "value": round(v, 1), "unit": "pairs/s", "n_query": n_steps * qps,
+           "n_cand": n_cand, "pairs": pairs, "ms_total": round(ms, 2), "scaling": "strong (candidate pairs sharded)",
+           "model_tflops": round(v * 8.33 / 1e3, 2), "config": "BASELINE configs[2], ITM-only forward, bf16 operands"}
+
+    if e2e:
+        # two pinned host step-batches (this rank's shard of the pairs of `qps` queries), alternated; H2D on a side stream
+        host = []
+        for s in range(2):
+            ii, ti = indices(s)
+            host.append((b["images"][ii.cpu()].pin_memory(), b["ori_input_ids"][ti.cpu()].pin_memory()))
+        stage = [(torch.empty_like(host[0][0], device=dev), torch.empty_like(host[0][1], device=dev)) for _ in range(2)]
+        ranks_host = [torch.empty((qps,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def run_e2e():
+            main = torch.cuda.current_stream()
+            copied = [torch.cuda.Event() for _ in range(2)]
+            consumed = [None, None]
+            ready = [None, None]
+
+            def put(i):
+                j = i % 2
+                with torch.cuda.stream(copy_stream):
+                    if consumed[j] is not None:
+                        copy_stream.wait_event(consumed[j])
+                    stage[j][0].copy_(host[j][0], non_blocking=True)
+                    stage[j][1].copy_(host[j][1], non_blocking=True)
+                    copied[j].record(copy_stream)
+            put(0)
+            for i in range(n_steps):
+                j = i % 2
+                if i + 1 < n_steps:
+                    put(i + 1)
+                main.wait_event(copied[j])
+                r = _rank_shard(model, stage[j][0], stage[j][1], qps, n_cand, lo, hi, rank, world)
+                consumed[j] = torch.cuda.Event()
+                consumed[j].record(main)
+                ranks_host[j].copy_(r, non_blocking=True)
+                ready[j] = torch.cuda.Event()
+                ready[j].record(main)
+                if i > 0:
+                    ready[1 - j].synchronize()
+            ready[(n_steps - 1) % 2].synchronize()
+        ms2 = timed(run_e2e)
+        h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
+        out["e2e"] = {"value": round(pairs / (ms2 / 1e3), 1), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": qps * 4, "ms_total": round(ms2, 2),
+                      "what": "pairs of every step copied from pinned host buffers (side stream, double-buffered), ranks read back"}
+    if profile_hook is not None and rank == 0 and world == 1:
+        try:
+            out.update(profile_hook(one))
+        except Exception as ex:      # reporting only
+            out["profile_error"] = repr(ex)[:200]
+    return out
 
 
 @torch.no_grad()
@@ -131,31 +189,3 @@ def _rank_shard(model, images, ids, Q, n_cand, lo, hi, rank, world):
     ranks = torch.empty((Q,), dtype=torch.int32, device=dev)
     k.itm_rank(logits, Q, n_cand, ranks)
     return ranks
-
-
-def fit_planted_itm(model, steps: int = 300, batch: int = 64, lr: float = 5e-4, weight_decay: float = 0.01, n_classes=None,
-                    log=None):
-    """Fits ``model`` (ITM head enabled) on the planted matched / mismatched pairs of ``synthetic.planted_pairs`` with the
-    own AdamW: the preparation step of the planted-positive retrieval protocol (see synthetic.py). Returns the list of
-    logged (step, loss, accuracy)."""
-    from .optim import AdamW, param_groups_no_decay
-    from .synthetic import PLANTED_CLASSES, planted_pairs
-    dev = next(model.parameters()).device
-    opt = AdamW(param_groups_no_decay(model, weight_decay), lr=lr)
-    model.train()
-    hist = []
-    for step in range(steps):
-        b = planted_pairs(batch, seed=step, n_classes=n_classes or PLANTED_CLASSES, device=dev)
-        for g in opt.param_groups:          # linear warm-up over the first 20 steps
-            g["lr"] = lr * min(1.0, (step + 1) / 20.0)
-        total, stats = model(b["images"], b["input_ids"], itm_labels=b["itm_labels"], only=("itm",))
-        opt.zero_grad()
-        total.backward()
-        opt.step()
-        if step % 25 == 0 or step == steps - 1:
-            s = stats.tolist()
-            hist.append((step, s[2], s[8] / batch))
-            if log is not None:
-                log(f"planted ITM fit step {step}: loss {s[2]:.4f} acc {s[8] / batch:.3f}")
-    model.eval()
-    return hist

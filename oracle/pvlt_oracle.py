@@ -415,3 +415,58 @@ def retrieval_rank(itm_logits):
     p = F.softmax(itm_logits.view(-1, 2).float(), -1)[:, 1]
     order = torch.sort(p, descending=True)[1]
     return int((order == 0).nonzero()[0, 0])
+
+
+def evaluate_vl_batch(sd, samples, loss_type, model="pvlt_tiny"):
+    """engine_grid_masking.py:186-300 for ONE batch (eval mode, fp32): three forwards (masked ids, original ids, masked
+    image) -> metrics dict with the reference's meter names and the summed weighted loss (weights :23)."""
+    B = samples["image"].shape[0]
+    res = dict(mlm_acc=0.0, itm_acc=0.0, sup_cls_acc=0.0, sub_cls_acc=0.0, t2i_psnr=0.0)
+    total = 0.0
+    with torch.no_grad():
+        o = forward(sd, samples["image"], samples["input_ids"], loss_type, model, training=False)
+        if o["mlm_logits"] is not None:      # :201-208
+            total += float(F.cross_entropy(o["mlm_logits"].view(-1, VOCAB), samples["mlm_labels"].view(-1), ignore_index=-1))
+            res["mlm_acc"] = compute_mlm_score(o["mlm_logits"], samples["mlm_labels"])
+        o = forward(sd, samples["image"], samples["ori_input_ids"], loss_type, model, training=False)
+        if o["itm_logits"] is not None:      # :223-229
+            total += float(F.cross_entropy(o["itm_logits"].view(-1, 2), samples["itm_labels"].view(-1)))
+            res["itm_acc"] = float(compute_score_with_logits(o["itm_logits"].view(-1, 2), samples["itm_labels"].view(-1)).sum()) / B
+        if o["sup_cls_logits"] is not None:  # :236-250
+            total += float(F.cross_entropy(o["sup_cls_logits"].view(-1, 48), samples["sup_cls_labels"].view(-1)))
+            total += float(F.cross_entropy(o["sub_cls_logits"].view(-1, 122), samples["sub_cls_labels"].view(-1)))
+            res["sup_cls_acc"] = float(compute_score_with_logits(o["sup_cls_logits"].view(-1, 48), samples["sup_cls_labels"].view(-1)).sum()) / B
+            res["sub_cls_acc"] = float(compute_score_with_logits(o["sub_cls_logits"].view(-1, 122), samples["sub_cls_labels"].view(-1)).sum()) / B
+        if loss_type.get("t2i"):             # :305-316
+            o = forward(sd, samples["masked_images"], samples["ori_input_ids"], loss_type, model, training=False)
+            total += float(10 * F.smooth_l1_loss(o["t2i_logits"], samples["image"]))
+            res["t2i_psnr"] = compute_psnr(o["t2i_logits"], samples["image"])
+    res["total_loss"] = total
+    return res
+
+
+def fit_itm_probe(sd, images, ids, labels, model="pvlt_tiny", steps=200, l2=1e-4):
+    """Planted-positive retrieval protocol (mvlt_b200/synthetic.py): K optimiser steps (L-BFGS, deterministic, zero init) on
+    the LAST ITM linear layer only (vl_heads.py:84-87), on fp32 reference features of the fit set. Returns a copy of ``sd``
+    with ``itm_head.linear.{weight,bias}`` replaced and ``itm_head.linear_bias`` zeroed."""
+    with torch.no_grad():
+        feats = []
+        for i in range(0, images.shape[0], 32):
+            _, tf = pyramid_features(sd, images[i:i + 32], ids[i:i + 32], model)
+            feats.append(_head_embed(sd, "itm_head_embed", tf[-1][:, 0:1, :]).reshape(-1, HIDDEN))
+        feats = torch.cat(feats)
+    W = torch.zeros((2, HIDDEN), requires_grad=True)
+    b = torch.zeros((2,), requires_grad=True)
+    opt = torch.optim.LBFGS([W, b], lr=1.0, max_iter=steps)
+
+    def closure():
+        opt.zero_grad()
+        loss = F.cross_entropy(feats @ W.t() + b, labels) + l2 * (W ** 2).sum()
+        loss.backward()
+        return loss
+    opt.step(closure)
+    out = dict(sd)
+    out["itm_head.linear.weight"] = W.detach().clone()
+    out["itm_head.linear.bias"] = b.detach().clone()
+    out["itm_head.linear_bias"] = torch.zeros(2)
+    return out

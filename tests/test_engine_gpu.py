@@ -197,3 +197,88 @@ def test_own_adamw_keeps_bf16_weight_copies_fresh_and_tracks_torch_adamw():
     for name in ("block1.0.mlp.fc1.weight", "block3.1.attn.kv.weight", "patch_embed2.proj.weight", "t2i_head.conv4.0.weight"):
         d = (pa[name] - pb[name]).abs().max().item()
         assert d <= 6 * 3e-4, (name, d)     # at most a few lr-sized steps apart (sign flips of ~zero gradients)
+
+
+@pytest.mark.parametrize("loss_type,tag", [(PRE, "pre"), ({"itm": 1, "mlm": 1, "t2i": 0, "cls": 1}, "enc")])
+def test_evaluate_vl_metrics_match_oracle(loss_type, tag):
+    """the reference-named eval loop (three forwards per batch on the fused metric path) against the fp32
+    oracle's restatement of engine_grid_masking.py:186-300 on the same weights, batches and grid-masked images."""
+    import numpy as np
+    import engine_grid_masking as E
+    from mvlt_b200 import masking
+    from oracle import grid_mask as ogm
+    from oracle import pvlt_oracle as O
+    import mvlt_b200
+    m = mvlt_b200.create_model("pvlt_tiny", pretrained=True, num_classes=1000, drop_rate=0.0, drop_path_rate=0.1,
+                               drop_block_rate=None, token_hidden_size=768, num_text_tokens=128, loss_type=dict(loss_type),
+                               pretrained_pth="")
+    sd = O.make_state_dict("pvlt_tiny", loss_type, seed=2)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    loader, want, n = [], {}, 0
+    for i in range(2):
+        b = O.make_inputs(6, seed=20 + i)
+        seeds = [masking.sample_seed(9, 6 * i + j) for j in range(6)]
+        mk = np.stack([ogm.masked_fill(b["images"][j].numpy(), ogm.expand(ogm.grid_py(seeds[j]))) for j in range(6)])
+        s = dict(b, image=b["images"], masked_images=torch.from_numpy(mk))
+        loader.append(s)
+        r = O.evaluate_vl_batch(sd, s, loss_type)
+        for k_, v in r.items():
+            want[k_] = want.get(k_, 0.0) + v * 6
+        n += 6
+
+    class A:
+        pass
+    a = A()
+    a.loss_type = loss_type
+    got = E.evaluate_vl(loader, m, torch.device("cuda"), a)
+    want = {k_: v / n for k_, v in want.items()}
+    assert abs(got["total_loss"] - want["total_loss"]) <= 2e-2 * max(1.0, want["total_loss"]), (got, want)
+    for key in ("mlm_acc", "itm_acc", "sup_cls_acc", "sub_cls_acc"):      # argmax decisions: at most one near-tie apart
+        assert abs(got[key] - want[key]) <= 1.0 / n + 1e-9, (key, got, want)
+    if loss_type["t2i"]:
+        assert abs(got["t2i_psnr"] - want["t2i_psnr"]) <= 0.05, (got["t2i_psnr"], want["t2i_psnr"])
+
+
+def test_planted_positive_retrieval_ranks_identical_to_fp32_oracle():
+    """north_star: "retrieval rankings must be identical for the synthetic protocol" (SURVEY 7 H3 option iii, README.md).
+    The planted-positive TIR protocol of mvlt_b200/synthetic.py: random-init PVLT-tiny encoder, last ITM linear layer fitted
+    by the fp32 oracle on brightness-planted pairs; 24 queries x 101 candidates. The rank of the positive -- the quantity
+    engine_grid_masking.py:360-384 computes -- from the bf16 sm_100a kernels must equal the fp32 oracle's for every query
+    (and the planted value), and so must acc@1/5/10 from the reference-named loop."""
+    import engine_grid_masking as E
+    import mvlt_b200
+    from mvlt_b200 import retrieval
+    from mvlt_b200.synthetic import planted_fit_set, planted_tir_query
+    from oracle import pvlt_oracle as O
+    lt = {"itm": 1, "mlm": 0, "t2i": 0, "cls": 0}
+    sd = O.make_state_dict("pvlt_tiny", lt, seed=4)
+    sd = O.fit_itm_probe(sd, *planted_fit_set(128))
+    m = mvlt_b200.create_model("pvlt_tiny", pretrained=True, num_classes=1000, drop_rate=0.0, drop_path_rate=0.1,
+                               drop_block_rate=None, token_hidden_size=768, num_text_tokens=128, loss_type=dict(lt),
+                               pretrained_pth="")
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    loader, rows = [], []
+    for q in range(24):
+        img, ids, planted = planted_tir_query(q)
+        ranks, logits = retrieval.rank_queries(m, img.cuda(), ids.cuda(), 101)
+        with torch.no_grad():
+            ref = torch.cat([O.forward(sd, img[i:i + 51], ids[i:i + 51], lt, training=False)["itm_logits"].view(-1, 2)
+                             for i in range(0, 101, 51)])
+        r_ref = O.retrieval_rank(ref)
+        lg = logits[0].cpu()
+        d_ref, d_gpu = ref[:, 1] - ref[:, 0], lg[:, 1] - lg[:, 0]
+        rows.append(dict(q=q, planted=planted, rank_gpu=int(ranks[0]), rank_oracle=r_ref,
+                         max_err=float((d_ref - d_gpu).abs().max()),
+                         margin=float((d_ref[1:] - d_ref[0]).abs().min())))
+        loader.append({"images_101": img.unsqueeze(0), "ori_input_ids_101": ids.unsqueeze(0), "info_list": []})
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(rows, open("gpurun_out/planted_retrieval.json", "w"), indent=1)
+    for r in rows:
+        assert r["rank_gpu"] == r["rank_oracle"] == r["planted"], r
+        assert r["margin"] > 4 * r["max_err"], r           # the protocol really is well conditioned
+    res = E.evaluate_retrieval(loader, m, torch.device("cuda"), _Args())
+    want = {f"acc@{k}": sum(int(r["rank_oracle"] < k) for r in rows) / 24 for k in (1, 5, 10)}
+    assert res == want, (res, want)

@@ -198,3 +198,36 @@ def test_benched_configuration_b128_matches_oracle(loss_type, tag):
     st = stats.cpu().tolist()
     got = {"total": st[0], "mlm": st[1], "itm": st[2], "sup_cls": st[3], "sub_cls": st[4], "t2i": st[5]}
     _compare_step(m, sd, batch, loss_type, got, dps, keep, f"grads_b128_{tag}.json")
+
+
+@pytest.mark.parametrize("arch", ["pvlt_medium", "pvlt_large"])
+def test_deeper_variants_match_oracle_once(arch):
+    """pvlt_medium / pvlt_large (pvlt.py:449-483): same kernels, deeper stages. One pre-training step at B = 1
+    against the fp32 oracle (losses + all gradients), drop-path on (rate 0.3, masks handed to the oracle)."""
+    from oracle import pvlt_oracle as O
+    torch.manual_seed(3)
+    m, sd = _model(PRE, drop_path=0.3, name=arch)
+    m.train()
+    batch = O.make_inputs(1, seed=6)
+    img, ids = batch["images"].cuda(), batch["input_ids"].cuda()
+    total, stats = m(img, ids, mlm_labels=batch["mlm_labels"], itm_labels=batch["itm_labels"], target_images=img)
+    total.backward()
+    dps, keep = _oracle_masks(m, 1)
+    st = stats.cpu().tolist()
+    got = {"total": st[0], "mlm": st[1], "itm": st[2], "t2i": st[5]}
+    _compare_step(m, sd, batch, PRE, got, dps, keep, f"grads_{arch}_pre.json", arch=arch)
+
+
+def test_stand_alone_gelu_module_matches_torch():
+    """libs/vl_heads.py:7-14: the reference's GELU class is callable on its own; ours runs the sm_100a kernel (fwd + bwd)."""
+    from mvlt_b200.libs.vl_heads import GELU
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = (torch.randn((37, 129), generator=g, device="cuda") * 3).requires_grad_(True)
+    y = GELU()(x)
+    y.backward(torch.ones_like(y))
+    xr = x.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.gelu(xr)
+    yr.backward(torch.ones_like(yr))
+    assert (y - yr).abs().max().item() <= 2e-6 and (x.grad - xr.grad).abs().max().item() <= 2e-6
+    xb = x.detach().to(torch.bfloat16)
+    assert (GELU()(xb).float() - torch.nn.functional.gelu(xb.float())).abs().max().item() <= 2e-2
