@@ -10,9 +10,10 @@
 //   warp 1      : tcgen05.mma issuer:  GEMM1  H_g[128 x 64]  = X W1_g^T            (K = C)   -> TMEM H buffer g % NH
 //                                      GEMM2  Y  [128 x C ] += A_g W2_g^T          (K = 64)  -> TMEM Y buffer tile % 2
 //                 GEMM2 runs two chunks behind GEMM1, so the tensor pipe never waits for the GELU warps
-//   warps 4..11 : GELU warps (lane quarter x column half): H_g (tcgen05.ld) + b1 -> exact-erf GELU (packed fp32x2) -> bf16
-//                 -> A_g in shared memory, written straight into the K-major SWIZZLE_128B layout GEMM2 reads
-//   warps 12..15: output warps: Y + b2, x drop-path factor, + fp32 residual -> 4 KB swizzled staging tile -> TMA store
+//   warps 4..19 : GELU warps (lane quarter x 16-column slice; 4 per SM sub-partition: the kernel is bound by their MUFU /
+//                 issue rate): H_g (tcgen05.ld) + b1 -> exact-erf GELU (packed fp32x2) -> bf16 -> A_g in shared memory,
+//                 written straight into the K-major SWIZZLE_128B layout GEMM2 reads
+//   warps 20..23: output warps: Y + b2, x drop-path factor, + fp32 residual -> 4 KB swizzled staging tile -> TMA store
 //
 // The same kernel serves inference (retrieval) and training; the backward recomputes H from X (mlp_bwd below) instead of
 // reading saved activations.
@@ -31,8 +32,8 @@ namespace {
 constexpr int BM = 128;            // rows per tile = TMEM lanes
 constexpr int CW = 64;             // hidden chunk width (bf16: one 128-byte swizzle row)
 constexpr int ATOM = BM * 128;     // 16 KB: [128 rows x 64 bf16] K-major SWIZZLE_128B atom
-constexpr int NTHREADS = 512;
-constexpr int GELU_WARP0 = 4, NUM_GELU_WARPS = 8, OUT_WARP0 = 12, NUM_OUT_WARPS = 4;
+constexpr int NTHREADS = 768;
+constexpr int GELU_WARP0 = 4, NUM_GELU_WARPS = 16, OUT_WARP0 = 20, NUM_OUT_WARPS = 4;
 constexpr int LAG = 2;             // GEMM2 of chunk g is issued after GEMM1 of chunk g + LAG
 constexpr int TMEM_COLS = 512;
 constexpr int Y_COL0 = 256;        // Y accumulators live in columns [256, 256 + 2 C); H buffers in [0, NH * 64)
@@ -207,7 +208,7 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   } else if (warp >= GELU_WARP0 && warp < GELU_WARP0 + NUM_GELU_WARPS) {
     // ===================== GELU warps =====================
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
-    const int half = (warp - GELU_WARP0) >> 2;    // 32-column half of the 64-column chunk
+    const int cq = (warp - GELU_WARP0) >> 2;      // 16-column slice of the 64-column chunk
     const uint32_t tlane = ((uint32_t)(quarter * 32) << 16);
     const uint32_t row = (uint32_t)(quarter * 32 + lane);
     const uint32_t a_row = smem_u32(smem + K::OFF_A) + row * 128u;
@@ -216,19 +217,19 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int hb = g % NH;
       const uint32_t ph = ((uint32_t)(g / NH)) & 1u;
       const int j = g % nch;
-      // bias of this chunk half: identical for every lane (L1 broadcast), fetched before the accumulator is waited for
-      float4 bv[8];
-      const float4* bp = reinterpret_cast<const float4*>(p.b1 + j * CW + half * 32);
+      // bias of this chunk slice: identical for every lane (L1 broadcast), fetched before the accumulator is waited for
+      float4 bv[4];
+      const float4* bp = reinterpret_cast<const float4*>(p.b1 + j * CW + cq * 16);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
+      for (int i = 0; i < 4; ++i) bv[i] = __ldg(bp + i);
       mbar_wait(&h_full[hb], ph);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + tlane + (uint32_t)(hb * CW + half * 32), r);
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + tlane + (uint32_t)(hb * CW + cq * 16), r);
       tmem_ld_wait();
-      uint32_t pk[16];
+      uint32_t pk[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const f32x2_t v0 = f2_add(f2_pack(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), f2_pack(bv[i].x, bv[i].y));
         const f32x2_t v1 = f2_add(f2_pack(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), f2_pack(bv[i].z, bv[i].w));
         float a, b;
@@ -240,8 +241,8 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_wait(&a_empty[hb], ph ^ 1u);           // GEMM2 of chunk g - NH has finished reading this A buffer
       const uint32_t base = a_row + (uint32_t)(hb * ATOM);
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        st_shared_v4(base + ((((uint32_t)(half * 4 + q)) ^ rx) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int q = 0; q < 2; ++q)
+        st_shared_v4(base + ((((uint32_t)(cq * 2 + q)) ^ rx) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       fence_proxy_async();     // generic-proxy stores -> visible to the tensor core
       tc_fence_before();       // this warp's TMEM reads precede the MMA that will overwrite the H buffer
       __syncwarp();
@@ -264,26 +265,31 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const float* res_row = p.residual + (long long)row * C;
 #pragma unroll 1
       for (int u = 0; u < C / 32; ++u) {
-        float4 rv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rv[i] = valid ? __ldg(reinterpret_cast<const float4*>(res_row + u * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (u == 0) {
           mbar_wait(&y_full[yb], ((uint32_t)tl >> 1) & 1u);
           tc_fence_after();
         }
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + tlane + (uint32_t)(Y_COL0 + yb * C + u * 32), r);
-        tmem_ld_wait();
         if (lane == 0) tma_store_wait_read();     // the previous unit's store has finished reading the staging tile
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + u * 32) + i);
-          const float o0 = fmaf(__uint_as_float(r[4 * i]) + b4.x, rs, rv[i].x);
-          const float o1 = fmaf(__uint_as_float(r[4 * i + 1]) + b4.y, rs, rv[i].y);
-          const float o2 = fmaf(__uint_as_float(r[4 * i + 2]) + b4.z, rs, rv[i].z);
-          const float o3 = fmaf(__uint_as_float(r[4 * i + 3]) + b4.w, rs, rv[i].w);
-          st_shared_v4(own + ((((uint32_t)i) ^ rx) << 4), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+        for (int hh = 0; hh < 2; ++hh) {          // 16 columns at a time keeps the register footprint small
+          float4 rv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            rv[i] = valid ? __ldg(reinterpret_cast<const float4*>(res_row + u * 32 + hh * 16) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_base + tlane + (uint32_t)(Y_COL0 + yb * C + u * 32 + hh * 16), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + u * 32 + hh * 16) + i);
+            const float o0 = fmaf(__uint_as_float(r[4 * i]) + b4.x, rs, rv[i].x);
+            const float o1 = fmaf(__uint_as_float(r[4 * i + 1]) + b4.y, rs, rv[i].y);
+            const float o2 = fmaf(__uint_as_float(r[4 * i + 2]) + b4.z, rs, rv[i].z);
+            const float o3 = fmaf(__uint_as_float(r[4 * i + 3]) + b4.w, rs, rv[i].w);
+            st_shared_v4(own + ((((uint32_t)(hh * 4 + i)) ^ rx) << 4), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2),
+                         __float_as_uint(o3));
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -347,6 +353,282 @@ int launch_fwd(const void* x, const void* w1, const void* w2, void* out, const M
   return 0;
 }
 
+
+// =====================================================================================================================
+// Backward of the fused MLP (C = 64): recomputes H = X W1^T + b1 instead of reading saved activations.
+//
+// A CTA owns a block of HB = 128 hidden units (W1 rows / W2 columns stay in shared memory) and a range of 128-row tiles;
+// dW1 / dW2 / db1 of its block accumulate in TMEM over ALL its tiles and are flushed once with fp32 reductions. Per tile:
+//
+//   warp 0      : TMA: X tile, dY tile (double-buffered)
+//   warp 1      : tcgen05.mma:  H_s  [128 x 64] = X  W1_s^T        (s = 0, 1: 64-column halves of the block)  -> TMEM
+//                               dH_s [128 x 64] = dY W2[:, s]                                                  -> TMEM
+//                 then, once the GELU warps have produced the two operand tiles:
+//                               dW2_blk [128 hid x C] += act^T dY      (A = act read MN-major, B = dY read MN-major)
+//                               dW1_blk [128 hid x C] += dh'^T X
+//                               db1_blk               += dh'^T 1       (N = 16 MMA against a tile of ones)
+//   warp 2      : TMA store of the dh' tile into dh'[M, HD] (consumed by the dX = dh' W1 GEMM that follows)
+//   warps 4..11 : (g, g') = gelu, gelu'(H + b1);  act = g,  dh' = dH * g'  -> bf16 K-major SWIZZLE_128B tiles in shared memory
+//
+// Replaces the autograd of /root/reference/libs/pvlt.py:65-71 (fc2 dX / dW / fc1 dW, db and the GELU backward); db2 and
+// dX = dh' W1 are taken by the column-sum kernel and the tcgen05 GEMM (engine.py).
+// =====================================================================================================================
+constexpr int BW_THREADS = 384;
+constexpr int HB = 128;
+constexpr int BW_OFF_W1 = 0;                        // [128 hid x 64 c] K-major
+constexpr int BW_OFF_W2 = ATOM;                     // 2 x [64 c x 64 hid] (MN-major B operand)
+constexpr int BW_OFF_T = 2 * ATOM;                  // 2 x { X | dY } tiles
+constexpr int BW_OFF_ACT = BW_OFF_T + 4 * ATOM;     // 2 atoms [128 rows x 64 hid]
+constexpr int BW_OFF_DH = BW_OFF_ACT + 2 * ATOM;
+constexpr int BW_OFF_ONES = BW_OFF_DH + 2 * ATOM;
+constexpr int BW_OFF_BAR = BW_OFF_ONES + 1024;
+constexpr int BW_SMEM = BW_OFF_BAR + 128;
+constexpr int COL_H = 0, COL_DH = 128, COL_DW1 = 256, COL_DW2 = 320, COL_ONES = 384;
+
+struct MlpBwdParams {
+  int M, HD;
+  int num_tiles, nb, nr;    // 128-row tiles, hidden blocks, tile ranges (grid = nb * nr)
+  const float* b1;
+  float* dW1;               // fp32 [HD, 64], accumulated with reductions
+  float* dW2;               // fp32 [64, HD]
+  float* db1;               // fp32 [HD]
+};
+
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {   // MN-major SWIZZLE_128B operand
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t instr_desc_mn(int n, int a_mn, int b_mn) {
+  return instr_desc(n) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16);
+}
+
+__global__ void __launch_bounds__(BW_THREADS, 1)
+mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+               const __grid_constant__ CUtensorMap tmDH, const __grid_constant__ MlpBwdParams p) {
+  constexpr int C = 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BW_OFF_BAR);
+  uint64_t* t_full = bars;            // [2] X and dY tile landed
+  uint64_t* t_empty = bars + 2;       // [2] the dW MMAs that read the tile retired
+  uint64_t* hd_full = bars + 4;       // [2] H_s and dH_s complete
+  uint64_t* hd_empty = bars + 6;      // [2] the eight GELU warps have read H_s / dH_s
+  uint64_t* a_full = bars + 8;        // act and dh' tiles written (eight GELU warps)
+  uint64_t* a_empty = bars + 9;       // the dW MMAs that read act / dh' retired
+  uint64_t* st_empty = bars + 10;     // the dh' TMA store has finished reading its tile
+  uint64_t* w_full = bars + 11;
+  uint64_t* done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 1);
+      mbar_init(&hd_full[i], 1);
+      mbar_init(&hd_empty[i], NUM_GELU_WARPS);
+    }
+    mbar_init(a_full, NUM_GELU_WARPS);
+    mbar_init(a_empty, 1);
+    mbar_init(st_empty, 1);
+    mbar_init(w_full, 1);
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmDH);
+  }
+  if (threadIdx.x < 256) reinterpret_cast<uint32_t*>(smem + BW_OFF_ONES)[threadIdx.x] = 0x3F803F80u;   // bf16 1.0
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int jb = (int)blockIdx.x % p.nb, rg = (int)blockIdx.x / p.nb;
+  int n_tiles = 0;
+  if (rg < p.num_tiles) n_tiles = (p.num_tiles - 1 - rg) / p.nr + 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, 2u * ATOM);
+      tma_load_4d(smem + BW_OFF_W1, &tmW1, w_full, 0, jb * HB, 0, 0);
+      tma_load_4d(smem + BW_OFF_W2, &tmW2, w_full, jb * HB, 0, 0, 0);
+      tma_load_4d(smem + BW_OFF_W2 + 8192, &tmW2, w_full, jb * HB + 64, 0, 0, 0);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int slot = i & 1, m0 = (rg + i * p.nr) * BM;
+        mbar_wait(&t_empty[slot], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&t_full[slot], 2u * ATOM);
+        tma_load_4d(smem + BW_OFF_T + slot * 2 * ATOM, &tmX, &t_full[slot], 0, m0, 0, 0);
+        tma_load_4d(smem + BW_OFF_T + slot * 2 * ATOM + ATOM, &tmDY, &t_full[slot], 0, m0, 0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_kk = instr_desc_mn(64, 0, 0), id_kn = instr_desc_mn(64, 0, 1), id_mm = instr_desc_mn(C, 1, 1),
+                     id_ones = instr_desc_mn(16, 1, 0);
+      const uint32_t sW1 = smem_u32(smem + BW_OFF_W1), sW2 = smem_u32(smem + BW_OFF_W2), sT = smem_u32(smem + BW_OFF_T),
+                     sAct = smem_u32(smem + BW_OFF_ACT), sDh = smem_u32(smem + BW_OFF_DH);
+      const uint64_t ones_desc = smem_desc(smem_u32(smem + BW_OFF_ONES), 0u);   // SBO = 0: every 8-row group re-reads the same rows
+      mbar_wait(w_full, 0);
+      auto issue_hd = [&](int i) {
+        const int slot = i & 1;
+        const uint32_t xa = sT + (uint32_t)(slot * 2 * ATOM), dya = xa + (uint32_t)ATOM;
+        mbar_wait(&t_full[slot], ((uint32_t)i >> 1) & 1u);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&hd_empty[s], ((uint32_t)i & 1u) ^ 1u);     // the GELU warps have read tile i - 1's H_s / dH_s
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)    // H_s = X W1_s^T: both K-major
+            umma_bf16(tmem_base + (uint32_t)(COL_H + s * 64), smem_desc(xa + (uint32_t)(k * 32), 1024u),
+                      smem_desc(sW1 + (uint32_t)(s * 8192 + k * 32), 1024u), id_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)    // dH_s = dY W2[:, s]: B = W2 rows (c) x 64 hidden columns, MN-major
+            umma_bf16(tmem_base + (uint32_t)(COL_DH + s * 64), smem_desc(dya + (uint32_t)(k * 32), 1024u),
+                      smem_desc_mn(sW2 + (uint32_t)(s * 8192 + k * 2048), 8192u), id_kn, k > 0 ? 1u : 0u);
+          umma_commit(&hd_full[s]);
+        }
+      };
+      if (n_tiles > 0) issue_hd(0);
+      for (int i = 0; i < n_tiles; ++i) {
+        if (i + 1 < n_tiles) issue_hd(i + 1);
+        const int slot = i & 1;
+        const uint32_t xa = sT + (uint32_t)(slot * 2 * ATOM), dya = xa + (uint32_t)ATOM;
+        mbar_wait(a_full, (uint32_t)i & 1u);
+        tc_fence_after();
+        const uint32_t acc0 = i > 0 ? 1u : 0u;
+#pragma unroll
+        for (int kq = 0; kq < BM / 16; ++kq) {   // K = the tile's 128 rows, 16 per step; A tiles are read MN-major (M = hidden)
+          const uint32_t acc = acc0 | (kq > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + COL_DW2, smem_desc_mn(sAct + (uint32_t)(kq * 2048), (uint32_t)ATOM),
+                    smem_desc_mn(dya + (uint32_t)(kq * 2048), 8192u), id_mm, acc);
+          umma_bf16(tmem_base + COL_DW1, smem_desc_mn(sDh + (uint32_t)(kq * 2048), (uint32_t)ATOM),
+                    smem_desc_mn(xa + (uint32_t)(kq * 2048), 8192u), id_mm, acc);
+          umma_bf16(tmem_base + COL_ONES, smem_desc_mn(sDh + (uint32_t)(kq * 2048), (uint32_t)ATOM), ones_desc, id_ones, acc);
+        }
+        umma_commit(a_empty);
+        umma_commit(&t_empty[slot]);
+      }
+      umma_commit(done);
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      for (int i = 0; i < n_tiles; ++i) {
+        const int m0 = (rg + i * p.nr) * BM;
+        mbar_wait(a_full, (uint32_t)i & 1u);     // (the writers fenced their generic-proxy stores before arriving)
+        tma_store_4d(&tmDH, smem_u32(smem + BW_OFF_DH), jb * HB, m0, 0, 0);
+        tma_store_4d(&tmDH, smem_u32(smem + BW_OFF_DH + ATOM), jb * HB + 64, m0, 0, 0);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(st_empty);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else if (warp >= GELU_WARP0) {
+    const int quarter = warp & 3, half = (warp - GELU_WARP0) >> 2;
+    const uint32_t tlane = ((uint32_t)(quarter * 32) << 16);
+    const uint32_t row = (uint32_t)(quarter * 32 + lane), rx = row & 7u;
+    const uint32_t act_row = smem_u32(smem + BW_OFF_ACT) + row * 128u, dh_row = smem_u32(smem + BW_OFF_DH) + row * 128u;
+    for (int i = 0; i < n_tiles; ++i) {
+      const uint32_t ph = (uint32_t)i & 1u;
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        mbar_wait(&hd_full[s], ph);
+        tc_fence_after();
+        uint32_t apk[16], dpk[16];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t rh[16], rd[16];
+          tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_H + s * 64 + half * 32 + hh * 16), rh);
+          tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_DH + s * 64 + half * 32 + hh * 16), rd);
+          const float4* bp = reinterpret_cast<const float4*>(p.b1 + jb * HB + s * 64 + half * 32 + hh * 16);
+          float4 bv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bv[q] = __ldg(bp + q);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            f32x2_t g0, d0, g1, d1;
+            gelu_and_grad2(f2_add(f2_pack(__uint_as_float(rh[4 * q]), __uint_as_float(rh[4 * q + 1])), f2_pack(bv[q].x, bv[q].y)), g0, d0);
+            gelu_and_grad2(f2_add(f2_pack(__uint_as_float(rh[4 * q + 2]), __uint_as_float(rh[4 * q + 3])), f2_pack(bv[q].z, bv[q].w)), g1, d1);
+            d0 = f2_mul(d0, f2_pack(__uint_as_float(rd[4 * q]), __uint_as_float(rd[4 * q + 1])));
+            d1 = f2_mul(d1, f2_pack(__uint_as_float(rd[4 * q + 2]), __uint_as_float(rd[4 * q + 3])));
+            float a, b;
+            f2_unpack(g0, a, b);
+            apk[hh * 8 + 2 * q] = pack_bf16x2(a, b);
+            f2_unpack(g1, a, b);
+            apk[hh * 8 + 2 * q + 1] = pack_bf16x2(a, b);
+            f2_unpack(d0, a, b);
+            dpk[hh * 8 + 2 * q] = pack_bf16x2(a, b);
+            f2_unpack(d1, a, b);
+            dpk[hh * 8 + 2 * q + 1] = pack_bf16x2(a, b);
+          }
+        }
+        tc_fence_before();       // this warp's TMEM reads precede the MMAs of the next tile into H_s / dH_s
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hd_empty[s]);
+        if (s == 0) {            // the previous tile's dW MMAs and dh' store have finished reading the operand tiles
+          mbar_wait(a_empty, ph ^ 1u);
+          mbar_wait(st_empty, ph ^ 1u);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = (uint32_t)(s * ATOM) + ((((uint32_t)(half * 4 + q)) ^ rx) << 4);
+          st_shared_v4(act_row + off, apk[4 * q], apk[4 * q + 1], apk[4 * q + 2], apk[4 * q + 3]);
+          st_shared_v4(dh_row + off, dpk[4 * q], dpk[4 * q + 1], dpk[4 * q + 2], dpk[4 * q + 3]);
+        }
+      }
+      fence_proxy_async();       // generic-proxy stores -> visible to the tensor core and the TMA engine
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+    }
+    // ---- flush the block's accumulators: dW1[hid, c], dW2[c, hid], db1[hid] (fp32 reductions; lane = hidden unit)
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (n_tiles > 0) {
+      const int hid = jb * HB + quarter * 32 + lane;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + tlane + (uint32_t)(COL_DW1 + half * 32), r);
+      tmem_ld_wait();
+      float* g1 = p.dW1 + (long long)hid * C + half * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g1 + 4 * q), "f"(__uint_as_float(r[4 * q])),
+                     "f"(__uint_as_float(r[4 * q + 1])), "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3]))
+                     : "memory");
+      tmem_ld_32x32(tmem_base + tlane + (uint32_t)(COL_DW2 + half * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(p.dW2 + (long long)(half * 32 + j) * p.HD + hid, __uint_as_float(r[j]));
+      if (half == 0) {
+        uint32_t o[16];
+        tmem_ld_32x16(tmem_base + tlane + (uint32_t)COL_ONES, o);
+        tmem_ld_wait();
+        atomicAdd(p.db1 + hid, __uint_as_float(o[0]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 }  // namespace
 
 // out[M, C] (fp32) = residual[M, C] (fp32) + rowscale[row / rows_per_scale] * (GELU(x W1^T + b1) W2^T + b2)
@@ -367,4 +649,59 @@ extern "C" int mvlt_mlp_fwd(const void* x_bf16, const void* w1_bf16, const float
   p.nch = HD / CW;
   p.b1 = b1; p.b2 = b2; p.residual = residual_f32; p.rowscale = rowscale_f32; p.rows_per_scale = rows_per_scale > 0 ? rows_per_scale : 1;
   return C == 64 ? launch_fwd<64>(x_bf16, w1_bf16, w2_bf16, out_f32, p, stream) : launch_fwd<128>(x_bf16, w1_bf16, w2_bf16, out_f32, p, stream);
+}
+
+
+// Backward of mvlt_mlp_fwd's branch for C = 64 (see mlp_bwd_kernel): given x_bf16 [M, 64] (the forward's input), dy_bf16
+// [M, 64] (gradient of the branch output, DropPath factor already applied), w1_bf16 [HD, 64], b1, w2_bf16 [64, HD]:
+//   dh_bf16 [M, HD]  = (dy W2) * gelu'(x W1^T + b1)            (written; feeds dX = dh W1 and nothing else)
+//   dW1 [HD, 64] += dh^T x,  dW2 [64, HD] += dy^T gelu(x W1^T + b1),  db1 [HD] += column sums of dh    (fp32, accumulated)
+// HD must be a multiple of 128. All pointers 16-byte aligned, tensors contiguous.
+extern "C" int mvlt_mlp_bwd(const void* x_bf16, const void* dy_bf16, const void* w1_bf16, const float* b1, const void* w2_bf16,
+                            void* dh_bf16, float* dW1_f32, float* dW2_f32, float* db1_f32, int M, int C, int HD, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MVLT_CHECK_ARG(x_bf16 && dy_bf16 && w1_bf16 && b1 && w2_bf16 && dh_bf16 && dW1_f32 && dW2_f32 && db1_f32, "mlp_bwd: null operand");
+  MVLT_CHECK_ARG(M > 0 && C == 64 && HD >= HB && HD % HB == 0, "mlp_bwd: unsupported shape M=%d C=%d HD=%d (C = 64, HD %% 128 == 0)", M, C, HD);
+  MVLT_CHECK_ARG(((((uintptr_t)x_bf16) | ((uintptr_t)dy_bf16) | ((uintptr_t)w1_bf16) | ((uintptr_t)w2_bf16) | ((uintptr_t)dh_bf16) |
+                   ((uintptr_t)dW1_f32) | ((uintptr_t)b1)) & 15) == 0, "mlp_bwd: operands must be 16-byte aligned");
+  MlpBwdParams p;
+  p.M = M; p.HD = HD;
+  p.num_tiles = (M + BM - 1) / BM;
+  p.nb = HD / HB;
+  p.nr = mvlt_num_sms() / p.nb;
+  if (p.nr < 1) p.nr = 1;
+  if (p.nr > p.num_tiles) p.nr = p.num_tiles;
+  p.b1 = b1; p.dW1 = dW1_f32; p.dW2 = dW2_f32; p.db1 = db1_f32;
+  CUtensorMap tmX, tmDY, tmW1, tmW2, tmDH;
+  int rc;
+  {
+    const uint64_t dims[4] = {64, (uint64_t)M, 1, 1};
+    const uint64_t str[3] = {128, (uint64_t)M * 128, (uint64_t)M * 128};
+    const uint32_t box[4] = {64, BM, 1, 1};
+    if ((rc = mvlt_tensor_map_4d(&tmX, x_bf16, dims, str, box, 0, 0)) != 0) return rc;
+    if ((rc = mvlt_tensor_map_4d(&tmDY, dy_bf16, dims, str, box, 0, 0)) != 0) return rc;
+  }
+  {
+    const uint64_t dims[4] = {64, (uint64_t)HD, 1, 1};
+    const uint64_t str[3] = {128, (uint64_t)HD * 128, (uint64_t)HD * 128};
+    const uint32_t box[4] = {64, HB, 1, 1};
+    if ((rc = mvlt_tensor_map_4d(&tmW1, w1_bf16, dims, str, box, 0, 0)) != 0) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)HD, 64, 1, 1};
+    const uint64_t str[3] = {(uint64_t)HD * 2, (uint64_t)HD * 128, (uint64_t)HD * 128};
+    const uint32_t box[4] = {64, 64, 1, 1};
+    if ((rc = mvlt_tensor_map_4d(&tmW2, w2_bf16, dims, str, box, 0, 0)) != 0) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)HD, (uint64_t)M, 1, 1};
+    const uint64_t str[3] = {(uint64_t)HD * 2, (uint64_t)M * HD * 2, (uint64_t)M * HD * 2};
+    const uint32_t box[4] = {64, BM, 1, 1};
+    if ((rc = mvlt_tensor_map_4d(&tmDH, dh_bf16, dims, str, box, 0, 0)) != 0) return rc;
+  }
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM + 1024); });
+  mvlt_launch(mlp_bwd_kernel, p.nb * p.nr, BW_THREADS, (size_t)BW_SMEM + 1024, stream, tmX, tmDY, tmW1, tmW2, tmDH, p);
+  MVLT_CHECK_LAUNCH();
+  return 0;
 }

@@ -47,6 +47,8 @@ FUSED_ATTENTION = os.environ.get("MVLT_FUSED_ATTN", "1") != "0"
 # fused attention backward (csrc/attn_bwd_tcgen05.cu: dQ, dK, dV in one kernel); MVLT_FUSED_ATTN_BWD=0 keeps the four-GEMM
 # path (dV, dP + softmax-backward epilogue, dQ, dK) for A/B measurements
 FUSED_ATTENTION_BWD = os.environ.get("MVLT_FUSED_ATTN_BWD", "1") != "0"
+# fused MLP (csrc/mlp_tcgen05.cu) for the thin stages (C = 64 / 128); MVLT_FUSED_MLP=0 keeps the two-GEMM path for A/B runs
+FUSED_MLP = os.environ.get("MVLT_FUSED_MLP", "1") != "0"
 
 
 def _empty(shape, dtype, dev):
@@ -237,14 +239,22 @@ class PVLTEngine:
         xn2 = _empty((M, C), BF16, dev)
         mean2, rstd2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
         k.layernorm_fwd(X1, P[pfx + ".norm2.weight"], P[pfx + ".norm2.bias"], xn2, 1e-6, M, C, mean=mean2, rstd=rstd2)
-        act = _empty((M, hidden), BF16, dev)
-        # training: the epilogue also stores gelu'(pre-activation) so that the backward GEMM epilogue is a multiply
-        hpre = _empty((M, hidden), BF16, dev) if save else None
-        k.gemm(xn2, Wb[pfx + ".mlp.fc1.weight"], act, bias=P[pfx + ".mlp.fc1.bias"],
-               act=k.ACT_GELU_SAVE_GRAD if save else k.ACT_GELU, preact_out=hpre)
         X2 = _empty((B, N, C), F32, dev)
-        k.gemm(act, Wb[pfx + ".mlp.fc2.weight"], X2.view(M, C), bias=P[pfx + ".mlp.fc2.bias"],
-               residual=X1.view(M, C), rowscale=dp[1] if dp else None, rows_per_scale=N)
+        fused_mlp = FUSED_MLP and C in k.MLP_FUSED_DIMS and (not save or C in k.MLP_FUSED_BWD_DIMS)
+        act = hpre = None
+        if fused_mlp:
+            # one kernel: fc1 -> GELU -> fc2 -> + bias, x drop-path, + residual; the [M, hidden] activation stays in TMEM /
+            # shared memory (csrc/mlp_tcgen05.cu). Training saves nothing: the backward recomputes fc1 from xn2.
+            k.mlp_fwd(xn2, Wb[pfx + ".mlp.fc1.weight"], P[pfx + ".mlp.fc1.bias"], Wb[pfx + ".mlp.fc2.weight"],
+                      P[pfx + ".mlp.fc2.bias"], X1.view(M, C), X2.view(M, C), rowscale=dp[1] if dp else None, rows_per_scale=N)
+        else:
+            act = _empty((M, hidden), BF16, dev)
+            # training: the epilogue also stores gelu'(pre-activation) so that the backward GEMM epilogue is a multiply
+            hpre = _empty((M, hidden), BF16, dev) if save else None
+            k.gemm(xn2, Wb[pfx + ".mlp.fc1.weight"], act, bias=P[pfx + ".mlp.fc1.bias"],
+                   act=k.ACT_GELU_SAVE_GRAD if save else k.ACT_GELU, preact_out=hpre)
+            k.gemm(act, Wb[pfx + ".mlp.fc2.weight"], X2.view(M, C), bias=P[pfx + ".mlp.fc2.bias"],
+                   residual=X1.view(M, C), rowscale=dp[1] if dp else None, rows_per_scale=N)
         if save:
             c.update(X=X, xn=xn, mean1=mean1, rstd1=rstd1, q=q, kvin=kvin, kv=kv, Pm=Pm, o=o, X1=X1, xn2=xn2,
                      mean2=mean2, rstd2=rstd2, act=act, hpre=hpre, dp=dp, Nk=Nk)
@@ -266,10 +276,17 @@ class PVLTEngine:
         if dy2 is None:
             dy2 = _empty((M, C), BF16, dev)
             k.cast_scale_bf16(dX2, dy2, M, C, rowscale=dp[1] if dp else None, rows_per_scale=N)
-        self._lin_param_grads(G, pfx + ".mlp.fc2.weight", pfx + ".mlp.fc2.bias", dy2, c["act"])
         dh = _empty((M, hidden), BF16, dev)
-        k.gemm(dy2, Wb[pfx + ".mlp.fc2.weight"].t(), dh, act=k.ACT_MUL_AUX, aux=c["hpre"])
-        self._lin_param_grads(G, pfx + ".mlp.fc1.weight", pfx + ".mlp.fc1.bias", dh, c["xn2"])
+        if c["act"] is None:
+            # fused forward saved nothing: one kernel recomputes fc1 from xn2 and produces dh = (dy W2) * gelu' together with the
+            # fc1 / fc2 weight gradients and the fc1 bias gradient (accumulated in TMEM over the rows); db2 = column sums of dy
+            k.mlp_bwd(c["xn2"], dy2, Wb[pfx + ".mlp.fc1.weight"], P[pfx + ".mlp.fc1.bias"], Wb[pfx + ".mlp.fc2.weight"], dh,
+                      G[pfx + ".mlp.fc1.weight"], G[pfx + ".mlp.fc2.weight"], G[pfx + ".mlp.fc1.bias"])
+            k.colsum(dy2, M, C, C, G[pfx + ".mlp.fc2.bias"])
+        else:
+            self._lin_param_grads(G, pfx + ".mlp.fc2.weight", pfx + ".mlp.fc2.bias", dy2, c["act"])
+            k.gemm(dy2, Wb[pfx + ".mlp.fc2.weight"].t(), dh, act=k.ACT_MUL_AUX, aux=c["hpre"])
+            self._lin_param_grads(G, pfx + ".mlp.fc1.weight", pfx + ".mlp.fc1.bias", dh, c["xn2"])
         dxn2 = dy2  # reuse
         k.gemm(dh, Wb[pfx + ".mlp.fc1.weight"].t(), dxn2)
         del dh

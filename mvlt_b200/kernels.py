@@ -288,6 +288,10 @@ def sr_attention_bwd(q, kv, do, p, dq, dkv, B, N, Nk, heads, scale):
          C.c_int(heads), C.c_float(scale))
 
 
+MLP_FUSED_DIMS = (64, 128)      # embedding widths the fused MLP forward supports (PVLT stages 1 and 2)
+MLP_FUSED_BWD_DIMS = (64,)        # ... and the widths whose recompute backward exists (training uses the fused path only there)
+
+
 def mlp_fwd(x, w1, b1, w2, b2, residual, out, rowscale=None, rows_per_scale=0):
     """out = residual + rowscale[row // rows_per_scale] * (gelu(x @ w1^T + b1) @ w2^T + b2), the hidden activation staying
     on-chip (csrc/mlp_tcgen05.cu). x bf16 [M, C], w1 bf16 [HD, C], w2 bf16 [C, HD], residual / out fp32 [M, C]; C in {64, 128}."""
@@ -305,6 +309,25 @@ def mlp_fwd(x, w1, b1, w2, b2, residual, out, rowscale=None, rows_per_scale=0):
         _lib.account_bytes("mlp_fwd", M * C_ * (2 + 4 + 4) + 4 * HD * C_)
     call("mlp_fwd", ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(residual), ptr(out), ptr(rowscale), C.c_int(rows_per_scale),
          C.c_int(M), C.c_int(C_), C.c_int(HD))
+
+
+def mlp_bwd(x, dy, w1, b1, w2, dh, dw1, dw2, db1):
+    """Backward of the fused MLP branch for C = 64 (csrc/mlp_tcgen05.cu): recomputes fc1 from ``x``; writes dh [M, HD] bf16 (=
+    (dy w2) * gelu'(x w1^T + b1)) and ACCUMULATES dw1 [HD, C], dw2 [C, HD], db1 [HD] (fp32). dX = dh @ w1 is a GEMM of its own."""
+    require_cuda(x, dy, w1, w2, dh, dw1, dw2, db1, b1)
+    M, C_ = x.shape
+    HD = w1.shape[0]
+    if (x.dtype != BF16 or dy.dtype != BF16 or w1.dtype != BF16 or w2.dtype != BF16 or dh.dtype != BF16 or dw1.dtype != F32
+            or dw2.dtype != F32 or db1.dtype != F32 or b1.dtype != F32 or tuple(dy.shape) != (M, C_) or tuple(w1.shape) != (HD, C_)
+            or tuple(w2.shape) != (C_, HD) or tuple(dh.shape) != (M, HD) or tuple(dw1.shape) != (HD, C_) or tuple(dw2.shape) != (C_, HD)
+            or db1.numel() != HD):
+        raise _lib.MvltError("mlp_bwd: x / dy bf16 [M, C], w1 bf16 [HD, C], w2 bf16 [C, HD], dh bf16 [M, HD], dw1 / dw2 / db1 fp32 required")
+    for t in (x, dy, w1, w2, dh, dw1, dw2, db1, b1):
+        if not t.is_contiguous():
+            raise _lib.MvltError("mlp_bwd: contiguous operands required")
+    if _lib.BYTES is not None:
+        _lib.account_bytes("mlp_bwd", M * C_ * 4 + M * HD * 2 + 12 * HD * C_)
+    call("mlp_bwd", ptr(x), ptr(dy), ptr(w1), ptr(b1), ptr(w2), ptr(dh), ptr(dw1), ptr(dw2), ptr(db1), C.c_int(M), C.c_int(C_), C.c_int(HD))
 
 
 def softmax_fwd(s, rows, nk):
