@@ -82,6 +82,26 @@ static inline cudaError_t mvlt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 
   cfg.numAttrs = mvlt_pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// same, as thread-block clusters of `cluster_x` CTAs (grid.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mvlt_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                              unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mvlt_pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -240,10 +260,27 @@ __device__ __forceinline__ void gelu_and_grad2(f32x2_t x, f32x2_t& g, f32x2_t& d
   g = f2_mul(x, cdf);
   dg = f2_fma(f2_mul(x, e), f2_splat(0.39894228040143267794f), cdf);
 }
+// gelu_erf(x) alone: gelu(x) = relu(x) - |x| * h with h = 0.5 * erfc(|x| / sqrt(2)) (h is the lower tail on both sides), which
+// needs no sign handling: 12 packed FP ops + 4 MUFU + 4 scalar ops per PAIR. Same A&S 7.1.26 tail as gelu_and_grad2, with
+// the polynomial coefficients negated so that the last FMA subtracts.
 __device__ __forceinline__ f32x2_t gelu2(f32x2_t x) {
-  f32x2_t g, dg;
-  gelu_and_grad2(x, g, dg);   // the derivative tail is dead code here and is eliminated
-  return g;
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  const f32x2_t ax = f2_pack(fabsf(x0), fabsf(x1));
+  const f32x2_t nw = f2_mul(f2_mul(x, x), f2_splat(-0.72134752044448170368f));   // -x^2/2 * log2(e)
+  float n0, n1;
+  f2_unpack(nw, n0, n1);
+  const f32x2_t e = f2_pack(ex2_approx(n0), ex2_approx(n1));                      // exp(-x^2/2)
+  const f32x2_t den = f2_fma(ax, f2_splat(0.23164189f), f2_splat(1.0f));         // 1 + 0.3275911 |x|/sqrt(2)
+  float d0, d1;
+  f2_unpack(den, d0, d1);
+  const f32x2_t t = f2_pack(rcp_approx(d0), rcp_approx(d1));
+  f32x2_t poly = f2_fma(f2_splat(-0.5307027145f), t, f2_splat(0.7265760135f));   // -(0.5 * A&S coefficients)
+  poly = f2_fma(poly, t, f2_splat(-0.7107068705f));
+  poly = f2_fma(poly, t, f2_splat(0.142248368f));
+  poly = f2_fma(poly, t, f2_splat(-0.127414796f));
+  const f32x2_t nh = f2_mul(f2_mul(poly, t), e);                                 // -0.5 * erfc(|x|/sqrt(2))
+  return f2_fma(ax, nh, f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -376,6 +413,62 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: two CTAs of one cluster on the two SMs of a TPC issue ONE 256-row UMMA ---------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // remote (or local) arrive through the cluster window
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; its bytes complete on the mbarrier at `bar_cluster_addr` (the leader's)
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {   // same warp id in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs, 256 rows] (+)= A[128 rows per CTA] * B[N/2 rows per CTA]; issued by one thread of the LEADER CTA
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this shared-memory offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b16 m;\n"
+      "mov.b16 m, 3;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
 }
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {

@@ -82,6 +82,7 @@ struct KParams {
   long long ldd, sD1, sD2;
   float alpha;
   int act, out_f32, atomic_add, rows_per_scale;
+  int pair;       // CTA-pair mode (cta_group::2): clusters of 2 CTAs share one 256-row UMMA; num_m_blocks counts row PAIRS
   int tma_store;  // D (and D2) leave the staging tiles through TMA bulk stores (tmD / tmD2) instead of LDS + STG
   int prefetch;   // EPI_AUX only: two staging tiles per epilogue warp, the aux unit of the next tile is fetched with cp.async
   // implicit 3x3 convolution operand (gemm_desc.h): tile/k-block index -> (b, y) pixel coordinates and (tap, c0)
@@ -102,7 +103,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 // instruction descriptor, kind::f16: c=f32 (bit4), a=bf16 (bit7), b=bf16 (bit10), a_major bit15, b_major bit16,
 // N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_instr_desc(int n, int a_mn, int b_mn) {
+__device__ __forceinline__ uint32_t make_instr_desc(int n, int a_mn, int b_mn, int m = BLOCK_M) {
   uint32_t d = 0;
   d |= 1u << 4;
   d |= 1u << 7;
@@ -110,7 +111,7 @@ __device__ __forceinline__ uint32_t make_instr_desc(int n, int a_mn, int b_mn) {
   d |= (uint32_t)(a_mn & 1) << 15;
   d |= (uint32_t)(b_mn & 1) << 16;
   d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(BLOCK_M >> 4) << 24;
+  d |= (uint32_t)(m >> 4) << 24;
   return d;
 }
 
@@ -572,7 +573,9 @@ __device__ __forceinline__ float softmax_bwd_unit(const KParams& p, uint32_t tad
   return acc;
 }
 
-template <int kEpi, bool kOutF32>
+// kPair: CTA-pair build (cta_group::2). A kernel that contains cta_group::2 instructions can only be launched as clusters
+// of two, so the pair path is a separate instantiation and the single-CTA build carries none of its code or registers.
+template <int kEpi, bool kOutF32, bool kPair = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
@@ -584,7 +587,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int b_stage_bytes = p.block_n * BLOCK_K * 2;
+  // CTA-pair mode: the two CTAs of a cluster (ranks 0 = leader, 1) each stage their own 128 A rows and HALF of the B tile;
+  // the leader issues tcgen05.mma.cta_group::2 (M = 256), each CTA's TMEM receives its 128 rows x block_n accumulator
+  constexpr int pair = kPair ? 1 : 0;
+  const uint32_t cta_rank = pair ? cluster_ctarank() : 0u;
+  const int cid = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // cluster (or CTA) index in the persistent grid
+  const int ncl = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int mb_mul = pair ? 2 : 1;
+  const int b_rows = pair ? (p.block_n >> 1) : p.block_n;               // B rows (or MN-major columns) staged by this CTA
+  const int b_stage_bytes = b_rows * BLOCK_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
 
   uint8_t* ones_tile = smem + (size_t)p.stages * stage_bytes;   // 1024-byte aligned (stage sizes are multiples of 4 KB)
@@ -602,7 +613,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < MAX_ACC; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], NUM_EPI_WARPS / 2);  // one elected lane per warp of the owning epilogue group
+      mbar_init(&tempty_bar[a], (NUM_EPI_WARPS / 2) * mb_mul);  // one elected lane per warp of the owning epilogue group (both CTAs of a pair)
     }
     fence_barrier_init();
   }
@@ -618,9 +629,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x < ONES_BYTES / 4) reinterpret_cast<uint32_t*>(ones_tile)[threadIdx.x] = 0x3F803F80u;
     fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (kPair) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything of this CTA can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // barrier / TMEM set-up above overlapped the previous kernel; global memory is only touched below
@@ -636,17 +651,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = cid; t < total_tiles; t += ncl) {
           const TileCoord tc = decode_tile(p, t);
-          const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * p.block_n;
+          const int m0 = (tc.m_blk * mb_mul + (int)cta_rank) * BLOCK_M, n0 = tc.n_blk * p.block_n;
           const int kb0 = tc.split * p.kb_per_split;
           const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * stage_bytes;
             uint8_t* sb = sa + A_STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
             const int k0 = kb * BLOCK_K;
+            if constexpr (kPair) {
+              // both CTAs' bytes complete on the LEADER's full barrier, which the leader arms for the two halves
+              const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0u);
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)stage_bytes);
+              if (!p.a_mn) {
+                tma_load_4d_2sm(sa, &tmA, lbar, k0, m0, tc.b2 * p.a_b2, tc.b1 * p.a_b1);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BLOCK_M / 64; ++j)
+                  tma_load_4d_2sm(sa + j * 8192, &tmA, lbar, m0 + j * 64, k0, tc.b2 * p.a_b2, tc.b1 * p.a_b1);
+              }
+              const int nb0 = n0 + (int)cta_rank * b_rows;     // this CTA's half of the B tile
+              if (!p.b_mn) {
+                tma_load_4d_2sm(sb, &tmB, lbar, k0, nb0, tc.b2 * p.b_b2, tc.b1 * p.b_b1);
+              } else {
+                for (int j = 0; j < b_rows / 64; ++j)
+                  tma_load_4d_2sm(sb + j * 8192, &tmB, lbar, nb0 + j * 64, k0, tc.b2 * p.b_b2, tc.b1 * p.b_b1);
+              }
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
+            }
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
             if (p.conv_mode == MVLT_CONV_A) {
               // A tile = 128 consecutive pixels x 64 channels of tap (kb / (C/64)): one shifted NHWC box
               uint32_t tap, cb, b0, rem, y0, xr;
@@ -691,8 +730,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      if (lane == 0) {
-        const uint32_t idesc = make_instr_desc(p.block_n, p.a_mn, p.b_mn);
+      if (lane == 0 && cta_rank == 0) {     // (pair mode: the leader CTA issues for both)
+        const uint32_t idesc = make_instr_desc(p.block_n, p.a_mn, p.b_mn, BLOCK_M * mb_mul);
         const uint32_t idesc_ones = make_instr_desc(ONES_N, p.a_mn, 0);
         const uint64_t ones_desc = make_smem_desc(smem_u32(ones_tile), 0u, 0u);   // SBO = 0: rows 8..15 re-read rows 0..7
         // K-major: 8-row groups are 1024 B apart (SBO); the single 128 B swizzle atom along K makes LBO unused.
@@ -702,7 +741,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         int local = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+        for (int t = cid; t < total_tiles; t += ncl, ++local) {
           const TileCoord tc = decode_tile(p, t);
           const int kb0 = tc.split * p.kb_per_split;
           const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
@@ -722,17 +761,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024u);
               const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024u);
-              umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if constexpr (kPair) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
               if (do_rowsum)   // row sums of the A tile: 128 x 16 x 16 MMA against the ones tile
                 umma_bf16(tmem_ones, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if constexpr (kPair) umma_commit_2sm(&empty_bar[stage]);   // frees the slot in BOTH CTAs
+            else umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          if constexpr (kPair) umma_commit_2sm(&tfull_bar[acc]);   // accumulator halves complete -> the epilogue warps of both CTAs
+          else umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
       }
     }
@@ -770,18 +812,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const TileCoord tc = decode_tile(p, tt);
           cb1 = tc.b1;
           cb2 = tc.b2;
-          r = tc.m_blk * BLOCK_M + quarter * 32;
+          r = (tc.m_blk * mb_mul + (int)cta_rank) * BLOCK_M + quarter * 32;
           v = min(32, p.M - r);
           o = (long long)tc.b1 * p.sD1 + (long long)tc.b2 * p.sD2 + (long long)r * p.ldd;
           c = tc.n_blk * p.block_n + half * 64;
         };
-        int t = blockIdx.x + group * gridDim.x;
+        int t = cid + group * ncl;
         if (t < total_tiles) {
           coords(t, rbo, rv, c0, rb, tb1, tb2);
           prefetch_rows_async(se, reinterpret_cast<const uint8_t*>(p.aux + rbo + c0), ld_bytes, lane, rv);
         }
-        for (int local = group; t < total_tiles; t += 2 * gridDim.x, local += 2) {
-          const int tn = t + 2 * gridDim.x;
+        for (int local = group; t < total_tiles; t += 2 * ncl, local += 2) {
+          const int tn = t + 2 * ncl;
           if (tn < total_tiles) coords(tn, rbo_n, rv_n, c0_n, rb_n, tb1_n, tb2_n);
           float rs = 1.f;
           if (p.rowscale != nullptr && lane < rv) rs = p.rowscale[(rb + lane) / p.rows_per_scale];
@@ -812,10 +854,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         total_tiles_done = true;
       }
     }
-    for (int local = group, t = blockIdx.x + group * gridDim.x; !total_tiles_done && t < total_tiles; t += 2 * gridDim.x, local += 2) {
+    uint32_t tempty_leader = 0u;   // the leader's MMA thread owns the accumulators of both CTAs
+    if constexpr (kPair) tempty_leader = mapa_shared(smem_u32(&tempty_bar[0]), 0u);
+    for (int local = group, t = cid + group * ncl; !total_tiles_done && t < total_tiles; t += 2 * ncl, local += 2) {
       const TileCoord tc = decode_tile(p, t);
       const int n0 = tc.n_blk * p.block_n;
-      const int row_base = tc.m_blk * BLOCK_M + quarter * 32;
+      const int row_base = (tc.m_blk * mb_mul + (int)cta_rank) * BLOCK_M + quarter * 32;
       const int rows_valid = min(32, p.M - row_base);          // <= 0 when the whole warp is past the M tail
       const long long batch_off = (long long)tc.b1 * p.sD1 + (long long)tc.b2 * p.sD2;
       const long long row_base_off = batch_off + (long long)row_base * p.ldd;
@@ -924,7 +968,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // all of this warp's TMEM reads are complete (wait::ld above): release the accumulator buffer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
   }
 
@@ -932,9 +979,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this lane's bulk stores have fully completed
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // both CTAs have drained their accumulators and no remote arrive is in flight
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (kPair) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -1087,7 +1136,12 @@ const KernelVariant kVariants[] = {
     {gemm_tcgen05_kernel<EPI_GELU, false>, "gelu/bf16"},         {gemm_tcgen05_kernel<EPI_AUX, false>, "aux/bf16"},
     {gemm_tcgen05_kernel<EPI_RESID, true>, "residual/f32"},      {gemm_tcgen05_kernel<EPI_SOFTMAX, false>, "softmax/bf16"},
     {gemm_tcgen05_kernel<EPI_SOFTMAX_BWD, false>, "softmax_bwd/bf16"},
+    // CTA-pair builds of the first five (index + 7)
+    {gemm_tcgen05_kernel<EPI_PLAIN, false, true>, "plain/bf16/pair"},   {gemm_tcgen05_kernel<EPI_PLAIN, true, true>, "plain/f32/pair"},
+    {gemm_tcgen05_kernel<EPI_GELU, false, true>, "gelu/bf16/pair"},     {gemm_tcgen05_kernel<EPI_AUX, false, true>, "aux/bf16/pair"},
+    {gemm_tcgen05_kernel<EPI_RESID, true, true>, "residual/f32/pair"},
 };
+constexpr int kPairVariantOffset = 7;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 // NHWC bf16 tensor X[b, y, x, c] as a 4-D map (c, x, y, b) whose box covers `pixels` consecutive pixels x 64 channels
@@ -1192,10 +1246,20 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   p.prefetch = (aux_kind && g->K <= 2 * BLOCK_K && g->N % 128 == 0 && (g->ldd % 8) == 0 && (g->sD1 % 8) == 0 && (g->sD2 % 8) == 0 &&
                 (g->block_n == 0 || g->block_n == 128)) ? 1 : 0;
   if (p.prefetch) p.block_n = 128;
-  const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+  // CTA-pair mode (cta_group::2) for the tensor-bound shapes: a 256 x block_n tile per cluster of two CTAs halves the B bytes
+  // each SM stages per k-block (32 KB instead of 48 KB at block_n = 256: 5 instead of 3 pipeline stages). Validated
+  // (tests/test_gemm_gpu.py passes with MVLT_GEMM_PAIR=1) but measured SLOWER than the single-CTA build on every PVLT shape
+  // (stage-4 MLP fc1 84.1 -> 90.8 us, fc2 72.0 -> 76.3 us, profiles/r2m_gemm_pair_ab.txt): these launches are bound by their
+  // GELU / residual epilogues and by wave quantisation, not by the operand fill. Opt-in: MVLT_GEMM_PAIR=1.
+  static const int pair_env = [] { const char* e = getenv("MVLT_GEMM_PAIR"); return e ? atoi(e) : 0; }();
+  p.pair = (pair_env && g->conv_mode == MVLT_CONV_NONE && g->rowsum == nullptr && !p.prefetch && g->split_k <= 1 && !g->atomic_add &&
+            g->act != MVLT_ACT_SOFTMAX && g->act != MVLT_ACT_SOFTMAX_BWD && g->K >= 4 * BLOCK_K && g->M >= 16 * BLOCK_M &&
+            p.block_n >= 128 && p.block_n % 128 == 0 && (long long)g->batch1 * g->batch2 == 1) ? 1 : 0;
+  const int stage_bytes = A_STAGE_BYTES + (p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
   p.stages = (p.prefetch ? SMEM_BUDGET - STAGING_BYTES : SMEM_BUDGET) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.num_m_blocks = (g->M + BLOCK_M - 1) / BLOCK_M;
+  if (p.pair) p.num_m_blocks = (p.num_m_blocks + 1) / 2;      // 256-row pairs; an odd last block is zero-filled / clipped
   p.num_n_blocks = (g->N + p.block_n - 1) / p.block_n;
   p.num_k_blocks = (g->K + BLOCK_K - 1) / BLOCK_K;
   int split = g->split_k > 1 ? g->split_k : 1;
@@ -1258,7 +1322,7 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   else rc = make_operand_map(&tmA, g->A, g->M, g->K, p.a_mn, g->lda, g->batch1, g->batch2, g->sA1, g->sA2, BLOCK_M, &p.a_b1, &p.a_b2);
   if (rc) return rc;
   if (g->conv_mode == MVLT_CONV_BT) rc = make_conv_map(&tmB, g, g->B, 64);
-  else rc = make_operand_map(&tmB, g->B, g->N, g->K, p.b_mn, g->ldb, g->batch1, g->batch2, g->sB1, g->sB2, p.block_n, &p.b_b1, &p.b_b2);
+  else rc = make_operand_map(&tmB, g->B, g->N, g->K, p.b_mn, g->ldb, g->batch1, g->batch2, g->sB1, g->sB2, p.pair ? p.block_n / 2 : p.block_n, &p.b_b1, &p.b_b2);
   if (rc) return rc;
 
   // > half of the SM's shared memory so two CTAs (each wanting all 512 TMEM columns) never share an SM
@@ -1280,7 +1344,12 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
       (long long)p.batch1 * p.batch2 * p.split_k * p.num_m_blocks * p.num_n_blocks;
   MVLT_CHECK_ARG(total_tiles < (1ll << 31), "mvlt_gemm: too many tiles");
   int grid = mvlt_num_sms();
-  if (total_tiles < grid) grid = (int)total_tiles;
+  if (p.pair) {
+    grid &= ~1;
+    if (2 * total_tiles < grid) grid = (int)(2 * total_tiles);
+  } else if (total_tiles < grid) {
+    grid = (int)total_tiles;
+  }
   // TMA-store epilogue (bulk tensor stores, or bulk tensor fp32 reductions for atomic_add): 16-byte aligned output pitch /
   // batch strides / base
   CUtensorMap tmD = tmA, tmD2 = tmA, tmDh = tmA, tmD2h = tmA;
@@ -1307,7 +1376,8 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
       p.tma_store = 1;
     }
   }
-  mvlt_launch(kVariants[pick_variant(g)].fn, grid, NUM_THREADS, smem, stream, tmA, tmB, tmD, tmD2, tmDh, tmD2h, p);
+  if (p.pair) mvlt_launch_cluster(kVariants[pick_variant(g) + kPairVariantOffset].fn, grid, NUM_THREADS, smem, stream, 2u, tmA, tmB, tmD, tmD2, tmDh, tmD2h, p);
+  else mvlt_launch(kVariants[pick_variant(g)].fn, grid, NUM_THREADS, smem, stream, tmA, tmB, tmD, tmD2, tmDh, tmD2h, p);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -65,6 +65,7 @@ struct MlpParams {
   const float* residual;    // fp32 [M, C]
   const float* rowscale;    // per-sample drop-path factor or nullptr
   int rows_per_scale;
+  int dbg;                  // tuning experiments only (MVLT_MLP_DBG): 1 = no residual read, 2 = identity instead of GELU, 4 = no output
 };
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes) {   // K-major SWIZZLE_128B operand
@@ -171,9 +172,14 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const uint32_t idesc1 = instr_desc(CW);    // GEMM1: N = 64 hidden columns
       const uint32_t idesc2 = instr_desc(C);     // GEMM2: N = C
       const uint32_t sX = smem_u32(smem + K::OFF_X), sW = smem_u32(smem + K::OFF_W), sA = smem_u32(smem + K::OFF_A);
+      int tl1 = 0, j1 = 0, tl2 = 0, j2 = 0;        // (tile, chunk-in-tile) of the GEMM1 / GEMM2 being issued: counters, no division
       for (int g = 0; g < total + LAG; ++g) {
         if (g < total) {                          // ---- GEMM1 of chunk g
-          const int tl = g / nch, j = g - tl * nch;
+          const int tl = tl1, j = j1;
+          if (++j1 == nch) {
+            j1 = 0;
+            ++tl1;
+          }
           const int xb = tl & 1, s = g % NS, hb = g % NH;
           if (j == 0) mbar_wait(&x_full[xb], ((uint32_t)tl >> 1) & 1u);
           mbar_wait(&w_full[s], ((uint32_t)(g / NS)) & 1u);
@@ -189,7 +195,11 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         if (g >= LAG) {                           // ---- GEMM2 of chunk g - LAG
           const int g2 = g - LAG;
-          const int tl = g2 / nch, j = g2 - tl * nch;
+          const int tl = tl2, j = j2;
+          if (++j2 == nch) {
+            j2 = 0;
+            ++tl2;
+          }
           const int yb = tl & 1, s = g2 % NS, hb = g2 % NH;
           mbar_wait(&a_full[hb], ((uint32_t)(g2 / NH)) & 1u);
           if (j == 0) mbar_wait(&y_empty[yb], (((uint32_t)tl >> 1) & 1u) ^ 1u);
@@ -213,10 +223,9 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const uint32_t row = (uint32_t)(quarter * 32 + lane);
     const uint32_t a_row = smem_u32(smem + K::OFF_A) + row * 128u;
     const uint32_t rx = row & 7u;
+    int hb = 0, j = 0;                            // g % NH and g % nch, kept as counters (no integer division per chunk)
+    uint32_t ph = 0;                              // (g / NH) & 1
     for (int g = 0; g < total; ++g) {
-      const int hb = g % NH;
-      const uint32_t ph = ((uint32_t)(g / NH)) & 1u;
-      const int j = g % nch;
       // bias of this chunk slice: identical for every lane (L1 broadcast), fetched before the accumulator is waited for
       float4 bv[4];
       const float4* bp = reinterpret_cast<const float4*>(p.b1 + j * CW + cq * 16);
@@ -247,6 +256,11 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();       // this warp's TMEM reads precede the MMA that will overwrite the H buffer
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[hb]);
+      if (++hb == NH) {
+        hb = 0;
+        ph ^= 1u;
+      }
+      if (++j == nch) j = 0;
     }
   } else if (warp >= OUT_WARP0) {
     // ===================== output warps =====================
@@ -269,6 +283,7 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           mbar_wait(&y_full[yb], ((uint32_t)tl >> 1) & 1u);
           tc_fence_after();
         }
+        if (p.dbg & 4) continue;
         if (lane == 0) tma_store_wait_read();     // the previous unit's store has finished reading the staging tile
         __syncwarp();
 #pragma unroll
@@ -276,7 +291,7 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           float4 rv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            rv[i] = valid ? __ldg(reinterpret_cast<const float4*>(res_row + u * 32 + hh * 16) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rv[i] = (valid && !(p.dbg & 1)) ? __ldg(reinterpret_cast<const float4*>(res_row + u * 32 + hh * 16) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
           uint32_t r[16];
           tmem_ld_32x16(tmem_base + tlane + (uint32_t)(Y_COL0 + yb * C + u * 32 + hh * 16), r);
           tmem_ld_wait();
@@ -368,12 +383,13 @@ int launch_fwd(const void* x, const void* w1, const void* w2, void* out, const M
 //                               dW1_blk [128 hid x C] += dh'^T X
 //                               db1_blk               += dh'^T 1       (N = 16 MMA against a tile of ones)
 //   warp 2      : TMA store of the dh' tile into dh'[M, HD] (consumed by the dX = dh' W1 GEMM that follows)
-//   warps 4..11 : (g, g') = gelu, gelu'(H + b1);  act = g,  dh' = dH * g'  -> bf16 K-major SWIZZLE_128B tiles in shared memory
+//   warps 4..19 : (g, g') = gelu, gelu'(H + b1);  act = g,  dh' = dH * g'  -> bf16 K-major SWIZZLE_128B tiles in shared memory
+//                 (lane quarter x 16-column slice: 4 warps per SM sub-partition, the kernel is MUFU / issue bound)
 //
 // Replaces the autograd of /root/reference/libs/pvlt.py:65-71 (fc2 dX / dW / fc1 dW, db and the GELU backward); db2 and
 // dX = dh' W1 are taken by the column-sum kernel and the tcgen05 GEMM (engine.py).
 // =====================================================================================================================
-constexpr int BW_THREADS = 384;
+constexpr int BW_THREADS = 640;      // warp 0 TMA, warp 1 MMA, warp 2 dh' store, warp 3 idle, warps 4..19 GELU / flush
 constexpr int HB = 128;
 constexpr int BW_OFF_W1 = 0;                        // [128 hid x 64 c] K-major
 constexpr int BW_OFF_W2 = ATOM;                     // 2 x [64 c x 64 hid] (MN-major B operand)
@@ -537,7 +553,7 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp >= GELU_WARP0) {
-    const int quarter = warp & 3, half = (warp - GELU_WARP0) >> 2;
+    const int quarter = warp & 3, cq = (warp - GELU_WARP0) >> 2;     // lane quarter, 16-column slice of a 64-column half
     const uint32_t tlane = ((uint32_t)(quarter * 32) << 16);
     const uint32_t row = (uint32_t)(quarter * 32 + lane), rx = row & 7u;
     const uint32_t act_row = smem_u32(smem + BW_OFF_ACT) + row * 128u, dh_row = smem_u32(smem + BW_OFF_DH) + row * 128u;
@@ -545,47 +561,44 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const uint32_t ph = (uint32_t)i & 1u;
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
+        const float4* bp = reinterpret_cast<const float4*>(p.b1 + jb * HB + s * 64 + cq * 16);
+        float4 bv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bv[q] = __ldg(bp + q);
         mbar_wait(&hd_full[s], ph);
         tc_fence_after();
-        uint32_t apk[16], dpk[16];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t rh[16], rd[16];
-          tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_H + s * 64 + half * 32 + hh * 16), rh);
-          tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_DH + s * 64 + half * 32 + hh * 16), rd);
-          const float4* bp = reinterpret_cast<const float4*>(p.b1 + jb * HB + s * 64 + half * 32 + hh * 16);
-          float4 bv[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) bv[q] = __ldg(bp + q);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            f32x2_t g0, d0, g1, d1;
-            gelu_and_grad2(f2_add(f2_pack(__uint_as_float(rh[4 * q]), __uint_as_float(rh[4 * q + 1])), f2_pack(bv[q].x, bv[q].y)), g0, d0);
-            gelu_and_grad2(f2_add(f2_pack(__uint_as_float(rh[4 * q + 2]), __uint_as_float(rh[4 * q + 3])), f2_pack(bv[q].z, bv[q].w)), g1, d1);
-            d0 = f2_mul(d0, f2_pack(__uint_as_float(rd[4 * q]), __uint_as_float(rd[4 * q + 1])));
-            d1 = f2_mul(d1, f2_pack(__uint_as_float(rd[4 * q + 2]), __uint_as_float(rd[4 * q + 3])));
-            float a, b;
-            f2_unpack(g0, a, b);
-            apk[hh * 8 + 2 * q] = pack_bf16x2(a, b);
-            f2_unpack(g1, a, b);
-            apk[hh * 8 + 2 * q + 1] = pack_bf16x2(a, b);
-            f2_unpack(d0, a, b);
-            dpk[hh * 8 + 2 * q] = pack_bf16x2(a, b);
-            f2_unpack(d1, a, b);
-            dpk[hh * 8 + 2 * q + 1] = pack_bf16x2(a, b);
-          }
-        }
+        uint32_t rh[16], rd[16];
+        tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_H + s * 64 + cq * 16), rh);
+        tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_DH + s * 64 + cq * 16), rd);
+        tmem_ld_wait();
         tc_fence_before();       // this warp's TMEM reads precede the MMAs of the next tile into H_s / dH_s
         __syncwarp();
         if (lane == 0) mbar_arrive(&hd_empty[s]);
+        uint32_t apk[8], dpk[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          f32x2_t g0, d0, g1, d1;
+          gelu_and_grad2(f2_add(f2_pack(__uint_as_float(rh[4 * q]), __uint_as_float(rh[4 * q + 1])), f2_pack(bv[q].x, bv[q].y)), g0, d0);
+          gelu_and_grad2(f2_add(f2_pack(__uint_as_float(rh[4 * q + 2]), __uint_as_float(rh[4 * q + 3])), f2_pack(bv[q].z, bv[q].w)), g1, d1);
+          d0 = f2_mul(d0, f2_pack(__uint_as_float(rd[4 * q]), __uint_as_float(rd[4 * q + 1])));
+          d1 = f2_mul(d1, f2_pack(__uint_as_float(rd[4 * q + 2]), __uint_as_float(rd[4 * q + 3])));
+          float a, b;
+          f2_unpack(g0, a, b);
+          apk[2 * q] = pack_bf16x2(a, b);
+          f2_unpack(g1, a, b);
+          apk[2 * q + 1] = pack_bf16x2(a, b);
+          f2_unpack(d0, a, b);
+          dpk[2 * q] = pack_bf16x2(a, b);
+          f2_unpack(d1, a, b);
+          dpk[2 * q + 1] = pack_bf16x2(a, b);
+        }
         if (s == 0) {            // the previous tile's dW MMAs and dh' store have finished reading the operand tiles
           mbar_wait(a_empty, ph ^ 1u);
           mbar_wait(st_empty, ph ^ 1u);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t off = (uint32_t)(s * ATOM) + ((((uint32_t)(half * 4 + q)) ^ rx) << 4);
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t off = (uint32_t)(s * ATOM) + ((((uint32_t)(cq * 2 + q)) ^ rx) << 4);
           st_shared_v4(act_row + off, apk[4 * q], apk[4 * q + 1], apk[4 * q + 2], apk[4 * q + 3]);
           st_shared_v4(dh_row + off, dpk[4 * q], dpk[4 * q + 1], dpk[4 * q + 2], dpk[4 * q + 3]);
         }
@@ -599,24 +612,23 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tc_fence_after();
     if (n_tiles > 0) {
       const int hid = jb * HB + quarter * 32 + lane;
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + tlane + (uint32_t)(COL_DW1 + half * 32), r);
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_DW1 + cq * 16), r);
       tmem_ld_wait();
-      float* g1 = p.dW1 + (long long)hid * C + half * 32;
+      float* g1 = p.dW1 + (long long)hid * C + cq * 16;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < 4; ++q)
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g1 + 4 * q), "f"(__uint_as_float(r[4 * q])),
                      "f"(__uint_as_float(r[4 * q + 1])), "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3]))
                      : "memory");
-      tmem_ld_32x32(tmem_base + tlane + (uint32_t)(COL_DW2 + half * 32), r);
+      tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_DW2 + cq * 16), r);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(p.dW2 + (long long)(half * 32 + j) * p.HD + hid, __uint_as_float(r[j]));
-      if (half == 0) {
-        uint32_t o[16];
-        tmem_ld_32x16(tmem_base + tlane + (uint32_t)COL_ONES, o);
+      for (int j = 0; j < 16; ++j) atomicAdd(p.dW2 + (long long)(cq * 16 + j) * p.HD + hid, __uint_as_float(r[j]));
+      if (cq == 0) {
+        tmem_ld_32x16(tmem_base + tlane + (uint32_t)COL_ONES, r);
         tmem_ld_wait();
-        atomicAdd(p.db1 + hid, __uint_as_float(o[0]));
+        atomicAdd(p.db1 + hid, __uint_as_float(r[0]));
       }
     }
   }
@@ -648,6 +660,8 @@ extern "C" int mvlt_mlp_fwd(const void* x_bf16, const void* w1_bf16, const float
   p.num_tiles = (M + BM - 1) / BM;
   p.nch = HD / CW;
   p.b1 = b1; p.b2 = b2; p.residual = residual_f32; p.rowscale = rowscale_f32; p.rows_per_scale = rows_per_scale > 0 ? rows_per_scale : 1;
+  static const int dbg = [] { const char* e = getenv("MVLT_MLP_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg;
   return C == 64 ? launch_fwd<64>(x_bf16, w1_bf16, w2_bf16, out_f32, p, stream) : launch_fwd<128>(x_bf16, w1_bf16, w2_bf16, out_f32, p, stream);
 }
 

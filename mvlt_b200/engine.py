@@ -74,6 +74,7 @@ class PVLTEngine:
         self._seed_base = None
         self._dp_rates = None
         self.last_rng = None
+        self._grad_layout = None
         from . import t2i as _t2i
         self.t2i = _t2i.T2IHead(self) if loss_type.get("t2i") else None
 
@@ -428,8 +429,10 @@ class PVLTEngine:
             Xprev, Hp, Wp = X, H, W
         return ctx
 
-    def encoder_bwd(self, ctx, dXs, G):
-        """dXs[i]: fp32 gradient wrt the output token buffer of stage i (or None). Accumulates into G."""
+    def encoder_bwd(self, ctx, dXs, G, on_segment=None):
+        """dXs[i]: fp32 gradient wrt the output token buffer of stage i (or None). Accumulates into G.
+        ``on_segment(k)`` is called as soon as every gradient of flat-buffer segment k (1 = stage 4 ... 4 = stage 1 + BERT
+        embeddings, see ``grad_segment``) has been enqueued: the data-parallel exchange of that segment can start there."""
         P, Wb, T = self.P, self.W, self.T
         B = ctx["B"]
         dev = ctx["ids"].device
@@ -487,6 +490,14 @@ class PVLTEngine:
                 if dXs[i - 1] is not None:   # t2i head gradients: fp32 [B, HWp, Cp], image rows of the previous stage
                     k.copy_rows(dXs[i - 1], dXp, B * Hp * Wp, Cp, dmap=(Hp * Wp, Np, 0), accumulate=True)
                 dX = dXp
+                # fold this stage's permuted conv-weight gradients back into the master [Co, Ci, kh, kw] layout (one launch):
+                # the stage's segment of the flat gradient buffer is complete after it
+                items = [(G[key], G[key[len("__perm__"):]]) for key in G
+                         if key.startswith(f"__perm__block{s}.") or key.startswith(f"__perm__patch_embed{s}.")]
+                if items:
+                    k.uncast_conv_wgrad_multi(items)
+                if on_segment is not None:
+                    on_segment(4 - i)
             else:
                 dy768 = _empty((B * T, HIDDEN), BF16, dev)
                 k.gemm(dte, Wb["text_embed1.0.weight"].t(), dy768)
@@ -497,11 +508,11 @@ class PVLTEngine:
                                  G["text_embeddings.position_embeddings.weight"],
                                  G["text_embeddings.token_type_embeddings.weight"], G["text_embeddings.LayerNorm.weight"],
                                  G["text_embeddings.LayerNorm.bias"], B * T, T, ctx["p_drop"], ctx["seed"])
-        # fold the permuted conv-weight gradients back into the master [Co, Ci, kh, kw] layout (one launch)
-        items = [(G[key], G[key[len("__perm__"):]]) for key in G
-                 if key.startswith("__perm__") and not key.startswith("__perm__t2i_head.")]
+        items = [(G[key], G[key[len("__perm__"):]]) for key in G if key.startswith("__perm__block1.")]
         if items:
             k.uncast_conv_wgrad_multi(items)
+        if on_segment is not None:
+            on_segment(4)
 
     # ------------------------------------------------------------------------------------------------
     # heads (pvlt.py:365-397)
@@ -608,16 +619,46 @@ class PVLTEngine:
     # ------------------------------------------------------------------------------------------------
     # gradient buffers
     # ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def grad_segment(name: str) -> int:
+        """Order in which the backward pass COMPLETES the gradient of a parameter: 0 = heads, 1..4 = stages 4..1 (stage 1
+        together with the BERT embeddings, whose scatter-add is the very last kernel). The flat gradient buffer is laid out
+        in this order so that each segment can be exchanged between data-parallel ranks while the rest is still computed."""
+        for s in (4, 3, 2, 1):
+            if (name.startswith(f"block{s}.") or name.startswith(f"patch_embed{s}.") or name.startswith(f"text_embed{s}.")
+                    or name == f"pos_embed{s}" or name == f"text_pos_embed{s}"):
+                return 5 - s
+        if name.startswith("text_embeddings."):
+            return 4
+        return 0
+
     def new_grads(self):
-        """One flat zeroed fp32 buffer, viewed per parameter (the tied decoder weight has no separate entry)."""
+        """One flat zeroed fp32 buffer, viewed per parameter (the tied decoder weight has no separate entry), laid out in
+        gradient-completion order (``grad_segment``); ``G["__segments__"]`` = [(begin, end)] element ranges of the segments."""
         dev = next(iter(self.P.values())).device
         total = sum((p.numel() + 3) // 4 * 4 for p in self.P.values())
         flat = torch.zeros(total, dtype=F32, device=dev)
-        G, off = {}, 0
-        for name, p in self.P.items():
+        if self._grad_layout is None:
+            order = sorted(self.P.keys(), key=lambda n: (self.grad_segment(n), n.startswith("text_embeddings.word")))
+            layout, bounds, off, cur = [], [], 0, 0
+            for name in order:
+                seg = self.grad_segment(name)
+                while cur < seg:
+                    bounds.append(off)
+                    cur += 1
+                layout.append((name, off))
+                off += (self.P[name].numel() + 3) // 4 * 4
+            while cur < 5:
+                bounds.append(off)
+                cur += 1
+            self._grad_layout = (layout, [(b, e) for b, e in zip([0] + bounds[:-1], bounds)])
+        layout, segments = self._grad_layout
+        G = {}
+        for name, off in layout:
+            p = self.P[name]
             G[name] = flat[off:off + p.numel()].view(p.shape)
-            off += (p.numel() + 3) // 4 * 4
         G["__flat__"] = flat
+        G["__segments__"] = segments
         # convolution weights accumulate their gradient in the GEMM-friendly permuted layout [Co, kh*kw*Ci]: one zeroed
         # arena for all of them, folded back into the master [Co, Ci, kh, kw] views by one launch per head / encoder
         convs = [(name, p) for name, p in self.P.items() if p.dim() == 4]

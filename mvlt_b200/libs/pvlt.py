@@ -111,16 +111,20 @@ class _PVLTFunction(torch.autograd.Function):
             raise MvltError("backward called on a forward that ran without gradient tracking")
         eng: PVLTEngine = model._engine()
         G = eng.new_grads()
-        if ctx.mode == "logits":
-            eng_backward_logits(eng, saved, gouts, G)
-        else:
-            eng_backward_losses(eng, saved, gouts[0], G)
-        ctx.saved = None
         sync = model.__dict__.get("_grad_sync")
-        if sync is not None:
-            # data parallelism without DistributedDataParallel's bucket copies: every gradient of the step already lives
-            # in ONE flat fp32 buffer, so the whole exchange is a single NCCL all-reduce (average) over NVLink
-            allreduce_flat_(G["__flat__"], sync)
+        # data parallelism without DistributedDataParallel's bucket copies: every gradient of the step lives in ONE flat fp32
+        # buffer laid out in completion order, and each segment (heads, stage 4, 3, 2, stage 1 + embeddings) is all-reduced
+        # (averaged) over NVLink on a side stream as soon as the hand-scheduled backward has finished it -- the exchange of
+        # everything but the last segment overlaps the remaining backward kernels (DDP's overlap at main_vl.py:297-299)
+        reducer = SegmentReducer(G["__flat__"], G["__segments__"], sync) if sync is not None else None
+        on_seg = reducer.segment_done if reducer is not None else None
+        if ctx.mode == "logits":
+            eng_backward_logits(eng, saved, gouts, G, on_seg)
+        else:
+            eng_backward_losses(eng, saved, gouts[0], G, on_seg)
+        ctx.saved = None
+        if reducer is not None:
+            reducer.finish()
         names = model._param_names
         return (None, None, None, None, None) + tuple(G[n] for n in names)
 
@@ -139,6 +143,60 @@ def allreduce_flat_(flat, group=None):
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp)
         flat.div_(world)
     return flat
+
+
+class SegmentReducer:
+    """Averages the segments of a flat gradient buffer over the data-parallel group, each as soon as it is complete.
+    CUDA: the all-reduce of segment k is enqueued on a side stream behind an event recorded on the compute stream, so it
+    runs under the backward kernels of the following segments; ``finish`` makes the compute stream wait for all of them.
+    CPU tensors (gloo tests): the same calls, synchronously."""
+
+    def __init__(self, flat, segments, group=True):
+        import torch.distributed as dist
+        self.flat, self.segments = flat, segments
+        self.group = None if group is True else group
+        self.world = dist.get_world_size(self.group)
+        self.cuda = flat.is_cuda
+        self.done = set()
+        self.events = []
+        if self.cuda and self.world > 1:
+            key = flat.device.index
+            side = _SIDE_STREAMS.get(key)
+            if side is None:
+                side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=flat.device)
+            self.side = side
+
+    def segment_done(self, k):
+        if self.world == 1 or k in self.done:
+            return
+        self.done.add(k)
+        b, e = self.segments[k]
+        if e <= b:
+            return
+        part = self.flat[b:e]
+        if not self.cuda:
+            allreduce_flat_(part, True if self.group is None else self.group)
+            return
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            allreduce_flat_(part, True if self.group is None else self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.events.append(ev)
+
+    def finish(self):
+        for k in range(len(self.segments)):
+            self.segment_done(k)
+        if self.cuda and self.world > 1:
+            main = torch.cuda.current_stream()
+            for ev in self.events:
+                main.wait_event(ev)
+
+
+_SIDE_STREAMS = {}
 
 
 def _heads_common_fwd(eng, enc, B):
@@ -182,7 +240,7 @@ def eng_forward_logits(eng: PVLTEngine, images, ids, training, save):
     return outs, saved
 
 
-def eng_backward_logits(eng: PVLTEngine, saved, gouts, G):
+def eng_backward_logits(eng: PVLTEngine, saved, gouts, G, on_segment=None):
     enc, hc, B, HW4 = saved["enc"], saved["hc"], saved["B"], saved["HW4"]
     T = eng.T
     dev = enc["ids"].device
@@ -205,7 +263,9 @@ def eng_backward_logits(eng: PVLTEngine, saved, gouts, G):
         k.t2i_up_loss(c["score"], None, g_t2i.contiguous().to(F32), dscore, None, None, 0.0, 1.0, None, B, h, w, 8, 0, True)
         df2, df3 = eng.t2i.backward(dscore, c, G, dX4)
         dXs[1], dXs[2] = df2, df3
-    eng.encoder_bwd(enc, dXs, G)
+    if on_segment is not None:
+        on_segment(0)       # every head gradient is enqueued
+    eng.encoder_bwd(enc, dXs, G, on_segment)
 
 
 def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
@@ -277,7 +337,7 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
     return (total, stats), saved
 
 
-def eng_backward_losses(eng: PVLTEngine, saved, gtotal, G):
+def eng_backward_losses(eng: PVLTEngine, saved, gtotal, G, on_segment=None):
     enc, hc, B, HW4 = saved["enc"], saved["hc"], saved["B"], saved["HW4"]
     T = eng.T
     dev = enc["ids"].device
@@ -301,7 +361,9 @@ def eng_backward_losses(eng: PVLTEngine, saved, gtotal, G):
         c = hc["t2i"]
         df2, df3 = eng.t2i.backward(c["dscore"], c, G, dX4, gscale=gs)
         dXs[1], dXs[2] = df2, df3
-    eng.encoder_bwd(enc, dXs, G)
+    if on_segment is not None:
+        on_segment(0)       # every head gradient is enqueued
+    eng.encoder_bwd(enc, dXs, G, on_segment)
 
 
 # ---- the model ---------------------------------------------------------------------------------------------

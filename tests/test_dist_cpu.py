@@ -104,3 +104,49 @@ def test_flat_gradient_allreduce_gloo_world2():
     for _, flat, v0 in res:
         assert flat == pytest.approx(want)
         assert v0 == [[0.0, 1.5], [3.0, 4.5]]
+
+
+def _segment_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mvlt_b200.libs.pvlt import SegmentReducer
+        flat = torch.arange(12, dtype=torch.float32) * (rank + 1)
+        red = SegmentReducer(flat, [(0, 4), (4, 4), (4, 9), (9, 9), (9, 12)], True)
+        red.segment_done(0)
+        after0 = flat.tolist()
+        red.segment_done(2)
+        red.segment_done(0)          # a repeated notification must not reduce the segment twice
+        red.finish()                 # reduces whatever was not announced (segment 4)
+        q.put((rank, after0, flat.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_segment_ordered_gradient_exchange_gloo_world2():
+    """The overlapped exchange of the training step: the flat gradient buffer is averaged segment by segment, in the order
+    the backward pass completes them; every element is reduced exactly once."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_segment_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, after0, final in res:
+        assert after0[:4] == pytest.approx([1.5 * i for i in range(4)])
+        assert after0[4:] == pytest.approx([float(i * (rank + 1)) for i in range(4, 12)])
+        assert final == pytest.approx([1.5 * i for i in range(12)])
+
+
+def test_gradient_layout_is_in_completion_order():
+    from mvlt_b200.engine import PVLTEngine
+    seg = PVLTEngine.grad_segment
+    assert seg("mlm_head.bias") == 0 and seg("t2i_head.conv4.0.weight") == 0 and seg("itm_head_embed.0.weight") == 0
+    assert seg("block4.1.mlp.fc1.weight") == 1 and seg("pos_embed4") == 1 and seg("patch_embed4.proj.weight") == 1
+    assert seg("block3.0.attn.sr.weight") == 2 and seg("text_embed2.0.weight") == 3 and seg("text_pos_embed1") == 4
+    assert seg("text_embeddings.word_embeddings.weight") == 4
