@@ -331,7 +331,7 @@ def instrumented_pass(run, nprof, hbm, tf_sus, peak_src):
         hbm_kernels = {"error": repr(ex)[:200]}
     allms = sum(tot.values())
     breakdown = {n: {"ms_per_step": round(tot[n] / nprof, 4), "launches_per_step": cnt[n] / nprof,
-                     "share": round(tot[n] / allms, 4)} for n in sorted(tot, key=lambda n: -tot[n])[:14]}
+                     "share": round(tot[n] / allms, 4)} for n in sorted(tot, key=lambda n: -tot[n])[:40]}
     gemm_ms = tot.get("gemm", 0.0)
     gemm_n = cnt.get("gemm", 0)
     # every launch against ITS OWN bound: max(algorithmic bytes / HBM peak, flops / tensor peak)

@@ -11,7 +11,8 @@ from pathlib import Path
 
 import torch
 
-_LIBPATH = Path(__file__).resolve().parent / "lib" / "libmvlt_b200.so"
+# MVLT_LIB: A/B runs of two in-tree builds of the SAME C-ABI (tuning aid; there is still no non-CUDA path)
+_LIBPATH = Path(os.environ.get("MVLT_LIB") or (Path(__file__).resolve().parent / "lib" / "libmvlt_b200.so"))
 _lib = None
 
 

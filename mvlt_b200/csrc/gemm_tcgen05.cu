@@ -590,12 +590,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // CTA-pair mode: the two CTAs of a cluster (ranks 0 = leader, 1) each stage their own 128 A rows and HALF of the B tile;
   // the leader issues tcgen05.mma.cta_group::2 (M = 256), each CTA's TMEM receives its 128 rows x block_n accumulator
   constexpr int pair = kPair ? 1 : 0;
-  const uint32_t cta_rank = pair ? cluster_ctarank() : 0u;
-  const int cid = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // cluster (or CTA) index in the persistent grid
-  const int ncl = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int mb_mul = pair ? 2 : 1;
-  const int b_rows = pair ? (p.block_n >> 1) : p.block_n;               // B rows (or MN-major columns) staged by this CTA
-  const int b_stage_bytes = b_rows * BLOCK_K * 2;
+  constexpr int mb_mul = kPair ? 2 : 1;
+  // cluster (or CTA) index / count of the persistent grid and this CTA's rank in its pair: re-materialised at every use
+  // (special registers / constant bank) instead of living in registers through the register-starved epilogue
+#define MVLT_CID (kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)
+#define MVLT_NCL (kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x)
+#define MVLT_RANK (kPair ? cluster_ctarank() : 0u)
+#define MVLT_BROWS (kPair ? (p.block_n >> 1) : p.block_n)   /* B rows (or MN-major columns) staged by this CTA */
+  const int b_stage_bytes = MVLT_BROWS * BLOCK_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
 
   uint8_t* ones_tile = smem + (size_t)p.stages * stage_bytes;   // 1024-byte aligned (stage sizes are multiples of 4 KB)
@@ -651,9 +653,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = cid; t < total_tiles; t += ncl) {
+        for (int t = MVLT_CID; t < total_tiles; t += MVLT_NCL) {
           const TileCoord tc = decode_tile(p, t);
-          const int m0 = (tc.m_blk * mb_mul + (int)cta_rank) * BLOCK_M, n0 = tc.n_blk * p.block_n;
+          const int m0 = (tc.m_blk * mb_mul + (int)MVLT_RANK) * BLOCK_M, n0 = tc.n_blk * p.block_n;
           const int kb0 = tc.split * p.kb_per_split;
           const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
           for (int kb = kb0; kb < kb1; ++kb) {
@@ -664,7 +666,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (kPair) {
               // both CTAs' bytes complete on the LEADER's full barrier, which the leader arms for the two halves
               const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0u);
-              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)stage_bytes);
+              if (MVLT_RANK == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)stage_bytes);
               if (!p.a_mn) {
                 tma_load_4d_2sm(sa, &tmA, lbar, k0, m0, tc.b2 * p.a_b2, tc.b1 * p.a_b1);
               } else {
@@ -672,11 +674,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int j = 0; j < BLOCK_M / 64; ++j)
                   tma_load_4d_2sm(sa + j * 8192, &tmA, lbar, m0 + j * 64, k0, tc.b2 * p.a_b2, tc.b1 * p.a_b1);
               }
-              const int nb0 = n0 + (int)cta_rank * b_rows;     // this CTA's half of the B tile
+              const int nb0 = n0 + (int)MVLT_RANK * MVLT_BROWS;     // this CTA's half of the B tile
               if (!p.b_mn) {
                 tma_load_4d_2sm(sb, &tmB, lbar, k0, nb0, tc.b2 * p.b_b2, tc.b1 * p.b_b1);
               } else {
-                for (int j = 0; j < b_rows / 64; ++j)
+                for (int j = 0; j < MVLT_BROWS / 64; ++j)
                   tma_load_4d_2sm(sb + j * 8192, &tmB, lbar, nb0 + j * 64, k0, tc.b2 * p.b_b2, tc.b1 * p.b_b1);
               }
               if (++stage == p.stages) {
@@ -730,7 +732,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      if (lane == 0 && cta_rank == 0) {     // (pair mode: the leader CTA issues for both)
+      if (lane == 0 && MVLT_RANK == 0) {     // (pair mode: the leader CTA issues for both)
         const uint32_t idesc = make_instr_desc(p.block_n, p.a_mn, p.b_mn, BLOCK_M * mb_mul);
         const uint32_t idesc_ones = make_instr_desc(ONES_N, p.a_mn, 0);
         const uint64_t ones_desc = make_smem_desc(smem_u32(ones_tile), 0u, 0u);   // SBO = 0: rows 8..15 re-read rows 0..7
@@ -741,7 +743,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         int local = 0;
-        for (int t = cid; t < total_tiles; t += ncl, ++local) {
+        for (int t = MVLT_CID; t < total_tiles; t += MVLT_NCL, ++local) {
           const TileCoord tc = decode_tile(p, t);
           const int kb0 = tc.split * p.kb_per_split;
           const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
@@ -812,18 +814,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const TileCoord tc = decode_tile(p, tt);
           cb1 = tc.b1;
           cb2 = tc.b2;
-          r = (tc.m_blk * mb_mul + (int)cta_rank) * BLOCK_M + quarter * 32;
+          r = (tc.m_blk * mb_mul + (int)MVLT_RANK) * BLOCK_M + quarter * 32;
           v = min(32, p.M - r);
           o = (long long)tc.b1 * p.sD1 + (long long)tc.b2 * p.sD2 + (long long)r * p.ldd;
           c = tc.n_blk * p.block_n + half * 64;
         };
-        int t = cid + group * ncl;
+        int t = MVLT_CID + group * MVLT_NCL;
         if (t < total_tiles) {
           coords(t, rbo, rv, c0, rb, tb1, tb2);
           prefetch_rows_async(se, reinterpret_cast<const uint8_t*>(p.aux + rbo + c0), ld_bytes, lane, rv);
         }
-        for (int local = group; t < total_tiles; t += 2 * ncl, local += 2) {
-          const int tn = t + 2 * ncl;
+        for (int local = group; t < total_tiles; t += 2 * MVLT_NCL, local += 2) {
+          const int tn = t + 2 * MVLT_NCL;
           if (tn < total_tiles) coords(tn, rbo_n, rv_n, c0_n, rb_n, tb1_n, tb2_n);
           float rs = 1.f;
           if (p.rowscale != nullptr && lane < rv) rs = p.rowscale[(rb + lane) / p.rows_per_scale];
@@ -856,10 +858,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     uint32_t tempty_leader = 0u;   // the leader's MMA thread owns the accumulators of both CTAs
     if constexpr (kPair) tempty_leader = mapa_shared(smem_u32(&tempty_bar[0]), 0u);
-    for (int local = group, t = cid + group * ncl; !total_tiles_done && t < total_tiles; t += 2 * ncl, local += 2) {
+    for (int local = group, t = MVLT_CID + group * MVLT_NCL; !total_tiles_done && t < total_tiles; t += 2 * MVLT_NCL, local += 2) {
       const TileCoord tc = decode_tile(p, t);
       const int n0 = tc.n_blk * p.block_n;
-      const int row_base = (tc.m_blk * mb_mul + (int)cta_rank) * BLOCK_M + quarter * 32;
+      const int row_base = (tc.m_blk * mb_mul + (int)MVLT_RANK) * BLOCK_M + quarter * 32;
       const int rows_valid = min(32, p.M - row_base);          // <= 0 when the whole warp is past the M tail
       const long long batch_off = (long long)tc.b1 * p.sD1 + (long long)tc.b2 * p.sD2;
       const long long row_base_off = batch_off + (long long)row_base * p.ldd;
@@ -986,6 +988,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
+#undef MVLT_CID
+#undef MVLT_NCL
+#undef MVLT_RANK
+#undef MVLT_BROWS
 
 // ---------------------------------------------------------------------------------------------
 // Host side: tensor-map cache + launch

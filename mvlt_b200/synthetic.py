@@ -43,7 +43,7 @@ def make_batch(batch: int, seed: int = 0, T: int = 128, img: int = 256, pin: boo
 # fit with the fp32 reference restatement). The fitted score is monotone in brightness with gaps of several logits per
 # 0.1 of brightness, so the rank of the positive (engine_grid_masking.py:360-384) is a well-conditioned quantity that the
 # bf16 kernels and the fp32 reference must agree on exactly: the positive sits at brightness 0.55, ``n_brighter`` decoys
-# are brighter (>= 0.72, they outrank it), the remaining candidates are darker (<= 0.38).
+# are brighter (>= 0.76, they outrank it), the remaining candidates are darker (<= 0.34).
 # ------------------------------------------------------------------------------------------------------------
 def brightness_images(levels: torch.Tensor, g: torch.Generator, img: int = 256, noise: float = 0.3):
     n = levels.shape[0]
@@ -63,8 +63,8 @@ def planted_tir_query(q: int, n_cand: int = 101):
     g = torch.Generator().manual_seed(8086 + 977 * q)
     n_brighter = q % 11
     n_dark = n_cand - 1 - n_brighter
-    levels = torch.cat([torch.tensor([0.55]), 0.72 + 0.18 * torch.rand(n_brighter, generator=g),
-                        0.10 + 0.28 * torch.rand(n_dark, generator=g)])
+    levels = torch.cat([torch.tensor([0.55]), 0.76 + 0.16 * torch.rand(n_brighter, generator=g),
+                        0.10 + 0.24 * torch.rand(n_dark, generator=g)])
     perm = torch.cat([torch.zeros(1, dtype=torch.long), 1 + torch.randperm(n_cand - 1, generator=g)])
     images = brightness_images(levels[perm], g)
     ids = make_batch(1, seed=1000 + q)["ori_input_ids"].repeat(n_cand, 1)
