@@ -641,6 +641,242 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
+
+// =====================================================================================================================
+// Backward of the fused MLP for C = 128 (PVLT stage 2). Same structure as mlp_bwd_kernel, re-proportioned so that the
+// accumulators fit TMEM and two tile slots fit shared memory: a CTA owns HB2 = 64 hidden units, and the weight-gradient
+// accumulators are kept TRANSPOSED (rows = the 128 input channels = TMEM lanes, columns = the 64 hidden units):
+//     H, dH [128 x 64]      as before (K = C = 128: 8 k-steps)
+//     dW1^T [128 c x 64 hid] += X^T dh'       (A = X tile read MN-major, B = dh' tile read MN-major)
+//     dW2   [128 c x 64 hid] += dY^T act      (the [C, HD] layout of fc2.weight's gradient directly)
+//     db1   (every row)      += 1^T dh'       (A = a tile of ones)
+// =====================================================================================================================
+constexpr int HB2 = 64;
+constexpr int B2_OFF_W1 = 0;                          // [64 hid x 128 c] K-major: 2 atoms of [64 rows x 128 B]
+constexpr int B2_OFF_W2 = ATOM;                       // [128 c x 64 hid]: MN-major B operand of dH
+constexpr int B2_OFF_T = 2 * ATOM;                    // 2 x { X (2 atoms) | dY (2 atoms) }
+constexpr int B2_OFF_ACT = B2_OFF_T + 8 * ATOM;       // [128 rows x 64 hid]
+constexpr int B2_OFF_DH = B2_OFF_ACT + ATOM;
+constexpr int B2_OFF_ONES = B2_OFF_DH + ATOM;
+constexpr int B2_OFF_BAR = B2_OFF_ONES + 1024;
+constexpr int B2_SMEM = B2_OFF_BAR + 128;
+constexpr int C2_H = 0, C2_DH = 64, C2_DW1 = 128, C2_DW2 = 192, C2_DB = 256;
+static_assert(B2_SMEM + 1024 <= 232448, "shared memory plan (C = 128 backward)");
+
+__global__ void __launch_bounds__(BW_THREADS, 1)
+mlp_bwd128_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                  const __grid_constant__ CUtensorMap tmDH, const __grid_constant__ MlpBwdParams p) {
+  constexpr int C = 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_OFF_BAR);
+  uint64_t* t_full = bars;            // [2]
+  uint64_t* t_empty = bars + 2;       // [2]
+  uint64_t* hd_full = bars + 4;
+  uint64_t* hd_empty = bars + 5;
+  uint64_t* a_full = bars + 6;
+  uint64_t* a_empty = bars + 7;
+  uint64_t* st_empty = bars + 8;
+  uint64_t* w_full = bars + 9;
+  uint64_t* done = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 1);
+    }
+    mbar_init(hd_full, 1);
+    mbar_init(hd_empty, NUM_GELU_WARPS);
+    mbar_init(a_full, NUM_GELU_WARPS);
+    mbar_init(a_empty, 1);
+    mbar_init(st_empty, 1);
+    mbar_init(w_full, 1);
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmDH);
+  }
+  if (threadIdx.x < 256) reinterpret_cast<uint32_t*>(smem + B2_OFF_ONES)[threadIdx.x] = 0x3F803F80u;   // bf16 1.0
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int jb = (int)blockIdx.x % p.nb, rg = (int)blockIdx.x / p.nb;
+  int n_tiles = 0;
+  if (rg < p.num_tiles) n_tiles = (p.num_tiles - 1 - rg) / p.nr + 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, 2u * ATOM);
+      tma_load_4d(smem + B2_OFF_W1, &tmW1, w_full, 0, jb * HB2, 0, 0);
+      tma_load_4d(smem + B2_OFF_W1 + 8192, &tmW1, w_full, 64, jb * HB2, 0, 0);
+      tma_load_4d(smem + B2_OFF_W2, &tmW2, w_full, jb * HB2, 0, 0, 0);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int slot = i & 1, m0 = (rg + i * p.nr) * BM;
+        uint8_t* t = smem + B2_OFF_T + slot * 4 * ATOM;
+        mbar_wait(&t_empty[slot], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&t_full[slot], 4u * ATOM);
+        tma_load_4d(t, &tmX, &t_full[slot], 0, m0, 0, 0);
+        tma_load_4d(t + ATOM, &tmX, &t_full[slot], 64, m0, 0, 0);
+        tma_load_4d(t + 2 * ATOM, &tmDY, &t_full[slot], 0, m0, 0, 0);
+        tma_load_4d(t + 3 * ATOM, &tmDY, &t_full[slot], 64, m0, 0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_kk = instr_desc_mn(HB2, 0, 0), id_kn = instr_desc_mn(HB2, 0, 1), id_mm = instr_desc_mn(HB2, 1, 1);
+      const uint32_t sW1 = smem_u32(smem + B2_OFF_W1), sW2 = smem_u32(smem + B2_OFF_W2), sT = smem_u32(smem + B2_OFF_T),
+                     sAct = smem_u32(smem + B2_OFF_ACT), sDh = smem_u32(smem + B2_OFF_DH);
+      const uint64_t ones_desc = smem_desc(smem_u32(smem + B2_OFF_ONES), 0u);   // LBO = SBO = 0: every atom aliases 1 KB of ones
+      mbar_wait(w_full, 0);
+      auto issue_hd = [&](int i) {
+        const int slot = i & 1;
+        const uint32_t xa = sT + (uint32_t)(slot * 4 * ATOM), dya = xa + 2u * ATOM;
+        mbar_wait(&t_full[slot], ((uint32_t)i >> 1) & 1u);
+        mbar_wait(hd_empty, ((uint32_t)i & 1u) ^ 1u);     // the GELU warps have read tile i - 1's H / dH
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k)    // H = X W1_blk^T: both K-major, K = 128 over two atoms
+          umma_bf16(tmem_base + C2_H, smem_desc(xa + (uint32_t)((k >> 2) * ATOM + (k & 3) * 32), 1024u),
+                    smem_desc(sW1 + (uint32_t)((k >> 2) * 8192 + (k & 3) * 32), 1024u), id_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k)    // dH = dY W2[:, blk]: B = 128 rows (c) x 64 hidden columns, MN-major
+          umma_bf16(tmem_base + C2_DH, smem_desc(dya + (uint32_t)((k >> 2) * ATOM + (k & 3) * 32), 1024u),
+                    smem_desc_mn(sW2 + (uint32_t)(k * 2048), 8192u), id_kn, k > 0 ? 1u : 0u);
+        umma_commit(hd_full);
+      };
+      if (n_tiles > 0) issue_hd(0);
+      for (int i = 0; i < n_tiles; ++i) {
+        if (i + 1 < n_tiles) issue_hd(i + 1);
+        const int slot = i & 1;
+        const uint32_t xa = sT + (uint32_t)(slot * 4 * ATOM), dya = xa + 2u * ATOM;
+        mbar_wait(a_full, (uint32_t)i & 1u);
+        tc_fence_after();
+        const uint32_t acc0 = i > 0 ? 1u : 0u;
+#pragma unroll
+        for (int kq = 0; kq < BM / 16; ++kq) {   // K = the tile's 128 rows; A tiles read MN-major (M = the 128 channels)
+          const uint32_t acc = acc0 | (kq > 0 ? 1u : 0u);
+          const uint64_t bdh = smem_desc_mn(sDh + (uint32_t)(kq * 2048), 8192u);
+          umma_bf16(tmem_base + C2_DW1, smem_desc_mn(xa + (uint32_t)(kq * 2048), (uint32_t)ATOM), bdh, id_mm, acc);
+          umma_bf16(tmem_base + C2_DW2, smem_desc_mn(dya + (uint32_t)(kq * 2048), (uint32_t)ATOM),
+                    smem_desc_mn(sAct + (uint32_t)(kq * 2048), 8192u), id_mm, acc);
+          umma_bf16(tmem_base + C2_DB, ones_desc, bdh, id_mm, acc);
+        }
+        umma_commit(a_empty);
+        umma_commit(&t_empty[slot]);
+      }
+      umma_commit(done);
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      for (int i = 0; i < n_tiles; ++i) {
+        const int m0 = (rg + i * p.nr) * BM;
+        mbar_wait(a_full, (uint32_t)i & 1u);
+        tma_store_4d(&tmDH, smem_u32(smem + B2_OFF_DH), jb * HB2, m0, 0, 0);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(st_empty);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else if (warp >= GELU_WARP0) {
+    const int quarter = warp & 3, cq = (warp - GELU_WARP0) >> 2;
+    const uint32_t tlane = ((uint32_t)(quarter * 32) << 16);
+    const uint32_t row = (uint32_t)(quarter * 32 + lane), rx = row & 7u;
+    const uint32_t act_row = smem_u32(smem + B2_OFF_ACT) + row * 128u, dh_row = smem_u32(smem + B2_OFF_DH) + row * 128u;
+    const float4* bp = reinterpret_cast<const float4*>(p.b1 + jb * HB2 + cq * 16);
+    float4 bv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bv[q] = __ldg(bp + q);      // the block's bias slice never changes: loaded once
+    for (int i = 0; i < n_tiles; ++i) {
+      const uint32_t ph = (uint32_t)i & 1u;
+      mbar_wait(hd_full, ph);
+      tc_fence_after();
+      uint32_t rh[16], rd[16];
+      tmem_ld_32x16(tmem_base + tlane + (uint32_t)(C2_H + cq * 16), rh);
+      tmem_ld_32x16(tmem_base + tlane + (uint32_t)(C2_DH + cq * 16), rd);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(hd_empty);
+      uint32_t apk[8], dpk[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        f32x2_t g0, d0, g1, d1;
+        gelu_and_grad2(f2_add(f2_pack(__uint_as_float(rh[4 * q]), __uint_as_float(rh[4 * q + 1])), f2_pack(bv[q].x, bv[q].y)), g0, d0);
+        gelu_and_grad2(f2_add(f2_pack(__uint_as_float(rh[4 * q + 2]), __uint_as_float(rh[4 * q + 3])), f2_pack(bv[q].z, bv[q].w)), g1, d1);
+        d0 = f2_mul(d0, f2_pack(__uint_as_float(rd[4 * q]), __uint_as_float(rd[4 * q + 1])));
+        d1 = f2_mul(d1, f2_pack(__uint_as_float(rd[4 * q + 2]), __uint_as_float(rd[4 * q + 3])));
+        float a, b;
+        f2_unpack(g0, a, b);
+        apk[2 * q] = pack_bf16x2(a, b);
+        f2_unpack(g1, a, b);
+        apk[2 * q + 1] = pack_bf16x2(a, b);
+        f2_unpack(d0, a, b);
+        dpk[2 * q] = pack_bf16x2(a, b);
+        f2_unpack(d1, a, b);
+        dpk[2 * q + 1] = pack_bf16x2(a, b);
+      }
+      mbar_wait(a_empty, ph ^ 1u);      // the previous tile's dW MMAs and dh' store have finished reading the operand tiles
+      mbar_wait(st_empty, ph ^ 1u);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t off = ((((uint32_t)(cq * 2 + q)) ^ rx) << 4);
+        st_shared_v4(act_row + off, apk[4 * q], apk[4 * q + 1], apk[4 * q + 2], apk[4 * q + 3]);
+        st_shared_v4(dh_row + off, dpk[4 * q], dpk[4 * q + 1], dpk[4 * q + 2], dpk[4 * q + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+    }
+    // ---- flush: lane = input channel c, columns = the block's hidden units
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (n_tiles > 0) {
+      const int c = quarter * 32 + lane, h0 = jb * HB2 + cq * 16;
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + tlane + (uint32_t)(C2_DW1 + cq * 16), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(p.dW1 + (long long)(h0 + j) * C + c, __uint_as_float(r[j]));   // dW1[hid, c]
+      tmem_ld_32x16(tmem_base + tlane + (uint32_t)(C2_DW2 + cq * 16), r);
+      tmem_ld_wait();
+      float* g2 = p.dW2 + (long long)c * p.HD + h0;                                                        // dW2[c, hid]
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g2 + 4 * q), "f"(__uint_as_float(r[4 * q])),
+                     "f"(__uint_as_float(r[4 * q + 1])), "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3]))
+                     : "memory");
+      if (quarter == 0) {     // every row of the db accumulator holds the same column sums: row 0 writes them
+        tmem_ld_32x16(tmem_base + tlane + (uint32_t)(C2_DB + cq * 16), r);
+        tmem_ld_wait();
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(p.db1 + h0 + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 }  // namespace
 
 // out[M, C] (fp32) = residual[M, C] (fp32) + rowscale[row / rows_per_scale] * (GELU(x W1^T + b1) W2^T + b2)
@@ -666,22 +902,24 @@ extern "C" int mvlt_mlp_fwd(const void* x_bf16, const void* w1_bf16, const float
 }
 
 
-// Backward of mvlt_mlp_fwd's branch for C = 64 (see mlp_bwd_kernel): given x_bf16 [M, 64] (the forward's input), dy_bf16
-// [M, 64] (gradient of the branch output, DropPath factor already applied), w1_bf16 [HD, 64], b1, w2_bf16 [64, HD]:
+// Backward of mvlt_mlp_fwd's branch (see mlp_bwd_kernel / mlp_bwd128_kernel): given x_bf16 [M, C] (the forward's input), dy_bf16
+// [M, C] (gradient of the branch output, DropPath factor already applied), w1_bf16 [HD, C], b1, w2_bf16 [C, HD], C in {64, 128}:
 //   dh_bf16 [M, HD]  = (dy W2) * gelu'(x W1^T + b1)            (written; feeds dX = dh W1 and nothing else)
-//   dW1 [HD, 64] += dh^T x,  dW2 [64, HD] += dy^T gelu(x W1^T + b1),  db1 [HD] += column sums of dh    (fp32, accumulated)
+//   dW1 [HD, C] += dh^T x,  dW2 [C, HD] += dy^T gelu(x W1^T + b1),  db1 [HD] += column sums of dh    (fp32, accumulated)
 // HD must be a multiple of 128. All pointers 16-byte aligned, tensors contiguous.
 extern "C" int mvlt_mlp_bwd(const void* x_bf16, const void* dy_bf16, const void* w1_bf16, const float* b1, const void* w2_bf16,
                             void* dh_bf16, float* dW1_f32, float* dW2_f32, float* db1_f32, int M, int C, int HD, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MVLT_CHECK_ARG(x_bf16 && dy_bf16 && w1_bf16 && b1 && w2_bf16 && dh_bf16 && dW1_f32 && dW2_f32 && db1_f32, "mlp_bwd: null operand");
-  MVLT_CHECK_ARG(M > 0 && C == 64 && HD >= HB && HD % HB == 0, "mlp_bwd: unsupported shape M=%d C=%d HD=%d (C = 64, HD %% 128 == 0)", M, C, HD);
+  MVLT_CHECK_ARG(M > 0 && (C == 64 || C == 128) && HD >= HB && HD % HB == 0,
+                 "mlp_bwd: unsupported shape M=%d C=%d HD=%d (C in {64, 128}, HD %% 128 == 0)", M, C, HD);
   MVLT_CHECK_ARG(((((uintptr_t)x_bf16) | ((uintptr_t)dy_bf16) | ((uintptr_t)w1_bf16) | ((uintptr_t)w2_bf16) | ((uintptr_t)dh_bf16) |
-                   ((uintptr_t)dW1_f32) | ((uintptr_t)b1)) & 15) == 0, "mlp_bwd: operands must be 16-byte aligned");
+                   ((uintptr_t)dW1_f32) | ((uintptr_t)dW2_f32) | ((uintptr_t)b1)) & 15) == 0, "mlp_bwd: operands must be 16-byte aligned");
+  const int hb = C == 64 ? HB : HB2;      // hidden units per CTA
   MlpBwdParams p;
   p.M = M; p.HD = HD;
   p.num_tiles = (M + BM - 1) / BM;
-  p.nb = HD / HB;
+  p.nb = HD / hb;
   p.nr = mvlt_num_sms() / p.nb;
   if (p.nr < 1) p.nr = 1;
   if (p.nr > p.num_tiles) p.nr = p.num_tiles;
@@ -689,22 +927,22 @@ extern "C" int mvlt_mlp_bwd(const void* x_bf16, const void* dy_bf16, const void*
   CUtensorMap tmX, tmDY, tmW1, tmW2, tmDH;
   int rc;
   {
-    const uint64_t dims[4] = {64, (uint64_t)M, 1, 1};
-    const uint64_t str[3] = {128, (uint64_t)M * 128, (uint64_t)M * 128};
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)M, 1, 1};
+    const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)M * C * 2, (uint64_t)M * C * 2};
     const uint32_t box[4] = {64, BM, 1, 1};
     if ((rc = mvlt_tensor_map_4d(&tmX, x_bf16, dims, str, box, 0, 0)) != 0) return rc;
     if ((rc = mvlt_tensor_map_4d(&tmDY, dy_bf16, dims, str, box, 0, 0)) != 0) return rc;
   }
   {
-    const uint64_t dims[4] = {64, (uint64_t)HD, 1, 1};
-    const uint64_t str[3] = {128, (uint64_t)HD * 128, (uint64_t)HD * 128};
-    const uint32_t box[4] = {64, HB, 1, 1};
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)HD, 1, 1};
+    const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)HD * C * 2, (uint64_t)HD * C * 2};
+    const uint32_t box[4] = {64, (uint32_t)hb, 1, 1};
     if ((rc = mvlt_tensor_map_4d(&tmW1, w1_bf16, dims, str, box, 0, 0)) != 0) return rc;
   }
   {
-    const uint64_t dims[4] = {(uint64_t)HD, 64, 1, 1};
-    const uint64_t str[3] = {(uint64_t)HD * 2, (uint64_t)HD * 128, (uint64_t)HD * 128};
-    const uint32_t box[4] = {64, 64, 1, 1};
+    const uint64_t dims[4] = {(uint64_t)HD, (uint64_t)C, 1, 1};
+    const uint64_t str[3] = {(uint64_t)HD * 2, (uint64_t)HD * C * 2, (uint64_t)HD * C * 2};
+    const uint32_t box[4] = {64, (uint32_t)C, 1, 1};
     if ((rc = mvlt_tensor_map_4d(&tmW2, w2_bf16, dims, str, box, 0, 0)) != 0) return rc;
   }
   {
@@ -714,8 +952,12 @@ extern "C" int mvlt_mlp_bwd(const void* x_bf16, const void* dy_bf16, const void*
     if ((rc = mvlt_tensor_map_4d(&tmDH, dh_bf16, dims, str, box, 0, 0)) != 0) return rc;
   }
   static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM + 1024); });
-  mvlt_launch(mlp_bwd_kernel, p.nb * p.nr, BW_THREADS, (size_t)BW_SMEM + 1024, stream, tmX, tmDY, tmW1, tmW2, tmDH, p);
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM + 1024);
+    cudaFuncSetAttribute(mlp_bwd128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM + 1024);
+  });
+  if (C == 64) mvlt_launch(mlp_bwd_kernel, p.nb * p.nr, BW_THREADS, (size_t)BW_SMEM + 1024, stream, tmX, tmDY, tmW1, tmW2, tmDH, p);
+  else mvlt_launch(mlp_bwd128_kernel, p.nb * p.nr, BW_THREADS, (size_t)B2_SMEM + 1024, stream, tmX, tmDY, tmW1, tmW2, tmDH, p);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

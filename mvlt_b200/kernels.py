@@ -289,7 +289,7 @@ def sr_attention_bwd(q, kv, do, p, dq, dkv, B, N, Nk, heads, scale):
 
 
 MLP_FUSED_DIMS = (64, 128)      # embedding widths the fused MLP forward supports (PVLT stages 1 and 2)
-MLP_FUSED_BWD_DIMS = (64,)        # ... and the widths whose recompute backward exists (training uses the fused path only there)
+MLP_FUSED_BWD_DIMS = (64, 128)        # ... and the widths whose recompute backward exists (training uses the fused path only there)
 
 
 def mlp_fwd(x, w1, b1, w2, b2, residual, out, rowscale=None, rows_per_scale=0):
@@ -312,7 +312,7 @@ def mlp_fwd(x, w1, b1, w2, b2, residual, out, rowscale=None, rows_per_scale=0):
 
 
 def mlp_bwd(x, dy, w1, b1, w2, dh, dw1, dw2, db1):
-    """Backward of the fused MLP branch for C = 64 (csrc/mlp_tcgen05.cu): recomputes fc1 from ``x``; writes dh [M, HD] bf16 (=
+    """Backward of the fused MLP branch, C in {64, 128} (csrc/mlp_tcgen05.cu): recomputes fc1 from ``x``; writes dh [M, HD] bf16 (=
     (dy w2) * gelu'(x w1^T + b1)) and ACCUMULATES dw1 [HD, C], dw2 [C, HD], db1 [HD] (fp32). dX = dh @ w1 is a GEMM of its own."""
     require_cuda(x, dy, w1, w2, dh, dw1, dw2, db1, b1)
     M, C_ = x.shape

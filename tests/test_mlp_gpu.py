@@ -54,12 +54,12 @@ def test_fused_mlp_forward_matches_fp32_reference(M, C, HD, droppath):
     assert torch.equal(res2, out)
 
 
-@pytest.mark.parametrize("M,HD", [(128 * 5, 512), (128 * 3 + 17, 512), (4224 * 4, 512), (64, 128), (128 * 40 + 5, 1024)])
-def test_fused_mlp_backward_matches_fp32_autograd(M, HD):
+@pytest.mark.parametrize("M,C,HD", [(128 * 5, 64, 512), (128 * 3 + 17, 64, 512), (4224 * 4, 64, 512), (64, 64, 128), (128 * 40 + 5, 64, 1024),
+                                    (128 * 5, 128, 1024), (128 * 3 + 17, 128, 1024), (1152 * 8, 128, 1024), (64, 128, 128), (128 * 30 + 5, 128, 512)])
+def test_fused_mlp_backward_matches_fp32_autograd(M, C, HD):
     """dh', dW1, dW2, db1 of the recompute backward vs fp32 autograd of the same branch (bf16-rounded operands); the
     accumulators must ADD to what the gradient buffers already hold."""
     from mvlt_b200 import kernels as k
-    C = 64
     x, w1, b1, w2, b2, _ = _inputs(M, C, HD, seed=7 + M)
     g = torch.Generator(device="cuda").manual_seed(99)
     dy = torch.randn((M, C), generator=g, device="cuda").to(BF16)
