@@ -498,24 +498,24 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                      sAct = smem_u32(smem + BW_OFF_ACT), sDh = smem_u32(smem + BW_OFF_DH);
       const uint64_t ones_desc = smem_desc(smem_u32(smem + BW_OFF_ONES), 0u);   // SBO = 0: every 8-row group re-reads the same rows
       mbar_wait(w_full, 0);
+      const uint32_t id_kk128 = instr_desc_mn(HB, 0, 0), id_kn128 = instr_desc_mn(HB, 0, 1);
       auto issue_hd = [&](int i) {
         const int slot = i & 1;
         const uint32_t xa = sT + (uint32_t)(slot * 2 * ATOM), dya = xa + (uint32_t)ATOM;
         mbar_wait(&t_full[slot], ((uint32_t)i >> 1) & 1u);
+        mbar_wait(&hd_empty[0], ((uint32_t)i & 1u) ^ 1u);     // the GELU warps have read tile i - 1's H / dH
+        tc_fence_after();
+        // both 64-column halves in ONE N = 128 instruction per k-step (a 128 x 64 x 16 UMMA costs about as much as a
+        // 128 x 128 x 16 one: 40 -> 32 instructions per tile)
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          mbar_wait(&hd_empty[s], ((uint32_t)i & 1u) ^ 1u);     // the GELU warps have read tile i - 1's H_s / dH_s
-          tc_fence_after();
+        for (int k = 0; k < 4; ++k)    // H = X W1_blk^T: both K-major, B = the block's 128 hidden rows
+          umma_bf16(tmem_base + (uint32_t)COL_H, smem_desc(xa + (uint32_t)(k * 32), 1024u), smem_desc(sW1 + (uint32_t)(k * 32), 1024u),
+                    id_kk128, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)    // H_s = X W1_s^T: both K-major
-            umma_bf16(tmem_base + (uint32_t)(COL_H + s * 64), smem_desc(xa + (uint32_t)(k * 32), 1024u),
-                      smem_desc(sW1 + (uint32_t)(s * 8192 + k * 32), 1024u), id_kk, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)    // dH_s = dY W2[:, s]: B = W2 rows (c) x 64 hidden columns, MN-major
-            umma_bf16(tmem_base + (uint32_t)(COL_DH + s * 64), smem_desc(dya + (uint32_t)(k * 32), 1024u),
-                      smem_desc_mn(sW2 + (uint32_t)(s * 8192 + k * 2048), 8192u), id_kn, k > 0 ? 1u : 0u);
-          umma_commit(&hd_full[s]);
-        }
+        for (int k = 0; k < 4; ++k)    // dH = dY W2[:, blk]: B = W2 rows (c) x 128 hidden columns, MN-major (two 64-wide atoms)
+          umma_bf16(tmem_base + (uint32_t)COL_DH, smem_desc(dya + (uint32_t)(k * 32), 1024u),
+                    smem_desc_mn(sW2 + (uint32_t)(k * 2048), 8192u), id_kn128, k > 0 ? 1u : 0u);
+        umma_commit(&hd_full[0]);
       };
       if (n_tiles > 0) issue_hd(0);
       for (int i = 0; i < n_tiles; ++i) {
@@ -565,15 +565,19 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         float4 bv[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) bv[q] = __ldg(bp + q);
-        mbar_wait(&hd_full[s], ph);
-        tc_fence_after();
+        if (s == 0) {
+          mbar_wait(&hd_full[0], ph);
+          tc_fence_after();
+        }
         uint32_t rh[16], rd[16];
         tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_H + s * 64 + cq * 16), rh);
         tmem_ld_32x16(tmem_base + tlane + (uint32_t)(COL_DH + s * 64 + cq * 16), rd);
         tmem_ld_wait();
-        tc_fence_before();       // this warp's TMEM reads precede the MMAs of the next tile into H_s / dH_s
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&hd_empty[s]);
+        if (s == 1) {
+          tc_fence_before();     // this warp's TMEM reads precede the MMAs of the next tile into H / dH
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&hd_empty[0]);
+        }
         uint32_t apk[8], dpk[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

@@ -288,8 +288,11 @@ def sr_attention_bwd(q, kv, do, p, dq, dkv, B, N, Nk, heads, scale):
          C.c_int(heads), C.c_float(scale))
 
 
-MLP_FUSED_DIMS = (64, 128)      # embedding widths the fused MLP forward supports (PVLT stages 1 and 2)
-MLP_FUSED_BWD_DIMS = (64, 128)        # ... and the widths whose recompute backward exists (training uses the fused path only there)
+MLP_FUSED_DIMS = (64, 128)      # embedding widths the fused MLP forward supports (PVLT stages 1 and 2): used at inference
+# ... and the widths whose recompute backward is used in TRAINING. Both backward kernels are validated (tests/test_mlp_gpu.py,
+# model parity with MVLT_FUSED_MLP_TRAIN=64,128), but at C = 128 the fused pair (172 + 347 us per block) is no faster than the
+# two-GEMM path it replaces (15.32 vs 15.25 ms per step, profiles/r2t_mlp_train_dims_ab.txt), so the default is stage 1 only.
+MLP_FUSED_BWD_DIMS = tuple(int(v) for v in __import__("os").environ.get("MVLT_FUSED_MLP_TRAIN", "64").split(",") if v)        # ... and the widths whose recompute backward exists (training uses the fused path only there)
 
 
 def mlp_fwd(x, w1, b1, w2, b2, residual, out, rowscale=None, rows_per_scale=0):

@@ -189,5 +189,10 @@ def test_validated_defaults_are_the_ones_shipped():
         assert E.FUSED_ATTENTION is True
     if "MVLT_FUSED_ATTN_BWD" not in os.environ:
         assert E.FUSED_ATTENTION_BWD is True
+    if "MVLT_FUSED_MLP" not in os.environ:
+        assert E.FUSED_MLP is True
+    if "MVLT_FUSED_MLP_TRAIN" not in os.environ:
+        from mvlt_b200 import kernels
+        assert kernels.MLP_FUSED_DIMS == (64, 128) and kernels.MLP_FUSED_BWD_DIMS == (64,)
     src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "mvlt_b200", "csrc", "common.cuh")).read()
     assert "#define MVLT_PDL_DEFAULT 1" in src
