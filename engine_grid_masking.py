@@ -112,7 +112,7 @@ def evaluate_vl(data_loader, model, device, args):
             itm_acc, sup_acc, sub_acc = s[8] / B, s[9] / B, s[10] / B
         if lt.get("t2i"):
             x = _masked(samples, images, device, step)
-            out = net(x, _dev(samples["ori_input_ids"], device))
+            out = net(x, _dev(samples["ori_input_ids"], device), heads=("t2i",))   # no [B, 128, 30522] MLM logits for a PSNR
             if out["t2i_logits"] is None:
                 raise Exception("t2i_logits is none, please check the settings!")
             psnr = compute_psnr(out["t2i_logits"], images)

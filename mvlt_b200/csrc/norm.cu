@@ -179,6 +179,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
     const TX* xr = x + (ok ? map_row(xm, r) : 0) * C;
     const float mu = ok ? mean[r] : 0.f, rs = ok ? rstd[r] : 0.f;
     float4 vdy[NV], vxh[NV];
+    // the residual-gradient operand and the drop-path factor are fetched together with dy / x (they are only needed after
+    // the two row reductions: loading them there exposed a second DRAM latency per row pass)
+    const long long drow = ok ? map_row(dxm, r) * C : 0;
+    float4 vadd[NV];
+    float dscale = 1.f;
+    if (ok && dx16 != nullptr && rowscale != nullptr) dscale = __ldg(rowscale + r / rows_per_scale);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 4 * G + sub * 4;
+      vadd[i] = (dx_add != nullptr && ok && i < nvec && c < C) ? *reinterpret_cast<const float4*>(dx_add + drow + c)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -212,25 +224,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
     s1 = group_sum<G>(s1) * inv_c;
     s2 = group_sum<G>(s2) * inv_c;
     if (!ok) continue;
-    const long long drow = map_row(dxm, r) * C;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = i * 4 * G + sub * 4;
       if (i < nvec && c < C) {
         float4 o;
-        o.x = rs * (vdy[i].x - s1 - vxh[i].x * s2);
-        o.y = rs * (vdy[i].y - s1 - vxh[i].y * s2);
-        o.z = rs * (vdy[i].z - s1 - vxh[i].z * s2);
-        o.w = rs * (vdy[i].w - s1 - vxh[i].w * s2);
-        if (dx_add) {
-          const float4 a = *reinterpret_cast<const float4*>(dx_add + drow + c);
-          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-        }
+        o.x = rs * (vdy[i].x - s1 - vxh[i].x * s2) + vadd[i].x;
+        o.y = rs * (vdy[i].y - s1 - vxh[i].y * s2) + vadd[i].y;
+        o.z = rs * (vdy[i].z - s1 - vxh[i].z * s2) + vadd[i].z;
+        o.w = rs * (vdy[i].w - s1 - vxh[i].w * s2) + vadd[i].w;
         store4<TDX>(dx + drow + c, o);
-        if (dx16 != nullptr) {   // bf16 copy (x drop-path scale) = the A operand of the next backward GEMMs
-          const float sc = rowscale ? rowscale[r / rows_per_scale] : 1.f;
-          store4<__nv_bfloat16>(dx16 + drow + c, make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc));
-        }
+        if (dx16 != nullptr)     // bf16 copy (x drop-path scale) = the A operand of the next backward GEMMs
+          store4<__nv_bfloat16>(dx16 + drow + c, make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale));
       }
     }
   }
@@ -391,8 +396,9 @@ extern "C" int mvlt_layernorm_bwd(const void* dy, int dy_f32, const int* dymap, 
   // tuning knobs (tools/ln_sweep.py): row passes per warp that amortise the dgamma / dbeta reductions, blocks per SM
   static const int min_passes = [] { const char* e = getenv("MVLT_LN_BWD_PASSES"); return e ? atoi(e) : 4; }();
   static const int bps_env = [] { const char* e = getenv("MVLT_LN_BWD_BPS"); return e ? atoi(e) : 0; }();
-  // resident 256-thread blocks per SM of the variant that will run (registers: 40-47 / 64 / 68-72 / 92-96 per thread)
-  const int blocks_per_sm = bps_env > 0 ? bps_env : (C <= 128 ? 6 : (C <= 384 ? 4 : (C <= 512 ? 3 : 2)));
+  // 256-thread blocks per SM (registers: 47-48 / 71-78 / 90-94 / 122 per thread with the prefetched residual operand).
+  // Measured with tools/ln_sweep.py (profiles/r2u_ln_bwd_sweep.txt): 4 / 3 / 2 is best for C <= 128 / <= 384 / wider.
+  const int blocks_per_sm = bps_env > 0 ? bps_env : (C <= 128 ? 4 : (C <= 384 ? 3 : 2));
   static const int vec_red_on = [] { const char* e = getenv("MVLT_LN_BWD_VEC"); return e ? atoi(e) : 1; }();
   long long b = ((long long)rows + wpb * rpw * min_passes - 1) / (wpb * rpw * min_passes);
   const long long cap = (long long)mvlt_num_sms() * blocks_per_sm;

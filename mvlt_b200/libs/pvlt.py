@@ -89,13 +89,13 @@ class _PVLTFunction(torch.autograd.Function):
     def forward(ctx, model, mode, batch, images, input_ids, *params):
         eng: PVLTEngine = model._engine()
         training = model.training
-        mode, grad_mode = mode
+        mode, grad_mode, heads = mode
         need_grad = grad_mode and any(p.requires_grad for p in params)   # (grad mode is always off inside forward)
         eng.embed_dropout = model.text_embeddings.dropout.p
         eng.prepare_weights()
         images = images.contiguous().to(F32)
         if mode == "logits":
-            outs, saved = eng_forward_logits(eng, images, input_ids, training, need_grad)
+            outs, saved = eng_forward_logits(eng, images, input_ids, training, need_grad, heads)
         else:
             outs, saved = eng_forward_losses(eng, images, input_ids, batch, training, need_grad)
         ctx.model, ctx.mode, ctx.saved = model, mode, saved
@@ -206,13 +206,17 @@ def _heads_common_fwd(eng, enc, B):
     return X4, HW4
 
 
-def eng_forward_logits(eng: PVLTEngine, images, ids, training, save):
-    """pvlt.py:358-401: returns the five logits tensors (None for disabled heads)."""
+def eng_forward_logits(eng: PVLTEngine, images, ids, training, save, heads=None):
+    """pvlt.py:358-401: returns the five logits tensors (None for disabled heads). ``heads``: optional subset of
+    {"mlm", "itm", "cls", "t2i"} to evaluate (the others come back as None, e.g. no [B, 128, 30522] logits for a caller
+    that only wants the reconstruction)."""
     B = images.shape[0]
     T = eng.T
     enc = eng.encoder_fwd(images, ids, training, save)
     X4, HW4 = _heads_common_fwd(eng, enc, B)
     lt = eng.loss_type
+    if heads is not None:
+        lt = {key: (v if key in heads else 0) for key, v in lt.items()}
     hc = {}
     mlm = itm = sup = sub = t2i = None
     if lt.get("mlm"):
@@ -509,18 +513,22 @@ class PyramidVisionLanguageTransformer(nn.Module):
 
     # -- public API
     def forward(self, input_images, input_ids, **fused):
-        """Returns the reference's logits dict (pvlt.py:358-401); disabled heads map to None.
+        """Returns the reference's logits dict (pvlt.py:358-401); disabled heads map to None. ``heads=("t2i",)`` (an
+        extension) evaluates only the named heads: the others map to None and cost nothing.
 
         With label keyword arguments (``mlm_labels=..., itm_labels=..., target_images=...``) it takes the fused
         loss path instead (see ``forward_losses``) -- routed through ``forward`` so that DistributedDataParallel's
         forward hook arms its gradient reducer for it as well."""
+        heads = fused.pop("heads", None)
         if fused:
             return self.forward_losses(input_images, input_ids, **fused)
         self._engine()
         params = self._params_list()[1]
-        mlm, itm, sup, sub, t2i = _PVLTFunction.apply(self, ("logits", torch.is_grad_enabled()), None, input_images,
-                                                            input_ids, *params)
+        mlm, itm, sup, sub, t2i = _PVLTFunction.apply(self, ("logits", torch.is_grad_enabled(), None if heads is None else tuple(heads)),
+                                                      None, input_images, input_ids, *params)
         lt = self.loss_type
+        if heads is not None:
+            lt = {key: (v if key in heads else 0) for key, v in lt.items()}
         return dict(mlm_logits=mlm if lt['mlm'] else None, itm_logits=itm if lt['itm'] else None,
                     sup_cls_logits=sup if lt['cls'] else None, sub_cls_logits=sub if lt['cls'] else None,
                     t2i_logits=t2i if lt['t2i'] else None)
@@ -548,7 +556,7 @@ class PyramidVisionLanguageTransformer(nn.Module):
         batch = dict(mlm_labels=mlm_labels, itm_labels=itm_labels, sup_cls_labels=sup_cls_labels,
                      sub_cls_labels=sub_cls_labels, target_images=target_images, weights=weights or {},
                      mlm_count=mlm_count, only=only)
-        return _PVLTFunction.apply(self, ("losses", torch.is_grad_enabled()), batch, input_images, input_ids, *params)
+        return _PVLTFunction.apply(self, ("losses", torch.is_grad_enabled(), None), batch, input_images, input_ids, *params)
 
 
 def _cfg(**kwargs):

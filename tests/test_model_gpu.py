@@ -231,3 +231,17 @@ def test_stand_alone_gelu_module_matches_torch():
     assert (y - yr).abs().max().item() <= 2e-6 and (x.grad - xr.grad).abs().max().item() <= 2e-6
     xb = x.detach().to(torch.bfloat16)
     assert (GELU()(xb).float() - torch.nn.functional.gelu(xb.float())).abs().max().item() <= 2e-2
+
+
+def test_dict_forward_head_selection():
+    """``model(images, ids, heads=(...))``: only the named heads are evaluated (evaluate_vl's PSNR pass must not materialise
+    the [B, 128, 30522] MLM logits); the selected outputs are bit-identical to the full call."""
+    from oracle import pvlt_oracle as O
+    m, _ = _model(PRE)
+    m.eval()
+    b = O.make_inputs(2, seed=8)
+    with torch.no_grad():
+        full = m(b["images"].cuda(), b["input_ids"].cuda())
+        part = m(b["images"].cuda(), b["input_ids"].cuda(), heads=("t2i", "itm"))
+    assert part["mlm_logits"] is None and part["sup_cls_logits"] is None
+    assert torch.equal(part["t2i_logits"], full["t2i_logits"]) and torch.equal(part["itm_logits"], full["itm_logits"])
