@@ -4,7 +4,8 @@
 // Default backward of the attention core (engine.py:_block_bwd; MVLT_FUSED_ATTN_BWD=0 selects the four-GEMM path for A/B
 // runs). Validated against fp32 autograd in tests/test_attention_gpu.py and through the model parity tests.
 //
-// One CTA (128 threads, 1 per SM: it owns all 512 TMEM columns) walks the (batch, head) strips assigned to it. For a
+// One CTA (256 threads = 8 warps, 1 per SM: it owns all 512 TMEM columns) walks the (batch, head) strips assigned to it; a
+// query row is shared by two threads (key-column halves), which halves the latency of the per-row softmax backward. For a
 // strip, K and V ([Nk x 64] each) stay in shared memory and dK / dV accumulate in TMEM across the strip's 128-row query
 // tiles; per tile (operands double-buffered, the next tile's TMA loads run under the current tile):
 //
@@ -37,10 +38,11 @@ constexpr int P_BYTES = 3 * TILE;            // 3 atoms of 64 keys
 constexpr int OFF_K = 0, OFF_V = KV_BYTES, OFF_T = 2 * KV_BYTES;
 constexpr int T_DO = 0, T_Q = TILE, T_P = 2 * TILE, T_BYTES = 2 * TILE + P_BYTES;   // 80 KB per tile slot
 constexpr int OFF_BAR = OFF_T + 2 * T_BYTES;
-constexpr int SMEM_USED = OFF_BAR + 128;
+constexpr int OFF_XCH = OFF_BAR + 128;        // [2][128] floats: partial row dot products exchanged between the column halves
+constexpr int SMEM_USED = OFF_XCH + 1024;
 constexpr int TMEM_COLS = 512;
 constexpr int COL_DV = 192, COL_DK = 320;   // two 64-column blocks each
-constexpr int THREADS = 128;
+constexpr int THREADS = 256;   // 8 warps: (TMEM lane quarter) x (key-column half); thread 0 also issues TMA and tcgen05.mma
 
 struct BwdParams {
   int B, heads, N, Nk, C;
@@ -103,7 +105,10 @@ sr_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's TMEM lane quarter; lane = row
+  const int quarter = warp & 3, half = warp >> 2;   // TMEM lane quarter this warp may access (warp id % 4), key-column half
+  const int row = quarter * 32 + (tid & 31);        // query row (TMEM lane) of this thread; two threads share a row
+  const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
   pdl_wait();
 
   const uint32_t sK_s = smem_u32(smem + OFF_K), sV_s = smem_u32(smem + OFF_V), sT_s = smem_u32(smem + OFF_T);
@@ -114,7 +119,8 @@ sr_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t idesc_dp = instr_desc(Nk, 0, 0);   // dP = dO V^T
   const uint32_t idesc_dq = instr_desc(HD, 0, 1);   // dQ = dS K
   const uint32_t idesc_kv = instr_desc(HD, 1, 1);   // dV += P^T dO, dK += dS^T Q
-  const uint32_t row_s = (uint32_t)tid * 128u, row_x = (uint32_t)(tid & 7);
+  const uint32_t row_s = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
+  const int nc_half = nchunk16 >> 1, c_lo = half * nc_half, c_hi = c_lo + nc_half;   // this thread's 16-column chunks
   const float scale = p.scale;
 
   uint32_t it = 0;        // tiles processed by this CTA (barrier phases)
@@ -173,9 +179,10 @@ sr_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       mbar_wait(s_bar, ph);
       tc_fence_after();
 
-      // ---- softmax backward for row `tid`: pass 1 = delta, pass 2 = dS in place over P
+      // ---- softmax backward for row `row`: pass 1 = delta (each column half its partial, exchanged through shared memory),
+      // pass 2 = dS in place over P
       float delta = 0.f;
-      for (int i = 0; i < nchunk16; ++i) {
+      for (int i = c_lo; i < c_hi; ++i) {
         uint32_t r[16];
         tmem_ld_32x16(taddr + (uint32_t)(i * 16), r);
         const uint32_t base = sP_s + (uint32_t)(i >> 2) * (uint32_t)TILE + row_s;
@@ -190,8 +197,11 @@ sr_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           delta = fmaf(f.y, __uint_as_float(r[2 * j + 1]), delta);
         }
       }
+      xch[half * BM + row] = delta;
+      __syncthreads();
+      delta += xch[(half ^ 1) * BM + row];
       mbar_wait(c_bar, ph);      // the tensor core has finished reading P (dV): it may be overwritten
-      for (int i = 0; i < nchunk16; ++i) {
+      for (int i = c_lo; i < c_hi; ++i) {
         uint32_t r[16];
         tmem_ld_32x16(taddr + (uint32_t)(i * 16), r);
         const uint32_t base = sP_s + (uint32_t)(i >> 2) * (uint32_t)TILE + row_s;
@@ -234,7 +244,8 @@ sr_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
       // ---- dQ epilogue: 64 fp32 columns -> bf16 -> swizzled tile in the dO buffer (MMA-A / MMA-C have retired)
 #pragma unroll
-      for (int i = 0; i < HD / 16; ++i) {
+      for (int ii = 0; ii < HD / 32; ++ii) {
+        const int i = half * (HD / 32) + ii;
         uint32_t r[16];
         tmem_ld_32x16(taddr + (uint32_t)(i * 16), r);
         tmem_ld_wait();
@@ -267,7 +278,8 @@ sr_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const uint32_t col = (uint32_t)((t < 2 ? COL_DK : COL_DV) + 64 * (t & 1));
       const uint32_t stage = sT_s + (uint32_t)(t < 3 ? (T_P + t * TILE) : (T_BYTES + T_P));
 #pragma unroll
-      for (int i = 0; i < HD / 16; ++i) {
+      for (int ii = 0; ii < HD / 32; ++ii) {
+        const int i = half * (HD / 32) + ii;
         uint32_t r[16];
         tmem_ld_32x16(taddr + col + (uint32_t)(i * 16), r);
         tmem_ld_wait();
