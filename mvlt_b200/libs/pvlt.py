@@ -117,7 +117,7 @@ class _PVLTFunction(torch.autograd.Function):
         # (averaged) over NVLink on a side stream as soon as the hand-scheduled backward has finished it -- the exchange of
         # everything but the last segment overlaps the remaining backward kernels (DDP's overlap at main_vl.py:297-299)
         reducer = SegmentReducer(G["__flat__"], G["__segments__"], sync) if sync is not None else None
-        on_seg = reducer.segment_done if reducer is not None else None
+        on_seg = reducer.segment_done if (reducer is not None and GRAD_SYNC_OVERLAP) else None
         if ctx.mode == "logits":
             eng_backward_logits(eng, saved, gouts, G, on_seg)
         else:
@@ -143,6 +143,10 @@ def allreduce_flat_(flat, group=None):
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp)
         flat.div_(world)
     return flat
+
+
+# MVLT_GRAD_OVERLAP=0: exchange all segments after the last backward kernel (A/B switch; same result)
+GRAD_SYNC_OVERLAP = __import__("os").environ.get("MVLT_GRAD_OVERLAP", "1") != "0"
 
 
 class SegmentReducer:
