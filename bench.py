@@ -340,6 +340,8 @@ def instrumented_pass(run, nprof, hbm, tf_sus, peak_src):
     hbm_bound_ms = sum(a.elapsed_time(e) for (a, e), (f, b, _) in zip(gev, glog) if b / (hbm * 1e9) >= f / (tf_sus * 1e12))
     tensor_rows = [(a.elapsed_time(e), f) for (a, e), (f, b, _) in zip(gev, glog) if b / (hbm * 1e9) < f / (tf_sus * 1e12)]
     t_ms, t_fl = sum(r[0] for r in tensor_rows), sum(r[1] for r in tensor_rows)
+    hbm_rows = [(a.elapsed_time(e), b) for (a, e), (f, b, _) in zip(gev, glog) if b / (hbm * 1e9) >= f / (tf_sus * 1e12)]
+    h_ms, h_by = sum(r[0] for r in hbm_rows), sum(r[1] for r in hbm_rows)
     ach_gbs = nbytes / (gemm_ms / 1e3) / 1e9 if gemm_ms > 0 else 0.0
     ach_tf = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
@@ -360,6 +362,9 @@ def instrumented_pass(run, nprof, hbm, tf_sus, peak_src):
             "tensor_bound_launches": {"ms_per_step": round(t_ms / nprof, 3), "launches_per_step": len(tensor_rows) / nprof,
                                       "achieved_tflops": round(t_fl / (t_ms / 1e3) / 1e12, 1) if t_ms > 0 else None,
                                       "frac_of_sustained_peak": round(t_fl / (t_ms / 1e3) / 1e12 / tf_sus, 4) if t_ms > 0 else None},
+            "hbm_bound_launches": {"ms_per_step": round(h_ms / nprof, 3), "launches_per_step": len(hbm_rows) / nprof,
+                                   "achieved_gbs": round(h_by / (h_ms / 1e3) / 1e9, 1) if h_ms > 0 else None,
+                                   "frac_of_hbm_peak": round(h_by / (h_ms / 1e3) / 1e9 / hbm, 4) if h_ms > 0 else None},
             "frac_of_own_roofline": round(ideal_ms / gemm_ms, 4) if gemm_ms else None,
             "flops_per_step": flops / nprof, "bytes_per_step": nbytes / nprof, "gemm_ms_per_step": round(gemm_ms / nprof, 3),
             "gemm_share_of_step": round(gemm_ms / allms, 4) if allms else None}

@@ -107,3 +107,28 @@ def test_token_mask_oracle_matches_reference_golden():
     assert n_random > 10                                  # the random.choice branch is exercised by the fixture
     lab = g["labels"]
     assert (lab[:, 0] == -1).all() and ((lab == -1) | (lab == g["ori"])).all()
+
+
+def test_oracle_equals_live_reference_when_staged():
+    """With baseline/_ref staged (tools/stage_reference.py; the build container and every gpurun snapshot have it) the
+    unmodified reference model itself is run next to the oracle: same weights, same batch -> same losses and logits."""
+    import contextlib
+    import io
+    import pytest
+    import torch
+    from baseline import ref_loader
+    from oracle import pvlt_oracle as O
+    if not ref_loader.available():
+        pytest.skip("baseline/_ref not staged")
+    lt = {"itm": 1, "mlm": 1, "t2i": 1, "cls": 0}
+    sd = O.make_state_dict("pvlt_tiny", lt, seed=1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ref_loader.build_model("pvlt_tiny", lt, state_dict=sd).eval()
+    b = O.make_inputs(2, seed=5)
+    with torch.no_grad():
+        ref = m(b["images"], b["input_ids"])
+        got = O.forward(sd, b["images"], b["input_ids"], lt, training=False)
+    for key in ("mlm_logits", "itm_logits", "t2i_logits"):
+        err = float((ref[key] - got[key]).abs().max() / (ref[key].abs().max() + 1e-12))
+        assert err <= 2e-5, (key, err)
+    assert ref["sup_cls_logits"] is None and got["sup_cls_logits"] is None
