@@ -179,19 +179,45 @@ def train_line(args, model_name, workload, K, Wm, rank, world, local, dev, detai
     devb = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in h.items()} for h in host]
     seeds = torch.tensor([masking.sample_seed(rank, i) for i in range(B)], dtype=torch.int64, device=dev)
 
-    def step(i, b, fwd=None):
+    # CUDA-graph mode (default; --no-graph keeps the per-launch path): the whole iteration -- forward, losses, backward, the
+    # gradient exchange and AdamW -- is captured once per static input buffer set and replayed (mvlt_b200/graph.py). The MLM
+    # head then runs on a FIXED row capacity (the labelled count + 10 % headroom, rounded up to the 128-row GEMM tile; padded
+    # rows carry the ignore label), and the grid masking of odd steps stays outside the graph (two launches).
+    gstep = None
+    use_graph = args.graph and not args.ddp
+    if use_graph:
+        from mvlt_b200.graph import GraphedStep
+        cap = None
+        if heads["mlm"]:
+            cap = -(-int(max(h["mlm_count"] for h in host) * 1.1) // 128) * 128
+        gstep = GraphedStep(model, opt, mlm_capacity=cap, warmup=1, enabled=False)
+    xm_bufs = {}
+
+    def step(i, b, fwd=None, tag="dev"):
         fwd = fwd or net
         img = b["images"]
-        if i % 2 == 1 and heads["t2i"]:   # engine_grid_masking.py:72-78: odd steps feed the grid-masked image
+        odd = i % 2 == 1 and bool(heads["t2i"])
+        if odd:   # engine_grid_masking.py:72-78: odd steps feed the grid-masked image
             grid = masking.grid_mask_batch(seeds + i * B, (img.shape[3], img.shape[2]), 0.5, 16, device=dev)
-            x = masking.apply_grid_mask(img, grid, 16)
+            if gstep is not None:       # static masked-image buffer per input buffer set
+                xm = xm_bufs.get(img.data_ptr())
+                if xm is None:
+                    xm = xm_bufs[img.data_ptr()] = torch.empty_like(img)
+                x = masking.apply_grid_mask(img, grid, 16, out=xm)
+            else:
+                x = masking.apply_grid_mask(img, grid, 16)
         else:
             x = img
         if heads["cls"]:
-            total, stats = fwd(x, b["input_ids"], sup_cls_labels=b["sup_cls_labels"], sub_cls_labels=b["sub_cls_labels"])
+            labels = dict(sup_cls_labels=b["sup_cls_labels"], sub_cls_labels=b["sub_cls_labels"])
         else:
-            total, stats = fwd(x, b["input_ids"], mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=img,
-                               mlm_count=b["mlm_count"])
+            labels = dict(mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=img)
+        if gstep is not None:
+            total, stats = gstep(x, b["input_ids"], key=(img.data_ptr(), odd), **labels)
+            return total
+        if heads["mlm"]:
+            labels["mlm_count"] = b["mlm_count"]
+        total, stats = fwd(x, b["input_ids"], **labels)
         total.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
@@ -269,6 +295,10 @@ def train_line(args, model_name, workload, K, Wm, rank, world, local, dev, detai
 
     for i in range(max(Wm, 3)):
         step(i, devb[i % 2])
+    if gstep is not None:        # capture (one graph per (buffer set, masked?) pair), then two replays of each
+        gstep.enabled = True
+        for i in range(6):
+            step(i, devb[i % 2])
     sampler = ClockSampler(local)
     if rank == 0 and detail:
         sampler.start()
@@ -278,7 +308,7 @@ def train_line(args, model_name, workload, K, Wm, rank, world, local, dev, detai
     clocks = sampler.stop() if (rank == 0 and detail) else None
     value = B * world * K / (ms / 1e3)
 
-    run_e2e(2)
+    run_e2e(6 if gstep is not None else 2)      # graph mode: eager warm-up, capture and one replay per staging buffer set
     ms_e2e = timed(run_e2e, K, whole_loop=True)
     e2e_value = B * world * K / (ms_e2e / 1e3)
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in E2E_KEYS)
@@ -291,9 +321,15 @@ def train_line(args, model_name, workload, K, Wm, rank, world, local, dev, detai
         "clocks": clocks,
         "model_tflops": round(value * gf_per_sample / 1e3, 2) if gf_per_sample else None,
         "model_flops_frac_of_bf16_peak": round(value * gf_per_sample / 1e3 / tf_sus, 4) if gf_per_sample else None,
+        "cuda_graph": None if gstep is None else {
+            "graphs": len(gstep._graphs), "kernels_per_replay": max(g["launches"] for g in gstep._graphs.values()) if gstep._graphs else 0,
+            "mlm_row_capacity": gstep.state.mlm_cap, "mlm_rows_labelled": [h["mlm_count"] for h in host] if heads["mlm"] else None,
+            "mlm_capacity_overflow": gstep.check_overflow()},
     }
     if not detail:
         model.enable_grad_sync(None)
+        if gstep is not None:
+            gstep.detach()
         return res
 
     # host-side cost of enqueueing one step (Python + ctypes + allocator), measured from an idle GPU without synchronising:
@@ -306,6 +342,9 @@ def train_line(args, model_name, workload, K, Wm, rank, world, local, dev, detai
 
     # ---- per-kernel breakdown (instrumented pass, NOT the reported value) -> roofline of the dominant kernel
     model.enable_grad_sync(None)      # the instrumented pass below runs on rank 0 alone: no collectives from here on
+    if gstep is not None:
+        gstep.enabled = False         # the instrumented pass times every launch: same kernels, launched one by one
+        gstep._graphs = {}
     if rank == 0:
         res.update(instrumented_pass(lambda i: step(i, devb[i % 2], fwd=model), 2, hbm, tf_sus, peak_src))
     return res
@@ -485,7 +524,8 @@ def run_ours(args):
                                     "bf16 weight copies in the same launch)",
                        "mlm_rows": "MLM head evaluated on labelled rows only (identical loss/gradients)",
                        "fused_attention": bool(__import__("mvlt_b200.engine", fromlist=["x"]).FUSED_ATTENTION),
-                       "fused_attention_bwd": bool(__import__("mvlt_b200.engine", fromlist=["x"]).FUSED_ATTENTION_BWD)},
+                       "fused_attention_bwd": bool(__import__("mvlt_b200.engine", fromlist=["x"]).FUSED_ATTENTION_BWD),
+                       "cuda_graph": main_res.get("cuda_graph")},
             "e2e": main_res["e2e"],
             "gpu_launches": main_res["launches"], "host_enqueue_ms_per_step": main_res.get("host_enqueue_ms_per_step"),
             "clocks": main_res["clocks"],
@@ -641,6 +681,8 @@ def main():
                     help="default pvlt_tiny = BASELINE configs[1]; pvlt_small = the configs[4] stand-in (SURVEY H9)")
     ap.add_argument("--workload", default="pretrain", choices=["pretrain", "recognition"],
                     help="pretrain = MLM+ITM+t2i heads (configs[1]); recognition = cls-only fine-tune step (configs[3])")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch every kernel of the step individually instead of replaying the captured CUDA graph")
     ap.add_argument("--ddp", action="store_true", help="wrap the model in torch DistributedDataParallel instead of the flat-buffer all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -417,6 +417,26 @@ extern "C" int mvlt_memset_zero(void* p, long long bytes, void* stream_) {
   return 0;
 }
 
+// ---- small host -> device parameter block, passed BY VALUE in the kernel arguments ------------------------------------
+// Per-step scalars that kernels of a captured CUDA graph read from device memory (dropout / drop-path seeds, AdamW learning
+// rate and bias corrections) are refreshed by this one-thread launch ahead of the replay: the 64 bytes travel inside the
+// launch itself, so there is no pinned staging buffer whose lifetime the caller would have to manage.
+struct SetValuesBlock { unsigned int w[16]; };
+__global__ void set_values_kernel(unsigned int* __restrict__ dst, const SetValuesBlock v, int nwords) {
+  pdl_prologue();
+  if (threadIdx.x < nwords) dst[threadIdx.x] = v.w[threadIdx.x];
+}
+// dst: device pointer (4-byte aligned); src_host: nbytes (a multiple of 4, <= 64) of host memory, read before the call returns
+extern "C" int mvlt_set_values(void* dst, const void* src_host, int nbytes, void* stream_) {
+  MVLT_CHECK_ARG(dst && src_host && nbytes > 0 && nbytes <= 64 && nbytes % 4 == 0, "set_values: 4..64 bytes, a multiple of 4");
+  SetValuesBlock v;
+  memset(&v, 0, sizeof(v));
+  memcpy(v.w, src_host, (size_t)nbytes);
+  mvlt_launch(set_values_kernel, 1, 32, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<unsigned int*>(dst), v, nbytes / 4);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int mvlt_cast_scale_bf16(const float* src, void* dst, long long rows, int C, const float* rowscale,
                                     int rows_per_scale, float alpha, void* stream_) {
   MVLT_CHECK_ARG(C % 8 == 0, "cast_scale: C=%d must be a multiple of 8", C);

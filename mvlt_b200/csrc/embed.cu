@@ -25,8 +25,10 @@ __global__ void __launch_bounds__(256) bert_embed_fwd_kernel(const long long* __
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out,
                                                              float* __restrict__ rstd_out, int rows, int T, float eps,
-                                                             float p_drop, unsigned long long seed) {
+                                                             float p_drop, unsigned long long seed,
+                                                             const unsigned long long* __restrict__ seed_dev) {
   pdl_prologue();
+  if (seed_dev != nullptr) seed = *seed_dev;   // seed read from device memory: a captured CUDA graph draws new masks per replay
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -75,8 +77,10 @@ __global__ void __launch_bounds__(256) bert_embed_bwd_kernel(const __nv_bfloat16
                                                              float* __restrict__ dword, float* __restrict__ dpos,
                                                              float* __restrict__ dtype_, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, int rows, int T, float p_drop,
-                                                             unsigned long long seed, int pad_id) {
+                                                             unsigned long long seed, int pad_id,
+                                                             const unsigned long long* __restrict__ seed_dev) {
   pdl_prologue();
+  if (seed_dev != nullptr) seed = *seed_dev;
   __shared__ float shg[8][HID];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -146,8 +150,9 @@ __global__ void __launch_bounds__(256) bert_embed_bwd_kernel(const __nv_bfloat16
 // ---- stochastic-depth / dropout keep factors from the counter-based hash (common.cuh) ---------------------------------
 // out[r, b] = hash_uniform(seed, r * cols + b) >= rate[r] ? 1 / (1 - rate[r]) : 0   (rate_per_row == nullptr: `rate` for all)
 __global__ void keep_scale_kernel(float* __restrict__ out, int rows, int cols, const float* __restrict__ rate_per_row, float rate,
-                                  unsigned long long seed) {
+                                  unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
   pdl_prologue();
+  if (seed_dev != nullptr) seed = *seed_dev;
   const long long n = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float r = rate_per_row ? rate_per_row[i / cols] : rate;
@@ -161,26 +166,29 @@ __global__ void keep_scale_kernel(float* __restrict__ out, int rows, int cols, c
 // one step in ONE launch: out fp32 [rows, cols] (rows = 2 * #blocks, cols = batch), rate_per_row fp32 [rows] on the device.
 // With rate_per_row == nullptr it writes the element-wise dropout factors bert_embed_fwd applies for (seed, rate) to a
 // [rows, cols = 768] activation (transformers BertEmbeddings.dropout) -- lets tests rebuild the mask a step drew.
+// seed_dev (optional, all three entry points of this file): when non-null the seed is READ FROM DEVICE MEMORY at execution time
+// and `seed` is ignored, so that a captured CUDA graph draws fresh masks on every replay.
 extern "C" int mvlt_keep_scale(float* out, int rows, int cols, const float* rate_per_row, float rate, unsigned long long seed,
-                               void* stream_) {
+                               const unsigned long long* seed_dev, void* stream_) {
   MVLT_CHECK_ARG(out && rows > 0 && cols > 0 && rate >= 0.f && rate < 1.f, "keep_scale: bad arguments");
   const long long n = (long long)rows * cols;
   int grid = (int)((n + 255) / 256);
   const int cap = mvlt_num_sms() * 8;
   if (grid > cap) grid = cap;
-  mvlt_launch(keep_scale_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_), out, rows, cols, rate_per_row, rate, seed);
+  mvlt_launch(keep_scale_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_), out, rows, cols, rate_per_row, rate, seed, seed_dev);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int mvlt_bert_embed_fwd(const long long* ids, const float* word, const float* pos, const float* type,
                                    const float* gamma, const float* beta, void* out_bf16, float* mean, float* rstd,
-                                   int rows, int T, float eps, float p_drop, unsigned long long seed, void* stream_) {
+                                   int rows, int T, float eps, float p_drop, unsigned long long seed,
+                                   const unsigned long long* seed_dev, void* stream_) {
   MVLT_CHECK_ARG(rows > 0 && T > 0 && T <= 512, "bert_embed_fwd: bad rows/T");
   int grid = (rows + 7) / 8;
   const int cap = mvlt_num_sms() * 8;
   if (grid > cap) grid = cap;
-  mvlt_launch(bert_embed_fwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_), ids, word, pos, type, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), mean, rstd, rows, T, eps, p_drop, seed);
+  mvlt_launch(bert_embed_fwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_), ids, word, pos, type, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), mean, rstd, rows, T, eps, p_drop, seed, seed_dev);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -188,14 +196,14 @@ extern "C" int mvlt_bert_embed_fwd(const long long* ids, const float* word, cons
 extern "C" int mvlt_bert_embed_bwd(const void* dy_bf16, const long long* ids, const float* word, const float* pos,
                                    const float* type, const float* gamma, const float* mean, const float* rstd,
                                    float* dword, float* dpos, float* dtype_, float* dgamma, float* dbeta, int rows, int T,
-                                   float p_drop, unsigned long long seed, int pad_id, void* stream_) {
+                                   float p_drop, unsigned long long seed, int pad_id, const unsigned long long* seed_dev, void* stream_) {
   MVLT_CHECK_ARG(rows > 0 && T > 0, "bert_embed_bwd: bad rows/T");
   int grid = (rows + 31) / 32;
   const int cap = mvlt_num_sms() * 2;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   mvlt_launch(bert_embed_bwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(dy_bf16), ids, word, pos, type, gamma, mean, rstd, dword, dpos, dtype_,
-      dgamma, dbeta, rows, T, p_drop, seed, pad_id);
+      dgamma, dbeta, rows, T, p_drop, seed, pad_id, seed_dev);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -12,7 +12,8 @@ namespace {
 // ---- deterministic compaction of labelled positions: idx[k] = k-th i with labels[i] != ignore -----------------
 __global__ void __launch_bounds__(1024) compact_labels_kernel(const long long* __restrict__ labels, int n, long long ignore,
                                                               int* __restrict__ idx, long long* __restrict__ lab_out,
-                                                              int* __restrict__ count) {
+                                                              int* __restrict__ count, int cap, float* __restrict__ count_f32,
+                                                              float* __restrict__ inv_count, float* __restrict__ overflow) {
   pdl_prologue();
   __shared__ int warp_tot[32];
   __shared__ int base;
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(1024) compact_labels_kernel(const long long* _
     __syncthreads();
     int off = base;
     for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    if (flag) {
+    if (flag && (cap <= 0 || off + within < cap)) {
       idx[off + within] = i;
       if (lab_out) lab_out[off + within] = lab;
     }
@@ -41,7 +42,19 @@ __global__ void __launch_bounds__(1024) compact_labels_kernel(const long long* _
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *count = base;
+  // fixed-capacity mode (cap > 0): the consumers run on exactly `cap` rows whatever the count is (static shapes: CUDA graphs,
+  // no device->host read of the count): the tail is padded with row 0 / the ignore label, which contributes nothing
+  const int cnt = base;
+  for (int k = cnt + (int)threadIdx.x; k < cap; k += blockDim.x) {
+    idx[k] = 0;
+    if (lab_out) lab_out[k] = ignore;
+  }
+  if (threadIdx.x == 0) {
+    *count = cnt;
+    if (count_f32) *count_f32 = (float)cnt;
+    if (inv_count) *inv_count = 1.0f / (float)(cnt > 0 ? cnt : 1);
+    if (overflow && cap > 0 && cnt > cap) *overflow = (float)cnt;   // more labelled rows than the capacity: the caller must check
+  }
 }
 
 struct RowMap3 { int group, stride, offset; };
@@ -109,8 +122,10 @@ template <typename T>
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                                                      int n_cls, long long ignore, float* __restrict__ lse_out,
                                                      float* __restrict__ loss_sum, float* __restrict__ total_sum, float scale,
-                                                     int* __restrict__ argmax_out, float* __restrict__ correct) {
+                                                     int* __restrict__ argmax_out, float* __restrict__ correct,
+                                                     const float* __restrict__ scale_dev) {
   pdl_prologue();
+  if (scale_dev != nullptr) scale *= *scale_dev;   // e.g. 1 / (#labelled rows) computed on the device by compact_labels
   __shared__ float sh[32];
   __shared__ int shi[32];
   const int r = blockIdx.x;
@@ -190,8 +205,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                                                      int n_cls, long long ignore, const float* __restrict__ lse,
                                                      T* __restrict__ dlogits, long long ldd, float scale,
-                                                     const float* __restrict__ gscale) {
+                                                     const float* __restrict__ gscale, const float* __restrict__ scale_dev) {
   pdl_prologue();
+  if (scale_dev != nullptr) scale *= *scale_dev;
   const int r = blockIdx.x;
   const long long lab = labels[r];
   const float g = scale * (gscale ? *gscale : 1.f);
@@ -322,11 +338,15 @@ inline int cap_grid(long long work_items, int threads, int per_sm = 8) {
 
 }  // namespace
 
+// cap > 0: fixed-capacity mode: idx_out / labels_out hold `cap` entries, the tail beyond the count is padded (row 0, ignore label);
+// count_f32_out / inv_count_out / overflow_out (optional device floats) receive the count, 1 / max(count, 1) and -- only when the
+// count exceeds the capacity -- the count (left untouched otherwise).
 extern "C" int mvlt_compact_labels(const long long* labels, int n, long long ignore, int* idx_out, long long* labels_out,
-                                   int* count_out, void* stream_) {
-  MVLT_CHECK_ARG(n > 0, "compact_labels: n must be positive");
+                                   int* count_out, int cap, float* count_f32_out, float* inv_count_out, float* overflow_out,
+                                   void* stream_) {
+  MVLT_CHECK_ARG(n > 0 && cap >= 0, "compact_labels: n must be positive");
   mvlt_launch(compact_labels_kernel, 1, 1024, 0, reinterpret_cast<cudaStream_t>(stream_), labels, n, ignore, idx_out, labels_out,
-                                                                                 count_out);
+                                                                                 count_out, cap, count_f32_out, inv_count_out, overflow_out);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -359,31 +379,31 @@ extern "C" int mvlt_scatter_rows(const void* src, int src_f32, const int* idx, i
 
 extern "C" int mvlt_ce_fwd(const void* logits, int logits_f32, long long ld, const long long* labels, int rows, int n_cls,
                            long long ignore, float* lse, float* loss_sum, float* total_sum, float scale, int* argmax_out,
-                           float* correct, void* stream_) {
+                           float* correct, const float* scale_dev, void* stream_) {
   MVLT_CHECK_ARG(rows > 0 && n_cls > 0, "ce_fwd: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (logits_f32)
     mvlt_launch(ce_fwd_kernel<float>, rows, 256, 0, st, reinterpret_cast<const float*>(logits), ld, labels, n_cls, ignore, lse,
-                                               loss_sum, total_sum, scale, argmax_out, correct);
+                                               loss_sum, total_sum, scale, argmax_out, correct, scale_dev);
   else
     mvlt_launch(ce_fwd_kernel<__nv_bfloat16>, rows, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(logits), ld, labels, n_cls,
-                                                       ignore, lse, loss_sum, total_sum, scale, argmax_out, correct);
+                                                       ignore, lse, loss_sum, total_sum, scale, argmax_out, correct, scale_dev);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int mvlt_ce_bwd(const void* logits, int logits_f32, long long ld, const long long* labels, int rows, int n_cls,
                            long long ignore, const float* lse, void* dlogits, long long ldd, float scale,
-                           const float* gscale_dev, void* stream_) {
+                           const float* gscale_dev, const float* scale_dev, void* stream_) {
   MVLT_CHECK_ARG(rows > 0 && n_cls > 0, "ce_bwd: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (logits_f32)
     mvlt_launch(ce_bwd_kernel<float>, rows, 256, 0, st, reinterpret_cast<const float*>(logits), ld, labels, n_cls, ignore, lse,
-                                               reinterpret_cast<float*>(dlogits), ldd, scale, gscale_dev);
+                                               reinterpret_cast<float*>(dlogits), ldd, scale, gscale_dev, scale_dev);
   else
     mvlt_launch(ce_bwd_kernel<__nv_bfloat16>, rows, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(logits), ld, labels, n_cls,
                                                        ignore, lse, reinterpret_cast<__nv_bfloat16*>(dlogits), ldd, scale,
-                                                       gscale_dev);
+                                                       gscale_dev, scale_dev);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

@@ -50,8 +50,14 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
 
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __restrict__ tensors, const AdamChunk* __restrict__ chunks,
                                                           int chunk_elems, float lr, float b1, float b2, float eps, float wd,
-                                                          float bc1, float bc2, const float* __restrict__ grad_scale, int zero_grads) {
+                                                          float bc1, float bc2, const float* __restrict__ grad_scale, int zero_grads,
+                                                          const float* __restrict__ hyper) {
   pdl_prologue();
+  if (hyper != nullptr) {   // {lr, bias_correction1, bias_correction2} read from device memory (CUDA-graph replays, schedulers)
+    lr = hyper[0];
+    bc1 = hyper[1];
+    bc2 = hyper[2];
+  }
   const AdamChunk ch = chunks[blockIdx.x];
   const AdamTensor t = tensors[ch.t];
   const long long n = min((long long)chunk_elems, t.n - ch.off);
@@ -99,14 +105,16 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __re
 
 }  // namespace
 
-// tensors: device array of AdamTensor; chunks: device array of n_chunks AdamChunk (one CTA each)
+// tensors: device array of AdamTensor; chunks: device array of n_chunks AdamChunk (one CTA each).
+// hyper_dev (optional): device float[3] = {lr, bias_correction1, bias_correction2} overriding the by-value arguments at
+// execution time (the values a captured CUDA graph must pick up on every replay)
 extern "C" int mvlt_adamw_multi(const void* tensors, const void* chunks, int n_chunks, int chunk_elems, float lr, float beta1,
                                 float beta2, float eps, float weight_decay, float bias_correction1, float bias_correction2,
-                                const float* grad_scale_dev, int zero_grads, void* stream_) {
+                                const float* grad_scale_dev, int zero_grads, const float* hyper_dev, void* stream_) {
   MVLT_CHECK_ARG(tensors && chunks && n_chunks > 0 && chunk_elems > 0, "adamw_multi: empty tables");
   MVLT_CHECK_ARG(bias_correction1 > 0.f && bias_correction2 > 0.f, "adamw_multi: bias corrections must be positive");
   mvlt_launch(adamw_multi_kernel, n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const AdamTensor*>(tensors), reinterpret_cast<const AdamChunk*>(chunks), chunk_elems, lr, beta1, beta2, eps,
-      weight_decay, bias_correction1, bias_correction2, grad_scale_dev, zero_grads);
+      weight_decay, bias_correction1, bias_correction2, grad_scale_dev, zero_grads, hyper_dev);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

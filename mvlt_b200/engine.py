@@ -75,6 +75,12 @@ class PVLTEngine:
         self._dp_rates = None
         self.last_rng = None
         self._grad_layout = None
+        # CUDA-graph support (mvlt_b200/graph.py): ``graph_state`` carries the device-resident per-step scalars a captured step
+        # reads instead of host values (dropout / drop-path seeds, fixed MLM row capacity and 1 / #labelled rows);
+        # ``static_grads`` keeps ONE persistent flat gradient buffer (same addresses every step) instead of a fresh allocation
+        self.graph_state = None
+        self.static_grads = False
+        self._static_flat = self._static_arena = None
         from . import t2i as _t2i
         self.t2i = _t2i.T2IHead(self) if loss_type.get("t2i") else None
 
@@ -128,6 +134,12 @@ class PVLTEngine:
         if self.t2i is not None:
             self.t2i.prepare_weights()
         self._w_version = ver
+
+    def prepare_static(self, dev):
+        """Device tables that depend on the configuration only (built once: no per-step host->device copy, and none inside a
+        stream capture)."""
+        if self._dp_rates is None or self._dp_rates.device != dev:
+            self._dp_rates = torch.tensor([r for r in self.dpr for _ in (0, 1)], device=dev, dtype=F32)
 
     def _next_seeds(self):
         """Seeds of this step's dropout / drop-path draws (counter-based hash, csrc/common.cuh). The stream is derived from
@@ -363,23 +375,28 @@ class PVLTEngine:
         ctx = {"B": B, "stages": [], "IH": IH, "IW": IW}
         # --- BERT embeddings (pvlt.py:326)
         p_drop = self.embed_dropout if training else 0.0
-        seed, dp_seed = self._next_seeds() if training else (0, 0)
+        gs = self.graph_state if training else None
+        if gs is not None:      # the seeds live in device memory, refreshed by GraphedStep ahead of every run / replay
+            seed, dp_seed, seed_dev, dp_seed_dev = 0, 0, gs.seeds[0:1], gs.seeds[1:2]
+        else:
+            seed, dp_seed = self._next_seeds() if training else (0, 0)
+            seed_dev = dp_seed_dev = None
         y768 = _empty((B * T, HIDDEN), BF16, dev)
         em, er = _empty((B * T,), F32, dev), _empty((B * T,), F32, dev)
         ids = ids.contiguous()
         k.bert_embed_fwd(ids, P["text_embeddings.word_embeddings.weight"], P["text_embeddings.position_embeddings.weight"],
                          P["text_embeddings.token_type_embeddings.weight"], P["text_embeddings.LayerNorm.weight"],
-                         P["text_embeddings.LayerNorm.bias"], y768, em, er, B * T, T, 1e-12, p_drop, seed)
-        ctx.update(ids=ids, em=em, er=er, p_drop=p_drop, seed=seed)
+                         P["text_embeddings.LayerNorm.bias"], y768, em, er, B * T, T, 1e-12, p_drop, seed, seed_dev=seed_dev)
+        ctx.update(ids=ids, em=em, er=er, p_drop=p_drop, seed=seed, seed_dev=seed_dev)
         # --- drop path factors: one [2*nblocks, B] draw per step
         nblk = sum(self.depths)
         dps = None
         if training and any(r > 0 for r in self.dpr):
-            if self._dp_rates is None or self._dp_rates.device != dev:   # built once: no per-step host->device copy
-                self._dp_rates = torch.tensor([r for r in self.dpr for _ in (0, 1)], device=dev, dtype=F32)
+            self.prepare_static(dev)
             dps = _empty((2 * nblk, B), F32, dev)
-            k.keep_scale(dps, 2 * nblk, B, rate_per_row=self._dp_rates, seed=dp_seed)
-        self.last_rng = dict(seed=seed, p_drop=p_drop, dp_seed=dp_seed, dps=dps)   # what this step drew (read back by the parity tests)
+            k.keep_scale(dps, 2 * nblk, B, rate_per_row=self._dp_rates, seed=dp_seed, seed_dev=dp_seed_dev)
+        self.last_rng = dict(seed=gs.host_seeds[0] if gs is not None else seed, p_drop=p_drop,
+                             dp_seed=gs.host_seeds[1] if gs is not None else dp_seed, dps=dps)   # what this step drew (read back by the parity tests)
         Xprev, Hp, Wp = None, IH, IW
         te_in = y768
         blk = 0
@@ -507,7 +524,8 @@ class PVLTEngine:
                                  ctx["em"], ctx["er"], G["text_embeddings.word_embeddings.weight"],
                                  G["text_embeddings.position_embeddings.weight"],
                                  G["text_embeddings.token_type_embeddings.weight"], G["text_embeddings.LayerNorm.weight"],
-                                 G["text_embeddings.LayerNorm.bias"], B * T, T, ctx["p_drop"], ctx["seed"])
+                                 G["text_embeddings.LayerNorm.bias"], B * T, T, ctx["p_drop"], ctx["seed"],
+                                 seed_dev=ctx.get("seed_dev"))
         items = [(G[key], G[key[len("__perm__"):]]) for key in G if key.startswith("__perm__block1.")]
         if items:
             k.uncast_conv_wgrad_multi(items)
@@ -637,7 +655,15 @@ class PVLTEngine:
         gradient-completion order (``grad_segment``); ``G["__segments__"]`` = [(begin, end)] element ranges of the segments."""
         dev = next(iter(self.P.values())).device
         total = sum((p.numel() + 3) // 4 * 4 for p in self.P.values())
-        flat = torch.zeros(total, dtype=F32, device=dev)
+        if self.static_grads:
+            # persistent buffer: the addresses the optimizer's pointer tables and a captured CUDA graph hold stay valid. The
+            # caller owns the protocol (one backward per optimizer step, gradients dropped before the next backward)
+            if self._static_flat is None or self._static_flat.device != dev or self._static_flat.numel() != total:
+                self._static_flat = torch.empty(total, dtype=F32, device=dev)
+            flat = self._static_flat
+            k.memset_zero(flat)
+        else:
+            flat = torch.zeros(total, dtype=F32, device=dev)
         if self._grad_layout is None:
             order = sorted(self.P.keys(), key=lambda n: (self.grad_segment(n), n.startswith("text_embeddings.word")))
             layout, bounds, off, cur = [], [], 0, 0
@@ -664,7 +690,13 @@ class PVLTEngine:
         convs = [(name, p) for name, p in self.P.items() if p.dim() == 4]
         ptotal = sum((p.numel() + 3) // 4 * 4 for _, p in convs)
         if ptotal:
-            arena = torch.zeros(ptotal, dtype=F32, device=dev)
+            if self.static_grads:
+                if self._static_arena is None or self._static_arena.device != dev or self._static_arena.numel() != ptotal:
+                    self._static_arena = torch.empty(ptotal, dtype=F32, device=dev)
+                arena = self._static_arena
+                k.memset_zero(arena)
+            else:
+                arena = torch.zeros(ptotal, dtype=F32, device=dev)
             off = 0
             for name, p in convs:
                 co, ci, kh, kw = p.shape

@@ -415,27 +415,34 @@ def uncast_conv_wgrad_multi(items):
         call("uncast_conv_wgrad_multi", (C.c_char * len(buf)).from_buffer(buf), C.c_int(len(chunk)))
 
 
-def bert_embed_fwd(ids, word, pos, typ, gamma, beta, out, mean, rstd, rows, T, eps, p_drop, seed):
+def bert_embed_fwd(ids, word, pos, typ, gamma, beta, out, mean, rstd, rows, T, eps, p_drop, seed, seed_dev=None):
+    """``seed_dev`` (all three hash-driven entry points): 1-element uint64-sized device tensor the kernel reads the seed from at
+    execution time instead of ``seed`` -- what lets a captured CUDA graph draw fresh masks on every replay."""
     call("bert_embed_fwd", ptr(ids), ptr(word), ptr(pos), ptr(typ), ptr(gamma), ptr(beta), ptr(out), ptr(mean),
-         ptr(rstd), C.c_int(rows), C.c_int(T), C.c_float(eps), C.c_float(p_drop), C.c_ulonglong(seed))
+         ptr(rstd), C.c_int(rows), C.c_int(T), C.c_float(eps), C.c_float(p_drop), C.c_ulonglong(seed), ptr(seed_dev))
 
 
 def bert_embed_bwd(dy, ids, word, pos, typ, gamma, mean, rstd, dword, dpos, dtype_, dgamma, dbeta, rows, T, p_drop,
-                   seed, pad_id=0):
+                   seed, pad_id=0, seed_dev=None):
     call("bert_embed_bwd", ptr(dy), ptr(ids), ptr(word), ptr(pos), ptr(typ), ptr(gamma), ptr(mean), ptr(rstd),
          ptr(dword), ptr(dpos), ptr(dtype_), ptr(dgamma), ptr(dbeta), C.c_int(rows), C.c_int(T), C.c_float(p_drop),
-         C.c_ulonglong(seed), C.c_int(pad_id))
+         C.c_ulonglong(seed), C.c_int(pad_id), ptr(seed_dev))
 
 
-def keep_scale(out, rows, cols, rate_per_row=None, rate=0.0, seed=0):
+def keep_scale(out, rows, cols, rate_per_row=None, rate=0.0, seed=0, seed_dev=None):
     """DropPath keep factors [rows, cols] (per-row rates on the device) or, with ``rate_per_row=None``, the element-wise
     dropout factors ``bert_embed_fwd`` applies for (seed, rate) (csrc/embed.cu)."""
-    call("keep_scale", ptr(out), C.c_int(rows), C.c_int(cols), ptr(rate_per_row), C.c_float(rate), C.c_ulonglong(seed))
+    call("keep_scale", ptr(out), C.c_int(rows), C.c_int(cols), ptr(rate_per_row), C.c_float(rate), C.c_ulonglong(seed),
+         ptr(seed_dev))
 
 
-def compact_labels(labels, n, ignore, idx_out, labels_out, count_out):
+def compact_labels(labels, n, ignore, idx_out, labels_out, count_out, cap=0, count_f32=None, inv_count=None, overflow=None):
+    """``cap`` > 0: fixed-capacity mode (static shapes for CUDA-graph capture): exactly ``cap`` entries of idx_out / labels_out
+    are written, the tail beyond the count padded with (row 0, ignore label) -- rows that contribute no loss and no gradient;
+    ``count_f32`` / ``inv_count`` (device floats) receive the count and 1 / max(count, 1), ``overflow`` the count when it
+    exceeds ``cap`` (untouched otherwise: zero it once and check it when convenient)."""
     call("compact_labels", ptr(labels), C.c_int(n), C.c_longlong(ignore), ptr(idx_out), ptr(labels_out),
-         ptr(count_out))
+         ptr(count_out), C.c_int(cap), ptr(count_f32), ptr(inv_count), ptr(overflow))
 
 
 def gather_rows(src, idx, n_idx, dst, Cdim, smap=None, lds=None):
@@ -449,15 +456,15 @@ def scatter_rows(src, idx, n_idx, dst, Cdim, dmap=None, ldd=None, accumulate=Fal
 
 
 def ce_fwd(logits, ld, labels, rows, n_cls, ignore, lse, loss_sum, scale, total_sum=None, argmax_out=None,
-           correct=None):
+           correct=None, scale_dev=None):
     call("ce_fwd", ptr(logits), _f32(logits), C.c_longlong(ld), ptr(labels), C.c_int(rows), C.c_int(n_cls),
          C.c_longlong(ignore), ptr(lse), ptr(loss_sum), ptr(total_sum), C.c_float(scale), ptr(argmax_out),
-         ptr(correct))
+         ptr(correct), ptr(scale_dev))
 
 
-def ce_bwd(logits, ld, labels, rows, n_cls, ignore, lse, dlogits, ldd, scale, gscale=None):
+def ce_bwd(logits, ld, labels, rows, n_cls, ignore, lse, dlogits, ldd, scale, gscale=None, scale_dev=None):
     call("ce_bwd", ptr(logits), _f32(logits), C.c_longlong(ld), ptr(labels), C.c_int(rows), C.c_int(n_cls),
-         C.c_longlong(ignore), ptr(lse), ptr(dlogits), C.c_longlong(ldd), C.c_float(scale), ptr(gscale))
+         C.c_longlong(ignore), ptr(lse), ptr(dlogits), C.c_longlong(ldd), C.c_float(scale), ptr(gscale), ptr(scale_dev))
 
 
 def small_linear_fwd(h, W, b1, b2, out, M, n, K):
@@ -504,6 +511,17 @@ def gelu_ew(x, out, dy=None):
 def cast2d(src, lds, dst, ldd, rows, Cdim, alpha=1.0):
     call("cast2d", ptr(src), _f32(src), C.c_longlong(lds), ptr(dst), _f32(dst), C.c_longlong(ldd),
          C.c_longlong(rows), C.c_int(Cdim), C.c_float(alpha))
+
+
+def set_values(dst, payload: bytes):
+    """Writes ``payload`` (4..64 bytes, a multiple of 4) to device memory at ``dst`` with a one-thread launch that carries the
+    bytes in its kernel arguments (csrc/elementwise.cu: no pinned staging; safe to call again immediately)."""
+    buf = (C.c_char * len(payload)).from_buffer_copy(payload)
+    call("set_values", ptr(dst), buf, C.c_int(len(payload)))
+
+
+def memset_zero(t):
+    call("memset_zero", ptr(t), C.c_longlong(t.numel() * t.element_size()))
 
 
 def zeros(shape, dtype, dev):

@@ -109,24 +109,32 @@ class _PVLTFunction(torch.autograd.Function):
         model, saved = ctx.model, ctx.saved
         if saved is None:
             raise MvltError("backward called on a forward that ran without gradient tracking")
-        eng: PVLTEngine = model._engine()
-        G = eng.new_grads()
-        sync = model.__dict__.get("_grad_sync")
-        # data parallelism without DistributedDataParallel's bucket copies: every gradient of the step lives in ONE flat fp32
-        # buffer laid out in completion order, and each segment (heads, stage 4, 3, 2, stage 1 + embeddings) is all-reduced
-        # (averaged) over NVLink on a side stream as soon as the hand-scheduled backward has finished it -- the exchange of
-        # everything but the last segment overlaps the remaining backward kernels (DDP's overlap at main_vl.py:297-299)
-        reducer = SegmentReducer(G["__flat__"], G["__segments__"], sync) if sync is not None else None
-        on_seg = reducer.segment_done if (reducer is not None and GRAD_SYNC_OVERLAP) else None
-        if ctx.mode == "logits":
-            eng_backward_logits(eng, saved, gouts, G, on_seg)
-        else:
-            eng_backward_losses(eng, saved, gouts[0], G, on_seg)
+        G = run_backward(model, ctx.mode, saved, gouts)
         ctx.saved = None
-        if reducer is not None:
-            reducer.finish()
         names = model._param_names
         return (None, None, None, None, None) + tuple(G[n] for n in names)
+
+
+def run_backward(model, mode, saved, gouts):
+    """The hand-scheduled backward of one forward (``saved``) into a flat gradient buffer, including the data-parallel
+    exchange when ``model.enable_grad_sync`` is on. Returns the gradient dict (``G[name]`` = view of the flat buffer).
+    Called by the autograd node above and, without autograd, by ``mvlt_b200.graph.GraphedStep``."""
+    eng: PVLTEngine = model._engine()
+    G = eng.new_grads()
+    sync = model.__dict__.get("_grad_sync")
+    # data parallelism without DistributedDataParallel's bucket copies: every gradient of the step lives in ONE flat fp32
+    # buffer laid out in completion order, and each segment (heads, stage 4, 3, 2, stage 1 + embeddings) is all-reduced
+    # (averaged) over NVLink on a side stream as soon as the hand-scheduled backward has finished it -- the exchange of
+    # everything but the last segment overlaps the remaining backward kernels (DDP's overlap at main_vl.py:297-299)
+    reducer = SegmentReducer(G["__flat__"], G["__segments__"], sync) if sync is not None else None
+    on_seg = reducer.segment_done if (reducer is not None and GRAD_SYNC_OVERLAP) else None
+    if mode == "logits":
+        eng_backward_logits(eng, saved, gouts, G, on_seg)
+    else:
+        eng_backward_losses(eng, saved, gouts[0], G, on_seg)
+    if reducer is not None:
+        reducer.finish()
+    return G
 
 
 def allreduce_flat_(flat, group=None):
@@ -297,19 +305,31 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
         idx = torch.empty((B * T,), dtype=torch.int32, device=dev)
         lab_c = torch.empty((B * T,), dtype=torch.int64, device=dev)
         cnt = torch.empty((1,), dtype=torch.int32, device=dev)
-        k.compact_labels(lab_dev, B * T, -1, idx, lab_c, cnt)
-        if batch.get("mlm_count") is not None:
-            n = int(batch["mlm_count"])          # supplied by the data pipeline: no device->host sync
+        gs = eng.graph_state
+        wm = w.get("mlm", MLM_LOSS_WEIGHT)
+        if gs is not None and gs.mlm_cap:
+            # static shapes (CUDA-graph capture): the head always runs on `mlm_cap` rows; rows beyond the labelled count are
+            # padded with (token 0, ignore label) and contribute neither loss nor gradient; the count, 1 / count (the CE
+            # scale) and an overflow flag stay on the device
+            n = min(int(gs.mlm_cap), B * T)
+            k.compact_labels(lab_dev, B * T, -1, idx, lab_c, cnt, cap=n, count_f32=stats[7:8], inv_count=gs.mlm_inv,
+                             overflow=gs.mlm_overflow)
+            scale, scale_dev = wm, gs.mlm_inv
         else:
-            n = int((labels != -1).sum()) if not labels.is_cuda else int(cnt.item())
+            k.compact_labels(lab_dev, B * T, -1, idx, lab_c, cnt)
+            if batch.get("mlm_count") is not None:
+                n = int(batch["mlm_count"])          # supplied by the data pipeline: no device->host sync
+            else:
+                n = int((labels != -1).sum()) if not labels.is_cuda else int(cnt.item())
+            scale, scale_dev = wm / max(n, 1), None
         if n > 0:
             lg, c = eng.mlm_fwd(X4, B, HW4, idx, n)
             lse = torch.empty((n,), dtype=F32, device=dev)
-            wm = w.get("mlm", MLM_LOSS_WEIGHT)
-            k.ce_fwd(lg, VOCAB_PAD, lab_c, n, VOCAB, -1, lse, stats[1:2], wm / n, total_sum=stats[0:1],
-                     correct=stats[6:7])
-            stats[7:8].fill_(float(n))
-            c.update(logits=lg, lse=lse, labels=lab_c, scale=wm / n, n=n)
+            k.ce_fwd(lg, VOCAB_PAD, lab_c, n, VOCAB, -1, lse, stats[1:2], scale, total_sum=stats[0:1],
+                     correct=stats[6:7], scale_dev=scale_dev)
+            if scale_dev is None:
+                stats[7:8].fill_(float(n))
+            c.update(logits=lg, lse=lse, labels=lab_c, scale=scale, scale_dev=scale_dev, n=n)
             hc["mlm"] = c
     for name, key, wkey in (("itm", "itm_labels", "itm"), ("sup_cls", "sup_cls_labels", "cls"),
                             ("sub_cls", "sub_cls_labels", "cls")):
@@ -356,7 +376,8 @@ def eng_backward_losses(eng: PVLTEngine, saved, gtotal, G, on_segment=None):
     if "mlm" in hc:
         c = hc["mlm"]
         lg = c["logits"]
-        k.ce_bwd(lg, VOCAB_PAD, c["labels"], c["n"], VOCAB, -1, c["lse"], lg, VOCAB_PAD, c["scale"], gs)   # in place
+        k.ce_bwd(lg, VOCAB_PAD, c["labels"], c["n"], VOCAB, -1, c["lse"], lg, VOCAB_PAD, c["scale"], gs,
+                 scale_dev=c.get("scale_dev"))   # in place
         eng.mlm_bwd(lg, c, B, HW4, dX4, G)
     for name in ("itm", "sup_cls", "sub_cls"):
         if name in hc:

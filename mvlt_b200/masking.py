@@ -36,14 +36,17 @@ def grid_mask_batch(seeds, input_size=(256, 256), mask_ratio=0.5, patch_size=16,
     return grid
 
 
-def apply_grid_mask(images: torch.Tensor, grid: torch.Tensor, patch_size=16, fill=1e-6, return_mask=False):
+def apply_grid_mask(images: torch.Tensor, grid: torch.Tensor, patch_size=16, fill=1e-6, return_mask=False, out=None):
     """masked_images = images.masked_fill(mask, 1e-6) with mask[b, 0, y, x] = grid[b, y//P, x//P]
     (fashion_gen.py:176). Optionally also returns the float mask [B,1,H,W] (the dataset's ``t2i_labels``)."""
     if not images.is_cuda or images.dtype != torch.float32:
         raise MvltError("apply_grid_mask expects a CUDA float32 [B,C,H,W] tensor")
     images = images.contiguous()
     B, Cc, H, W = images.shape
-    out = torch.empty_like(images)
+    if out is None:
+        out = torch.empty_like(images)
+    elif out.shape != images.shape or out.dtype != images.dtype or not out.is_cuda or not out.is_contiguous():
+        raise MvltError("apply_grid_mask: `out` must be a contiguous CUDA tensor shaped like the images")
     mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=images.device) if return_mask else None
     k.masked_fill(images, grid.contiguous(), out, mask, B, Cc, H, W, patch_size, fill)
     return (out, mask) if return_mask else out

@@ -34,6 +34,65 @@ class AdamW(torch.optim.Optimizer):
             raise ValueError("invalid AdamW hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}
+        self._hyper = None      # device fp32 [n_groups, 4] = {lr, bias_correction1, bias_correction2, 0}: see enable_device_hyper
+        self._hyper_t = None
+
+    # ---- device-resident hyper-parameters (CUDA-graph replays) -------------------------------------------------------------
+    def enable_device_hyper(self, on=True):
+        """Make ``step`` read {lr, bias corrections} from device memory instead of passing them by value, so that a captured
+        step picks up the current values on every replay. The caller then runs ``advance()`` once ahead of every step (eager
+        or replayed): it increments the step count and writes the values of THAT step (one small launch, no host sync)."""
+        if not on:
+            self._sync_steps()
+            self._hyper = self._hyper_t = None
+            return
+        ps = [p for g in self.param_groups for p in g["params"]]
+        dev = ps[0].device
+        steps = {int(self.state[p]["step"]) for p in ps if len(self.state.get(p, {}))}
+        if len(steps) > 1:
+            raise MvltError("parameters must share their step count")
+        self._hyper_t = steps.pop() if steps else 0
+        self._hyper = torch.zeros((len(self.param_groups), 4), dtype=torch.float32, device=dev)
+
+    def prepare(self):
+        """Allocate the moment buffers and build the device pointer tables for the CURRENT ``p.grad`` tensors without taking a
+        step (the host -> device table upload cannot happen inside a stream capture)."""
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            for p in ps:
+                self._state(p)
+            if ps:
+                self._group_tables(gi, ps)
+
+    def advance(self):
+        if self._hyper is None:
+            raise MvltError("advance() needs enable_device_hyper()")
+        self._hyper_t += 1
+        t = self._hyper_t
+        payload = b""
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            payload += struct.pack("<ffff", group["lr"], 1.0 - b1 ** t, 1.0 - b2 ** t, 0.0)
+        from . import kernels as k
+        for off in range(0, len(payload), 64):      # 4 groups per launch
+            k.set_values(self._hyper.view(-1)[off // 4:], payload[off:off + 64])
+
+    def _sync_steps(self):
+        if self._hyper_t is not None:
+            for st in self.state.values():
+                if "step" in st:
+                    st["step"] = self._hyper_t
+
+    def state_dict(self):
+        self._sync_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}
+        if self._hyper is not None:
+            steps = {int(st["step"]) for st in self.state.values() if "step" in st}
+            self._hyper_t = steps.pop() if len(steps) == 1 else 0
 
     def _state(self, p):
         st = self.state[p]
@@ -90,19 +149,24 @@ class AdamW(torch.optim.Optimizer):
                     raise MvltError("mvlt_b200.optim.AdamW needs contiguous parameters and gradients")
                 self._state(p)
             # torch.optim.AdamW checkpoints (main_vl.py:340) carry ``step`` as a 0-dim tensor: accept both forms
-            steps = {int(self.state[p]["step"]) for p in ps}
-            if len(steps) != 1:
-                raise MvltError("parameters of one group must share their step count")
-            t = steps.pop() + 1
+            if self._hyper is not None:
+                t = max(self._hyper_t, 1)      # the kernel reads lr / bias corrections of this step from self._hyper[gi]
+            else:
+                steps = {int(self.state[p]["step"]) for p in ps}
+                if len(steps) != 1:
+                    raise MvltError("parameters of one group must share their step count")
+                t = steps.pop() + 1
             b1, b2 = group["betas"]
             tt, ct, nchunks = self._group_tables(gi, ps)
             if _lib.BYTES is not None:   # p, m, v read + written, g read: 28 bytes per parameter
                 _lib.account_bytes("adamw_multi", 28 * sum(p.numel() for p in ps))
             call("adamw_multi", ptr(tt), ptr(ct), C.c_int(nchunks), C.c_int(CHUNK), C.c_float(group["lr"]), C.c_float(b1),
                  C.c_float(b2), C.c_float(group["eps"]), C.c_float(group["weight_decay"]), C.c_float(1.0 - b1 ** t),
-                 C.c_float(1.0 - b2 ** t), ptr(grad_scale), C.c_int(0))
-            for p in ps:
-                self.state[p]["step"] = t
+                 C.c_float(1.0 - b2 ** t), ptr(grad_scale), C.c_int(0),
+                 ptr(self._hyper[gi]) if self._hyper is not None else C.c_void_p(0))
+            if self._hyper is None:
+                for p in ps:
+                    self.state[p]["step"] = t
         # the kernel writes through raw pointers, which autograd's version counters do not see: parameters whose bf16 compute
         # copy this launch could not refresh (none registered yet) and cached derived tables (resized position embeddings) are
         # invalidated through the package-wide epoch instead

@@ -72,6 +72,35 @@ for n, p in synced.named_parameters():
         bad += 1
 print(f"rank {rank}: parameters differing across ranks after 3 steps: {bad}", flush=True)
 assert bad == 0
+
+# (3) the same exchange captured inside the CUDA graph of the whole iteration (mvlt_b200/graph.py): after replays the parameters
+#     are still bit-identical on every rank, and they moved (the replays really stepped the optimizer)
+from mvlt_b200.graph import GraphedStep  # noqa: E402
+gs = GraphedStep(synced, opt, mlm_capacity=256, warmup=1)
+static = {k: v.to(dev) for k, v in make_batch(B, seed=rank).items()}
+before = {n: p.detach().clone() for n, p in synced.named_parameters()}
+for step in range(5):
+    bb = make_batch(B, seed=2000 * step + rank)
+    for k, v in bb.items():
+        static[k].copy_(v.to(dev))
+    total, stats = gs(static["images"], static["input_ids"], mlm_labels=static["mlm_labels"], itm_labels=static["itm_labels"],
+                      target_images=static["images"])
+    assert torch.isfinite(total).item()
+assert gs.captured() and not gs.check_overflow()
+bad = moved = 0
+for n, p in synced.named_parameters():
+    lo, hi = p.detach().clone(), p.detach().clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    bad += int(not torch.equal(lo, hi))
+    moved += int(not torch.equal(p.detach(), before[n]))
+print(f"rank {rank}: graph replays: parameters differing across ranks: {bad}; parameters that moved: {moved}", flush=True)
+assert bad == 0 and moved > 200
+gs.detach()          # graphs that captured NCCL work must be destroyed before the communicator is
+del gs
+import gc  # noqa: E402
+gc.collect()
+torch.cuda.synchronize()
 dist.destroy_process_group()
 if rank == 0:
     print("dist_check OK")
