@@ -34,12 +34,50 @@ def _dev(x, device):
     return x.to(device, non_blocking=True) if torch.is_tensor(x) else x
 
 
-def _masked(samples, images, device, step, seed=0):
+def _masked(samples, images, device, step, seed=0, out=None):
+    """``out``: optional static device buffer the masked batch is written into (CUDA-graph mode)."""
     if "masked_images" in samples:
+        if out is not None:
+            return out.copy_(samples["masked_images"], non_blocking=True)
         return _dev(samples["masked_images"], device)
     B = images.shape[0]
     seeds = [masking.sample_seed(seed, step * B + i) for i in range(B)]
-    return masking.apply_grid_mask(images, masking.grid_mask_batch(seeds, (images.shape[3], images.shape[2]), 0.5, 16, device))
+    return masking.apply_grid_mask(images, masking.grid_mask_batch(seeds, (images.shape[3], images.shape[2]), 0.5, 16, device),
+                                   out=out)
+
+
+def _graphed_step(model, optimizer, loss_scaler, max_norm, model_ema, args, batch_rows):
+    """CUDA-graph replay of the iteration (mvlt_b200/graph.py) when asked for (``args.cuda_graph`` or MVLT_CUDA_GRAPH=1) and
+    possible: own AdamW, no loss scaler / clipping / EMA hooks between backward and step, no DistributedDataParallel wrapper
+    (``model.enable_grad_sync()`` is the data-parallel mode that can be captured). One GraphedStep per model, kept across epochs."""
+    import os
+    want = bool(getattr(args, "cuda_graph", False)) or os.environ.get("MVLT_CUDA_GRAPH", "0") == "1"
+    if not want or loss_scaler is not None or max_norm or model_ema is not None or hasattr(model, "module"):
+        return None
+    from mvlt_b200.graph import GraphedStep
+    from mvlt_b200.optim import AdamW
+    if not isinstance(optimizer, AdamW):
+        return None
+    gs = model.__dict__.get("_graphed_step")
+    if gs is None or gs.opt is not optimizer or gs.model._engine() is not gs.eng:
+        cap = getattr(args, "mlm_capacity", None)
+        if not cap and model.loss_type.get("mlm"):      # 15 % of the word pieces are masked: 20 % of all rows bounds the count
+            cap = -(-int(0.2 * batch_rows) // 128) * 128
+        gs = GraphedStep(model, optimizer, mlm_capacity=cap, warmup=1)
+        model.__dict__["_graphed_step"] = gs
+        model.__dict__["_graphed_static"] = {}
+    return gs
+
+
+def _static_copy(model, name, src, device):
+    """The captured graph reads its inputs from fixed device buffers: copy the batch into them (H2D for host batches)."""
+    bufs = model.__dict__["_graphed_static"]
+    key = (name, tuple(src.shape), src.dtype)       # one buffer per shape: a short last batch must not move the full-size one
+    t = bufs.get(key)
+    if t is None:
+        t = bufs[key] = torch.empty(src.shape, dtype=src.dtype, device=device)
+    t.copy_(src, non_blocking=True)
+    return t
 
 
 def train_one_epoch_vl(model: torch.nn.Module, criterion, data_loader: Iterable, optimizer: torch.optim.Optimizer,
@@ -51,26 +89,48 @@ def train_one_epoch_vl(model: torch.nn.Module, criterion, data_loader: Iterable,
     logger = MetricLogger(delimiter="  ")
     logger.add_meter("lr", SmoothedValue(window_size=1, fmt="{value:.6f}"))
     loss_type = _net(model).loss_type
+    weights = {"mlm": MLM_LOSS_WEIGHT, "itm": ITM_LOSS_WEIGHT, "t2i": T2I_LOSS_WEIGHT, "cls": 1}
+    gstep = None
     for idx, samples in enumerate(logger.log_every(data_loader, 10, f"Epoch: [{epoch}]")):
-        images = _dev(samples["image"], device)
-        ids = _dev(samples["ori_input_ids" if USE_ORI_INPUT_IDS else "input_ids"], device)
-        x = images
-        if idx % 2 == 1 and loss_type.get("t2i"):          # :72-78 odd steps feed the grid-masked image
-            x = _masked(samples, images, device, idx, seed=epoch)
-        mlm_labels = samples.get("mlm_labels")
-        total, stats = model(x, ids, mlm_labels=mlm_labels, itm_labels=samples.get("itm_labels"),
-                             sup_cls_labels=samples.get("sup_cls_labels"), sub_cls_labels=samples.get("sub_cls_labels"),
-                             target_images=images,
-                             weights={"mlm": MLM_LOSS_WEIGHT, "itm": ITM_LOSS_WEIGHT, "t2i": T2I_LOSS_WEIGHT, "cls": 1})
-        optimizer.zero_grad()
-        if loss_scaler is not None:   # timm NativeScaler call convention (engine_grid_masking.py:126-127)
-            loss_scaler(total, optimizer, clip_grad=max_norm if max_norm else None, parameters=model.parameters(),
-                        create_graph=False)
+        if idx == 0 and set_training_mode:
+            B0, T0 = samples["input_ids"].shape[:2]
+            gstep = _graphed_step(model, optimizer, loss_scaler, max_norm, model_ema, args, B0 * T0)
+        masked_step = idx % 2 == 1 and bool(loss_type.get("t2i"))      # :72-78 odd steps feed the grid-masked image
+        if gstep is not None:
+            # whole iteration (forward, losses, backward, gradient exchange, AdamW, zero_grad) as one captured graph per
+            # (masked?, batch shape): the batch is copied into static device buffers, per-step scalars live on the device
+            net = _net(model)
+            images = _static_copy(net, "image", samples["image"], device)
+            ids = _static_copy(net, "ids", samples["ori_input_ids" if USE_ORI_INPUT_IDS else "input_ids"], device)
+            labels = {k: _static_copy(net, k, samples[k], device)
+                      for k in ("mlm_labels", "itm_labels", "sup_cls_labels", "sub_cls_labels") if samples.get(k) is not None}
+            x = images
+            if masked_step:
+                bufs = net.__dict__["_graphed_static"]
+                mkey = ("masked", tuple(images.shape), images.dtype)
+                if mkey not in bufs:
+                    bufs[mkey] = torch.empty_like(images)
+                x = _masked(samples, images, device, idx, seed=epoch, out=bufs[mkey])
+            total, stats = gstep(x, ids, key=(masked_step, tuple(images.shape)), target_images=images, weights=weights, **labels)
         else:
-            total.backward()
-            if max_norm:
-                torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
-            optimizer.step()
+            images = _dev(samples["image"], device)
+            ids = _dev(samples["ori_input_ids" if USE_ORI_INPUT_IDS else "input_ids"], device)
+            x = images
+            if masked_step:
+                x = _masked(samples, images, device, idx, seed=epoch)
+            mlm_labels = samples.get("mlm_labels")
+            total, stats = model(x, ids, mlm_labels=mlm_labels, itm_labels=samples.get("itm_labels"),
+                                 sup_cls_labels=samples.get("sup_cls_labels"), sub_cls_labels=samples.get("sub_cls_labels"),
+                                 target_images=images, weights=weights)
+            optimizer.zero_grad()
+            if loss_scaler is not None:   # timm NativeScaler call convention (engine_grid_masking.py:126-127)
+                loss_scaler(total, optimizer, clip_grad=max_norm if max_norm else None, parameters=model.parameters(),
+                            create_graph=False)
+            else:
+                total.backward()
+                if max_norm:
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
+                optimizer.step()
         if model_ema is not None:
             model_ema.update(model)
         s = stats.tolist()                                   # the step's single device->host read
@@ -79,6 +139,10 @@ def train_one_epoch_vl(model: torch.nn.Module, criterion, data_loader: Iterable,
                   f"t2i={s[5]}), raise NaN value")
         logger.update(total_loss=s[0], loss_mlm=s[1], loss_itm=s[2], loss_sup_cls=s[3], loss_sub_cls=s[4], loss_t2i=s[5])
         logger.update(lr=optimizer.param_groups[0]["lr"])
+    if gstep is not None and gstep.check_overflow():
+        from mvlt_b200._lib import MvltError
+        raise MvltError(f"a batch held more MLM-labelled tokens than the captured step's row capacity ({gstep.state.mlm_cap}): "
+                        "set args.mlm_capacity higher")
     logger.synchronize_between_processes()
     print("Averaged stats:", logger)
     return {k: m.global_avg for k, m in logger.meters.items()}

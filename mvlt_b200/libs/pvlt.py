@@ -307,7 +307,7 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
         cnt = torch.empty((1,), dtype=torch.int32, device=dev)
         gs = eng.graph_state
         wm = w.get("mlm", MLM_LOSS_WEIGHT)
-        if gs is not None and gs.mlm_cap:
+        if gs is not None and gs.mlm_cap and training and save:
             # static shapes (CUDA-graph capture): the head always runs on `mlm_cap` rows; rows beyond the labelled count are
             # padded with (token 0, ignore label) and contribute neither loss nor gradient; the count, 1 / count (the CE
             # scale) and an overflow flag stay on the device

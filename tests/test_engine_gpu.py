@@ -37,20 +37,26 @@ class _Args:
     eval_retrieval_itr = False
 
 
-@pytest.mark.parametrize("own_optimizer", [False, True])
+@pytest.mark.parametrize("own_optimizer", [False, True, "graph"])
 def test_train_and_eval_loops_run_and_learn(own_optimizer):
+    """``"graph"``: the same loop with ``args.cuda_graph`` -- every iteration after the first two is a CUDA-graph replay."""
     import engine_grid_masking as E
     m = _model(PRE, drop_path=0.0)
     m.text_embeddings.dropout.p = 0.0
+    args = _Args()
+    args.cuda_graph = own_optimizer == "graph"
     if own_optimizer:     # the multi-tensor sm_100a AdamW with timm's no-decay grouping (main_vl.py:308)
         from mvlt_b200.optim import AdamW, param_groups_no_decay
         opt = AdamW(param_groups_no_decay(m, 0.01), lr=2e-4)
     else:
         opt = torch.optim.AdamW(m.parameters(), lr=2e-4)
     data = _loader(2, 8) * 6                        # 12 steps over two fixed batches: the loss must go down
-    s0 = E.train_one_epoch_vl(m, None, data[:2], opt, torch.device("cuda"), 0, None, args=_Args())
+    s0 = E.train_one_epoch_vl(m, None, data[:2], opt, torch.device("cuda"), 0, None, args=args)
     for ep in range(1, 5):
-        s1 = E.train_one_epoch_vl(m, None, data[:2], opt, torch.device("cuda"), ep, None, args=_Args())
+        s1 = E.train_one_epoch_vl(m, None, data[:2], opt, torch.device("cuda"), ep, None, args=args)
+    if args.cuda_graph:
+        gs = m.__dict__["_graphed_step"]
+        assert len(gs._graphs) == 2 and gs.launches_per_replay((False, (8, 3, 256, 256))) > 100     # unmasked / masked iteration
     assert all(math.isfinite(v) for v in s1.values())
     assert s1["total_loss"] < s0["total_loss"] - 0.2, (s0, s1)
     ev = E.evaluate_vl(_loader(2, 8), m, torch.device("cuda"), _Args())
