@@ -164,6 +164,54 @@ __global__ void __launch_bounds__(256) patchify_nchw_kernel(const float* __restr
   }
 }
 
+// Fast path of the above for the geometry PVLT uses (P = 4, Kpad = Cin * 16, W % 4 == 0, oh % 2 == 0): one float4 load IS the
+// four kx of one (patch, ci, ky), i.e. 8 contiguous output bytes. A block iteration covers TWO rows of patches of one image:
+// all its loads (6 x 16 B per thread) are issued before the first use, the [2][ow][Kpad] tile is transposed through shared
+// memory (rows padded by 8 B: conflict-free 8-byte stores) and leaves as fully coalesced 8-byte stores.
+template <int CIN>
+__global__ void __launch_bounds__(256) patchify_nchw4_kernel(const float* __restrict__ img, uint2* __restrict__ dst, int B, int H, int W) {
+  pdl_prologue();
+  extern __shared__ __align__(16) unsigned char patch_sh[];
+  uint2* tile = reinterpret_cast<uint2*>(patch_sh);
+  constexpr int U = CIN * 4;                 // 8-byte units per patch row (Kpad * 2 / 8)
+  constexpr int UP = U + 1;                  // padded pitch
+  const int ow = W >> 2, oh = H >> 2;
+  const int per_ch = 8 * ow;                 // float4 loads per channel per iteration (8 image rows)
+  const int n_ld = CIN * per_ch;
+  const int n_st = 2 * ow * U;
+  for (int blk = blockIdx.x; blk < B * (oh >> 1); blk += gridDim.x) {
+    const int oy2 = blk % (oh >> 1), b = blk / (oh >> 1);
+    const float4* base = reinterpret_cast<const float4*>(img + ((long long)b * CIN * H + (long long)oy2 * 8) * W);
+    __syncthreads();                         // the previous iteration's tile has been read
+    for (int i0 = threadIdx.x; i0 < n_ld; i0 += 6 * blockDim.x) {
+      float4 v[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int i = i0 + j * blockDim.x;
+        if (i < n_ld) {
+          const int ci = i / per_ch, f = i - ci * per_ch;
+          v[j] = __ldg(base + (long long)ci * (H * (W >> 2)) + f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int i = i0 + j * blockDim.x;
+        if (i < n_ld) {
+          const int ci = i / per_ch, f = i - ci * per_ch;
+          const int yl = f / ow, ox = f - yl * ow;
+          tile[((yl >> 2) * ow + ox) * UP + ci * 4 + (yl & 3)] = make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
+        }
+      }
+    }
+    __syncthreads();
+    uint2* out = dst + (long long)blk * n_st;
+    for (int e = threadIdx.x; e < n_st; e += blockDim.x) {
+      const int pch = e / U, j = e - pch * U;
+      out[e] = tile[pch * UP + j];
+    }
+  }
+}
+
 // ---- generic strided row copy with dtype conversion ----------------------------------------------------------
 struct RowMap2 { int group, stride, offset; };
 __device__ __forceinline__ long long map_row2(const RowMap2& m, long long r) {
@@ -495,6 +543,16 @@ extern "C" int mvlt_patchify_nchw(const float* img, void* dst_bf16, int B, int C
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   MVLT_CHECK_ARG(Kpad % 8 == 0 && Kpad >= Cin * P * P && W % P == 0 && H % P == 0 && (W / P) * Kpad * 2 <= 96 * 1024,
                  "patchify_nchw: unsupported geometry (W=%d P=%d Kpad=%d)", W, P, Kpad);
+  if (P == 4 && Cin == 3 && Kpad == Cin * 16 && W % 4 == 0 && (H / 4) % 2 == 0 && ((uintptr_t)img & 15) == 0 && ((uintptr_t)dst_bf16 & 7) == 0) {
+    int grid4 = B * (H / 8);
+    const int cap4 = mvlt_num_sms() * 6;
+    if (grid4 > cap4) grid4 = cap4;
+    const size_t smem4 = (size_t)2 * (W / 4) * (Cin * 4 + 1) * 8;
+    MVLT_CHECK_ARG(smem4 <= 48 * 1024, "patchify_nchw: image too wide (W=%d)", W);
+    mvlt_launch(patchify_nchw4_kernel<3>, grid4, 256, smem4, st, img, reinterpret_cast<uint2*>(dst_bf16), B, H, W);
+    MVLT_CHECK_LAUNCH();
+    return 0;
+  }
   const size_t smem = (size_t)(W / P) * Kpad * 2;
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {

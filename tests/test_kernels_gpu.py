@@ -390,9 +390,10 @@ def test_batch_reduce_chunked(B, n, stride_pad, acc):
     _close(out, ref, 1e-5, 1e-4, "batch_reduce")
 
 
-def test_patchify_nchw_full_image():
+@pytest.mark.parametrize("Kp", [64, 48])      # 48 = the engine's geometry (float4 fast path), 64 = the padded generic kernel
+def test_patchify_nchw_full_image(Kp):
     from mvlt_b200 import kernels as k
-    B, P, Kp = 3, 4, 64
+    B, P = 3, 4
     img = torch.rand((B, 3, 256, 256), generator=_g(11), device="cuda")
     pat = torch.full((B * 4096, Kp), 7.0, dtype=BF16, device="cuda")
     k.patchify_nchw(img, pat, B, 3, 256, 256, P, Kp)
