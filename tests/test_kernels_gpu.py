@@ -399,7 +399,8 @@ def test_patchify_nchw_full_image(Kp):
     k.patchify_nchw(img, pat, B, 3, 256, 256, P, Kp)
     ref = F.unfold(img, P, stride=P).permute(0, 2, 1).reshape(B * 4096, 48)
     assert torch.equal(pat[:, :48], ref.to(BF16))
-    assert float(pat[:, 48:].abs().max()) == 0.0
+    if Kp > 48:
+        assert float(pat[:, 48:].abs().max()) == 0.0
 
 
 def test_token_mask_bit_exact_vs_oracle_and_reference_golden():

@@ -23,6 +23,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--dump-gemms", action="store_true")
 ap.add_argument("--retrieval", action="store_true")
+ap.add_argument("--graph", action="store_true",
+                help="profile ONE CUDA-graph replay of the whole iteration (forward, losses, backward, AdamW; mvlt_b200/graph.py): "
+                     "ncu reports the kernel nodes of the graph individually")
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -52,6 +55,31 @@ def step(i):
 for i in range(2):
     step(i)
 torch.cuda.synchronize()
+
+if args.graph:
+    from mvlt_b200.graph import GraphedStep
+    from mvlt_b200.optim import AdamW, param_groups_no_decay
+    opt = AdamW(param_groups_no_decay(m, 0.01), lr=1e-4)
+    gs = GraphedStep(m, opt, mlm_capacity=-(-int(n * 1.1) // 128) * 128, warmup=1)
+    xm = torch.empty_like(b["images"])
+    masking.apply_grid_mask(b["images"], masking.grid_mask_batch(seeds + 1), out=xm)
+
+    def gstep():
+        return gs(xm, b["input_ids"], mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=b["images"])
+    gstep()                      # eager warm-up of the graph-mode code path
+    _lib.GEMM_LOG = []           # descriptors of the captured iteration, in node order
+    gstep()                      # capture + first replay
+    log, _lib.GEMM_LOG = _lib.GEMM_LOG, None
+    gstep()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    gstep()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(log, open("gpurun_out/gemm_desc_log.json", "w"))
+    print(f"graph replay profiled: {gs.launches_per_replay()} kernel nodes, {len(log)} GEMM descriptors")
+    sys.exit(0)
 
 if args.dump_gemms:
     rows = []
