@@ -81,6 +81,12 @@ class PVLTEngine:
         self.graph_state = None
         self.static_grads = False
         self._static_flat = self._static_arena = None
+        # weight-gradient side stream (set by GraphedStep): the dW / bias-gradient launches feed nothing but the optimizer, so
+        # they run as a parallel branch of the captured graph and fill the SMs that the tails and the small launches of the
+        # dX chain leave idle. Operands are kept alive (and never reused in place) until the branch is joined.
+        self.wgrad_stream = None
+        self._wgrad_keep = []
+        self._wgrad_pending = False
         from . import t2i as _t2i
         self.t2i = _t2i.T2IHead(self) if loss_type.get("t2i") else None
 
@@ -167,14 +173,40 @@ class PVLTEngine:
     # ------------------------------------------------------------------------------------------------
     # helpers
     # ------------------------------------------------------------------------------------------------
+    def side_launch(self, fn, *keep):
+        """Run ``fn()`` (launches that only produce parameter gradients) on the weight-gradient side stream, ordered after
+        everything enqueued on the current stream so far; ``keep``: the tensors it reads (held until ``wgrad_join``). Without
+        a side stream it simply runs in line."""
+        side = self.wgrad_stream
+        if side is None:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._wgrad_keep.append(keep)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            fn()
+        self._wgrad_pending = True
+
+    def wgrad_join(self):
+        """The current stream waits for every side-stream launch so far (before gradients are folded, exchanged or applied)."""
+        if self.wgrad_stream is not None and self._wgrad_pending:
+            ev = torch.cuda.Event()
+            ev.record(self.wgrad_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self._wgrad_pending = False
+        self._wgrad_keep.clear()
+
     def _lin_param_grads(self, G, wname, bname, dy, x, wgrad=None):
         """dW += dy^T x (split-K, fp32 atomics straight into the gradient buffer); db += column sums of dy (same launch)."""
         rows, co = dy.shape
         ci = x.shape[1]
         tgt = wgrad if wgrad is not None else G[wname].view(co, -1)
         # the bias gradient db = dy^T 1 rides on the same GEMM (one extra N=16 MMA per k-step against a tile of ones)
-        k.gemm(dy.t(), x.t(), tgt, atomic_add=True, split_k=_split_k(co, ci, rows),
-               rowsum=G[bname] if bname is not None else None)
+        self.side_launch(lambda: k.gemm(dy.t(), x.t(), tgt, atomic_add=True, split_k=_split_k(co, ci, rows),
+                                        rowsum=G[bname] if bname is not None else None), dy, x)
 
     def _pos(self, stage, H, W, dev):
         """pvlt.py:291-297,341-344: bilinear resize of the position table (cached per weight version)."""
@@ -295,12 +327,13 @@ class PVLTEngine:
             # fc1 / fc2 weight gradients and the fc1 bias gradient (accumulated in TMEM over the rows); db2 = column sums of dy
             k.mlp_bwd(c["xn2"], dy2, Wb[pfx + ".mlp.fc1.weight"], P[pfx + ".mlp.fc1.bias"], Wb[pfx + ".mlp.fc2.weight"], dh,
                       G[pfx + ".mlp.fc1.weight"], G[pfx + ".mlp.fc2.weight"], G[pfx + ".mlp.fc1.bias"])
-            k.colsum(dy2, M, C, C, G[pfx + ".mlp.fc2.bias"])
+            self.side_launch(lambda: k.colsum(dy2, M, C, C, G[pfx + ".mlp.fc2.bias"]), dy2)
         else:
             self._lin_param_grads(G, pfx + ".mlp.fc2.weight", pfx + ".mlp.fc2.bias", dy2, c["act"])
             k.gemm(dy2, Wb[pfx + ".mlp.fc2.weight"].t(), dh, act=k.ACT_MUL_AUX, aux=c["hpre"])
             self._lin_param_grads(G, pfx + ".mlp.fc1.weight", pfx + ".mlp.fc1.bias", dh, c["xn2"])
-        dxn2 = dy2  # reuse
+        # (in place over dy2 -- unless weight-gradient launches that still read dy2 may be pending on the side stream)
+        dxn2 = dy2 if self.wgrad_stream is None else _empty((M, C), BF16, dev)
         k.gemm(dh, Wb[pfx + ".mlp.fc1.weight"].t(), dxn2)
         del dh
         dX1 = _empty((B, N, C), F32, dev)
@@ -320,7 +353,7 @@ class PVLTEngine:
         dkv5 = dkv.view(B, Nk, 2, heads, HEAD_DIM)
         dk4, dv4 = dkv5[:, :, 0].permute(0, 2, 1, 3), dkv5[:, :, 1].permute(0, 2, 1, 3)
         Pm = c["Pm"]
-        dq = dyp  # reuse
+        dq = dyp if self.wgrad_stream is None else _empty((M, C), BF16, dev)   # dyp is still read by the side-stream dW GEMM
         if FUSED_ATTENTION_BWD and Nk <= k.SR_ATTENTION_MAX_NK:
             k.sr_attention_bwd(c["q"], c["kv"], do, Pm, dq, dkv, B, N, Nk, heads, HEAD_DIM ** -0.5)
         else:
@@ -509,6 +542,7 @@ class PVLTEngine:
                 dX = dXp
                 # fold this stage's permuted conv-weight gradients back into the master [Co, Ci, kh, kw] layout (one launch):
                 # the stage's segment of the flat gradient buffer is complete after it
+                self.wgrad_join()      # the stage's weight gradients (side stream) are complete
                 items = [(G[key], G[key[len("__perm__"):]]) for key in G
                          if key.startswith(f"__perm__block{s}.") or key.startswith(f"__perm__patch_embed{s}.")]
                 if items:
@@ -526,6 +560,7 @@ class PVLTEngine:
                                  G["text_embeddings.token_type_embeddings.weight"], G["text_embeddings.LayerNorm.weight"],
                                  G["text_embeddings.LayerNorm.bias"], B * T, T, ctx["p_drop"], ctx["seed"],
                                  seed_dev=ctx.get("seed_dev"))
+        self.wgrad_join()
         items = [(G[key], G[key[len("__perm__"):]]) for key in G if key.startswith("__perm__block1.")]
         if items:
             k.uncast_conv_wgrad_multi(items)

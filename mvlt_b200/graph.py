@@ -16,6 +16,7 @@ is captured with the step. There is no CPU path here either: capture needs the s
 """
 from __future__ import annotations
 
+import os
 import struct
 from typing import Dict, Optional
 
@@ -48,7 +49,8 @@ class GraphedStep:
     largest expected count is best); ``check_overflow()`` tells, with a device->host read, whether any batch exceeded it.
     """
 
-    def __init__(self, model, optimizer, mlm_capacity: Optional[int] = None, warmup: int = 1, enabled: bool = True):
+    def __init__(self, model, optimizer, mlm_capacity: Optional[int] = None, warmup: int = 1, enabled: bool = True,
+                 parallel_wgrad: Optional[bool] = None):
         from .optim import AdamW
         if not isinstance(optimizer, AdamW):
             raise MvltError("GraphedStep needs mvlt_b200.optim.AdamW (its hyper-parameters must be readable from device memory)")
@@ -60,6 +62,10 @@ class GraphedStep:
         self.state = GraphState(dev, mlm_capacity or 0)
         self.warmup = max(int(warmup), 0)
         self.enabled = enabled
+        # weight-gradient launches as a parallel branch of the graph (engine.side_launch); MVLT_GRAPH_WGRAD_BRANCH=0 for the A/B
+        if parallel_wgrad is None:
+            parallel_wgrad = os.environ.get("MVLT_GRAPH_WGRAD_BRANCH", "1") != "0"
+        self.parallel_wgrad = bool(parallel_wgrad)
         self._graphs: Dict[object, dict] = {}
         self._calls: Dict[object, int] = {}
         self._pool = None
@@ -70,6 +76,7 @@ class GraphedStep:
         eng, opt = self.eng, self.opt
         eng.graph_state = self.state
         eng.static_grads = True
+        eng.wgrad_stream = torch.cuda.Stream(device=eng._device) if self.parallel_wgrad else None
         eng.prepare_weights()
         eng.prepare_static(eng._device)
         opt.enable_device_hyper(True)
@@ -86,6 +93,7 @@ class GraphedStep:
         """Back to the plain eager path (host-side seeds / hyper-parameters, freshly allocated gradients)."""
         self.eng.graph_state = None
         self.eng.static_grads = False
+        self.eng.wgrad_stream = None
         self.opt.enable_device_hyper(False)
         self._graphs = {}
 

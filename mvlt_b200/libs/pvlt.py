@@ -132,6 +132,7 @@ def run_backward(model, mode, saved, gouts):
         eng_backward_logits(eng, saved, gouts, G, on_seg)
     else:
         eng_backward_losses(eng, saved, gouts[0], G, on_seg)
+    eng.wgrad_join()
     if reducer is not None:
         reducer.finish()
     return G
@@ -280,6 +281,7 @@ def eng_backward_logits(eng: PVLTEngine, saved, gouts, G, on_segment=None):
         df2, df3 = eng.t2i.backward(dscore, c, G, dX4)
         dXs[1], dXs[2] = df2, df3
     if on_segment is not None:
+        eng.wgrad_join()    # (head weight gradients launched on the side stream included)
         on_segment(0)       # every head gradient is enqueued
     eng.encoder_bwd(enc, dXs, G, on_segment)
 
@@ -391,6 +393,7 @@ def eng_backward_losses(eng: PVLTEngine, saved, gtotal, G, on_segment=None):
         df2, df3 = eng.t2i.backward(c["dscore"], c, G, dX4, gscale=gs)
         dXs[1], dXs[2] = df2, df3
     if on_segment is not None:
+        eng.wgrad_join()    # (head weight gradients launched on the side stream included)
         on_segment(0)       # every head gradient is enqueued
     eng.encoder_bwd(enc, dXs, G, on_segment)
 

@@ -99,7 +99,9 @@ class T2IHead:
         # written once per step) gradient views, no scratch buffers and no copies.
         k.bn_bwd(dout, c["y"], aff[0], aff[2], aff[3], G[pfx + ".1.bias"], G[pfx + ".1.weight"], dy, rows, Co, c["training"])
         key = "__perm__" + pfx + ".0.weight"
-        k.conv3x3_wgrad(dy, c["x"], B, H, W, Ci, c["xs"][1], c["xs"][0], G[key], split_k=_split_k(Co, 9 * Ci, rows))
+        x_in, xs = c["x"], c["xs"]
+        self.e.side_launch(lambda: k.conv3x3_wgrad(dy, x_in, B, H, W, Ci, xs[1], xs[0], G[key], split_k=_split_k(Co, 9 * Ci, rows)),
+                           dy, x_in)      # weight gradient: parallel branch of the captured graph (engine.side_launch)
         if dst is not None:
             Wt = self.W[pfx + ".0.weight^T"]
             linear = dst_pix_stride == Ci and dst_batch_stride == H * W * Ci
@@ -217,5 +219,6 @@ class T2IHead:
         dfeat2 = torch.empty((B, Hl * Wl, Cl), dtype=F32, device=dev)
         self._convbn_bwd("reduction1", g_low, c["r1"], G, dfeat2, Hl * Wl * Cl, Cl)
         # fold the permuted 3x3 weight gradients back to [Co, Ci, 3, 3] (one launch for the eleven units)
+        self.e.wgrad_join()
         k.uncast_conv_wgrad_multi([(G["__perm__t2i_head.%s.0.weight" % u], G["t2i_head.%s.0.weight" % u]) for u in UNITS])
         return dfeat2, dfeat3
