@@ -18,6 +18,7 @@ residual stream, LayerNorm / softmax / losses in fp32, bf16 GEMM operands with f
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 from typing import Dict, List, Optional
@@ -87,6 +88,10 @@ class PVLTEngine:
         self.wgrad_stream = None
         self._wgrad_keep = []
         self._wgrad_pending = False
+        # further parallel branches of the captured graph (set by GraphedStep): [0] the spatial-reduction key/value chain of a
+        # block next to its query projection, [1] the t2i head next to the MLM / ITM heads (forward and backward)
+        self.branch_streams = None
+        self._branch_done = []
         from . import t2i as _t2i
         self.t2i = _t2i.T2IHead(self) if loss_type.get("t2i") else None
 
@@ -199,6 +204,32 @@ class PVLTEngine:
             self._wgrad_pending = False
         self._wgrad_keep.clear()
 
+    @contextlib.contextmanager
+    def branch(self, idx):
+        """``with eng.branch(i):`` -- the launches inside run on branch stream i, ordered after everything enqueued on the
+        current stream so far; ``join_branches()`` makes the current stream wait for them. Without branch streams (the
+        per-launch path) the body simply runs in line."""
+        st = self.branch_streams[idx] if self.branch_streams else None
+        if st is None:
+            yield
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(st):
+            st.wait_event(ev)
+            yield
+            done = torch.cuda.Event()
+            done.record(st)
+        self._branch_done.append(done)
+
+    def join_branches(self):
+        if self._branch_done:
+            main = torch.cuda.current_stream()
+            for ev in self._branch_done:
+                main.wait_event(ev)
+            self._branch_done.clear()
+
     def _lin_param_grads(self, G, wname, bname, dy, x, wgrad=None):
         """dW += dy^T x (split-K, fp32 atomics straight into the gradient buffer); db += column sums of dy (same launch)."""
         rows, co = dy.shape
@@ -243,27 +274,30 @@ class PVLTEngine:
         mean1, rstd1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
         k.layernorm_fwd(X, P[pfx + ".norm1.weight"], P[pfx + ".norm1.bias"], xn, 1e-6, M, C, mean=mean1, rstd=rstd1)
         q = _empty((M, C), BF16, dev)
-        k.gemm(xn, Wb[pfx + ".attn.q.weight"], q, bias=P[pfx + ".attn.q.bias"])
-        if R > 1:
-            oh, ow = H // R, W // R
-            Nk = oh * ow + T
-            patches = _empty((B * oh * ow, R * R * C), BF16, dev)
-            k.patchify(xn, N * C, patches, B, H, W, C, R)
-            sr = _empty((B * oh * ow, C), BF16, dev)
-            k.gemm(patches, Wb[pfx + ".attn.sr.weight"], sr, bias=P[pfx + ".attn.sr.bias"])
-            kvin = _empty((B * Nk, C), BF16, dev)
-            srm, srr = _empty((B * oh * ow,), F32, dev), _empty((B * oh * ow,), F32, dev)
-            k.layernorm_fwd(sr, P[pfx + ".attn.norm.weight"], P[pfx + ".attn.norm.bias"], kvin, 1e-5, B * oh * ow, C,
-                            ymap=(oh * ow, Nk, 0), mean=srm, rstd=srr)
-            k.copy_rows(xn, kvin, B * T, C, smap=(T, N, HW), dmap=(T, Nk, oh * ow))
-            c.update(patches=patches, sr=sr, srm=srm, srr=srr)
-        else:
-            Nk = N
-            kvin = xn
+        Nk = (H // R) * (W // R) + T if R > 1 else N
         if Nk % 32 != 0 or Nk > 256:
             raise MvltError(f"K/V length {Nk} unsupported by the fused softmax epilogue (need a multiple of 32, <= 256)")
         kv = _empty((B * Nk, 2 * C), BF16, dev)
-        k.gemm(kvin, Wb[pfx + ".attn.kv.weight"], kv, bias=P[pfx + ".attn.kv.bias"])
+        # the key/value chain (spatial reduction: patchify, conv-as-GEMM, LayerNorm, text rows, then the kv projection) only
+        # meets the query projection at the attention kernel: its small launches run as a parallel branch of a captured graph
+        with self.branch(0):
+            if R > 1:
+                oh, ow = H // R, W // R
+                patches = _empty((B * oh * ow, R * R * C), BF16, dev)
+                k.patchify(xn, N * C, patches, B, H, W, C, R)
+                sr = _empty((B * oh * ow, C), BF16, dev)
+                k.gemm(patches, Wb[pfx + ".attn.sr.weight"], sr, bias=P[pfx + ".attn.sr.bias"])
+                kvin = _empty((B * Nk, C), BF16, dev)
+                srm, srr = _empty((B * oh * ow,), F32, dev), _empty((B * oh * ow,), F32, dev)
+                k.layernorm_fwd(sr, P[pfx + ".attn.norm.weight"], P[pfx + ".attn.norm.bias"], kvin, 1e-5, B * oh * ow, C,
+                                ymap=(oh * ow, Nk, 0), mean=srm, rstd=srr)
+                k.copy_rows(xn, kvin, B * T, C, smap=(T, N, HW), dmap=(T, Nk, oh * ow))
+                c.update(patches=patches, sr=sr, srm=srm, srr=srr)
+            else:
+                kvin = xn
+            k.gemm(kvin, Wb[pfx + ".attn.kv.weight"], kv, bias=P[pfx + ".attn.kv.bias"])
+        k.gemm(xn, Wb[pfx + ".attn.q.weight"], q, bias=P[pfx + ".attn.q.bias"])
+        self.join_branches()
         q4 = q.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3)
         kv5 = kv.view(B, Nk, 2, heads, HEAD_DIM)
         k4, v4 = kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3)
@@ -506,13 +540,15 @@ class PVLTEngine:
             pe_tab = P[f"pos_embed{s}"]
             side = int(round(math.sqrt(pe_tab.shape[1] - (1 if s == 4 else 0))))
             gtab = G[f"pos_embed{s}"][0, 1:] if s == 4 else G[f"pos_embed{s}"][0]
-            if HW == P["pos_embed1"].shape[1]:
-                k.batch_reduce(dX, N * C, B, HW * C, gtab, accumulate=True)
-            else:
-                dpos = _empty((HW, C), F32, dev)
-                k.batch_reduce(dX, N * C, B, HW * C, dpos)
-                k.pos_resize_bwd(dpos, gtab, side, side, H, W, C)
-            k.batch_reduce(dX.view(-1)[HW * C:], N * C, B, T * C, G[f"text_pos_embed{s}"], accumulate=True)
+            def pos_grads(dX=dX, gtab=gtab, side=side, H=H, W=W, C=C, HW=HW, N=N, s=s):
+                if HW == P["pos_embed1"].shape[1]:
+                    k.batch_reduce(dX, N * C, B, HW * C, gtab, accumulate=True)
+                else:
+                    dpos = _empty((HW, C), F32, dev)
+                    k.batch_reduce(dX, N * C, B, HW * C, dpos)
+                    k.pos_resize_bwd(dpos, gtab, side, side, H, W, C)
+                k.batch_reduce(dX.view(-1)[HW * C:], N * C, B, T * C, G[f"text_pos_embed{s}"], accumulate=True)
+            self.side_launch(pos_grads, dX)      # parameter gradients only: off the dX chain
             # patch embed backward
             dpe = _empty((B * HW, C), BF16, dev)
             k.layernorm_bwd(dX, sc["pe"], sc["pem"], sc["per"], P[f"patch_embed{s}.norm.weight"], dpe, B * HW, C,
@@ -542,12 +578,12 @@ class PVLTEngine:
                 dX = dXp
                 # fold this stage's permuted conv-weight gradients back into the master [Co, Ci, kh, kw] layout (one launch):
                 # the stage's segment of the flat gradient buffer is complete after it
-                self.wgrad_join()      # the stage's weight gradients (side stream) are complete
                 items = [(G[key], G[key[len("__perm__"):]]) for key in G
                          if key.startswith(f"__perm__block{s}.") or key.startswith(f"__perm__patch_embed{s}.")]
-                if items:
-                    k.uncast_conv_wgrad_multi(items)
+                if items:      # (on the weight-gradient stream when there is one: it follows the GEMMs that fill the arena)
+                    self.side_launch(lambda: k.uncast_conv_wgrad_multi(items))
                 if on_segment is not None:
+                    self.wgrad_join()      # the stage's weight gradients (side stream) are complete
                     on_segment(4 - i)
             else:
                 dy768 = _empty((B * T, HIDDEN), BF16, dev)
@@ -560,10 +596,10 @@ class PVLTEngine:
                                  G["text_embeddings.token_type_embeddings.weight"], G["text_embeddings.LayerNorm.weight"],
                                  G["text_embeddings.LayerNorm.bias"], B * T, T, ctx["p_drop"], ctx["seed"],
                                  seed_dev=ctx.get("seed_dev"))
-        self.wgrad_join()
         items = [(G[key], G[key[len("__perm__"):]]) for key in G if key.startswith("__perm__block1.")]
         if items:
-            k.uncast_conv_wgrad_multi(items)
+            self.side_launch(lambda: k.uncast_conv_wgrad_multi(items))
+        self.wgrad_join()
         if on_segment is not None:
             on_segment(4)
 
@@ -647,9 +683,11 @@ class PVLTEngine:
         n_rows = c["n_rows"]
         dev = dlogits.device
         # tied decoder: dE += dlogits^T hl  (lands in word_embeddings.grad next to the gather's scatter-add)
-        k.gemm(dlogits.t(), c["hl"].t(), G["text_embeddings.word_embeddings.weight"], atomic_add=True,
-               split_k=_split_k(VOCAB, HIDDEN, n_rows))
-        k.colsum(dlogits, n_rows, VOCAB, VOCAB_PAD, G["mlm_head.bias"])
+        def decoder_grads():
+            k.gemm(dlogits.t(), c["hl"].t(), G["text_embeddings.word_embeddings.weight"], atomic_add=True,
+                   split_k=_split_k(VOCAB, HIDDEN, n_rows))
+            k.colsum(dlogits, n_rows, VOCAB, VOCAB_PAD, G["mlm_head.bias"])
+        self.side_launch(decoder_grads, dlogits, c["hl"])
         # dH = dlogits E: only ~700 labelled rows but K = 30522 -> split-K into a zeroed fp32 buffer (18 tiles otherwise)
         dhl = k.zeros((n_rows, HIDDEN), F32, dev)
         k.gemm(dlogits, Wb["text_embeddings.word_embeddings.weight"].t(), dhl, atomic_add=True,

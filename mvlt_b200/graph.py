@@ -77,6 +77,8 @@ class GraphedStep:
         eng.graph_state = self.state
         eng.static_grads = True
         eng.wgrad_stream = torch.cuda.Stream(device=eng._device) if self.parallel_wgrad else None
+        nb = int(os.environ.get("MVLT_GRAPH_BRANCHES", "2")) if self.parallel_wgrad else 0      # A/B: 0 / 1 / 2 extra branches
+        eng.branch_streams = [torch.cuda.Stream(device=eng._device) if i < nb else None for i in range(2)] if nb else None
         eng.prepare_weights()
         eng.prepare_static(eng._device)
         opt.enable_device_hyper(True)
@@ -94,6 +96,7 @@ class GraphedStep:
         self.eng.graph_state = None
         self.eng.static_grads = False
         self.eng.wgrad_stream = None
+        self.eng.branch_streams = None
         self.opt.enable_device_hyper(False)
         self._graphs = {}
 

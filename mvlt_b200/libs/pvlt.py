@@ -301,6 +301,22 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
     hc = {}
     only = batch.get("only")
     want = lambda name: only is None or name in only
+    if lt.get("t2i") and want("t2i") and batch.get("target_images") is not None:
+        # (first, and as a parallel branch of a captured graph: its ~60 small launches run next to the MLM / ITM heads)
+        with eng.branch(1):
+            feats = [(enc["stages"][i]["out"], enc["stages"][i]["H"], enc["stages"][i]["W"], EMBED_DIMS[i]) for i in (1, 2, 3)]
+            score, c = eng.t2i.forward(feats, B, training)
+            h, wd = feats[0][1], feats[0][2]
+            target = batch["target_images"].contiguous().to(F32)
+            wt = w.get("t2i", T2I_LOSS_WEIGHT)
+            numel = B * 3 * h * 8 * wd * 8
+            # training: the same launch also produces d loss / d score (for an upstream gradient of 1; the real one is a device
+            # scalar folded into the first backward kernel), so the target image is read once per step, not twice
+            dscore = k.zeros((B * h * wd, 3), F32, dev) if save else None
+            k.t2i_up_loss(score, target, None, dscore, stats[5:6], stats[0:1], wt / numel, wt / numel if save else 0.0, None, B, h,
+                          wd, 8, 1, bool(save))
+            c.update(score=score, dscore=dscore)
+            hc["t2i"] = c
     if lt.get("mlm") and want("mlm") and batch.get("mlm_labels") is not None:
         labels = batch["mlm_labels"]
         lab_dev = labels.to(dev, non_blocking=True).contiguous().view(-1)
@@ -348,20 +364,7 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
                  correct=stats[slot + 6:slot + 7])
         c.update(logits=lg, lse=lse, labels=lab, scale=wt / B)
         hc[name] = c
-    if lt.get("t2i") and want("t2i") and batch.get("target_images") is not None:
-        feats = [(enc["stages"][i]["out"], enc["stages"][i]["H"], enc["stages"][i]["W"], EMBED_DIMS[i]) for i in (1, 2, 3)]
-        score, c = eng.t2i.forward(feats, B, training)
-        h, wd = feats[0][1], feats[0][2]
-        target = batch["target_images"].contiguous().to(F32)
-        wt = w.get("t2i", T2I_LOSS_WEIGHT)
-        numel = B * 3 * h * 8 * wd * 8
-        # training: the same launch also produces d loss / d score (for an upstream gradient of 1; the real one is a device
-        # scalar folded into the first backward kernel), so the target image is read once per step, not twice
-        dscore = k.zeros((B * h * wd, 3), F32, dev) if save else None
-        k.t2i_up_loss(score, target, None, dscore, stats[5:6], stats[0:1], wt / numel, wt / numel if save else 0.0, None, B, h, wd,
-                      8, 1, bool(save))
-        c.update(score=score, dscore=dscore)
-        hc["t2i"] = c
+    eng.join_branches()
     total = stats[0]
     saved = dict(enc=enc, hc=hc, B=B, HW4=HW4) if save else None
     return (total, stats), saved
@@ -375,6 +378,11 @@ def eng_backward_losses(eng: PVLTEngine, saved, gtotal, G, on_segment=None):
     dX4 = k.zeros((B, N4, EMBED_DIMS[-1]), F32, dev)
     dXs = [None, None, None, dX4]
     gs = gtotal.to(F32).contiguous() if gtotal is not None else None
+    if "t2i" in hc:      # parallel branch of a captured graph (disjoint rows of dX4: image rows here, text rows below)
+        with eng.branch(1):
+            c = hc["t2i"]
+            df2, df3 = eng.t2i.backward(c["dscore"], c, G, dX4, gscale=gs)
+            dXs[1], dXs[2] = df2, df3
     if "mlm" in hc:
         c = hc["mlm"]
         lg = c["logits"]
@@ -388,10 +396,7 @@ def eng_backward_losses(eng: PVLTEngine, saved, gtotal, G, on_segment=None):
             dl = torch.empty((B, n_cls), dtype=F32, device=dev)
             k.ce_bwd(c["logits"], n_cls, c["labels"], B, n_cls, -100, c["lse"], dl, n_cls, c["scale"], gs)
             eng.small_head_bwd(dl, c, name, B, HW4, dX4, G)
-    if "t2i" in hc:
-        c = hc["t2i"]
-        df2, df3 = eng.t2i.backward(c["dscore"], c, G, dX4, gscale=gs)
-        dXs[1], dXs[2] = df2, df3
+    eng.join_branches()
     if on_segment is not None:
         eng.wgrad_join()    # (head weight gradients launched on the side stream included)
         on_segment(0)       # every head gradient is enqueued

@@ -127,7 +127,13 @@ class T2IHead:
         T = self.e.T
         dev = Xl.device
         c = {}
-        low, c["r1"] = self._convbn_fwd("reduction1", Xl, (Hl * Wl + T) * Cl, Cl, B, Hl, Wl, Cl, training)
+        # BatchNorm sums of this pass: zeroed HERE, ahead of any branch (a unit on a branch stream must not be the one that zeroes)
+        self._arena = k.zeros((len(UNITS), 2, 3 * CH), F32, dev)
+        self._arena_used = 0
+        # reduction1 (the large 32x32 map) is not needed before cat3: as a parallel branch of a captured graph its full-size
+        # launches run next to the small 16x16 / 8x8 chains below (engine.branch; in line on the per-launch path)
+        with self.e.branch(0):
+            low, c["r1"] = self._convbn_fwd("reduction1", Xl, (Hl * Wl + T) * Cl, Cl, B, Hl, Wl, Cl, training)
         mid, c["r2"] = self._convbn_fwd("reduction2", Xm, (Hm * Wm + T) * Cm, Cm, B, Hm, Wm, Cm, training)
         high, c["r3"] = self._convbn_fwd("reduction3", Xh, (Hh * Wh + T) * Chh, Chh, B, Hh, Wh, Chh, training)
         rows_m, rows_l = B * Hm * Wm, B * Hl * Wl
@@ -146,6 +152,7 @@ class T2IHead:
         k.upsample2x_fwd(cat2, Hm * Wm * 2 * CH, 2 * CH, up_x21, B, Hm, Wm, CH)
         A3, c["u3"] = self._convbn_fwd("conv_upsample3", up_x21, Hl * Wl * CH, CH, B, Hl, Wl, CH, training)
         cat3 = torch.empty((rows_l, 3 * CH), dtype=BF16, device=dev)
+        self.e.join_branches()
         k.ew_mul(A2, CH, 0, cat3, 3 * CH, 0, rows_l, CH, b=A3, b_ld=CH, c2=low, c2_ld=CH)    # x3_1
         up_x22 = torch.empty((rows_l, 2 * CH), dtype=BF16, device=dev)
         k.upsample2x_fwd(x2_2, Hm * Wm * 2 * CH, 2 * CH, up_x22, B, Hm, Wm, 2 * CH)
@@ -189,6 +196,10 @@ class T2IHead:
         k.ew_mul(d_cat3, 3 * CH, 0, dA2, CH, 0, rows_l, CH, b=c["A3"], b_ld=CH, c2=c["low"], c2_ld=CH)
         k.ew_mul(d_cat3, 3 * CH, 0, dA3, CH, 0, rows_l, CH, b=c["A2"], b_ld=CH, c2=c["low"], c2_ld=CH)
         k.ew_mul(d_cat3, 3 * CH, 0, g_low, CH, 0, rows_l, CH, b=c["A2"], b_ld=CH, c2=c["A3"], c2_ld=CH)
+        # reduction1's backward (large map; feeds only the stage-2 token gradient) as a parallel branch next to the chains below
+        dfeat2 = torch.empty((B, Hl * Wl, Cl), dtype=F32, device=dev)
+        with self.e.branch(0):
+            self._convbn_bwd("reduction1", g_low, c["r1"], G, dfeat2, Hl * Wl * Cl, Cl)
         d_up_x21 = new(rows_l, CH)
         self._convbn_bwd("conv_upsample3", dA3, c["u3"], G, d_up_x21, Hl * Wl * CH, CH)
         g_x21 = new(rows_m, CH)
@@ -216,9 +227,8 @@ class T2IHead:
         self._convbn_bwd("reduction3", g_high, c["r3"], G, dX4, N4 * Chh, Chh, accumulate=True)
         dfeat3 = torch.empty((B, Hm * Wm, Cm), dtype=F32, device=dev)
         self._convbn_bwd("reduction2", g_mid, c["r2"], G, dfeat3, Hm * Wm * Cm, Cm)
-        dfeat2 = torch.empty((B, Hl * Wl, Cl), dtype=F32, device=dev)
-        self._convbn_bwd("reduction1", g_low, c["r1"], G, dfeat2, Hl * Wl * Cl, Cl)
+        self.e.join_branches()
         # fold the permuted 3x3 weight gradients back to [Co, Ci, 3, 3] (one launch for the eleven units)
-        self.e.wgrad_join()
-        k.uncast_conv_wgrad_multi([(G["__perm__t2i_head.%s.0.weight" % u], G["t2i_head.%s.0.weight" % u]) for u in UNITS])
+        self.e.side_launch(lambda: k.uncast_conv_wgrad_multi([(G["__perm__t2i_head.%s.0.weight" % u], G["t2i_head.%s.0.weight" % u])
+                                                              for u in UNITS]))
         return dfeat2, dfeat3
