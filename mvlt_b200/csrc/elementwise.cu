@@ -112,9 +112,10 @@ __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ src
   }
 }
 
-// inverse: dpatch bf16 [B*oh*ow, R*R*C] -> dst fp32 NHWC rows (writes, does not accumulate)
+// inverse: dpatch bf16 [B*oh*ow, R*R*C] -> dst fp32 NHWC rows (writes; accumulate != 0: adds to what is there)
 __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
-                                                         long long dst_batch_stride, int B, int H, int W, int C, int R) {
+                                                         long long dst_batch_stride, int B, int H, int W, int C, int R,
+                                                         int accumulate) {
   pdl_prologue();
   const int c8n = C / 8;
   const long long total = (long long)B * H * W * c8n;
@@ -130,8 +131,14 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __
     const uint4 u = *reinterpret_cast<const uint4*>(src + srow * ((long long)R * R * C) + (long long)(ky * R + kx) * C + c8 * 8);
     float* d = dst + (long long)b * dst_batch_stride + ((long long)yh * W + xw) * C + c8 * 8;
     float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-    *reinterpret_cast<float4*>(d) = make_float4(f0.x, f0.y, f1.x, f1.y);
-    *reinterpret_cast<float4*>(d + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+    float4 o0 = make_float4(f0.x, f0.y, f1.x, f1.y), o1 = make_float4(f2.x, f2.y, f3.x, f3.y);
+    if (accumulate) {
+      const float4 a0 = *reinterpret_cast<const float4*>(d), a1 = *reinterpret_cast<const float4*>(d + 4);
+      o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
+      o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
+    }
+    *reinterpret_cast<float4*>(d) = o0;
+    *reinterpret_cast<float4*>(d + 4) = o1;
   }
 }
 
@@ -529,10 +536,10 @@ extern "C" int mvlt_patchify(const void* src, int src_f32, long long src_batch_s
 }
 
 extern "C" int mvlt_unpatchify(const void* src_bf16, float* dst, long long dst_batch_stride, int B, int H, int W, int C,
-                               int R, void* stream_) {
+                               int R, int accumulate, void* stream_) {
   MVLT_CHECK_ARG(C % 8 == 0 && H % R == 0 && W % R == 0, "unpatchify: bad shape");
   const long long total = (long long)B * H * W * (C / 8);
-  mvlt_launch(unpatchify_kernel, cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(src_bf16), dst, dst_batch_stride, B, H, W, C, R);
+  mvlt_launch(unpatchify_kernel, cap_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const __nv_bfloat16*>(src_bf16), dst, dst_batch_stride, B, H, W, C, R, accumulate);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

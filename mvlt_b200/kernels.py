@@ -355,9 +355,9 @@ def patchify(src, src_batch_stride, dst, B, H, W, Cdim, R):
          C.c_int(W), C.c_int(Cdim), C.c_int(R))
 
 
-def unpatchify(src, dst, dst_batch_stride, B, H, W, Cdim, R):
+def unpatchify(src, dst, dst_batch_stride, B, H, W, Cdim, R, accumulate=False):
     call("unpatchify", ptr(src), ptr(dst), C.c_longlong(dst_batch_stride), C.c_int(B), C.c_int(H), C.c_int(W),
-         C.c_int(Cdim), C.c_int(R))
+         C.c_int(Cdim), C.c_int(R), C.c_int(1 if accumulate else 0))
 
 
 def patchify_nchw(img, dst, B, Cin, H, W, P, Kpad):

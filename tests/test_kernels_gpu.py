@@ -197,6 +197,10 @@ def test_colsum_patchify_copy_rows():
     back = torch.zeros((B, N, C), device="cuda")
     k.unpatchify(pat, back, N * C, B, H, W, C, R)
     assert torch.equal(back[:, :H * W], tok[:, :H * W].to(BF16).float()) and float(back[:, H * W:].abs().max()) == 0
+    base = torch.randn((B, N, C), generator=_g(4), device="cuda")
+    acc = base.clone()
+    k.unpatchify(pat, acc, N * C, B, H, W, C, R, accumulate=True)        # += mode (the branch-parallel backward)
+    assert torch.equal(acc[:, :H * W], base[:, :H * W] + tok[:, :H * W].to(BF16).float()) and torch.equal(acc[:, H * W:], base[:, H * W:])
     dst = torch.zeros((B * T, C), dtype=BF16, device="cuda")
     k.copy_rows(tok, dst, B * T, C, smap=(T, N, H * W))
     assert torch.equal(dst, tok[:, H * W:].reshape(B * T, C).to(BF16))
