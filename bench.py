@@ -323,6 +323,7 @@ def train_line(args, model_name, workload, K, Wm, rank, world, local, dev, detai
         "model_flops_frac_of_bf16_peak": round(value * gf_per_sample / 1e3 / tf_sus, 4) if gf_per_sample else None,
         "cuda_graph": None if gstep is None else {
             "graphs": len(gstep._graphs), "kernels_per_replay": max(g["launches"] for g in gstep._graphs.values()) if gstep._graphs else 0,
+            "parallel_branches": "weight-gradient stream + t2i head + key/value chain" if gstep.eng.wgrad_stream is not None else "none",
             "mlm_row_capacity": gstep.state.mlm_cap, "mlm_rows_labelled": [h["mlm_count"] for h in host] if heads["mlm"] else None,
             "mlm_capacity_overflow": gstep.check_overflow()},
     }
@@ -343,8 +344,10 @@ def train_line(args, model_name, workload, K, Wm, rank, world, local, dev, detai
     # ---- per-kernel breakdown (instrumented pass, NOT the reported value) -> roofline of the dominant kernel
     model.enable_grad_sync(None)      # the instrumented pass below runs on rank 0 alone: no collectives from here on
     if gstep is not None:
-        gstep.enabled = False         # the instrumented pass times every launch: same kernels, launched one by one
+        gstep.enabled = False         # the instrumented pass times every launch: same kernels, launched one by one ...
         gstep._graphs = {}
+        gstep.eng.wgrad_stream = None     # ... and on ONE stream (no parallel branches), so that every kernel is timed alone
+        gstep.eng.branch_streams = None
     if rank == 0:
         res.update(instrumented_pass(lambda i: step(i, devb[i % 2], fwd=model), 2, hbm, tf_sus, peak_src))
     return res

@@ -223,6 +223,12 @@ class PVLTEngine:
             done.record(st)
         self._branch_done.append(done)
 
+    def enable_branches(self, n: int):
+        """``n`` > 0: give this engine ``n`` (<= 2) branch streams outside a GraphedStep as well, so that e.g. the key/value
+        chain of every block overlaps the query projection in a forward-only sweep; 0 turns them off."""
+        dev = next(iter(self.P.values())).device
+        self.branch_streams = [torch.cuda.Stream(device=dev) if i < n else None for i in range(2)] if n > 0 else None
+
     def join_branches(self):
         if self._branch_done:
             main = torch.cuda.current_stream()

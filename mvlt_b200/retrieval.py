@@ -78,6 +78,8 @@ def bench_sweep(dev, rank, world, n_query=1000, n_cand=101, queries_per_step=8, 
         for p in model.parameters():
             dist.broadcast(p.data, 0)
         _lib.params_written()   # .data writes bypass the version counters the engine's bf16 weight copies are keyed on
+    import os
+    model._engine().enable_branches(int(os.environ.get("MVLT_RETR_BRANCHES", "0")))     # A/B: key/value chain on a branch stream
     b = make_batch(pool, seed=99)
     img_pool = b["images"].to(dev)
     ids_pool = b["ori_input_ids"].to(dev)
