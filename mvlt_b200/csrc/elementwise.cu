@@ -492,6 +492,25 @@ extern "C" int mvlt_set_values(void* dst, const void* src_host, int nbytes, void
   return 0;
 }
 
+// ---- measurement aid: keep the stream busy for `ns` nanoseconds -------------------------------------------------------------
+// bench.py's instrumented pass puts a CUDA-event pair around every launch; launched one by one from Python the GPU would
+// idle between kernels and every event interval would include the host's launch latency. A spin ahead of the step lets the
+// host enqueue the whole step first, so that the intervals measure kernels, not the launch path.
+__global__ void spin_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(2000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+extern "C" int mvlt_spin(long long ns, void* stream_) {
+  MVLT_CHECK_ARG(ns >= 0 && ns <= 2000000000LL, "spin: 0 .. 2 s");
+  spin_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream_)>>>((unsigned long long)ns);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int mvlt_cast_scale_bf16(const float* src, void* dst, long long rows, int C, const float* rowscale,
                                     int rows_per_scale, float alpha, void* stream_) {
   MVLT_CHECK_ARG(C % 8 == 0, "cast_scale: C=%d must be a multiple of 8", C);

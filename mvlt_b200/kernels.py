@@ -520,6 +520,11 @@ def set_values(dst, payload: bytes):
     call("set_values", ptr(dst), buf, C.c_int(len(payload)))
 
 
+def spin(ms: float):
+    """Occupy the current stream for ``ms`` milliseconds (measurement aid, see csrc/elementwise.cu)."""
+    call("spin", C.c_longlong(int(ms * 1e6)))
+
+
 def memset_zero(t):
     call("memset_zero", ptr(t), C.c_longlong(t.numel() * t.element_size()))
 
