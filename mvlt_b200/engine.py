@@ -236,6 +236,15 @@ class PVLTEngine:
                 main.wait_event(ev)
             self._branch_done.clear()
 
+    def wgrad_event(self):
+        """An event marking everything enqueued on the weight-gradient stream so far (None without pending side launches): the
+        gradient exchange of a finished segment waits for it ON ITS OWN stream -- the compute stream does not stall."""
+        if self.wgrad_stream is None or not self._wgrad_pending:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.wgrad_stream)
+        return ev
+
     def _lin_param_grads(self, G, wname, bname, dy, x, wgrad=None):
         """dW += dy^T x (split-K, fp32 atomics straight into the gradient buffer); db += column sums of dy (same launch)."""
         rows, co = dy.shape
@@ -589,8 +598,7 @@ class PVLTEngine:
                 if items:      # (on the weight-gradient stream when there is one: it follows the GEMMs that fill the arena)
                     self.side_launch(lambda: k.uncast_conv_wgrad_multi(items))
                 if on_segment is not None:
-                    self.wgrad_join()      # the stage's weight gradients (side stream) are complete
-                    on_segment(4 - i)
+                    on_segment(4 - i, self.wgrad_event())      # (the exchange also waits for the stage's side-stream weight gradients)
             else:
                 dy768 = _empty((B * T, HIDDEN), BF16, dev)
                 k.gemm(dte, Wb["text_embed1.0.weight"].t(), dy768)
@@ -607,7 +615,7 @@ class PVLTEngine:
             self.side_launch(lambda: k.uncast_conv_wgrad_multi(items))
         self.wgrad_join()
         if on_segment is not None:
-            on_segment(4)
+            on_segment(4, None)
 
     # ------------------------------------------------------------------------------------------------
     # heads (pvlt.py:365-397)

@@ -179,7 +179,8 @@ class SegmentReducer:
                 side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=flat.device)
             self.side = side
 
-    def segment_done(self, k):
+    def segment_done(self, k, also_wait=None):
+        """``also_wait``: optional extra CUDA event (work on another stream that also writes the segment) the exchange waits for."""
         if self.world == 1 or k in self.done:
             return
         self.done.add(k)
@@ -195,6 +196,8 @@ class SegmentReducer:
         ready.record(main)
         with torch.cuda.stream(self.side):
             self.side.wait_event(ready)
+            if also_wait is not None:
+                self.side.wait_event(also_wait)
             allreduce_flat_(part, True if self.group is None else self.group)
             ev = torch.cuda.Event()
             ev.record(self.side)
@@ -281,8 +284,7 @@ def eng_backward_logits(eng: PVLTEngine, saved, gouts, G, on_segment=None):
         df2, df3 = eng.t2i.backward(dscore, c, G, dX4)
         dXs[1], dXs[2] = df2, df3
     if on_segment is not None:
-        eng.wgrad_join()    # (head weight gradients launched on the side stream included)
-        on_segment(0)       # every head gradient is enqueued
+        on_segment(0, eng.wgrad_event())       # every head gradient is enqueued (weight gradients: on the side stream)
     eng.encoder_bwd(enc, dXs, G, on_segment)
 
 
@@ -398,8 +400,7 @@ def eng_backward_losses(eng: PVLTEngine, saved, gtotal, G, on_segment=None):
             eng.small_head_bwd(dl, c, name, B, HW4, dX4, G)
     eng.join_branches()
     if on_segment is not None:
-        eng.wgrad_join()    # (head weight gradients launched on the side stream included)
-        on_segment(0)       # every head gradient is enqueued
+        on_segment(0, eng.wgrad_event())       # every head gradient is enqueued (weight gradients: on the side stream)
     eng.encoder_bwd(enc, dXs, G, on_segment)
 
 
