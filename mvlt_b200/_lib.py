@@ -35,6 +35,8 @@ class GemmDesc(C.Structure):
         ("rows_per_scale", C.c_int32), ("split_k", C.c_int32), ("block_n", C.c_int32),
         ("conv_mode", C.c_int32), ("conv_B", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32),
         ("conv_C", C.c_int32), ("conv_pix_stride", C.c_int64), ("conv_batch_stride", C.c_int64),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p),
+        ("ln_eps", C.c_float),
     ]
 
 

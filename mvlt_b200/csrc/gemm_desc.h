@@ -61,6 +61,17 @@ typedef struct mvlt_gemm_desc {
   int32_t conv_mode;
   int32_t conv_B, conv_H, conv_W, conv_C;           // C % 64 == 0; W <= 64 and 64 % W == 0; (H*W) % 64 == 0
   int64_t conv_pix_stride, conv_batch_stride;       // element strides of X (x -> x+1, b -> b+1); y stride = W * pix_stride
+  // LayerNorm of the OUTPUT rows fused into the residual epilogue (active when ln_gamma != NULL). Needs: residual, fp32 D,
+  // N == 64 or 128 == the tile width (the whole row in one tile), no batch, no split-K, 16-byte aligned D / D2, and
+  // D2 = bf16 [M, N] with D's leading dimension:  D2[m, :] = (D[m, :] - mean_m) * rstd_m * ln_gamma + ln_beta
+  // (statistics over the N columns of the final fp32 row, biased variance, rstd = rsqrt(var + ln_eps));
+  // ln_mean / ln_rstd: optional fp32 [M] outputs for the LayerNorm backward. Replaces a separate LayerNorm pass over D
+  // (reference: x = x + drop_path(attn(norm1(x))); norm2(x), libs/pvlt.py:140-143).
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
 } mvlt_gemm_desc;
 
 #ifdef __cplusplus

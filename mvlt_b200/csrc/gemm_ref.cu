@@ -53,6 +53,7 @@ __global__ void gemm_ref_kernel(const mvlt_gemm_desc g) {
 extern "C" int mvlt_gemm_ref(const mvlt_gemm_desc* g, void* stream) {
   MVLT_CHECK_ARG(g && g->A && g->B && g->D, "mvlt_gemm_ref: null argument");
   MVLT_CHECK_ARG(g->rowsum == nullptr, "mvlt_gemm_ref: rowsum is only implemented by the tcgen05 kernel");
+  MVLT_CHECK_ARG(g->ln_gamma == nullptr, "mvlt_gemm_ref: the fused LayerNorm epilogue is only implemented by the tcgen05 kernel");
   MVLT_CHECK_ARG(g->conv_mode == MVLT_CONV_NONE, "mvlt_gemm_ref: implicit convolution operands are only implemented by the tcgen05 kernel");
   MVLT_CHECK_ARG(g->act != MVLT_ACT_SOFTMAX && g->act != MVLT_ACT_SOFTMAX_BWD,
                  "mvlt_gemm_ref: the row-wise softmax epilogues are only implemented by the tcgen05 kernel");

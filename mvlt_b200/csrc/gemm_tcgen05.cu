@@ -85,6 +85,13 @@ struct KParams {
   int pair;       // CTA-pair mode (cta_group::2): clusters of 2 CTAs share one 256-row UMMA; num_m_blocks counts row PAIRS
   int tma_store;  // D (and D2) leave the staging tiles through TMA bulk stores (tmD / tmD2) instead of LDS + STG
   int prefetch;   // EPI_AUX only: two staging tiles per epilogue warp, the aux unit of the next tile is fetched with cp.async
+  int warp_stage_bytes;   // staging bytes per epilogue warp: 4096, or 8192 (prefetch; fused LayerNorm with 2 units per warp)
+  // fused LayerNorm of the output rows (EPI_RESID, fp32 out, N == block_n == 64 | 128): see gemm_desc.h
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
   // implicit 3x3 convolution operand (gemm_desc.h): tile/k-block index -> (b, y) pixel coordinates and (tap, c0)
   int conv_mode, conv_W, conv_C;
   FastDiv div_hw, div_w, div_cb, div_c;   // pixels / (H*W), / W; k-block / (C/64); column / C
@@ -573,6 +580,69 @@ __device__ __forceinline__ float softmax_bwd_unit(const KParams& p, uint32_t tad
   return acc;
 }
 
+// ---- fused LayerNorm of the output rows (residual epilogue, fp32 out, the whole row in this tile) ------------------------------
+// Pass 1, one unit (32 fp32 columns) of this lane's row: v = residual + rs * (alpha * acc + bias) -> D through the staging tile
+// (which KEEPS v afterwards: one tile per unit of the warp), row sum and sum of squares accumulated on the way.
+__device__ __forceinline__ void resid_ln_pass1(const KParams& p, uint32_t taddr, long long row_base_off, int lane, int rows_valid,
+                                               int col0, float rs, const StageAddr& s, const StoreCtx& sc, float& sum, float& sq) {
+  uint32_t ex[32];
+  load_rows_via_stage<8>(s, reinterpret_cast<const uint8_t*>(p.residual + row_base_off + col0), p.ldd * 4, lane, rows_valid, ex);
+  const f32x2_t rs2 = f2_splat(rs);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint32_t r[16];
+    tmem_ld_32x16(taddr + (uint32_t)(16 * i), r);
+    tmem_ld_wait();
+    f32x2_t v2[8];
+    scale_bias16<true>(p, r, col0 + 16 * i, v2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v2[j] = f2_fma(rs2, v2[j], f2_pack(__uint_as_float(ex[16 * i + 2 * j]), __uint_as_float(ex[16 * i + 2 * j + 1])));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a, b, c, d;
+      f2_unpack(v2[2 * j], a, b);
+      f2_unpack(v2[2 * j + 1], c, d);
+      sum += (a + b) + (c + d);
+      sq = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, sq))));
+      st_shared_v4(own_piece<8>(s, 4 * i + j), __float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d));
+    }
+  }
+  tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);   // returns once the TMA engine has READ the tile
+}
+__device__ __forceinline__ float4 ld_nc_v4_ordered(const float* ptr) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr));
+  return r;
+}
+// Pass 2, same unit: v back from the staging tile, normalised, bf16 -> the tile again in the 64-byte-row layout -> D2.
+__device__ __forceinline__ void resid_ln_pass2(const KParams& p, int lane, int col0, float mean, float rstd, const StageAddr& s,
+                                               const StoreCtx& sc) {
+  float v[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint4 t = ld_shared_v4(own_piece<8>(s, q));
+    v[4 * q] = __uint_as_float(t.x); v[4 * q + 1] = __uint_as_float(t.y);
+    v[4 * q + 2] = __uint_as_float(t.z); v[4 * q + 3] = __uint_as_float(t.w);
+  }
+  __syncwarp();   // every lane holds its fp32 row before the tile is rewritten as 32 rows x 64 bytes
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // (volatile loads: they stay behind the previous half's staging stores instead of all 64 values being hoisted and spilled)
+      const float4 g4 = ld_nc_v4_ordered(p.ln_gamma + col0 + 16 * h + 4 * j);
+      const float4 b4 = ld_nc_v4_ordered(p.ln_beta + col0 + 16 * h + 4 * j);
+      const float* vv = &v[16 * h + 4 * j];
+      pk[2 * j] = pack_bf16x2(fmaf((vv[0] - mean) * rstd, g4.x, b4.x), fmaf((vv[1] - mean) * rstd, g4.y, b4.y));
+      pk[2 * j + 1] = pack_bf16x2(fmaf((vv[2] - mean) * rstd, g4.z, b4.z), fmaf((vv[3] - mean) * rstd, g4.w, b4.w));
+    }
+    stage_put_bf16<4>(s, h, pk);
+  }
+  tma_flush(sc.tmD2h, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
+}
+
 // kPair: CTA-pair build (cta_group::2). A kernel that contains cta_group::2 instructions can only be launched as clusters
 // of two, so the pair path is a separate instantiation and the single-CTA build carries none of its code or registers.
 template <int kEpi, bool kOutF32, bool kPair = false>
@@ -795,7 +865,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int split = (nchunks + 1) >> 1;
     const int c_begin = half ? split : 0;
     const int c_end = half ? nchunks : split;
-    const uint32_t stage = smem_u32(stage_base) + (uint32_t)ew * (p.prefetch ? 8192u : 4096u);
+    const uint32_t stage = smem_u32(stage_base) + (uint32_t)ew * (uint32_t)p.warp_stage_bytes;
     const uint32_t partner_stage = smem_u32(stage_base) + (uint32_t)(ew ^ 8) * 4096u;
     const StageAddr sa = make_stage_addr(stage, lane);
     const int pair_bar = 1 + group * 4 + quarter;   // named barriers 1..8 (0 is __syncthreads)
@@ -934,6 +1004,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             softmax_bwd_unit<4, 1>(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, dot, sa, ssc);
             ci += 1;
+          }
+        }
+      } else if (kEpi == EPI_RESID && kOutF32 && p.ln_gamma != nullptr) {
+        // ---- residual epilogue + LayerNorm of the finished row (the whole row is in this tile: n0 == 0). Pass 1 per unit:
+        // D + partial (sum, sum of squares), exchanged with the partner warp of the other column half; pass 2: normalise
+        // from the staging tiles (one per unit, they still hold the fp32 values) and store the bf16 operand of the next GEMM.
+        // Both warps of a pair always meet on the named barrier, rows past M included (their stores are clipped by the maps).
+        if constexpr (kEpi == EPI_RESID && kOutF32) {
+          float sum = 0.f, sq = 0.f;
+          for (int ci = c_begin, u = 0; ci < c_end; ++ci, ++u) {
+            const StageAddr su = make_stage_addr(stage + (uint32_t)u * 4096u, lane);
+            resid_ln_pass1(p, taddr0 + (uint32_t)(ci * 32), row_base_off, lane, rows_valid, ci * 32, rs, su, ssc, sum, sq);
+          }
+          const uint32_t xchg = smem_u32(stage_base) + (uint32_t)NUM_EPI_WARPS * (uint32_t)p.warp_stage_bytes;
+          const float2 o = pair_exchange(xchg + (uint32_t)ew * 256u, xchg + (uint32_t)(ew ^ 8) * 256u, pair_bar, lane, make_float2(sum, sq));
+          const float inv_n = 1.f / (float)p.N;
+          const float mean = (sum + o.x) * inv_n;
+          const float var = fmaxf(fmaf(-mean, mean, (sq + o.y) * inv_n), 0.f);
+          const float rstd = rsqrtf(var + p.ln_eps);
+          if (half == 0 && lane < rows_valid) {
+            if (p.ln_mean != nullptr) p.ln_mean[row_base + lane] = mean;
+            if (p.ln_rstd != nullptr) p.ln_rstd[row_base + lane] = rstd;
+          }
+          for (int ci = c_begin, u = 0; ci < c_end; ++ci, ++u) {
+            const StageAddr su = make_stage_addr(stage + (uint32_t)u * 4096u, lane);
+            resid_ln_pass2(p, lane, ci * 32, mean, rstd, su, ssc);
           }
         }
       } else if (rows_valid > 0) {
@@ -1233,7 +1329,14 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   MVLT_CHECK_ARG(!(g->residual && !g->out_f32), "mvlt_gemm: residual (fp32) needs an fp32 output");
   MVLT_CHECK_ARG(!(g->residual && g->aux), "mvlt_gemm: residual and aux are mutually exclusive");
   MVLT_CHECK_ARG(!(g->aux && g->out_f32), "mvlt_gemm: aux (bf16) needs a bf16 output");
-  MVLT_CHECK_ARG(!(g->D2 && g->out_f32), "mvlt_gemm: D2 (bf16) needs a bf16 output");
+  const bool ln = g->ln_gamma != nullptr;
+  MVLT_CHECK_ARG(!(g->D2 && g->out_f32 && !ln), "mvlt_gemm: D2 (bf16) needs a bf16 output");
+  if (ln)
+    MVLT_CHECK_ARG(g->ln_beta && g->D2 && g->residual && g->out_f32 && (g->N == 64 || g->N == 128) && g->act == MVLT_ACT_NONE &&
+                       !g->atomic_add && g->split_k <= 1 && g->batch1 == 1 && g->batch2 == 1 && g->conv_mode == MVLT_CONV_NONE &&
+                       (g->block_n == 0 || g->block_n == g->N) && g->ldd % 8 == 0 && ((uintptr_t)g->ln_gamma & 15) == 0 &&
+                       ((uintptr_t)g->ln_beta & 15) == 0 && g->rowsum == nullptr,
+                   "mvlt_gemm: the fused LayerNorm epilogue needs residual + fp32 D + bf16 D2, N = 64 | 128 in one tile, no batch / split-K");
   MVLT_CHECK_ARG(!(g->act == MVLT_ACT_GELU_SAVE_GRAD && g->out_f32), "mvlt_gemm: gelu_save_grad needs a bf16 output");
   MVLT_CHECK_ARG(!(g->atomic_add && (g->residual || g->aux || g->act != MVLT_ACT_NONE)),
                  "mvlt_gemm: atomic_add only combines with alpha / bias / rowscale");
@@ -1252,17 +1355,21 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   p.prefetch = (aux_kind && g->K <= 2 * BLOCK_K && g->N % 128 == 0 && (g->ldd % 8) == 0 && (g->sD1 % 8) == 0 && (g->sD2 % 8) == 0 &&
                 (g->block_n == 0 || g->block_n == 128)) ? 1 : 0;
   if (p.prefetch) p.block_n = 128;
+  if (ln) p.block_n = g->N;
+  p.warp_stage_bytes = p.prefetch ? 8192 : (ln ? 4096 * (g->N / 64) : 4096);
+  const int staging_total = NUM_EPI_WARPS * p.warp_stage_bytes + (ln ? 4096 : 0);   // (+ the LayerNorm partial-sum exchange area)
+  p.ln_gamma = g->ln_gamma; p.ln_beta = g->ln_beta; p.ln_mean = g->ln_mean; p.ln_rstd = g->ln_rstd; p.ln_eps = g->ln_eps;
   // CTA-pair mode (cta_group::2) for the tensor-bound shapes: a 256 x block_n tile per cluster of two CTAs halves the B bytes
   // each SM stages per k-block (32 KB instead of 48 KB at block_n = 256: 5 instead of 3 pipeline stages). Validated
   // (tests/test_gemm_gpu.py passes with MVLT_GEMM_PAIR=1) but measured SLOWER than the single-CTA build on every PVLT shape
   // (stage-4 MLP fc1 84.1 -> 90.8 us, fc2 72.0 -> 76.3 us, profiles/r2m_gemm_pair_ab.txt): these launches are bound by their
   // GELU / residual epilogues and by wave quantisation, not by the operand fill. Opt-in: MVLT_GEMM_PAIR=1.
   static const int pair_env = [] { const char* e = getenv("MVLT_GEMM_PAIR"); return e ? atoi(e) : 0; }();
-  p.pair = (pair_env && g->conv_mode == MVLT_CONV_NONE && g->rowsum == nullptr && !p.prefetch && g->split_k <= 1 && !g->atomic_add &&
+  p.pair = (pair_env && !ln && g->conv_mode == MVLT_CONV_NONE && g->rowsum == nullptr && !p.prefetch && g->split_k <= 1 && !g->atomic_add &&
             g->act != MVLT_ACT_SOFTMAX && g->act != MVLT_ACT_SOFTMAX_BWD && g->K >= 4 * BLOCK_K && g->M >= 16 * BLOCK_M &&
             p.block_n >= 128 && p.block_n % 128 == 0 && (long long)g->batch1 * g->batch2 == 1) ? 1 : 0;
   const int stage_bytes = A_STAGE_BYTES + (p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
-  p.stages = (p.prefetch ? SMEM_BUDGET - STAGING_BYTES : SMEM_BUDGET) / stage_bytes;
+  p.stages = (SMEM_BUDGET + STAGING_BYTES - staging_total) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.num_m_blocks = (g->M + BLOCK_M - 1) / BLOCK_M;
   if (p.pair) p.num_m_blocks = (p.num_m_blocks + 1) / 2;      // 256-row pairs; an odd last block is zero-filled / clipped
@@ -1333,7 +1440,7 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
 
   // > half of the SM's shared memory so two CTAs (each wanting all 512 TMEM columns) never share an SM
   size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 2048 /*ones tile + barriers, keeps staging 1 KB aligned*/ +
-                STAGING_BYTES * (p.prefetch ? 2 : 1);
+                (size_t)staging_total;
   if (smem < 120 * 1024) smem = 120 * 1024;
   static std::once_flag attr_once;
   static int launch_regs_ok = 1;
@@ -1371,6 +1478,10 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
         rc = make_output_map(&tmD2, g, g->D2, 0);
         if (rc) return rc;
       }
+      if (ln) {            // the bf16 normalised rows leave as 32-column units
+        rc = make_output_map(&tmD2h, g, g->D2, 0, 64);
+        if (rc) return rc;
+      }
       if (!g->out_f32) {   // 32-column remainder units of bf16 outputs
         rc = make_output_map(&tmDh, g, g->D, 0, 64);
         if (rc) return rc;
@@ -1382,6 +1493,7 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
       p.tma_store = 1;
     }
   }
+  MVLT_CHECK_ARG(!ln || p.tma_store, "mvlt_gemm: the fused LayerNorm epilogue needs 16-byte aligned D / D2 (TMA stores)");
   if (p.pair) mvlt_launch_cluster(kVariants[pick_variant(g) + kPairVariantOffset].fn, grid, NUM_THREADS, smem, stream, 2u, tmA, tmB, tmD, tmD2, tmDh, tmD2h, p);
   else mvlt_launch(kVariants[pick_variant(g)].fn, grid, NUM_THREADS, smem, stream, tmA, tmB, tmD, tmD2, tmDh, tmD2h, p);
   MVLT_CHECK_LAUNCH();

@@ -50,6 +50,10 @@ FUSED_ATTENTION = os.environ.get("MVLT_FUSED_ATTN", "1") != "0"
 FUSED_ATTENTION_BWD = os.environ.get("MVLT_FUSED_ATTN_BWD", "1") != "0"
 # fused MLP (csrc/mlp_tcgen05.cu) for the thin stages (C = 64 / 128); MVLT_FUSED_MLP=0 keeps the two-GEMM path for A/B runs
 FUSED_MLP = os.environ.get("MVLT_FUSED_MLP", "1") != "0"
+# LayerNorm (norm2) folded into the epilogue of the attention-projection GEMM for the thin stages (C = 64 / 128: the row fits
+# one tile): the fp32 rows are normalised on their way out instead of being re-read by a LayerNorm pass; MVLT_FUSED_LN=0 for A/B
+FUSED_LN = os.environ.get("MVLT_FUSED_LN", "1") != "0"
+FUSED_LN_DIMS = (64, 128)
 
 
 def _empty(shape, dtype, dev):
@@ -327,12 +331,19 @@ class PVLTEngine:
             k.gemm(q4, k4, Pm, alpha=HEAD_DIM ** -0.5, act=k.ACT_SOFTMAX)   # softmax fused into the QK^T epilogue
             k.gemm(Pm, v4.transpose(-1, -2), o.view(B, N, heads, HEAD_DIM).permute(0, 2, 1, 3))
         X1 = _empty((B, N, C), F32, dev)
-        k.gemm(o, Wb[pfx + ".attn.proj.weight"], X1.view(M, C), bias=P[pfx + ".attn.proj.bias"],
-               residual=X.view(M, C), rowscale=dp[0] if dp else None, rows_per_scale=N)
-        # ---- MLP branch
         xn2 = _empty((M, C), BF16, dev)
         mean2, rstd2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
-        k.layernorm_fwd(X1, P[pfx + ".norm2.weight"], P[pfx + ".norm2.bias"], xn2, 1e-6, M, C, mean=mean2, rstd=rstd2)
+        if FUSED_LN and C in FUSED_LN_DIMS:
+            # x = x + drop_path(proj(attn)) and norm2(x) in ONE kernel (pvlt.py:141-142): the epilogue normalises the row it just
+            # finished (it spans one tile) and also writes the bf16 operand of the MLP
+            k.gemm(o, Wb[pfx + ".attn.proj.weight"], X1.view(M, C), bias=P[pfx + ".attn.proj.bias"],
+                   residual=X.view(M, C), rowscale=dp[0] if dp else None, rows_per_scale=N,
+                   ln=(P[pfx + ".norm2.weight"], P[pfx + ".norm2.bias"], xn2, mean2, rstd2, 1e-6))
+        else:
+            k.gemm(o, Wb[pfx + ".attn.proj.weight"], X1.view(M, C), bias=P[pfx + ".attn.proj.bias"],
+                   residual=X.view(M, C), rowscale=dp[0] if dp else None, rows_per_scale=N)
+            # ---- MLP branch
+            k.layernorm_fwd(X1, P[pfx + ".norm2.weight"], P[pfx + ".norm2.bias"], xn2, 1e-6, M, C, mean=mean2, rstd=rstd2)
         X2 = _empty((B, N, C), F32, dev)
         fused_mlp = FUSED_MLP and C in k.MLP_FUSED_DIMS and (not save or C in k.MLP_FUSED_BWD_DIMS)
         act = hpre = None

@@ -41,7 +41,7 @@ def _operand(t: torch.Tensor, name: str):
 
 
 def _build_gemm_desc(a, b, out, alpha, bias, act, preact_out, aux, residual, rowscale, rows_per_scale, atomic_add, split_k,
-                     block_n, rowsum):
+                     block_n, rowsum, ln_out=None):
     """Validate one GEMM signature and build its descriptor (everything except the device pointers)."""
     a_mn, lda, abs_, ast = _operand(a, "a")
     b_mn, ldb, bbs, bst = _operand(b, "b")
@@ -90,10 +90,11 @@ def _build_gemm_desc(a, b, out, alpha, bias, act, preact_out, aux, residual, row
     d.split_k = split_k
     d.block_n = block_n
     nb = b1 * b2
-    extra = sum(M * N * nb * t.element_size() for t in (aux, preact_out, residual) if t is not None)
+    extra = sum(M * N * nb * t.element_size() for t in (aux, preact_out, residual, ln_out) if t is not None)
     acct = (2.0 * M * N * K * nb, (M * K + N * K) * 2.0 * nb + M * N * nb * out.element_size() + extra,
             f"gemm M={M} N={N} K={K} b={nb} amn={a_mn} bmn={b_mn} out={'f32' if out.dtype == F32 else 'bf16'} act={act} "
-            f"res={int(residual is not None)} atomic={int(atomic_add)} split={split_k} rowsum={int(rowsum is not None)}")
+            f"res={int(residual is not None)} atomic={int(atomic_add)} split={split_k} rowsum={int(rowsum is not None)}"
+            + (" ln=1" if ln_out is not None else ""))
     return d, C.byref(d), acct
 
 
@@ -105,11 +106,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
          aux: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          rowscale: Optional[torch.Tensor] = None, rows_per_scale: int = 0, atomic_add: bool = False,
          split_k: int = 0, block_n: int = 0, rowsum: Optional[torch.Tensor] = None,
-         impl: str = "tcgen05") -> torch.Tensor:
+         ln=None, impl: str = "tcgen05") -> torch.Tensor:
     """out[..., M, N] = epilogue(alpha * a[..., M, K] @ b[..., N, K]^T)   (see csrc/gemm_desc.h).
 
     ``a``/``b`` may be arbitrary 2-4 D views with one unit stride among the last two dims (K-major or
     MN-major); leading dims are batch dims (broadcast with stride 0 / size 1 allowed).
+
+    ``ln = (gamma, beta, out_bf16, mean, rstd, eps)``: LayerNorm of the finished fp32 rows fused into the residual epilogue
+    (N = 64 | 128; ``mean`` / ``rstd`` fp32 [M] or None): ``out_bf16`` = the normalised rows, the next GEMM's operand.
 
     A training step repeats the same ~250 GEMM signatures every iteration: the validated descriptor of each signature
     (geometry, strides, dtypes, epilogue options) is cached and only its device pointers are refreshed per call, which
@@ -121,14 +125,22 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
            rows_per_scale, atomic_add, split_k, block_n,
            None if bias is None else (bias.dtype, bias.shape), None if preact_out is None else (preact_out.dtype, preact_out.stride()),
            None if aux is None else (aux.dtype, aux.stride()), None if residual is None else (residual.dtype, residual.stride()),
-           rowscale is None, None if rowsum is None else (rowsum.dtype, rowsum.shape, rowsum.stride()))
+           rowscale is None, None if rowsum is None else (rowsum.dtype, rowsum.shape, rowsum.stride()),
+           None if ln is None else (ln[2].stride(), ln[3] is None, ln[4] is None, float(ln[5])))
     ent = _GEMM_CACHE.get(key)
     if ent is None:
-        for t in (bias, preact_out, aux, residual, rowscale, rowsum):
+        if ln is not None:
+            g_, b_, o_, m_, r_, _eps = ln
+            if (residual is None or out.dtype != F32 or o_.dtype != BF16 or o_.stride() != out.stride() or g_.dtype != F32
+                    or b_.dtype != F32 or g_.numel() != out.shape[-1] or b_.numel() != out.shape[-1] or preact_out is not None
+                    or any(t is not None and (t.dtype != F32 or t.numel() != out.shape[-2] or not t.is_contiguous()) for t in (m_, r_))):
+                raise _lib.MvltError("gemm ln=(gamma, beta, out_bf16, mean, rstd, eps): needs residual, fp32 out, bf16 out_bf16 with "
+                                     "out's strides, fp32 gamma / beta [N], fp32 mean / rstd [M]")
+        for t in (bias, preact_out, aux, residual, rowscale, rowsum) + (tuple(ln[:5]) if ln is not None else ()):
             if t is not None and not t.is_cuda:
                 raise _lib.MvltError("mvlt_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
         ent = _build_gemm_desc(a, b, out, alpha, bias, act, preact_out, aux, residual, rowscale, rows_per_scale, atomic_add,
-                               split_k, block_n, rowsum)
+                               split_k, block_n, rowsum, None if ln is None else ln[2])
         if len(_GEMM_CACHE) > 4096:
             _GEMM_CACHE.clear()
         _GEMM_CACHE[key] = ent
@@ -142,6 +154,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 
     d.residual = None if residual is None else residual.data_ptr()
     d.rowscale = None if rowscale is None else rowscale.data_ptr()
     d.rowsum = None if rowsum is None else rowsum.data_ptr()
+    if ln is not None:
+        d.ln_gamma, d.ln_beta, d.D2 = ln[0].data_ptr(), ln[1].data_ptr(), ln[2].data_ptr()
+        d.ln_mean = None if ln[3] is None else ln[3].data_ptr()
+        d.ln_rstd = None if ln[4] is None else ln[4].data_ptr()
+        d.ln_eps = float(ln[5])
+    else:
+        d.ln_gamma = None
     if _lib.PROFILE is not None or _lib.GEMM_LOG is not None:
         _lib.account_gemm(*acct)
     call("gemm" if impl == "tcgen05" else "gemm_ref", ref)

@@ -48,6 +48,46 @@ def test_gemm_layouts(a_mn, b_mn, M, N, K, out_dtype):
     _check(out, _ref(a, b), K, f"layout a_mn={a_mn} b_mn={b_mn} {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("M,N,K", [(4224 * 3, 64, 64), (1152 * 2 + 77, 128, 128), (640, 128, 1024), (300, 64, 512)])
+def test_gemm_residual_epilogue_with_fused_layernorm(M, N, K):
+    """x1 = residual + rowscale * (a b^T + bias) (fp32) and LayerNorm(x1) (bf16) + its (mean, rstd) from ONE launch
+    (reference: x = x + drop_path(attn.proj(...)); norm2(x), /root/reference/libs/pvlt.py:141-142), vs torch in fp32.
+    Row counts that are not multiples of the 128-row tile exercise the clipped tail."""
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a, b = _rand((M, K), g, 0.5), _rand((N, K), g, 0.2)
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = torch.randn((M, N), generator=g, device="cuda") * 2.0 + 0.7          # a non-zero row mean
+    rps = 64
+    rs = torch.rand((M + rps - 1) // rps, generator=g, device="cuda")
+    gamma = torch.randn(N, generator=g, device="cuda")
+    beta = torch.randn(N, generator=g, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=F32)
+    xn = torch.full((M, N), float("nan"), device="cuda", dtype=BF16)
+    mean = torch.full((M,), float("nan"), device="cuda")
+    rstd = torch.full((M,), float("nan"), device="cuda")
+    k.gemm(a, b, out, bias=bias, residual=res, rowscale=rs, rows_per_scale=rps, ln=(gamma, beta, xn, mean, rstd, 1e-6))
+    torch.cuda.synchronize()
+    ref = res + rs.repeat_interleave(rps)[:M, None] * (_ref(a, b) + bias)
+    _check(out, ref, K, "residual (ln mode)")
+    # the LayerNorm is compared on the kernel's OWN fp32 rows: what is tested here is the fused normalisation
+    mu = out.mean(1)
+    var = out.var(1, unbiased=False)
+    assert torch.allclose(mean, mu, rtol=1e-4, atol=1e-5), (mean - mu).abs().max()
+    assert torch.allclose(rstd, (var + 1e-6).rsqrt(), rtol=2e-4, atol=1e-5), (rstd - (var + 1e-6).rsqrt()).abs().max()
+    ln_ref = torch.nn.functional.layer_norm(out, (N,), gamma, beta, 1e-6)
+    err = (xn.float() - ln_ref).abs().max().item()
+    assert err <= 1e-2 * ln_ref.abs().max().item() + 1e-3, err
+    assert torch.isfinite(xn.float()).all()
+    # a second launch without statistics outputs, and the plain residual epilogue on the same operands still agrees
+    out2 = torch.empty_like(out)
+    xn2 = torch.empty_like(xn)
+    k.gemm(a, b, out2, bias=bias, residual=res, rowscale=rs, rows_per_scale=rps, ln=(gamma, beta, xn2, None, None, 1e-6))
+    out3 = torch.empty_like(out)
+    k.gemm(a, b, out3, bias=bias, residual=res, rowscale=rs, rows_per_scale=rps)
+    assert torch.equal(out2, out) and torch.equal(xn2, xn) and torch.equal(out3, out)
+
+
 def test_gemm_matches_simt_ref_bitwise_structure():
     """Same descriptor through the SIMT cross-check kernel and the tcgen05 kernel."""
     from mvlt_b200 import kernels as k
