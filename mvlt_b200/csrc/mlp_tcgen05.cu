@@ -66,6 +66,13 @@ struct MlpParams {
   const float* rowscale;    // per-sample drop-path factor or nullptr
   int rows_per_scale;
   int dbg;                  // tuning experiments only (MVLT_MLP_DBG): 1 = no residual read, 2 = identity instead of GELU, 4 = no output
+  // LayerNorm of the OUTPUT rows (the next block's norm1) fused into the output warps (ln_gamma != nullptr): every lane owns a
+  // whole row, so the statistics need no exchange; the normalised bf16 rows leave through a second tensor map
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;           // optional fp32 [M]
+  float* ln_rstd;
+  float ln_eps;
 };
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes) {   // K-major SWIZZLE_128B operand
@@ -88,7 +95,7 @@ __device__ __forceinline__ uint32_t instr_desc(int n) {   // kind::f16, bf16 x b
 
 template <int C>
 __global__ void __launch_bounds__(NTHREADS, 1)
-mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmLn, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ MlpParams p) {
   using K = Cfg<C>;
@@ -277,6 +284,7 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       float rs = 1.f;
       if (p.rowscale != nullptr && valid) rs = p.rowscale[row / p.rows_per_scale];
       const float* res_row = p.residual + (long long)row * C;
+      float ln_sum = 0.f, ln_sq = 0.f;
 #pragma unroll 1
       for (int u = 0; u < C / 32; ++u) {
         if (u == 0) {
@@ -302,6 +310,8 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const float o1 = fmaf(__uint_as_float(r[4 * i + 1]) + b4.y, rs, rv[i].y);
             const float o2 = fmaf(__uint_as_float(r[4 * i + 2]) + b4.z, rs, rv[i].z);
             const float o3 = fmaf(__uint_as_float(r[4 * i + 3]) + b4.w, rs, rv[i].w);
+            ln_sum += (o0 + o1) + (o2 + o3);
+            ln_sq = fmaf(o0, o0, fmaf(o1, o1, fmaf(o2, o2, fmaf(o3, o3, ln_sq))));
             st_shared_v4(own + ((((uint32_t)(hh * 4 + i)) ^ rx) << 4), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2),
                          __float_as_uint(o3));
           }
@@ -311,6 +321,54 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (lane == 0) {
           tma_store_4d(&tmOut, tile_s, u * 32, m0 + quarter * 32, 0, 0);   // rows past M are clipped by the tensor map
           tma_store_commit();
+        }
+      }
+      if (p.ln_gamma != nullptr && !(p.dbg & 4)) {
+        // ---- LayerNorm of the finished rows (the next block's norm1, libs/pvlt.py:140): second pass over the accumulator
+        // (still in TMEM) and the residual (L1 / L2 now), same arithmetic -> the same fp32 values, normalised and stored as
+        // the bf16 operand of the next block's q / kv projections, 64 columns (= 128-byte rows of the staging tile) at a time
+        const float mean = ln_sum * (1.f / (float)C);
+        const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, ln_sq * (1.f / (float)C)), 0.f) + p.ln_eps);
+        if (valid) {
+          if (p.ln_mean != nullptr) p.ln_mean[row] = mean;
+          if (p.ln_rstd != nullptr) p.ln_rstd[row] = rstd;
+        }
+#pragma unroll 1
+        for (int u2 = 0; u2 < C / 64; ++u2) {
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            const int c0 = u2 * 64 + hh * 16;
+            float4 rv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              rv[i] = (valid && !(p.dbg & 1)) ? __ldg(reinterpret_cast<const float4*>(res_row + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t r[16];
+            tmem_ld_32x16(tmem_base + tlane + (uint32_t)(Y_COL0 + yb * C + c0), r);
+            tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + c0) + i);
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c0) + i);
+              const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c0) + i);
+              const float o0 = fmaf(__uint_as_float(r[4 * i]) + b4.x, rs, rv[i].x);
+              const float o1 = fmaf(__uint_as_float(r[4 * i + 1]) + b4.y, rs, rv[i].y);
+              const float o2 = fmaf(__uint_as_float(r[4 * i + 2]) + b4.z, rs, rv[i].z);
+              const float o3 = fmaf(__uint_as_float(r[4 * i + 3]) + b4.w, rs, rv[i].w);
+              pk[2 * i] = pack_bf16x2(fmaf((o0 - mean) * rstd, g4.x, e4.x), fmaf((o1 - mean) * rstd, g4.y, e4.y));
+              pk[2 * i + 1] = pack_bf16x2(fmaf((o2 - mean) * rstd, g4.z, e4.z), fmaf((o3 - mean) * rstd, g4.w, e4.w));
+            }
+            st_shared_v4(own + ((((uint32_t)(hh * 2)) ^ rx) << 4), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(own + ((((uint32_t)(hh * 2 + 1)) ^ rx) << 4), pk[4], pk[5], pk[6], pk[7]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmLn, tile_s, u2 * 64, m0 + quarter * 32, 0, 0);
+            tma_store_commit();
+          }
         }
       }
       tc_fence_before();
@@ -329,9 +387,9 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 template <int C>
-int launch_fwd(const void* x, const void* w1, const void* w2, void* out, const MlpParams& p, cudaStream_t stream) {
+int launch_fwd(const void* x, const void* w1, const void* w2, void* out, void* ln_out, const MlpParams& p, cudaStream_t stream) {
   using K = Cfg<C>;
-  CUtensorMap tmX, tmW1, tmW2, tmOut;
+  CUtensorMap tmX, tmW1, tmW2, tmOut, tmLn;
   int rc;
   {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.M, 1, 1};
@@ -357,13 +415,20 @@ int launch_fwd(const void* x, const void* w1, const void* w2, void* out, const M
     const uint32_t box[4] = {32, 32, 1, 1};
     if ((rc = mvlt_tensor_map_4d(&tmOut, out, dims, str, box, 1, 0)) != 0) return rc;
   }
+  tmLn = tmOut;
+  if (ln_out != nullptr) {   // bf16 [M, C] normalised rows: boxes of 32 rows x 64 columns (128-byte rows, SWIZZLE_128B)
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.M, 1, 1};
+    const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)p.M * C * 2, (uint64_t)p.M * C * 2};
+    const uint32_t box[4] = {64, 32, 1, 1};
+    if ((rc = mvlt_tensor_map_4d(&tmLn, ln_out, dims, str, box, 0, 0)) != 0) return rc;
+  }
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(mlp_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_USED + 1024);
   });
   int grid = mvlt_num_sms();
   if (p.num_tiles < grid) grid = p.num_tiles;
-  mvlt_launch(mlp_fwd_kernel<C>, grid, NTHREADS, (size_t)K::SMEM_USED + 1024, stream, tmX, tmW1, tmW2, tmOut, p);
+  mvlt_launch(mlp_fwd_kernel<C>, grid, NTHREADS, (size_t)K::SMEM_USED + 1024, stream, tmLn, tmX, tmW1, tmW2, tmOut, p);
   MVLT_CHECK_LAUNCH();
   return 0;
 }
@@ -886,9 +951,13 @@ mlp_bwd128_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 // out[M, C] (fp32) = residual[M, C] (fp32) + rowscale[row / rows_per_scale] * (GELU(x W1^T + b1) W2^T + b2)
 //   x_bf16 [M, C], w1_bf16 [HD, C], b1 fp32 [HD], w2_bf16 [C, HD], b2 fp32 [C]; all contiguous, 16-byte aligned.
 //   C in {64, 128}, HD a multiple of 64; rowscale_f32 may be null (no DropPath). ``out`` may alias ``residual``.
+// ln_* (optional, all NULL / 0 for none): LayerNorm of the output rows fused into the same launch -- ln_out_bf16 [M, C] =
+// (out - mean) * rstd * ln_gamma + ln_beta (biased variance over the C columns, rstd = rsqrt(var + ln_eps)), ln_mean / ln_rstd
+// fp32 [M] (optional) for the LayerNorm backward: the next block's norm1 without re-reading the fp32 rows
 extern "C" int mvlt_mlp_fwd(const void* x_bf16, const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
                             const float* residual_f32, float* out_f32, const float* rowscale_f32, int rows_per_scale, int M,
-                            int C, int HD, void* stream_) {
+                            int C, int HD, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, float* ln_mean,
+                            float* ln_rstd, float ln_eps, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MVLT_CHECK_ARG(x_bf16 && w1_bf16 && b1 && w2_bf16 && b2 && residual_f32 && out_f32, "mlp_fwd: null operand");
   MVLT_CHECK_ARG(M > 0 && (C == 64 || C == 128) && HD >= 64 && HD % 64 == 0, "mlp_fwd: unsupported shape M=%d C=%d HD=%d", M, C, HD);
@@ -902,7 +971,14 @@ extern "C" int mvlt_mlp_fwd(const void* x_bf16, const void* w1_bf16, const float
   p.b1 = b1; p.b2 = b2; p.residual = residual_f32; p.rowscale = rowscale_f32; p.rows_per_scale = rows_per_scale > 0 ? rows_per_scale : 1;
   static const int dbg = [] { const char* e = getenv("MVLT_MLP_DBG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg;
-  return C == 64 ? launch_fwd<64>(x_bf16, w1_bf16, w2_bf16, out_f32, p, stream) : launch_fwd<128>(x_bf16, w1_bf16, w2_bf16, out_f32, p, stream);
+  MVLT_CHECK_ARG((ln_gamma == nullptr) == (ln_out_bf16 == nullptr) && (ln_gamma == nullptr) == (ln_beta == nullptr),
+                 "mlp_fwd: ln_gamma, ln_beta and ln_out go together");
+  MVLT_CHECK_ARG(((((uintptr_t)ln_gamma) | ((uintptr_t)ln_beta) | ((uintptr_t)ln_out_bf16)) & 15) == 0, "mlp_fwd: ln operands must be 16-byte aligned");
+  MVLT_CHECK_ARG(ln_gamma == nullptr || (const void*)out_f32 != (const void*)residual_f32,
+                 "mlp_fwd: the fused LayerNorm re-reads the residual after the output is stored: out must not alias it");
+  p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.ln_mean = ln_mean; p.ln_rstd = ln_rstd; p.ln_eps = ln_eps;
+  return C == 64 ? launch_fwd<64>(x_bf16, w1_bf16, w2_bf16, out_f32, ln_out_bf16, p, stream)
+                 : launch_fwd<128>(x_bf16, w1_bf16, w2_bf16, out_f32, ln_out_bf16, p, stream);
 }
 
 

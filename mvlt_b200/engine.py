@@ -280,7 +280,10 @@ class PVLTEngine:
     # ------------------------------------------------------------------------------------------------
     # transformer block
     # ------------------------------------------------------------------------------------------------
-    def _block_fwd(self, X, pfx, i, B, H, W, dp, save):
+    def _block_fwd(self, X, pfx, i, B, H, W, dp, save, pre_norm=None, next_pfx=None):
+        """``pre_norm``: (xn, mean, rstd) of this block's norm1 when the previous block's MLP already produced it;
+        ``next_pfx``: name of the next block of the stage -- its norm1 is then folded into this block's last kernel when that
+        kernel can do it (C = 64 / 128), and returned as the third value (None otherwise)."""
         P, Wb, T = self.P, self.W, self.T
         C, R, heads = EMBED_DIMS[i], SR_RATIOS[i], NUM_HEADS[i]
         HW, N = H * W, H * W + T
@@ -289,9 +292,12 @@ class PVLTEngine:
         hidden = C * MLP_RATIOS[i]
         c = {}
         # ---- attention branch
-        xn = _empty((M, C), BF16, dev)
-        mean1, rstd1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
-        k.layernorm_fwd(X, P[pfx + ".norm1.weight"], P[pfx + ".norm1.bias"], xn, 1e-6, M, C, mean=mean1, rstd=rstd1)
+        if pre_norm is not None:
+            xn, mean1, rstd1 = pre_norm
+        else:
+            xn = _empty((M, C), BF16, dev)
+            mean1, rstd1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
+            k.layernorm_fwd(X, P[pfx + ".norm1.weight"], P[pfx + ".norm1.bias"], xn, 1e-6, M, C, mean=mean1, rstd=rstd1)
         q = _empty((M, C), BF16, dev)
         Nk = (H // R) * (W // R) + T if R > 1 else N
         if Nk % 32 != 0 or Nk > 256:
@@ -347,11 +353,17 @@ class PVLTEngine:
         X2 = _empty((B, N, C), F32, dev)
         fused_mlp = FUSED_MLP and C in k.MLP_FUSED_DIMS and (not save or C in k.MLP_FUSED_BWD_DIMS)
         act = hpre = None
+        # the next block's norm1 from this block's last kernel (its rows are complete there): (gamma, beta, xn, mean, rstd, eps)
+        nxt = ln_next = None
+        if next_pfx is not None and FUSED_LN and C in FUSED_LN_DIMS:
+            nxt = (_empty((M, C), BF16, dev), _empty((M,), F32, dev), _empty((M,), F32, dev))
+            ln_next = (P[next_pfx + ".norm1.weight"], P[next_pfx + ".norm1.bias"], nxt[0], nxt[1], nxt[2], 1e-6)
         if fused_mlp:
             # one kernel: fc1 -> GELU -> fc2 -> + bias, x drop-path, + residual; the [M, hidden] activation stays in TMEM /
             # shared memory (csrc/mlp_tcgen05.cu). Training saves nothing: the backward recomputes fc1 from xn2.
             k.mlp_fwd(xn2, Wb[pfx + ".mlp.fc1.weight"], P[pfx + ".mlp.fc1.bias"], Wb[pfx + ".mlp.fc2.weight"],
-                      P[pfx + ".mlp.fc2.bias"], X1.view(M, C), X2.view(M, C), rowscale=dp[1] if dp else None, rows_per_scale=N)
+                      P[pfx + ".mlp.fc2.bias"], X1.view(M, C), X2.view(M, C), rowscale=dp[1] if dp else None, rows_per_scale=N,
+                      ln=ln_next)
         else:
             act = _empty((M, hidden), BF16, dev)
             # training: the epilogue also stores gelu'(pre-activation) so that the backward GEMM epilogue is a multiply
@@ -359,11 +371,11 @@ class PVLTEngine:
             k.gemm(xn2, Wb[pfx + ".mlp.fc1.weight"], act, bias=P[pfx + ".mlp.fc1.bias"],
                    act=k.ACT_GELU_SAVE_GRAD if save else k.ACT_GELU, preact_out=hpre)
             k.gemm(act, Wb[pfx + ".mlp.fc2.weight"], X2.view(M, C), bias=P[pfx + ".mlp.fc2.bias"],
-                   residual=X1.view(M, C), rowscale=dp[1] if dp else None, rows_per_scale=N)
+                   residual=X1.view(M, C), rowscale=dp[1] if dp else None, rows_per_scale=N, ln=ln_next)
         if save:
             c.update(X=X, xn=xn, mean1=mean1, rstd1=rstd1, q=q, kvin=kvin, kv=kv, Pm=Pm, o=o, X1=X1, xn2=xn2,
                      mean2=mean2, rstd2=rstd2, act=act, hpre=hpre, dp=dp, Nk=Nk)
-        return X2, c
+        return X2, c, nxt
 
     def _block_bwd(self, dX2, c, pfx, i, B, H, W, G, dy2=None, next_dp=None):
         """``dy2``: bf16 copy of dX2 already scaled by this block's MLP drop-path mask (written by the LayerNorm backward
@@ -529,9 +541,11 @@ class PVLTEngine:
             if save:
                 sc.update(patches=patches, pe=pe, pem=pem, per=per, te_in=te_in, te=te, tem=tem, ter=ter)
             sc["blocks"] = []
+            pre_norm = None
             for j in range(self.depths[i]):
                 dp = (dps[2 * blk], dps[2 * blk + 1]) if dps is not None else None
-                X, bc = self._block_fwd(X, f"block{s}.{j}", i, B, H, W, dp, save)
+                X, bc, pre_norm = self._block_fwd(X, f"block{s}.{j}", i, B, H, W, dp, save, pre_norm=pre_norm,
+                                                  next_pfx=f"block{s}.{j + 1}" if j + 1 < self.depths[i] else None)
                 sc["blocks"].append(bc)
                 blk += 1
             sc["out"] = X

@@ -314,9 +314,10 @@ MLP_FUSED_DIMS = (64, 128)      # embedding widths the fused MLP forward support
 MLP_FUSED_BWD_DIMS = tuple(int(v) for v in __import__("os").environ.get("MVLT_FUSED_MLP_TRAIN", "64").split(",") if v)        # ... and the widths whose recompute backward exists (training uses the fused path only there)
 
 
-def mlp_fwd(x, w1, b1, w2, b2, residual, out, rowscale=None, rows_per_scale=0):
+def mlp_fwd(x, w1, b1, w2, b2, residual, out, rowscale=None, rows_per_scale=0, ln=None):
     """out = residual + rowscale[row // rows_per_scale] * (gelu(x @ w1^T + b1) @ w2^T + b2), the hidden activation staying
-    on-chip (csrc/mlp_tcgen05.cu). x bf16 [M, C], w1 bf16 [HD, C], w2 bf16 [C, HD], residual / out fp32 [M, C]; C in {64, 128}."""
+    on-chip (csrc/mlp_tcgen05.cu). x bf16 [M, C], w1 bf16 [HD, C], w2 bf16 [C, HD], residual / out fp32 [M, C]; C in {64, 128}.
+    ``ln = (gamma, beta, out_bf16, mean, rstd, eps)``: LayerNorm of the output rows (the next block's norm1) from the same launch."""
     require_cuda(x, w1, w2, residual, out, b1, b2, rowscale)
     M, C_ = x.shape
     HD = w1.shape[0]
@@ -327,10 +328,18 @@ def mlp_fwd(x, w1, b1, w2, b2, residual, out, rowscale=None, rows_per_scale=0):
     for t in (x, w1, w2, residual, out, b1, b2):
         if not t.is_contiguous():
             raise _lib.MvltError("mlp_fwd: contiguous operands required")
+    g_ = b_ = o_ = m_ = r_ = None
+    eps = 0.0
+    if ln is not None:
+        g_, b_, o_, m_, r_, eps = ln
+        require_cuda(g_, b_, o_, m_, r_)
+        if (g_.dtype != F32 or b_.dtype != F32 or g_.numel() != C_ or b_.numel() != C_ or o_.dtype != BF16 or tuple(o_.shape) != (M, C_)
+                or not o_.is_contiguous() or any(t is not None and (t.dtype != F32 or t.numel() != M or not t.is_contiguous()) for t in (m_, r_))):
+            raise _lib.MvltError("mlp_fwd ln=(gamma, beta, out_bf16, mean, rstd, eps): fp32 gamma / beta [C], contiguous bf16 out [M, C], fp32 mean / rstd [M]")
     if _lib.BYTES is not None:
-        _lib.account_bytes("mlp_fwd", M * C_ * (2 + 4 + 4) + 4 * HD * C_)
+        _lib.account_bytes("mlp_fwd", M * C_ * (2 + 4 + 4 + (2 if ln is not None else 0)) + 4 * HD * C_)
     call("mlp_fwd", ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(residual), ptr(out), ptr(rowscale), C.c_int(rows_per_scale),
-         C.c_int(M), C.c_int(C_), C.c_int(HD))
+         C.c_int(M), C.c_int(C_), C.c_int(HD), ptr(g_), ptr(b_), ptr(o_), ptr(m_), ptr(r_), C.c_float(float(eps)))
 
 
 def mlp_bwd(x, dy, w1, b1, w2, dh, dw1, dw2, db1):

@@ -22,6 +22,32 @@ def _inputs(M, C, HD, seed):
     return x, w1, b1, w2, b2, res
 
 
+@pytest.mark.parametrize("M,C,HD", [(128 * 3 + 17, 64, 512), (4224 * 3, 64, 512), (1152 * 2 + 40, 128, 1024)])
+def test_fused_mlp_forward_with_layernorm_of_the_output(M, C, HD):
+    """The next block's norm1 from the same launch (/root/reference/libs/pvlt.py:140-143): output unchanged, the normalised
+    bf16 rows and (mean, rstd) equal LayerNorm of the kernel's own fp32 output."""
+    from mvlt_b200 import kernels as k
+    x, w1, b1, w2, b2, res = _inputs(M, C, HD, seed=M + C + 1)
+    res = res * 2.0 + 0.5
+    g = torch.Generator(device="cuda").manual_seed(9)
+    gamma, beta = torch.randn(C, generator=g, device="cuda"), torch.randn(C, generator=g, device="cuda")
+    rs = (torch.arange((M + 95) // 96, device="cuda") % 3 != 1).float() * 1.5
+    out0 = torch.empty((M, C), device="cuda")
+    k.mlp_fwd(x, w1, b1, w2, b2, res, out0, rowscale=rs, rows_per_scale=96)
+    out = torch.full((M, C), float("nan"), device="cuda")
+    xn = torch.full((M, C), float("nan"), device="cuda", dtype=BF16)
+    mean, rstd = torch.full((M,), float("nan"), device="cuda"), torch.full((M,), float("nan"), device="cuda")
+    k.mlp_fwd(x, w1, b1, w2, b2, res, out, rowscale=rs, rows_per_scale=96, ln=(gamma, beta, xn, mean, rstd, 1e-6))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out0)
+    mu, var = out.mean(1), out.var(1, unbiased=False)
+    assert torch.allclose(mean, mu, rtol=1e-4, atol=1e-5) and torch.allclose(rstd, (var + 1e-6).rsqrt(), rtol=2e-4, atol=1e-5)
+    ref = torch.nn.functional.layer_norm(out, (C,), gamma, beta, 1e-6)
+    assert float((xn.float() - ref).abs().max()) <= 1e-2 * float(ref.abs().max()) + 1e-3
+    with pytest.raises(Exception):      # in-place output is refused in this mode (the second pass re-reads the residual)
+        k.mlp_fwd(x, w1, b1, w2, b2, res, res, ln=(gamma, beta, xn, mean, rstd, 1e-6))
+
+
 @pytest.mark.parametrize("M,C,HD", SHAPES)
 @pytest.mark.parametrize("droppath", [False, True])
 def test_fused_mlp_forward_matches_fp32_reference(M, C, HD, droppath):
