@@ -63,7 +63,10 @@ template <typename TI, typename TO, int G, int NV, int RU>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, RowMap xm, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, TO* __restrict__ y, RowMap ym,
                                                      const float* __restrict__ post_add, float* __restrict__ mean_out,
-                                                     float* __restrict__ rstd_out, int rows, int C, float eps) {
+                                                     float* __restrict__ rstd_out, int rows, int C, float eps,
+                                                     const float* __restrict__ gamma2, const float* __restrict__ beta2,
+                                                     __nv_bfloat16* __restrict__ y2, float* __restrict__ mean2_out,
+                                                     float* __restrict__ rstd2_out, float eps2) {
   pdl_prologue();
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, sub = lane % G;
@@ -127,6 +130,48 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, R
             o.x += p4.x; o.y += p4.y; o.z += p4.z; o.w += p4.w;
           }
           store4<TO>(yr + c, o);
+          v[u][i] = o;      // (kept for the chained LayerNorm below)
+        }
+      }
+      if (gamma2 != nullptr) {
+        // ---- chained LayerNorm of the row just written (the first block's norm1 over the stage-embedding output, which is
+        // LayerNorm + position embedding itself): second output y2 (bf16, y's row map), statistics at the MAPPED row index
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = i * 4 * G + sub * 4;
+          if (i < nvec && c < C) s2 += v[u][i].x + v[u][i].y + v[u][i].z + v[u][i].w;
+        }
+        const float m2 = group_sum<G>(s2) * inv_c;
+        float q2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = i * 4 * G + sub * 4;
+          if (i < nvec && c < C) {
+            const float a = v[u][i].x - m2, b = v[u][i].y - m2, cc = v[u][i].z - m2, d = v[u][i].w - m2;
+            q2 += a * a + b * b + cc * cc + d * d;
+          }
+        }
+        const float r2 = rsqrtf(group_sum<G>(q2) * inv_c + eps2);
+        const long long mr = map_row(ym, r);
+        if (sub == 0 && mean2_out != nullptr) {
+          mean2_out[mr] = m2;
+          rstd2_out[mr] = r2;
+        }
+        __nv_bfloat16* y2r = y2 + mr * C;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = i * 4 * G + sub * 4;
+          if (i < nvec && c < C) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma2 + c));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta2 + c));
+            float4 o;
+            o.x = (v[u][i].x - m2) * r2 * g.x + b.x;
+            o.y = (v[u][i].y - m2) * r2 * g.y + b.y;
+            o.z = (v[u][i].z - m2) * r2 * g.z + b.z;
+            o.w = (v[u][i].w - m2) * r2 * g.w + b.w;
+            store4<__nv_bfloat16>(y2r + c, o);
+          }
         }
       }
     }
@@ -351,11 +396,17 @@ int ln_grid(int rows, int wpb) {
 }  // namespace
 
 // x_f32 / y_f32: 1 = fp32, 0 = bf16.  map arrays are {group, stride, offset}; group <= 0 means identity.
+// gamma2 / beta2 / y2_bf16 / mean2 / rstd2 / eps2 (optional, NULL for none): a SECOND LayerNorm chained onto the row just written
+// (y2 = LN(y; gamma2, beta2, eps2), bf16, rows placed by ymap; mean2 / rstd2 fp32 indexed by the mapped row): the first block's
+// norm1 over the stage embedding (libs/pvlt.py:346-348) without re-reading the fp32 rows.
 extern "C" int mvlt_layernorm_fwd(const void* x, int x_f32, const int* xmap, const float* gamma, const float* beta,
                                   void* y, int y_f32, const int* ymap, const float* post_add, float* mean,
-                                  float* rstd, int rows, int C, float eps, void* stream_) {
+                                  float* rstd, int rows, int C, float eps, const float* gamma2, const float* beta2,
+                                  void* y2_bf16, float* mean2, float* rstd2, float eps2, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   MVLT_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && C <= 128 * LN_MAX_VEC, "layernorm_fwd: unsupported C=%d", C);
+  MVLT_CHECK_ARG((gamma2 == nullptr) == (y2_bf16 == nullptr) && (gamma2 == nullptr) == (beta2 == nullptr) && (mean2 == nullptr) == (rstd2 == nullptr),
+                 "layernorm_fwd: gamma2 / beta2 / y2 go together, and so do mean2 / rstd2");
   RowMap xm{xmap && xmap[0] > 0 ? xmap[0] : rows, xmap && xmap[0] > 0 ? xmap[1] : rows, xmap && xmap[0] > 0 ? xmap[2] : 0};
   RowMap ym{ymap && ymap[0] > 0 ? ymap[0] : rows, ymap && ymap[0] > 0 ? ymap[1] : rows, ymap && ymap[0] > 0 ? ymap[2] : 0};
   // rows per block = 8 warps x (32 / G) x RU
@@ -363,7 +414,8 @@ extern "C" int mvlt_layernorm_fwd(const void* x, int x_f32, const int* xmap, con
   const int grid = ln_grid(rows, rpb);
 #define LN_FWD_CALL(TI, TO, G, NV, RU)                                                                          \
   mvlt_launch(ln_fwd_kernel<TI, TO, G, NV, RU>, grid, 256, 0, st, reinterpret_cast<const TI*>(x), xm, gamma, beta,           \
-                                                         reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps)
+                                                         reinterpret_cast<TO*>(y), ym, post_add, mean, rstd, rows, C, eps, \
+                                                         gamma2, beta2, reinterpret_cast<__nv_bfloat16*>(y2_bf16), mean2, rstd2, eps2)
 #define LAUNCH(TI, TO)                                    \
   do {                                                    \
     if (C <= 64) LN_FWD_CALL(TI, TO, 16, 1, 4);           \

@@ -525,8 +525,14 @@ class PVLTEngine:
             k.gemm(patches, Wb[f"patch_embed{s}.proj.weight"], pe, bias=P[f"patch_embed{s}.proj.bias"])
             X = _empty((B, N, C), F32, dev)
             pem, per = _empty((B * HW,), F32, dev), _empty((B * HW,), F32, dev)
+            # the first block's norm1 is chained onto the two stage-embedding LayerNorms (they write its input rows): the fp32
+            # token buffer is not re-read by a LayerNorm pass of its own
+            pre0 = chain0 = None
+            if FUSED_LN and self.depths[i] > 0:
+                pre0 = (_empty((B * N, C), BF16, dev), _empty((B * N,), F32, dev), _empty((B * N,), F32, dev))
+                chain0 = (P[f"block{s}.0.norm1.weight"], P[f"block{s}.0.norm1.bias"], pre0[0], pre0[1], pre0[2], 1e-6)
             k.layernorm_fwd(pe, P[f"patch_embed{s}.norm.weight"], P[f"patch_embed{s}.norm.bias"], X, 1e-5, B * HW, C,
-                            ymap=(HW, N, 0), post_add=self._pos(s, H, W, dev), mean=pem, rstd=per)
+                            ymap=(HW, N, 0), post_add=self._pos(s, H, W, dev), mean=pem, rstd=per, chain=chain0)
             # text embed (pvlt.py:205-208,339)
             if i > 0:
                 Cp = EMBED_DIMS[i - 1]
@@ -537,11 +543,11 @@ class PVLTEngine:
             k.gemm(te_in, Wb[f"text_embed{s}.0.weight"], te, bias=P[f"text_embed{s}.0.bias"])
             tem, ter = _empty((B * T,), F32, dev), _empty((B * T,), F32, dev)
             k.layernorm_fwd(te, P[f"text_embed{s}.1.weight"], P[f"text_embed{s}.1.bias"], X, 1e-5, B * T, C,
-                            ymap=(T, N, HW), post_add=P[f"text_pos_embed{s}"], mean=tem, rstd=ter)
+                            ymap=(T, N, HW), post_add=P[f"text_pos_embed{s}"], mean=tem, rstd=ter, chain=chain0)
             if save:
                 sc.update(patches=patches, pe=pe, pem=pem, per=per, te_in=te_in, te=te, tem=tem, ter=ter)
             sc["blocks"] = []
-            pre_norm = None
+            pre_norm = pre0
             for j in range(self.depths[i]):
                 dp = (dps[2 * blk], dps[2 * blk + 1]) if dps is not None else None
                 X, bc, pre_norm = self._block_fwd(X, f"block{s}.{j}", i, B, H, W, dp, save, pre_norm=pre_norm,

@@ -251,12 +251,22 @@ def _f32(t):
     raise _lib.MvltError(f"expected fp32/bf16 tensor, got {t.dtype}")
 
 
-def layernorm_fwd(x, gamma, beta, y, eps, rows, Cdim, xmap=None, ymap=None, post_add=None, mean=None, rstd=None):
+def layernorm_fwd(x, gamma, beta, y, eps, rows, Cdim, xmap=None, ymap=None, post_add=None, mean=None, rstd=None, chain=None):
+    """``chain = (gamma2, beta2, y2_bf16, mean2, rstd2, eps2)``: a second LayerNorm of the row just written, from the same launch
+    (y2 uses y's row map; mean2 / rstd2 are indexed by the mapped row)."""
     require_cuda(x, y)
+    g2 = b2 = y2 = m2 = r2 = None
+    eps2 = 0.0
+    if chain is not None:
+        g2, b2, y2, m2, r2, eps2 = chain
+        require_cuda(g2, b2, y2, m2, r2)
+        if y2.dtype != BF16 or g2.dtype != F32 or b2.dtype != F32 or g2.numel() != Cdim or b2.numel() != Cdim:
+            raise _lib.MvltError("layernorm_fwd chain=(gamma2, beta2, y2_bf16, mean2, rstd2, eps2): fp32 gamma2 / beta2 [C], bf16 y2")
     if _lib.BYTES is not None:
-        _lib.account_bytes("layernorm_fwd", rows * Cdim * (x.element_size() + y.element_size()))
+        _lib.account_bytes("layernorm_fwd", rows * Cdim * (x.element_size() + y.element_size() + (2 if chain is not None else 0)))
     call("layernorm_fwd", ptr(x), _f32(x), _map(xmap), ptr(gamma), ptr(beta), ptr(y), _f32(y), _map(ymap),
-         ptr(post_add), ptr(mean), ptr(rstd), C.c_int(rows), C.c_int(Cdim), C.c_float(eps))
+         ptr(post_add), ptr(mean), ptr(rstd), C.c_int(rows), C.c_int(Cdim), C.c_float(eps), ptr(g2), ptr(b2), ptr(y2), ptr(m2),
+         ptr(r2), C.c_float(float(eps2)))
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, rows, Cdim, dymap=None, xmap=None, dxmap=None, dx_add=None,

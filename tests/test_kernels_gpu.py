@@ -158,6 +158,23 @@ def test_layernorm_row_maps_and_post_add():
     ref = F.layer_norm(pe.float(), (C,)).view(B, HW, C) + pos
     _close(X[:, :HW], ref, 1e-5, 1e-5, "rowmap+pos")
     assert float(X[:, HW:].abs().max()) == 0.0
+    # chained second LayerNorm of the rows just written (the first block's norm1), for every width the encoder uses
+    for C2 in (64, 128, 320, 512):
+        pe2 = torch.randn((B * HW, C2), generator=_g(C2), device="cuda").to(BF16)
+        pos2 = torch.randn((HW, C2), generator=_g(C2 + 1), device="cuda") * 0.5 + 0.3
+        g1, b1 = torch.randn(C2, generator=_g(3), device="cuda"), torch.randn(C2, generator=_g(4), device="cuda")
+        g2, b2 = torch.randn(C2, generator=_g(5), device="cuda"), torch.randn(C2, generator=_g(6), device="cuda")
+        X2 = torch.zeros((B, N, C2), device="cuda")
+        xn = torch.zeros((B, N, C2), device="cuda", dtype=BF16)
+        m2, r2 = torch.zeros(B * N, device="cuda"), torch.zeros(B * N, device="cuda")
+        k.layernorm_fwd(pe2, g1, b1, X2, 1e-5, B * HW, C2, ymap=(HW, N, 0), post_add=pos2, chain=(g2, b2, xn, m2, r2, 1e-6))
+        y1 = F.layer_norm(pe2.float(), (C2,), g1, b1, 1e-5).view(B, HW, C2) + pos2
+        _close(X2[:, :HW], y1, 1e-5, 1e-4, "chain: first norm")
+        y2 = F.layer_norm(X2[:, :HW], (C2,), g2, b2, 1e-6)
+        _close(xn[:, :HW], y2, 1e-2, 1e-2, "chain: second norm")
+        _close(m2.view(B, N)[:, :HW], X2[:, :HW].mean(-1), 1e-4, 1e-5, "chain: mean")
+        _close(r2.view(B, N)[:, :HW], (X2[:, :HW].var(-1, unbiased=False) + 1e-6).rsqrt(), 1e-3, 1e-5, "chain: rstd")
+        assert float(xn[:, HW:].float().abs().max()) == 0.0 and float(m2.view(B, N)[:, HW:].abs().max()) == 0.0
 
 
 def test_softmax_fwd_bwd():
