@@ -36,12 +36,12 @@ class GemmDesc(C.Structure):
         ("conv_mode", C.c_int32), ("conv_B", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32),
         ("conv_C", C.c_int32), ("conv_pix_stride", C.c_int64), ("conv_batch_stride", C.c_int64),
         ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p),
-        ("ln_eps", C.c_float),
+        ("ln_eps", C.c_float), ("conv_R", C.c_int32),
     ]
 
 
 ACT_NONE, ACT_GELU, ACT_DGELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_SOFTMAX, ACT_SOFTMAX_BWD = 0, 1, 2, 3, 4, 5, 6
-CONV_NONE, CONV_A, CONV_BT = 0, 1, 2
+CONV_NONE, CONV_A, CONV_BT, CONV_PATCH_A = 0, 1, 2, 3
 
 
 def lib_path() -> Path:

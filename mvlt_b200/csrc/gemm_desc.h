@@ -32,7 +32,12 @@ enum {
   MVLT_ACT_SOFTMAX_BWD = 6,     // D = alpha * aux * (acc - sum_n aux * acc)         (aux = P; acc = dP -> dS)
 };
 
-enum { MVLT_CONV_NONE = 0, MVLT_CONV_A = 1, MVLT_CONV_BT = 2 };
+// MVLT_CONV_PATCH_A: A := the patch matrix of a convolution with kernel = stride = conv_R (PVLT's spatial-reduction and
+// patch-embedding convolutions, libs/pvlt.py:103-104,168) over an NHWC bf16 tensor X[b, y, x, c] with pixel stride conv_C:
+// patches[(b, oy, ox), (ky*R + kx)*C + c] = X[b, oy*R + ky, ox*R + kx, c] is never materialised -- a 5-D tensor map
+// (kx*C + c | ox | ky | oy | b) describes it in place and one box per k-block lands as the usual K-major operand tile.
+// Needs (H/R)*(W/R) == 64 output pixels per image and (R*C) % 64 == 0; M = B*64, K = R*R*C, a_mn = 0.
+enum { MVLT_CONV_NONE = 0, MVLT_CONV_A = 1, MVLT_CONV_BT = 2, MVLT_CONV_PATCH_A = 3 };
 
 typedef struct mvlt_gemm_desc {
   const void* A;  // bf16
@@ -72,6 +77,7 @@ typedef struct mvlt_gemm_desc {
   float* ln_mean;
   float* ln_rstd;
   float ln_eps;
+  int32_t conv_R;          // MVLT_CONV_PATCH_A: kernel = stride of the convolution (conv_H / conv_W are the INPUT map size)
 } mvlt_gemm_desc;
 
 #ifdef __cplusplus

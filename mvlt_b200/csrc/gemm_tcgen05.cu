@@ -758,7 +758,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               continue;
             }
             mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-            if (p.conv_mode == MVLT_CONV_A) {
+            if (p.conv_mode == MVLT_CONV_PATCH_A) {
+              // A tile = the 2 x 64 output pixels of two images x 64 elements of kernel row ky = kb / (R*C/64): one 5-D box
+              uint32_t ky, cb;
+              fast_divmod(p.div_cb, (uint32_t)kb, ky, cb);
+              tma_load_5d(sa, &tmA, &full_bar[stage], (int)cb * 64, 0, (int)ky, 0, m0 >> 6);
+            } else if (p.conv_mode == MVLT_CONV_A) {
               // A tile = 128 consecutive pixels x 64 channels of tap (kb / (C/64)): one shifted NHWC box
               uint32_t tap, cb, b0, rem, y0, xr;
               fast_divmod(p.div_cb, (uint32_t)kb, tap, cb);
@@ -1262,6 +1267,29 @@ int make_conv_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base, i
   return get_tensor_map(out, base, dims, str, box);
 }
 
+// NHWC bf16 tensor X as the 5-D patch view (kx*C + c, ox, ky, oy, b) of a kernel = stride = R convolution; box = 64 elements x
+// all ox x one ky x all oy x 2 images = 128 rows x 128 bytes (not cached: a handful of launches per forward use it)
+int make_patch_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base) {
+  const int R = g->conv_R, C = g->conv_C, ow = g->conv_W / R, oh = g->conv_H / R;
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    mvlt_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MVLT_ERR_DRIVER;
+  }
+  cuuint64_t gdim[5] = {(cuuint64_t)R * C, (cuuint64_t)ow, (cuuint64_t)R, (cuuint64_t)oh, (cuuint64_t)g->conv_B};
+  cuuint64_t gstr[4] = {(cuuint64_t)R * C * 2, (cuuint64_t)g->conv_W * C * 2, (cuuint64_t)R * g->conv_W * C * 2,
+                        (cuuint64_t)g->conv_batch_stride * 2};
+  cuuint32_t bx[5] = {64, (cuuint32_t)ow, 1, (cuuint32_t)oh, 2};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mvlt_set_error("cuTensorMapEncodeTiled (5-D patch view) failed (%d): B=%d H=%d W=%d C=%d R=%d", (int)r, g->conv_B, g->conv_H, g->conv_W, C, R);
+    return MVLT_ERR_DRIVER;
+  }
+  return 0;
+}
+
 // Output tensor D (or D2) as a 4-D map (n, m, batch2, batch1) whose box is one staging tile: 32 rows x 128 bytes
 // (SWIZZLE_128B), or 32 rows x 64 bytes (SWIZZLE_64B) for the 32-column bf16 remainder units
 int make_output_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base, int f32, int row_bytes = 128) {
@@ -1412,7 +1440,17 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   CUtensorMap tmA, tmB;
   int rc = 0;
   p.conv_mode = g->conv_mode;
-  if (g->conv_mode != MVLT_CONV_NONE) {
+  if (g->conv_mode == MVLT_CONV_PATCH_A) {
+    const int R = g->conv_R;
+    MVLT_CHECK_ARG(g->batch1 == 1 && g->batch2 == 1 && !g->a_mn && !p.pair, "mvlt_gemm: the patch view is a plain K-major A operand");
+    MVLT_CHECK_ARG(R > 1 && g->conv_B > 0 && g->conv_C > 0 && g->conv_H % R == 0 && g->conv_W % R == 0 &&
+                       (g->conv_H / R) * (g->conv_W / R) == 64 && ((long long)R * g->conv_C) % 64 == 0 && g->conv_pix_stride == g->conv_C &&
+                       g->conv_batch_stride % 8 == 0 && ((uintptr_t)g->A & 15) == 0 && g->conv_W / R <= 256 && g->conv_H / R <= 256,
+                   "mvlt_gemm: unsupported patch geometry B=%d H=%d W=%d C=%d R=%d (need 64 output pixels per image, R*C %% 64 == 0)",
+                   g->conv_B, g->conv_H, g->conv_W, g->conv_C, R);
+    MVLT_CHECK_ARG(g->M == g->conv_B * 64 && g->K == R * R * g->conv_C, "mvlt_gemm: patch view needs M = B*64, K = R*R*C");
+    p.div_cb = make_fastdiv((uint32_t)(R * g->conv_C / 64));
+  } else if (g->conv_mode != MVLT_CONV_NONE) {
     const long long HW = (long long)g->conv_H * g->conv_W, pix = HW * g->conv_B;
     MVLT_CHECK_ARG(g->conv_mode == MVLT_CONV_A || g->conv_mode == MVLT_CONV_BT, "mvlt_gemm: bad conv_mode %d", g->conv_mode);
     MVLT_CHECK_ARG(g->batch1 == 1 && g->batch2 == 1, "mvlt_gemm: implicit convolution is not batched");
@@ -1431,7 +1469,8 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
       MVLT_CHECK_ARG(g->K == pix && g->N == 9 * g->conv_C && g->b_mn && p.block_n % 64 == 0,
                      "mvlt_gemm: conv B^T needs K = B*H*W, N = 9*C, MN-major");
   }
-  if (g->conv_mode == MVLT_CONV_A) rc = make_conv_map(&tmA, g, g->A, BLOCK_M);
+  if (g->conv_mode == MVLT_CONV_PATCH_A) rc = make_patch_map(&tmA, g, g->A);
+  else if (g->conv_mode == MVLT_CONV_A) rc = make_conv_map(&tmA, g, g->A, BLOCK_M);
   else rc = make_operand_map(&tmA, g->A, g->M, g->K, p.a_mn, g->lda, g->batch1, g->batch2, g->sA1, g->sA2, BLOCK_M, &p.a_b1, &p.a_b2);
   if (rc) return rc;
   if (g->conv_mode == MVLT_CONV_BT) rc = make_conv_map(&tmB, g, g->B, 64);

@@ -54,6 +54,9 @@ FUSED_MLP = os.environ.get("MVLT_FUSED_MLP", "1") != "0"
 # one tile): the fp32 rows are normalised on their way out instead of being re-read by a LayerNorm pass; MVLT_FUSED_LN=0 for A/B
 FUSED_LN = os.environ.get("MVLT_FUSED_LN", "1") != "0"
 FUSED_LN_DIMS = (64, 128)
+# spatial-reduction convolution (kernel = stride = R) with its patch matrix read in place through a 5-D TMA view instead of a
+# patchify pass (csrc/gemm_desc.h MVLT_CONV_PATCH_A); MVLT_PATCH_VIEW=0 for the A/B
+PATCH_VIEW = os.environ.get("MVLT_PATCH_VIEW", "1") != "0"
 
 
 def _empty(shape, dtype, dev):
@@ -308,10 +311,16 @@ class PVLTEngine:
         with self.branch(0):
             if R > 1:
                 oh, ow = H // R, W // R
-                patches = _empty((B * oh * ow, R * R * C), BF16, dev)
-                k.patchify(xn, N * C, patches, B, H, W, C, R)
                 sr = _empty((B * oh * ow, C), BF16, dev)
-                k.gemm(patches, Wb[pfx + ".attn.sr.weight"], sr, bias=P[pfx + ".attn.sr.bias"])
+                if PATCH_VIEW and k.conv_patch_supported(H, W, C, R):
+                    # the GEMM reads the patches of xn in place (5-D TMA view): no patchify pass on the forward path; the
+                    # backward materialises them on the weight-gradient stream, where only the dW GEMM wants them
+                    patches = None
+                    k.conv_patch_gemm(xn, B, H, W, C, R, N * C, Wb[pfx + ".attn.sr.weight"], sr, bias=P[pfx + ".attn.sr.bias"])
+                else:
+                    patches = _empty((B * oh * ow, R * R * C), BF16, dev)
+                    k.patchify(xn, N * C, patches, B, H, W, C, R)
+                    k.gemm(patches, Wb[pfx + ".attn.sr.weight"], sr, bias=P[pfx + ".attn.sr.bias"])
                 kvin = _empty((B * Nk, C), BF16, dev)
                 srm, srr = _empty((B * oh * ow,), F32, dev), _empty((B * oh * ow,), F32, dev)
                 k.layernorm_fwd(sr, P[pfx + ".attn.norm.weight"], P[pfx + ".attn.norm.bias"], kvin, 1e-5, B * oh * ow, C,
@@ -447,8 +456,18 @@ class PVLTEngine:
             k.layernorm_bwd(dkvin, c["sr"], c["srm"], c["srr"], P[pfx + ".attn.norm.weight"], dsr, B * oh * ow, C,
                             dymap=(oh * ow, Nk, 0), dgamma=G[pfx + ".attn.norm.weight"],
                             dbeta=G[pfx + ".attn.norm.bias"])
-            self._lin_param_grads(G, None, pfx + ".attn.sr.bias", dsr, c["patches"],
-                                  wgrad=self._conv_wgrad(G, pfx + ".attn.sr.weight"))
+            if c["patches"] is None:      # forward read them in place: materialise for the weight-gradient GEMM, off the dX chain
+                xn_s = c["xn"]
+
+                def sr_wgrad(dsr=dsr, xn_s=xn_s):
+                    patches = _empty((B * oh * ow, R * R * C), BF16, dev)
+                    k.patchify(xn_s, N * C, patches, B, H, W, C, R)
+                    k.gemm(dsr.t(), patches.t(), self._conv_wgrad(G, pfx + ".attn.sr.weight"), atomic_add=True,
+                           split_k=_split_k(C, R * R * C, B * oh * ow), rowsum=G[pfx + ".attn.sr.bias"])
+                self.side_launch(sr_wgrad, dsr, xn_s)
+            else:
+                self._lin_param_grads(G, None, pfx + ".attn.sr.bias", dsr, c["patches"],
+                                      wgrad=self._conv_wgrad(G, pfx + ".attn.sr.weight"))
             dpatch = _empty((B * oh * ow, R * R * C), BF16, dev)
             k.gemm(dsr, Wb[pfx + ".attn.sr.weight"].t(), dpatch)
             k.unpatchify(dpatch, dxn, N * C, B, H, W, C, R)

@@ -9,6 +9,7 @@ from typing import Optional
 import torch
 
 from . import _lib
+from ._lib import CONV_PATCH_A  # noqa: F401
 from ._lib import (ACT_DGELU, ACT_GELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_NONE, ACT_SOFTMAX, ACT_SOFTMAX_BWD, CONV_A,
                    CONV_BT, GemmDesc, call, ptr, require_cuda)
 
@@ -200,6 +201,39 @@ def conv3x3_gemm(x, B, H, W, Cdim, pix_stride, batch_stride, w, out, *, residual
     if _lib.PROFILE is not None or _lib.GEMM_LOG is not None:   # algorithmic bytes: X once (not the 9x im2col matrix) + weights + output (+ residual)
         _lib.account_gemm(2.0 * M * N * K, (M * Cdim + N * K) * 2.0 + M * N * out.element_size() * (2 if residual is not None else 1),
                           f"conv3x3 M={M} N={N} K={K} HxW={H}x{W} out={'f32' if out.dtype == F32 else 'bf16'} res={int(residual is not None)}")
+    call("gemm", C.byref(d))
+    return out
+
+
+def conv_patch_supported(H, W, Cdim, R):
+    """Geometry the in-place patch view handles (csrc/gemm_desc.h MVLT_CONV_PATCH_A): 64 output pixels per image."""
+    return R > 1 and H % R == 0 and W % R == 0 and (H // R) * (W // R) == 64 and (R * Cdim) % 64 == 0
+
+
+def conv_patch_gemm(x, B, H, W, Cdim, R, batch_stride, w, out, *, bias=None):
+    """Convolution with kernel = stride = R over NHWC bf16 ``x`` (pixel stride Cdim, ``batch_stride`` elements between images) as
+    ONE GEMM whose A operand is the patch matrix read in place through a 5-D TMA view -- no patchify pass, no patch buffer:
+    out[(b, oy, ox), n] = sum_k patches[(b, oy, ox), k] * w[n, k] (+ bias), k = (ky*R + kx)*C + c. ``w``: bf16 [N, R*R*C]
+    (the engine's permuted conv weight), ``out``: bf16 / fp32 [B*64, N]."""
+    require_cuda(x, w, out, bias)
+    M, N, K = B * 64, w.shape[0], R * R * Cdim
+    if (x.dtype != BF16 or w.dtype != BF16 or not conv_patch_supported(H, W, Cdim, R) or w.shape[1] != K or w.stride(1) != 1
+            or tuple(out.shape) != (M, N) or out.stride(1) != 1 or (bias is not None and (bias.dtype != F32 or bias.numel() != N))):
+        raise _lib.MvltError(f"conv_patch_gemm: unsupported operands (B={B} H={H} W={W} C={Cdim} R={R}, w {tuple(w.shape)}, out {tuple(out.shape)})")
+    d = GemmDesc()
+    d.A, d.B, d.D = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    d.bias = None if bias is None else bias.data_ptr()
+    d.M, d.N, d.K = M, N, K
+    d.a_mn, d.b_mn = 0, 0
+    d.lda, d.ldb, d.ldd = K, w.stride(0), out.stride(0)
+    d.batch1 = d.batch2 = 1
+    d.alpha = 1.0
+    d.out_f32 = 1 if out.dtype == F32 else 0
+    d.conv_mode, d.conv_B, d.conv_H, d.conv_W, d.conv_C, d.conv_R = CONV_PATCH_A, B, H, W, Cdim, R
+    d.conv_pix_stride, d.conv_batch_stride = Cdim, batch_stride
+    if _lib.PROFILE is not None or _lib.GEMM_LOG is not None:
+        _lib.account_gemm(2.0 * M * N * K, (M * K + N * K) * 2.0 + M * N * out.element_size(),
+                          f"conv_patch M={M} N={N} K={K} HxW={H}x{W} R={R} out={'f32' if out.dtype == F32 else 'bf16'}")
     call("gemm", C.byref(d))
     return out
 

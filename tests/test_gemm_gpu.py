@@ -88,6 +88,35 @@ def test_gemm_residual_epilogue_with_fused_layernorm(M, N, K):
     assert torch.equal(out2, out) and torch.equal(xn2, xn) and torch.equal(out3, out)
 
 
+@pytest.mark.parametrize("B,H,C,R", [(3, 64, 64, 8), (4, 32, 128, 4), (5, 16, 320, 2)])
+def test_conv_patch_view_equals_patchify_then_gemm(B, H, C, R):
+    """Spatial-reduction convolution (kernel = stride = R, /root/reference/libs/pvlt.py:103-104) with the patch matrix read in
+    place through the 5-D TMA view == the same GEMM on a materialised patch buffer (same tiles, same k order: bit for bit), and
+    == torch's conv2d on the bf16-rounded operands. Token-buffer layout: image rows followed by 128 text rows per sample; an
+    odd batch exercises the zero-filled second image of the last tile."""
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + C)
+    T, W = 128, H
+    N = H * W + T
+    x = _rand((B, N, C), g)
+    w = _rand((C, R * R * C), g, (R * R * C) ** -0.5)          # [Co, (ky, kx, ci)]: the engine's permuted conv weight
+    bias = torch.randn(C, generator=g, device="cuda")
+    oh = H // R
+    assert k.conv_patch_supported(H, W, C, R)
+    out = torch.full((B * oh * oh, C), float("nan"), device="cuda", dtype=BF16)
+    k.conv_patch_gemm(x, B, H, W, C, R, N * C, w, out, bias=bias)
+    patches = torch.empty((B * oh * oh, R * R * C), device="cuda", dtype=BF16)
+    k.patchify(x, N * C, patches, B, H, W, C, R)
+    ref = torch.empty_like(out)
+    k.gemm(patches, w, ref, bias=bias)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    img = x[:, :H * W].reshape(B, H, W, C).permute(0, 3, 1, 2).float()
+    wt = w.float().view(C, R, R, C).permute(0, 3, 1, 2)
+    conv = torch.nn.functional.conv2d(img, wt, bias, stride=R).permute(0, 2, 3, 1).reshape(B * oh * oh, C)
+    _check(out, conv, R * R * C, "patch view vs conv2d")
+
+
 def test_gemm_matches_simt_ref_bitwise_structure():
     """Same descriptor through the SIMT cross-check kernel and the tcgen05 kernel."""
     from mvlt_b200 import kernels as k
