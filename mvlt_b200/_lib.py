@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
         ("conv_mode", C.c_int32), ("conv_B", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32),
         ("conv_C", C.c_int32), ("conv_pix_stride", C.c_int64), ("conv_batch_stride", C.c_int64),
         ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p),
-        ("ln_eps", C.c_float), ("conv_R", C.c_int32),
+        ("ln_eps", C.c_float), ("conv_R", C.c_int32), ("patch_store", C.c_int32),
     ]
 
 

@@ -77,7 +77,12 @@ typedef struct mvlt_gemm_desc {
   float* ln_mean;
   float* ln_rstd;
   float ln_eps;
-  int32_t conv_R;          // MVLT_CONV_PATCH_A: kernel = stride of the convolution (conv_H / conv_W are the INPUT map size)
+  int32_t conv_R;          // MVLT_CONV_PATCH_A / patch_store: kernel = stride of the convolution (conv_H / conv_W: INPUT map size)
+  // patch_store != 0: the OUTPUT is the same patch view (the input gradient of that convolution, i.e. "unpatchify" fused into the
+  // store): D is the fp32 NHWC tensor dX[b, y, x, c] (pixel stride conv_C, image stride conv_batch_stride) and element
+  // (m = (b, oy, ox), n = (ky*R + kx)*C + c) of the product is written to dX[b, oy*R + ky, ox*R + kx, c] -- every pixel exactly
+  // once. Needs out_f32, no epilogue operands, M = conv_B*64, N = R*R*C, the geometry rules of MVLT_CONV_PATCH_A; ldd is ignored.
+  int32_t patch_store;
 } mvlt_gemm_desc;
 
 #ifdef __cplusplus

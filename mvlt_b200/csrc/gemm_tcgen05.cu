@@ -83,6 +83,8 @@ struct KParams {
   float alpha;
   int act, out_f32, atomic_add, rows_per_scale;
   int pair;       // CTA-pair mode (cta_group::2): clusters of 2 CTAs share one 256-row UMMA; num_m_blocks counts row PAIRS
+  int patch_store;   // fp32 D is the 5-D patch view of an NHWC tensor (gemm_desc.h): units leave through cp.async.bulk.tensor.5d
+  int patch_rc;      // R * C: columns per kernel row of that view
   int tma_store;  // D (and D2) leave the staging tiles through TMA bulk stores (tmD / tmD2) instead of LDS + STG
   int prefetch;   // EPI_AUX only: two staging tiles per epilogue warp, the aux unit of the next tile is fetched with cp.async
   int warp_stage_bytes;   // staging bytes per epilogue warp: 4096, or 8192 (prefetch; fused LayerNorm with 2 units per warp)
@@ -316,6 +318,20 @@ __device__ __forceinline__ void tma_flush(const CUtensorMap* tm, uint32_t tile_s
   __syncwarp();
 }
 
+// one 32-row x 32-fp32-column unit of the product into the patch view of dX: rows = 4 oy x 8 ox of one image, columns = 32
+// consecutive (kx, c) of one kernel row ky
+__device__ __forceinline__ void tma_flush_patch(const KParams& p, const CUtensorMap* tm, uint32_t tile_s, int col0, int row, int lane) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    const int ky = col0 / p.patch_rc;
+    tma_store_5d(tm, tile_s, col0 - ky * p.patch_rc, 0, ky, (row & 63) >> 3, row >> 6);
+    tma_store_commit();
+    tma_store_wait_read();
+  }
+  __syncwarp();
+}
+
 template <int kEpi, bool kOutF32, int P>
 __device__ __forceinline__ void epilogue_unit_compute(const KParams& p, uint32_t taddr, long long row_base_off, int lane,
                                                       int rows_valid, int col0, float rs, const StageAddr& s,
@@ -378,7 +394,9 @@ __device__ __forceinline__ void epilogue_unit_compute(const KParams& p, uint32_t
   }
   if constexpr (kOutF32) {
     uint8_t* g = reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(p.D) + row_base_off + col0);
-    if (kEpi == EPI_PLAIN && p.atomic_add) {
+    if (kEpi == EPI_PLAIN && p.patch_store) {
+      tma_flush_patch(p, sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc.row, lane);
+    } else if (kEpi == EPI_PLAIN && p.atomic_add) {
       if (p.tma_store) tma_flush<true>(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
       else stage_flush<8, true>(s, g, ld_bytes, lane, rows_valid);
     } else if (p.tma_store) tma_flush(sc.tmD, s.w8 - (uint32_t)lane * 128u, col0, sc, lane);
@@ -1290,6 +1308,28 @@ int make_patch_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base) 
   return 0;
 }
 
+// fp32 NHWC tensor dX as the 5-D patch view (kx*C + c, ox, ky, oy, b); box = one staging tile: 32 fp32 x 8 ox x 1 ky x 4 oy x 1 image
+int make_patch_store_map(CUtensorMap* out, const mvlt_gemm_desc* g) {
+  const int R = g->conv_R, C = g->conv_C, ow = g->conv_W / R, oh = g->conv_H / R;
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    mvlt_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MVLT_ERR_DRIVER;
+  }
+  cuuint64_t gdim[5] = {(cuuint64_t)R * C, (cuuint64_t)ow, (cuuint64_t)R, (cuuint64_t)oh, (cuuint64_t)g->conv_B};
+  cuuint64_t gstr[4] = {(cuuint64_t)R * C * 4, (cuuint64_t)g->conv_W * C * 4, (cuuint64_t)R * g->conv_W * C * 4,
+                        (cuuint64_t)g->conv_batch_stride * 4};
+  cuuint32_t bx[5] = {32, (cuuint32_t)ow, 1, 4, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, g->D, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mvlt_set_error("cuTensorMapEncodeTiled (5-D patch store) failed (%d): B=%d H=%d W=%d C=%d R=%d", (int)r, g->conv_B, g->conv_H, g->conv_W, C, R);
+    return MVLT_ERR_DRIVER;
+  }
+  return 0;
+}
+
 // Output tensor D (or D2) as a 4-D map (n, m, batch2, batch1) whose box is one staging tile: 32 rows x 128 bytes
 // (SWIZZLE_128B), or 32 rows x 64 bytes (SWIZZLE_64B) for the 32-column bf16 remainder units
 int make_output_map(CUtensorMap* out, const mvlt_gemm_desc* g, const void* base, int f32, int row_bytes = 128) {
@@ -1372,9 +1412,23 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
                  "mvlt_gemm: aux is only consumed by the mul_aux / dgelu / softmax_bwd epilogues");
   MVLT_CHECK_ARG(!(g->rowscale && g->rows_per_scale <= 0), "mvlt_gemm: rowscale needs rows_per_scale");
 
+  if (g->patch_store) {
+    const int R = g->conv_R;
+    MVLT_CHECK_ARG(g->out_f32 && !g->atomic_add && g->split_k <= 1 && !g->bias && !g->residual && !g->aux && !g->D2 && !g->rowscale &&
+                       !g->rowsum && !ln && g->act == MVLT_ACT_NONE && g->batch1 == 1 && g->batch2 == 1 && g->conv_mode == MVLT_CONV_NONE,
+                   "mvlt_gemm: patch_store takes a plain fp32 product (no epilogue operands, no batch, no split-K)");
+    MVLT_CHECK_ARG(R > 1 && g->conv_B > 0 && g->conv_C > 0 && g->conv_H % R == 0 && g->conv_W % R == 0 && g->conv_W / R == 8 &&
+                       g->conv_H / R == 8 && ((long long)R * g->conv_C) % 64 == 0 && g->conv_pix_stride == g->conv_C &&
+                       g->conv_batch_stride % 4 == 0 && ((uintptr_t)g->D & 15) == 0 && g->M == g->conv_B * 64 &&
+                       g->N == R * R * g->conv_C,
+                   "mvlt_gemm: unsupported patch_store geometry B=%d H=%d W=%d C=%d R=%d M=%d N=%d (need an 8 x 8 reduced map)",
+                   g->conv_B, g->conv_H, g->conv_W, g->conv_C, R, g->M, g->N);
+  }
   KParams p;
   memset(&p, 0, sizeof(p));
   p.M = g->M; p.N = g->N; p.K = g->K;
+  p.patch_store = g->patch_store ? 1 : 0;
+  p.patch_rc = g->patch_store ? g->conv_R * g->conv_C : 1;
   p.block_n = (g->act == MVLT_ACT_SOFTMAX || g->act == MVLT_ACT_SOFTMAX_BWD) ? g->N : pick_block_n(g);
   MVLT_CHECK_ARG(p.block_n >= 32 && p.block_n <= 256 && p.block_n % (g->b_mn ? 64 : 32) == 0,
                  "mvlt_gemm: unsupported block_n %d", p.block_n);
@@ -1393,7 +1447,7 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   // (stage-4 MLP fc1 84.1 -> 90.8 us, fc2 72.0 -> 76.3 us, profiles/r2m_gemm_pair_ab.txt): these launches are bound by their
   // GELU / residual epilogues and by wave quantisation, not by the operand fill. Opt-in: MVLT_GEMM_PAIR=1.
   static const int pair_env = [] { const char* e = getenv("MVLT_GEMM_PAIR"); return e ? atoi(e) : 0; }();
-  p.pair = (pair_env && !ln && g->conv_mode == MVLT_CONV_NONE && g->rowsum == nullptr && !p.prefetch && g->split_k <= 1 && !g->atomic_add &&
+  p.pair = (pair_env && !ln && !g->patch_store && g->conv_mode == MVLT_CONV_NONE && g->rowsum == nullptr && !p.prefetch && g->split_k <= 1 && !g->atomic_add &&
             g->act != MVLT_ACT_SOFTMAX && g->act != MVLT_ACT_SOFTMAX_BWD && g->K >= 4 * BLOCK_K && g->M >= 16 * BLOCK_M &&
             p.block_n >= 128 && p.block_n % 128 == 0 && (long long)g->batch1 * g->batch2 == 1) ? 1 : 0;
   const int stage_bytes = A_STAGE_BYTES + (p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
@@ -1432,7 +1486,7 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
   p.D = g->D; p.D2 = g->D2; p.bias = g->bias;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(g->aux);
   p.residual = g->residual; p.rowscale = g->rowscale;
-  p.ldd = g->ldd; p.sD1 = g->sD1; p.sD2 = g->sD2;
+  p.ldd = g->patch_store ? g->N : g->ldd; p.sD1 = g->sD1; p.sD2 = g->sD2;   // (patch_store: D is addressed by its tensor map only)
   p.alpha = g->alpha;
   p.act = g->act; p.out_f32 = g->out_f32; p.atomic_add = g->atomic_add;
   p.rows_per_scale = g->rows_per_scale > 0 ? g->rows_per_scale : 1;
@@ -1510,7 +1564,11 @@ extern "C" int mvlt_gemm(const mvlt_gemm_desc* g, void* stream_) {
     const bool ok = ((uintptr_t)g->D & 15) == 0 && (g->ldd * es) % 16 == 0 && (g->sD1 * es) % 16 == 0 && (g->sD2 * es) % 16 == 0 &&
                     (g->batch1 == 1 || g->sD1 != 0) && (g->batch2 == 1 || g->sD2 != 0) &&
                     (g->D2 == nullptr || ((uintptr_t)g->D2 & 15) == 0);
-    if (ok) {
+    if (g->patch_store) {
+      rc = make_patch_store_map(&tmD, g);
+      if (rc) return rc;
+      p.tma_store = 1;
+    } else if (ok) {
       rc = make_output_map(&tmD, g, g->D, g->out_f32);
       if (rc) return rc;
       if (g->D2 != nullptr) {

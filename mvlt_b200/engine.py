@@ -57,6 +57,7 @@ FUSED_LN_DIMS = (64, 128)
 # spatial-reduction convolution (kernel = stride = R) with its patch matrix read in place through a 5-D TMA view instead of a
 # patchify pass (csrc/gemm_desc.h MVLT_CONV_PATCH_A); MVLT_PATCH_VIEW=0 for the A/B
 PATCH_VIEW = os.environ.get("MVLT_PATCH_VIEW", "1") != "0"
+PATCH_STORE = PATCH_VIEW and os.environ.get("MVLT_PATCH_STORE", "1") != "0"     # the input gradient stored through the same view
 
 
 def _empty(shape, dtype, dev):
@@ -468,9 +469,13 @@ class PVLTEngine:
             else:
                 self._lin_param_grads(G, None, pfx + ".attn.sr.bias", dsr, c["patches"],
                                       wgrad=self._conv_wgrad(G, pfx + ".attn.sr.weight"))
-            dpatch = _empty((B * oh * ow, R * R * C), BF16, dev)
-            k.gemm(dsr, Wb[pfx + ".attn.sr.weight"].t(), dpatch)
-            k.unpatchify(dpatch, dxn, N * C, B, H, W, C, R)
+            if PATCH_STORE and k.conv_patch_supported(H, W, C, R) and oh == 8 and ow == 8:
+                # the input-gradient GEMM stores through the patch view: fp32 straight into the image rows of dxn
+                k.conv_patch_dgrad(dsr, Wb[pfx + ".attn.sr.weight"], dxn, B, H, W, C, R, N * C)
+            else:
+                dpatch = _empty((B * oh * ow, R * R * C), BF16, dev)
+                k.gemm(dsr, Wb[pfx + ".attn.sr.weight"].t(), dpatch)
+                k.unpatchify(dpatch, dxn, N * C, B, H, W, C, R)
             k.gemm(dq, Wb[pfx + ".attn.q.weight"].t(), dxn, residual=dxn)
         else:
             k.gemm(dkv, Wb[pfx + ".attn.kv.weight"].t(), dxn)

@@ -238,6 +238,33 @@ def conv_patch_gemm(x, B, H, W, Cdim, R, batch_stride, w, out, *, bias=None):
     return out
 
 
+def conv_patch_dgrad(dy, w, dx, B, H, W, Cdim, R, batch_stride):
+    """Input gradient of the kernel = stride = R convolution: dX[b, oy*R + ky, ox*R + kx, c] = sum_n dy[(b, oy, ox), n] *
+    w[n, (ky*R + kx)*C + c], written straight into the fp32 NHWC rows of ``dx`` (pixel stride Cdim, ``batch_stride`` elements
+    between images) through the 5-D TMA view -- the "unpatchify" pass and the bf16 patch-gradient buffer disappear.
+    ``dy``: bf16 [B*64, N] rows, ``w``: bf16 [N, R*R*C]. Every image pixel is written exactly once; other rows of ``dx`` untouched."""
+    require_cuda(dy, w, dx)
+    M, Nn, K = B * 64, R * R * Cdim, w.shape[0]
+    if (dy.dtype != BF16 or w.dtype != BF16 or dx.dtype != F32 or not conv_patch_supported(H, W, Cdim, R) or H // R != 8
+            or tuple(dy.shape) != (M, K) or dy.stride(1) != 1 or w.shape[1] != Nn or w.stride(1) != 1):
+        raise _lib.MvltError(f"conv_patch_dgrad: unsupported operands (B={B} H={H} W={W} C={Cdim} R={R}, dy {tuple(dy.shape)}, w {tuple(w.shape)})")
+    d = GemmDesc()
+    d.A, d.B, d.D = dy.data_ptr(), w.data_ptr(), dx.data_ptr()
+    d.M, d.N, d.K = M, Nn, K
+    d.a_mn, d.b_mn = 0, 1                      # B = w^T: [N = R*R*C, K = Co] read MN-major from w [Co, R*R*C]
+    d.lda, d.ldb, d.ldd = dy.stride(0), w.stride(0), Nn
+    d.batch1 = d.batch2 = 1
+    d.alpha = 1.0
+    d.out_f32 = 1
+    d.patch_store = 1
+    d.conv_B, d.conv_H, d.conv_W, d.conv_C, d.conv_R = B, H, W, Cdim, R
+    d.conv_pix_stride, d.conv_batch_stride = Cdim, batch_stride
+    if _lib.PROFILE is not None or _lib.GEMM_LOG is not None:
+        _lib.account_gemm(2.0 * M * Nn * K, (M * K + Nn * K) * 2.0 + M * Nn * 4.0, f"conv_patch_dgrad M={M} N={Nn} K={K} HxW={H}x{W} R={R}")
+    call("gemm", C.byref(d))
+    return dx
+
+
 def conv3x3_wgrad(dy, x, B, H, W, Cdim, pix_stride, batch_stride, out, *, split_k: int = 0):
     """out[co, tap*C + c] += sum_{b,y,x} dy[(b,y,x), co] * X[b, y+tap//3-1, x+tap%3-1, c]  (fp32 atomic accumulation).
 

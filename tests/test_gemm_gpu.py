@@ -117,6 +117,30 @@ def test_conv_patch_view_equals_patchify_then_gemm(B, H, C, R):
     _check(out, conv, R * R * C, "patch view vs conv2d")
 
 
+@pytest.mark.parametrize("B,H,C,R", [(3, 64, 64, 8), (4, 32, 128, 4), (5, 16, 320, 2)])
+def test_conv_patch_store_equals_gemm_then_unpatchify(B, H, C, R):
+    """Input gradient of the spatial-reduction convolution stored through the 5-D view == GEMM into a patch-gradient buffer +
+    unpatchify (up to the bf16 rounding of that buffer, which the fused store does not have), text rows untouched."""
+    from mvlt_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(B * 10 + C)
+    T, W = 128, H
+    N = H * W + T
+    oh = H // R
+    dy = _rand((B * oh * oh, C), g)
+    w = _rand((C, R * R * C), g, C ** -0.5)
+    dx = torch.full((B, N, C), 7.0, device="cuda")
+    k.conv_patch_dgrad(dy, w, dx, B, H, W, C, R, N * C)
+    dpatch = torch.empty((B * oh * oh, R * R * C), device="cuda", dtype=F32)
+    k.gemm(dy, w.t(), dpatch)
+    ref = torch.full((B, N, C), 7.0, device="cuda")
+    k.unpatchify(dpatch.to(BF16), ref, N * C, B, H, W, C, R)
+    torch.cuda.synchronize()
+    assert torch.equal(dx[:, H * W:], ref[:, H * W:])                      # text rows untouched
+    exact = dpatch.view(B, oh, oh, R, R, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H * W, C)
+    assert torch.equal(dx[:, :H * W], exact)                               # the fp32 product itself, placed pixel by pixel
+    _check(ref[:, :H * W], exact, C, "unpatchify path (bf16-rounded)", atol_scale=2.0)
+
+
 def test_gemm_matches_simt_ref_bitwise_structure():
     """Same descriptor through the SIMT cross-check kernel and the tcgen05 kernel."""
     from mvlt_b200 import kernels as k
