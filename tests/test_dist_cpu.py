@@ -115,7 +115,7 @@ def _segment_worker(rank, world, port, q):
         red = SegmentReducer(flat, [(0, 4), (4, 4), (4, 9), (9, 9), (9, 12)], True)
         red.segment_done(0)
         after0 = flat.tolist()
-        red.segment_done(2)
+        red.segment_done(2, None)    # (the engine's call form: an optional event of the weight-gradient stream, None on CPU)
         red.segment_done(0)          # a repeated notification must not reduce the segment twice
         red.finish()                 # reduces whatever was not announced (segment 4)
         q.put((rank, after0, flat.tolist()))
