@@ -336,10 +336,14 @@ def eng_forward_losses(eng: PVLTEngine, images, ids, batch, training, save):
                              overflow=gs.mlm_overflow)
             scale, scale_dev = wm, gs.mlm_inv
         else:
-            k.compact_labels(lab_dev, B * T, -1, idx, lab_c, cnt)
             if batch.get("mlm_count") is not None:
-                n = int(batch["mlm_count"])          # supplied by the data pipeline: no device->host sync
+                # supplied by the data pipeline: no device->host sync. The count is the caller's claim, so the compaction runs
+                # in its fixed-capacity form: exactly n index rows are written (a claim above the real count is padded with
+                # ignored rows, one below it drops the surplus), and the head can never gather through an unwritten index
+                n = min(max(int(batch["mlm_count"]), 0), B * T)
+                k.compact_labels(lab_dev, B * T, -1, idx, lab_c, cnt, cap=n)
             else:
+                k.compact_labels(lab_dev, B * T, -1, idx, lab_c, cnt)
                 n = int((labels != -1).sum()) if not labels.is_cuda else int(cnt.item())
             scale, scale_dev = wm / max(n, 1), None
         if n > 0:

@@ -69,3 +69,26 @@ def planted_tir_query(q: int, n_cand: int = 101):
     images = brightness_images(levels[perm], g)
     ids = make_batch(1, seed=1000 + q)["ori_input_ids"].repeat(n_cand, 1)
     return images, ids, n_brighter
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Planted recognition protocol (the recognition loop, engine_grid_masking.py:396-462, against the fp32 reference). Same idea as
+# the retrieval protocol: the class is planted in image brightness and ONLY the last linear layer of the two category heads
+# (768 -> 48 / 122) is fitted on reference features. The random encoder's response to brightness saturates for bright
+# images, so the four levels sit where it is steep (equal steps of the response, not of the brightness): the argmax of a
+# sample is then decided by a margin of a few logits, and the bf16 kernels and the fp32 reference must predict the same class.
+# ------------------------------------------------------------------------------------------------------------
+PLANTED_CLS_LEVELS = (0.05, 0.12, 0.22, 0.55)
+PLANTED_SUP_CLASSES = (5, 17, 29, 41)        # of the 48 M-CR categories
+PLANTED_SUB_CLASSES = (3, 40, 77, 110)       # of the 122 S-CR categories
+
+
+def planted_cls_set(n: int, seed: int = 0):
+    """(images, ori_input_ids, sup_cls_labels [n, 1], sub_cls_labels [n, 1]): a sample's category pair is one of four,
+    carried by its brightness level (+- 0.01); captions are varied and carry no signal."""
+    g = torch.Generator().manual_seed(4004 + seed)
+    c = torch.randint(0, 4, (n,), generator=g)
+    levels = torch.tensor(PLANTED_CLS_LEVELS)[c] + (torch.rand(n, generator=g) - 0.5) * 0.02
+    images = brightness_images(levels, g, noise=0.1)
+    ids = make_batch(n, seed=50 + seed)["ori_input_ids"]
+    return images, ids, torch.tensor(PLANTED_SUP_CLASSES)[c].view(n, 1), torch.tensor(PLANTED_SUB_CLASSES)[c].view(n, 1)

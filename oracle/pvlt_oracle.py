@@ -470,3 +470,36 @@ def fit_itm_probe(sd, images, ids, labels, model="pvlt_tiny", steps=200, l2=1e-4
     out["itm_head.linear.bias"] = b.detach().clone()
     out["itm_head.linear_bias"] = torch.zeros(2)
     return out
+
+
+def fit_cls_probes(sd, images, ids, sup_labels, sub_labels, model="pvlt_tiny", steps=500, l2=1e-4):
+    """Planted recognition protocol (mvlt_b200/synthetic.py:planted_cls_set): the LAST linear layer of the two category
+    heads (vl_heads.py:101-104; 768 -> 48 / 122) fitted on fp32 reference features of the fit set (L-BFGS with a strong-Wolfe
+    line search, zero init, deterministic). Returns a copy of ``sd`` with ``{sup,sub}_cls_head.linear.{weight,bias}`` replaced
+    and ``linear_bias`` zeroed."""
+    with torch.no_grad():
+        tfs = []
+        for i in range(0, images.shape[0], 32):
+            _, tf = pyramid_features(sd, images[i:i + 32], ids[i:i + 32], model)
+            tfs.append(tf[-1][:, 0:1, :])
+        tf0 = torch.cat(tfs)
+    out = dict(sd)
+    for name, labels in (("sup_cls", sup_labels), ("sub_cls", sub_labels)):
+        with torch.no_grad():
+            feats = _head_embed(sd, f"{name}_head_embed", tf0).reshape(-1, HIDDEN)
+        n_cls = sd[f"{name}_head.linear.weight"].shape[0]
+        W = torch.zeros((n_cls, HIDDEN), requires_grad=True)
+        b = torch.zeros((n_cls,), requires_grad=True)
+        opt = torch.optim.LBFGS([W, b], lr=1.0, max_iter=steps, line_search_fn="strong_wolfe")
+        y = labels.view(-1)
+
+        def closure():
+            opt.zero_grad()
+            loss = F.cross_entropy(feats @ W.t() + b, y) + l2 * (W ** 2).sum()
+            loss.backward()
+            return loss
+        opt.step(closure)
+        out[f"{name}_head.linear.weight"] = W.detach().clone()
+        out[f"{name}_head.linear.bias"] = b.detach().clone()
+        out[f"{name}_head.linear_bias"] = torch.zeros(n_cls)
+    return out

@@ -120,6 +120,52 @@ def test_recognition_loop():
     assert 0 <= res["sup"][0] <= 1 and 0 <= res["sub"][0] <= 1
 
 
+def test_planted_recognition_loop_predictions_identical_to_fp32_oracle():
+    """the reference-named recognition loop (engine_grid_masking.py:396-462) on the planted recognition protocol
+    (mvlt_b200/synthetic.py:planted_cls_set; last linear layer of the two category heads fitted by the fp32 oracle on
+    brightness-planted classes). The 48- / 122-way argmax decisions of the bf16 sm_100a kernels must equal the fp32 oracle's
+    sample by sample, so accuracy and macro / micro / weighted F1 of the loop are the oracle's, and the protocol must be
+    well conditioned (decision margin above twice the largest logit error of the sample)."""
+    import json, os
+    import engine_grid_masking as E
+    import mvlt_b200
+    from mvlt_b200.synthetic import planted_cls_set
+    from oracle import pvlt_oracle as O
+    sd = O.fit_cls_probes(O.make_state_dict("pvlt_tiny", CLS, seed=5), *planted_cls_set(96, seed=0))
+    m = mvlt_b200.create_model("pvlt_tiny", pretrained=True, num_classes=1000, drop_rate=0.0, drop_path_rate=0.1,
+                               drop_block_rate=None, token_hidden_size=768, num_text_tokens=128, loss_type=dict(CLS),
+                               pretrained_pth="")
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    loader, rows, preds = [], [], {"sup": [], "sub": []}
+    labels = {"sup": [], "sub": []}
+    for i in range(3):
+        images, ids, sup, sub = planted_cls_set(16, seed=1 + i)
+        loader.append({"images": images, "ori_input_ids": ids, "sup_cls_labels": sup, "sub_cls_labels": sub})
+        with torch.no_grad():
+            got = m(images.cuda(), ids.cuda())
+            ref = O.forward(sd, images, ids, CLS, training=False)
+        for nm, lab in (("sup", sup), ("sub", sub)):
+            lg, lr = got[f"{nm}_cls_logits"].view(16, -1).float().cpu(), ref[f"{nm}_cls_logits"].view(16, -1)
+            top = lr.topk(2, dim=-1).values
+            for j in range(16):
+                rows.append(dict(head=nm, sample=16 * i + j, label=int(lab[j]), pred_gpu=int(lg[j].argmax()),
+                                 pred_oracle=int(lr[j].argmax()), margin=float(top[j, 0] - top[j, 1]),
+                                 max_err=float((lg[j] - lr[j]).abs().max())))
+            preds[nm] += lr.argmax(-1).tolist()
+            labels[nm] += lab.view(-1).tolist()
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(rows, open("gpurun_out/planted_recognition.json", "w"), indent=1)
+    for r in rows:
+        assert r["pred_oracle"] == r["label"], r                      # the fp32 oracle solves the planted task
+        assert r["margin"] > 2 * r["max_err"], r                      # ... with room: bf16 noise cannot flip a decision
+        assert r["pred_gpu"] == r["pred_oracle"], r
+    res = E.evaluate_recognition(loader, m, torch.device("cuda"), _Args())
+    for nm in ("sup", "sub"):
+        want = E.calculate_cls_metrics(labels[nm], preds[nm])
+        assert tuple(res[nm]) == tuple(want), (nm, res[nm], want)
+
+
 def test_full_batch_properties_b128():
     """BASELINE configs[1] size (B=128): finite step, MLM loss ~ ln(30522) at random init, forward repeatable."""
     from mvlt_b200.synthetic import make_batch

@@ -245,3 +245,26 @@ def test_dict_forward_head_selection():
         part = m(b["images"].cuda(), b["input_ids"].cuda(), heads=("t2i", "itm"))
     assert part["mlm_logits"] is None and part["sup_cls_logits"] is None
     assert torch.equal(part["t2i_logits"], full["t2i_logits"]) and torch.equal(part["itm_logits"], full["itm_logits"])
+
+
+def test_supplied_mlm_count_is_a_claim_not_an_index_bound():
+    """``mlm_count`` (supplied by the data pipeline so that the step needs no device->host read) is the caller's claim: the
+    label compaction runs in its fixed-capacity form, so an over-claim is padded with ignored rows (same loss sum, mean over
+    the claimed count), an under-claim drops the surplus rows, and the head never gathers through an unwritten index."""
+    from oracle import pvlt_oracle as O
+    m, _ = _model(PRE)
+    m.eval()
+    batch = O.make_inputs(2, seed=3)
+    img, ids = batch["images"].cuda(), batch["input_ids"].cuda()
+    n = int((batch["mlm_labels"] != -1).sum())
+    kw = dict(mlm_labels=batch["mlm_labels"], itm_labels=batch["itm_labels"], target_images=img)
+    with torch.no_grad():
+        base = m(img, ids, **kw)[1].cpu()                       # count taken from the labels
+        exact = m(img, ids, mlm_count=n, **kw)[1].cpu()
+        over = m(img, ids, mlm_count=n + 9, **kw)[1].cpu()
+        under = m(img, ids, mlm_count=n - 1, **kw)[1].cpu()
+    assert torch.allclose(exact[:7], base[:7], rtol=1e-4, atol=1e-6), (exact, base)
+    assert abs(float(over[1]) * (n + 9) - float(base[1]) * n) <= 1e-3 * float(base[1]) * n, (over, base, n)
+    assert float(over[6]) == float(base[6])                        # correct-prediction counter: padded rows never count
+    assert torch.allclose(over[2:6], base[2:6], rtol=1e-4, atol=1e-6)
+    assert torch.isfinite(under).all() and 0 < float(under[1]) * (n - 1) <= float(base[1]) * n * (1 + 1e-3), (under, base)

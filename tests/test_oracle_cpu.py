@@ -132,3 +132,21 @@ def test_oracle_equals_live_reference_when_staged():
         err = float((ref[key] - got[key]).abs().max() / (ref[key].abs().max() + 1e-12))
         assert err <= 2e-5, (key, err)
     assert ref["sup_cls_logits"] is None and got["sup_cls_logits"] is None
+
+
+def test_planted_recognition_protocol_is_well_conditioned_on_the_oracle():
+    """The planted recognition protocol (mvlt_b200/synthetic.py:planted_cls_set + oracle.fit_cls_probes) on the fp32 oracle
+    alone: the fitted category heads classify a held-out set perfectly and every argmax is decided by more than a logit --
+    the property the GPU test (tests/test_engine_gpu.py) relies on when it demands identical predictions from bf16 kernels."""
+    from mvlt_b200.synthetic import planted_cls_set
+    lt = {"itm": 0, "mlm": 0, "t2i": 0, "cls": 1}
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
+    sd = O.fit_cls_probes(O.make_state_dict("pvlt_tiny", lt, seed=5), *planted_cls_set(96, seed=0))
+    images, ids, sup, sub = planted_cls_set(24, seed=1)
+    with torch.no_grad():
+        out = O.forward(sd, images, ids, lt, training=False)
+    for key, labels in (("sup_cls_logits", sup), ("sub_cls_logits", sub)):
+        lg = out[key].view(24, -1)
+        top = lg.topk(2, dim=-1).values
+        assert torch.equal(lg.argmax(-1), labels.view(-1)), key
+        assert float((top[:, 0] - top[:, 1]).min()) > 1.0, (key, float((top[:, 0] - top[:, 1]).min()))
