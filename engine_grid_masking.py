@@ -46,24 +46,30 @@ def _masked(samples, images, device, step, seed=0, out=None):
                                    out=out)
 
 
+def _own_adamw(optimizer):
+    from mvlt_b200.optim import AdamW
+    return isinstance(optimizer, AdamW)
+
+
 def _graphed_step(model, optimizer, loss_scaler, max_norm, model_ema, args, batch_rows):
     """CUDA-graph replay of the iteration (mvlt_b200/graph.py) when asked for (``args.cuda_graph`` or MVLT_CUDA_GRAPH=1) and
-    possible: own AdamW, no loss scaler / clipping / EMA hooks between backward and step, no DistributedDataParallel wrapper
-    (``model.enable_grad_sync()`` is the data-parallel mode that can be captured). One GraphedStep per model, kept across epochs."""
+    possible: own AdamW, no loss scaler / EMA hooks between backward and step, no DistributedDataParallel wrapper
+    (``model.enable_grad_sync()`` is the data-parallel mode that can be captured); gradient clipping (``max_norm``) is captured
+    with the step (AdamW.step(max_norm=...): norm and coefficient stay on the device). One GraphedStep per model, kept across epochs."""
     import os
     want = bool(getattr(args, "cuda_graph", False)) or os.environ.get("MVLT_CUDA_GRAPH", "0") == "1"
-    if not want or loss_scaler is not None or max_norm or model_ema is not None or hasattr(model, "module"):
+    if not want or loss_scaler is not None or model_ema is not None or hasattr(model, "module"):
         return None
     from mvlt_b200.graph import GraphedStep
     from mvlt_b200.optim import AdamW
     if not isinstance(optimizer, AdamW):
         return None
     gs = model.__dict__.get("_graphed_step")
-    if gs is None or gs.opt is not optimizer or gs.model._engine() is not gs.eng:
+    if gs is None or gs.opt is not optimizer or gs.model._engine() is not gs.eng or gs.max_norm != (float(max_norm) if max_norm else None):
         cap = getattr(args, "mlm_capacity", None)
         if not cap and model.loss_type.get("mlm"):      # 15 % of the word pieces are masked: 20 % of all rows bounds the count
             cap = -(-int(0.2 * batch_rows) // 128) * 128
-        gs = GraphedStep(model, optimizer, mlm_capacity=cap, warmup=1)
+        gs = GraphedStep(model, optimizer, mlm_capacity=cap, warmup=1, max_norm=max_norm or None)
         model.__dict__["_graphed_step"] = gs
         model.__dict__["_graphed_static"] = {}
     return gs
@@ -128,9 +134,12 @@ def train_one_epoch_vl(model: torch.nn.Module, criterion, data_loader: Iterable,
                             create_graph=False)
             else:
                 total.backward()
-                if max_norm:
-                    torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
-                optimizer.step()
+                if max_norm and _own_adamw(optimizer):
+                    optimizer.step(max_norm=max_norm)       # norm + clip coefficient on the device, folded into the AdamW read
+                else:
+                    if max_norm:
+                        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
+                    optimizer.step()
         if model_ema is not None:
             model_ema.update(model)
         s = stats.tolist()                                   # the step's single device->host read

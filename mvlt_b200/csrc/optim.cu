@@ -103,6 +103,55 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __re
   }
 }
 
+// ---- gradient-norm clipping folded into the optimizer step (timm NativeScaler / torch.nn.utils.clip_grad_norm_ semantics,
+// engine_grid_masking.py:126-127 with --clip-grad): the gradients are READ once more (4 B per parameter) for their squared sum,
+// never rewritten: the clip coefficient is a device scalar that adamw_multi multiplies into every gradient as it loads it.
+// Deterministic (no atomics): one partial per chunk, summed in a fixed order, so data-parallel ranks holding identical
+// gradients compute bit-identical coefficients and their parameters stay bit-identical.
+__global__ void __launch_bounds__(256) grad_sumsq_multi_kernel(const AdamTensor* __restrict__ tensors, const AdamChunk* __restrict__ chunks,
+                                                               int chunk_elems, float* __restrict__ partials) {
+  pdl_prologue();
+  __shared__ float sh[32];
+  const AdamChunk ch = chunks[blockIdx.x];
+  const AdamTensor t = tensors[ch.t];
+  const long long n = min((long long)chunk_elems, t.n - ch.off);
+  const float* g = t.g + ch.off;
+  float s = 0.f;
+  const long long n4 = ((((uintptr_t)g) & 15) == 0) ? n / 4 : 0;
+  for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    s = fmaf(g4.x, g4.x, s);
+    s = fmaf(g4.y, g4.y, s);
+    s = fmaf(g4.z, g4.z, s);
+    s = fmaf(g4.w, g4.w, s);
+  }
+  for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) s = fmaf(g[i], g[i], s);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// out[0] = in_scale * min(1, max_norm / (norm + 1e-6)), out[1] = norm = |in_scale| * sqrt(sum of the partials)
+__global__ void __launch_bounds__(256) grad_clip_scale_kernel(const float* __restrict__ partials, int n, float max_norm,
+                                                              const float* __restrict__ in_scale, float* __restrict__ out) {
+  pdl_prologue();
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partials[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float is = in_scale ? *in_scale : 1.f;
+    const float norm = (float)sqrt(sh[0]) * fabsf(is);
+    const float coef = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+    out[0] = coef * is;
+    out[1] = norm;
+  }
+}
+
 }  // namespace
 
 // tensors: device array of AdamTensor; chunks: device array of n_chunks AdamChunk (one CTA each).
@@ -115,6 +164,26 @@ extern "C" int mvlt_adamw_multi(const void* tensors, const void* chunks, int n_c
   MVLT_CHECK_ARG(bias_correction1 > 0.f && bias_correction2 > 0.f, "adamw_multi: bias corrections must be positive");
   mvlt_launch(adamw_multi_kernel, n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const AdamTensor*>(tensors), reinterpret_cast<const AdamChunk*>(chunks), chunk_elems, lr, beta1, beta2, eps,
       weight_decay, bias_correction1, bias_correction2, grad_scale_dev, zero_grads, hyper_dev);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+// partials_out[c] = sum of squared gradients of chunk c (the tables of mvlt_adamw_multi; n_chunks floats are written).
+extern "C" int mvlt_grad_sumsq_multi(const void* tensors, const void* chunks, int n_chunks, int chunk_elems, float* partials_out,
+                                     void* stream_) {
+  MVLT_CHECK_ARG(tensors && chunks && partials_out && n_chunks > 0 && chunk_elems > 0, "grad_sumsq_multi: empty tables");
+  mvlt_launch(grad_sumsq_multi_kernel, n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream_), reinterpret_cast<const AdamTensor*>(tensors), reinterpret_cast<const AdamChunk*>(chunks), chunk_elems, partials_out);
+  MVLT_CHECK_LAUNCH();
+  return 0;
+}
+
+// Gradient-clipping coefficient from the chunk partials of every group (summed in a fixed order):
+//   out2[1] = total_norm = |s| * sqrt(sum partials),  out2[0] = s * min(1, max_norm / (total_norm + 1e-6))     (s = *in_scale_dev or 1)
+// out2[0] is the grad_scale_dev operand of mvlt_adamw_multi (torch.nn.utils.clip_grad_norm_ semantics; max_norm <= 0: no clipping).
+extern "C" int mvlt_grad_clip_scale(const float* partials, int n_partials, float max_norm, const float* in_scale_dev, float* out2,
+                                    void* stream_) {
+  MVLT_CHECK_ARG(partials && out2 && n_partials > 0, "grad_clip_scale: empty partials");
+  mvlt_launch(grad_clip_scale_kernel, 1, 256, 0, reinterpret_cast<cudaStream_t>(stream_), partials, n_partials, max_norm, in_scale_dev, out2);
   MVLT_CHECK_LAUNCH();
   return 0;
 }

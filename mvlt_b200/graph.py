@@ -47,10 +47,11 @@ class GraphedStep:
     next replay overwrites. ``model`` may have ``enable_grad_sync`` on (the exchange is captured); a DistributedDataParallel
     wrapper is not supported here. ``mlm_capacity`` bounds the labelled rows per batch (a multiple of 128 just above the
     largest expected count is best); ``check_overflow()`` tells, with a device->host read, whether any batch exceeded it.
+    ``max_norm``: clip the global gradient norm ahead of the update (``--clip-grad``), on the device, inside the graph.
     """
 
     def __init__(self, model, optimizer, mlm_capacity: Optional[int] = None, warmup: int = 1, enabled: bool = True,
-                 parallel_wgrad: Optional[bool] = None):
+                 parallel_wgrad: Optional[bool] = None, max_norm: Optional[float] = None):
         from .optim import AdamW
         if not isinstance(optimizer, AdamW):
             raise MvltError("GraphedStep needs mvlt_b200.optim.AdamW (its hyper-parameters must be readable from device memory)")
@@ -62,6 +63,9 @@ class GraphedStep:
         self.state = GraphState(dev, mlm_capacity or 0)
         self.warmup = max(int(warmup), 0)
         self.enabled = enabled
+        # gradient-norm clipping (main_vl.py --clip-grad) folded into the captured optimizer step: norm and coefficient stay on
+        # the device (AdamW.step(max_norm=...)); ``optimizer.last_grad_norm`` holds the norm of the last step
+        self.max_norm = float(max_norm) if max_norm else None
         # weight-gradient launches as a parallel branch of the graph (engine.side_launch); MVLT_GRAPH_WGRAD_BRANCH=0 for the A/B
         if parallel_wgrad is None:
             parallel_wgrad = os.environ.get("MVLT_GRAPH_WGRAD_BRANCH", "1") != "0"
@@ -123,7 +127,7 @@ class GraphedStep:
         for name, p in eng.P.items():
             if p.requires_grad:
                 p.grad = G[name]
-        self.opt.step()
+        self.opt.step(max_norm=self.max_norm)
         self.opt.zero_grad(set_to_none=True)
         return total, stats
 

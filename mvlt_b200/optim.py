@@ -36,6 +36,8 @@ class AdamW(torch.optim.Optimizer):
         self._tables = {}
         self._hyper = None      # device fp32 [n_groups, 4] = {lr, bias_correction1, bias_correction2, 0}: see enable_device_hyper
         self._hyper_t = None
+        self._clip_part = self._clip_out = None     # gradient-clipping scratch: per-chunk squared sums, {coefficient, total norm}
+        self.last_grad_norm = None                  # 1-element device tensor: total gradient norm of the last clipped step
 
     # ---- device-resident hyper-parameters (CUDA-graph replays) -------------------------------------------------------------
     def enable_device_hyper(self, on=True):
@@ -63,6 +65,7 @@ class AdamW(torch.optim.Optimizer):
                 self._state(p)
             if ps:
                 self._group_tables(gi, ps)
+        self._clip_buffers()
 
     def advance(self):
         if self._hyper is None:
@@ -131,23 +134,64 @@ class AdamW(torch.optim.Optimizer):
         self._tables[gi] = (key, tt, ct, nchunks)
         return tt, ct, nchunks
 
+    def _checked(self, group):
+        ps = [p for p in group["params"] if p.grad is not None]
+        for p in ps:
+            if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32:
+                raise MvltError("mvlt_b200.optim.AdamW needs fp32 CUDA parameters and gradients (no CPU fallback)")
+            if not p.is_contiguous() or not p.grad.is_contiguous():
+                raise MvltError("mvlt_b200.optim.AdamW needs contiguous parameters and gradients")
+            self._state(p)
+        return ps
+
+    def _clip_buffers(self):
+        """Scratch of the fused gradient clipping, sized for the chunk tables built so far (allocated outside stream captures
+        when ``prepare`` is used)."""
+        total = sum(t[3] for t in self._tables.values())
+        if total and (self._clip_part is None or self._clip_part.numel() < total):
+            dev = next(iter(self._tables.values()))[1].device
+            self._clip_part = torch.empty((total,), dtype=torch.float32, device=dev)
+            self._clip_out = torch.empty((2,), dtype=torch.float32, device=dev)
+        return total
+
+    def _clip_scale(self, max_norm, grad_scale):
+        """torch.nn.utils.clip_grad_norm_ folded into the step (csrc/optim.cu): per-chunk squared sums of every gradient (one
+        launch per group, the AdamW chunk tables), then ONE small launch that sums them in a fixed order and writes
+        {grad_scale * min(1, max_norm / (norm + 1e-6)), norm} to device memory. The gradients themselves are not rewritten: the
+        AdamW kernel multiplies the coefficient in as it reads them. No host synchronisation (``last_grad_norm`` stays on the
+        device), deterministic, capturable in a CUDA graph."""
+        plan = []
+        for gi, group in enumerate(self.param_groups):
+            ps = self._checked(group)
+            if ps:
+                plan.append(self._group_tables(gi, ps))
+        if not plan:
+            return grad_scale
+        total = self._clip_buffers()
+        off = 0
+        for tt, ct, nchunks in plan:
+            call("grad_sumsq_multi", ptr(tt), ptr(ct), C.c_int(nchunks), C.c_int(CHUNK), ptr(self._clip_part[off:]))
+            off += nchunks
+        call("grad_clip_scale", ptr(self._clip_part), C.c_int(off), C.c_float(float(max_norm)), ptr(grad_scale), ptr(self._clip_out))
+        self.last_grad_norm = self._clip_out[1:2]
+        return self._clip_out[0:1]
+
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=None):
-        """``grad_scale``: optional 1-element fp32 device tensor multiplied into every gradient (e.g. 1 / loss scale)."""
+    def step(self, closure=None, grad_scale=None, max_norm=None):
+        """``grad_scale``: optional 1-element fp32 device tensor multiplied into every gradient (e.g. 1 / loss scale).
+        ``max_norm`` > 0: clip the global gradient norm like ``torch.nn.utils.clip_grad_norm_(params, max_norm)`` ahead of the
+        update (timm NativeScaler's ``clip_grad``, engine_grid_masking.py:126-127), computed and applied on the device; the
+        norm (of the ``grad_scale``-d gradients) is left in ``last_grad_norm``."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if max_norm is not None and max_norm > 0:
+            grad_scale = self._clip_scale(max_norm, grad_scale)
         for gi, group in enumerate(self.param_groups):
-            ps = [p for p in group["params"] if p.grad is not None]
+            ps = self._checked(group)
             if not ps:
                 continue
-            for p in ps:
-                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32:
-                    raise MvltError("mvlt_b200.optim.AdamW needs fp32 CUDA parameters and gradients (no CPU fallback)")
-                if not p.is_contiguous() or not p.grad.is_contiguous():
-                    raise MvltError("mvlt_b200.optim.AdamW needs contiguous parameters and gradients")
-                self._state(p)
             # torch.optim.AdamW checkpoints (main_vl.py:340) carry ``step`` as a 0-dim tensor: accept both forms
             if self._hyper is not None:
                 t = max(self._hyper_t, 1)      # the kernel reads lr / bias corrections of this step from self._hyper[gi]

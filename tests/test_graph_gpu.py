@@ -188,3 +188,54 @@ def test_graph_capacity_overflow_is_flagged():
     for _ in range(2):
         gs(b["images"], b["input_ids"], mlm_labels=b["mlm_labels"], itm_labels=b["itm_labels"], target_images=b["images"])
     assert gs.check_overflow()
+
+
+def test_graph_step_with_fused_gradient_clipping():
+    """--clip-grad (main_vl.py:62, engine_grid_masking.py:126) inside the captured iteration: GraphedStep(max_norm=...) computes
+    the global gradient norm and the clip coefficient on the device. With the learning rate at 0 both models keep equal
+    parameters, so the norm of every replayed step must equal torch.nn.utils.clip_grad_norm_'s on the per-launch model."""
+    from mvlt_b200.graph import GraphedStep
+    from mvlt_b200.synthetic import make_batch
+    B, max_norm = 8, 0.05
+    batches = [{k: v.cuda() for k, v in make_batch(B, seed=i).items()} for i in range(2)]
+    keys = ("sup_cls_labels", "sub_cls_labels")
+
+    def set_lr(opt, lr):
+        for g in opt.param_groups:
+            g["lr"] = lr
+
+    torch.manual_seed(11)
+    ma = _model(CLS, seed=5)
+    oa = _opt(ma)
+    set_lr(oa, 0.0)
+    want = []
+    for i in range(4):
+        b = batches[i % 2]
+        total, _ = ma(b["images"], b["input_ids"], **{k: b[k] for k in keys})
+        total.backward()
+        want.append(float(torch.nn.utils.clip_grad_norm_(ma.parameters(), max_norm)))
+        oa.step()
+        oa.zero_grad(set_to_none=True)
+
+    torch.manual_seed(11)
+    mb = _model(CLS, seed=5)
+    ob = _opt(mb)
+    set_lr(ob, 0.0)
+    gs = GraphedStep(mb, ob, warmup=1, max_norm=max_norm)
+    static = {k: torch.empty_like(v) for k, v in batches[0].items()}
+    for i in range(4):
+        for k, v in batches[i % 2].items():
+            static[k].copy_(v)
+        gs(static["images"], static["input_ids"], **{k: static[k] for k in keys})
+        got, coef = float(ob.last_grad_norm), float(ob._clip_out[0])
+        assert abs(got - want[i]) <= 1e-2 * want[i], (i, got, want[i])
+        assert abs(coef - min(1.0, max_norm / (got + 1e-6))) <= 1e-5, (i, coef, got)
+    assert gs.captured()
+    assert min(want) > max_norm                         # the clipping was active
+    p0 = {n: p.detach().clone() for n, p in mb.named_parameters()}
+    set_lr(ob, 3e-4)
+    for k, v in batches[0].items():
+        static[k].copy_(v)
+    gs(static["images"], static["input_ids"], **{k: static[k] for k in keys})
+    moved = sum(float((p.detach() - p0[n]).abs().sum()) for n, p in mb.named_parameters())
+    assert moved > 0 and all(torch.isfinite(p).all() for p in mb.parameters())

@@ -85,3 +85,60 @@ def test_adamw_refreshes_registered_bf16_shadows():
     assert torch.equal(w_c3.view(64, 9, 128), c3.detach().view(64, 128, 9).permute(0, 2, 1).to(torch.bfloat16))
     # input-gradient layout: w16t[ci, t, co] = w[co, ci, 8 - t]
     assert torch.equal(w_c3t.view(128, 9, 64), c3.detach().view(64, 128, 9).flip(-1).permute(1, 2, 0).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("max_norm", [0.37, 1e6])
+def test_adamw_fused_gradient_clipping_matches_torch_clip_grad_norm(max_norm):
+    """AdamW.step(max_norm=...) (per-chunk squared sums + one coefficient launch, multiplied into the gradients as the AdamW
+    kernel reads them) vs torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW. eps is large on purpose: Adam's update is
+    invariant to a uniform gradient scale when eps -> 0, so a wrong coefficient would otherwise go unnoticed."""
+    from mvlt_b200.optim import AdamW
+    g = torch.Generator(device="cuda").manual_seed(9)
+    shapes = [(3000, 768), (512,), (320, 64, 2, 2), (3,), (1, 50, 64), (7, 13), (16385,), (1030,)]
+    ours = [torch.nn.Parameter(torch.randn(s, generator=g, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+
+    def groups(ps):
+        return [{"params": [p for p in ps if p.ndim > 1], "weight_decay": 0.05}, {"params": [p for p in ps if p.ndim <= 1], "weight_decay": 0.0}]
+    o1 = AdamW(groups(ours), lr=3e-3, eps=1e-2)
+    o2 = torch.optim.AdamW(groups(ref), lr=3e-3, eps=1e-2)
+    inv_scale = torch.tensor([0.5], device="cuda")
+    for step in range(3):
+        for a, b in zip(ours, ref):
+            gr = torch.randn(a.shape, generator=g, device="cuda") * (1e-4 * 10 ** step)
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        before = [a.grad.clone() for a in ours]
+        if step == 2:       # with an incoming gradient scale (1 / loss scale): the norm is that of the unscaled gradients
+            for b in ref:
+                b.grad.mul_(0.5)
+        want = torch.nn.utils.clip_grad_norm_(ref, max_norm)
+        o1.step(max_norm=max_norm, grad_scale=inv_scale if step == 2 else None)
+        o2.step()
+        got = float(o1.last_grad_norm)
+        assert abs(got - float(want)) <= 1e-5 * float(want), (step, got, float(want))
+        coef = min(1.0, max_norm / (float(want) + 1e-6)) * (0.5 if step == 2 else 1.0)
+        assert abs(float(o1._clip_out[0]) - coef) <= 1e-5 * coef, (step, float(o1._clip_out[0]), coef)
+        for a, g0 in zip(ours, before):      # the gradients themselves are left as they were (the coefficient is applied on read)
+            assert torch.equal(a.grad, g0)
+    for a, b in zip(ours, ref):
+        err = (a - b).abs().max().item()
+        assert err <= 4e-6 * max(1.0, b.abs().max().item()), (tuple(a.shape), err)
+
+
+def test_adamw_fused_clipping_is_deterministic():
+    """No atomics in the norm: the same gradients give bit-identical coefficients (data-parallel ranks must stay bit-identical)."""
+    from mvlt_b200.optim import AdamW
+    g = torch.Generator(device="cuda").manual_seed(1)
+    p = torch.nn.Parameter(torch.randn((4_000_037,), generator=g, device="cuda"))
+    q = torch.nn.Parameter(torch.randn((129, 513), generator=g, device="cuda"))
+    gp, gq = torch.randn(p.shape, generator=g, device="cuda"), torch.randn(q.shape, generator=g, device="cuda")
+    outs = []
+    for _ in range(3):
+        o = AdamW([p, q], lr=0.0, weight_decay=0.0)
+        p.grad, q.grad = gp, gq
+        o.step(max_norm=1.0)
+        outs.append(o._clip_out.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    want = float(torch.sqrt(gp.double().pow(2).sum() + gq.double().pow(2).sum()))
+    assert abs(float(outs[0][1]) - want) <= 1e-5 * want
