@@ -8,7 +8,7 @@ ours:       PVLT-tiny pre-training step (BASELINE.json configs[1]): bf16 operand
             Fashion-Gen-shaped data, grid masking on odd steps, MLM + ITM + t2i(MVM) losses, backward, AdamW step.
             `value` = samples/s with inputs resident in HBM; `e2e` = same metric from pinned HOST buffers (H2D of the
             step's inputs + D2H of the loss inside the timed region). Also reports the candidate-sharded ITM retrieval
-            sweep (configs[2]) as `retrieval`, the GEMM-kernel roofline and the CPU baseline (oracle port, rank 0).
+            sweep (configs[2]) as `retrieval`, the GEMM-kernel roofline and the CPU baseline (live reference, rank 0).
             Sub-lines of the same run: `sub_benches.recognition` (configs[3], cls-only fine-tune step) and
             `sub_benches.pvlt_small` (configs[4] stand-in), `gpu_eager_reference` (the LIVE reference model under bf16
             autocast + torch.optim.AdamW on the same GPU: the library-kernel bar the hand-written kernels must beat).
