@@ -12,7 +12,12 @@ hi = next(i for i, r in enumerate(rows) if "Source" in r)
 h = rows[hi]
 isrc, iex = h.index("Source"), h.index("Instructions Executed")
 ist = h.index("Warp Stall Sampling (All Samples)")
-body = [r for r in rows[hi + 1:] if len(r) == len(h)]
+body = []
+for r in rows[hi + 1:]:      # first kernel of the report only (a second launch repeats the header rows)
+    if "Source" in r or (r and r[0] == "Kernel Name"):
+        break
+    if len(r) == len(h):
+        body.append(r)
 tot = sum(int(r[iex]) for r in body)
 print("total warp instructions", tot)
 c, s = Counter(), Counter()
