@@ -202,8 +202,11 @@ class AdamW(torch.optim.Optimizer):
                 t = steps.pop() + 1
             b1, b2 = group["betas"]
             tt, ct, nchunks = self._group_tables(gi, ps)
-            if _lib.BYTES is not None:   # p, m, v read + written, g read: 28 bytes per parameter
-                _lib.account_bytes("adamw_multi", 28 * sum(p.numel() for p in ps))
+            if _lib.BYTES is not None:   # p, m, v read + written, g read: 28 bytes per parameter; + 2 per refreshed bf16 copy
+                def _copies(p):
+                    sh = getattr(p, "_mvlt_shadow", None)
+                    return 0 if sh is None or not sh[0] else (1 if sh[2] is None else 2)
+                _lib.account_bytes("adamw_multi", sum(p.numel() * (28 + 2 * _copies(p)) for p in ps))
             call("adamw_multi", ptr(tt), ptr(ct), C.c_int(nchunks), C.c_int(CHUNK), C.c_float(group["lr"]), C.c_float(b1),
                  C.c_float(b2), C.c_float(group["eps"]), C.c_float(group["weight_decay"]), C.c_float(1.0 - b1 ** t),
                  C.c_float(1.0 - b2 ** t), ptr(grad_scale), C.c_int(0),
