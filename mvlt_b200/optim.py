@@ -28,6 +28,18 @@ def param_groups_no_decay(model, weight_decay):
     return [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}]
 
 
+def step_bytes(params) -> int:
+    """Algorithmic bytes of one AdamW launch over ``params``: p, m, v read + written and g read (28 B per parameter), plus
+    2 B per bf16 compute copy the same launch rewrites (``p._mvlt_shadow``: one copy for Linear / embedding / k = s
+    convolution weights, two for the 3x3 convolutions, none for parameters the kernels read in fp32)."""
+    total = 0
+    for p in params:
+        sh = getattr(p, "_mvlt_shadow", None)
+        copies = 0 if sh is None or not sh[0] else (1 if sh[2] is None else 2)
+        total += p.numel() * (28 + 2 * copies)
+    return total
+
+
 class AdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
@@ -202,11 +214,8 @@ class AdamW(torch.optim.Optimizer):
                 t = steps.pop() + 1
             b1, b2 = group["betas"]
             tt, ct, nchunks = self._group_tables(gi, ps)
-            if _lib.BYTES is not None:   # p, m, v read + written, g read: 28 bytes per parameter; + 2 per refreshed bf16 copy
-                def _copies(p):
-                    sh = getattr(p, "_mvlt_shadow", None)
-                    return 0 if sh is None or not sh[0] else (1 if sh[2] is None else 2)
-                _lib.account_bytes("adamw_multi", sum(p.numel() * (28 + 2 * _copies(p)) for p in ps))
+            if _lib.BYTES is not None:
+                _lib.account_bytes("adamw_multi", step_bytes(ps))
             call("adamw_multi", ptr(tt), ptr(ct), C.c_int(nchunks), C.c_int(CHUNK), C.c_float(group["lr"]), C.c_float(b1),
                  C.c_float(b2), C.c_float(group["eps"]), C.c_float(group["weight_decay"]), C.c_float(1.0 - b1 ** t),
                  C.c_float(1.0 - b2 ** t), ptr(grad_scale), C.c_int(0),

@@ -146,6 +146,17 @@ def test_bench_hbm_kernel_table_and_byte_accounting():
     assert row["ms_per_step"] == 1.0 and row["launches_per_step"] == 2.0 and row["algorithmic_gb_per_step"] == 3.0
 
 
+def test_adamw_step_bytes_counts_the_bf16_copies():
+    """bench.py's AdamW roofline: 28 B per parameter + 2 B per bf16 compute copy the launch rewrites."""
+    import torch
+    from mvlt_b200.optim import step_bytes
+    a, b, c, d = (torch.nn.Parameter(torch.zeros(s)) for s in ((10, 4), (8, 2, 3, 3), (7,), (5, 5)))
+    a._mvlt_shadow = (1, torch.zeros(40, dtype=torch.bfloat16), None, 0, 0, 0, 0)
+    b._mvlt_shadow = (2, torch.zeros(144, dtype=torch.bfloat16), torch.zeros(144, dtype=torch.bfloat16), 8, 2, 9, 18)
+    c._mvlt_shadow = (0, None, None, 0, 0, 0, 0)
+    assert step_bytes([a, b, c, d]) == 40 * 30 + 144 * 32 + 7 * 28 + 25 * 28
+
+
 def test_entrypoints_register_with_timm_and_hubconf(monkeypatch):
     """main_vl.py:16,259: ``from libs import pvlt`` registers pvlt_* with timm's registry; hubconf exports them."""
     import importlib
