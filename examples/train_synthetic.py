@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--cuda-graph", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--retrieval-queries", type=int, default=4)
+    ap.add_argument("--checkpoint", default=None, help="write a reference-format checkpoint here and resume from it (main_vl.py:327-346)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -108,6 +109,12 @@ def main():
         rc = E.evaluate_recognition(loader, model, device, args)
         if rank == 0:
             print("evaluate_recognition:", rc)
+    if args.checkpoint and rank == 0:
+        from mvlt_b200.utils import load_checkpoint
+        torch.save({"model": model.state_dict(), "optimizer": optimizer.state_dict(), "lr_scheduler": sched.state_dict(),
+                    "epoch": args.epochs - 1}, args.checkpoint)
+        missing, unexpected, next_epoch = load_checkpoint(model, args.checkpoint, optimizer, sched)
+        print(f"checkpoint round trip: missing {len(missing)}, unexpected {len(unexpected)}, next epoch {next_epoch}")
     if rank == 0:
         print(f"done: {total_steps} steps/rank, total_loss {first['total_loss']:.4f} -> {last['total_loss']:.4f}")
     if world > 1:
