@@ -150,3 +150,36 @@ def test_planted_recognition_protocol_is_well_conditioned_on_the_oracle():
         top = lg.topk(2, dim=-1).values
         assert torch.equal(lg.argmax(-1), labels.view(-1)), key
         assert float((top[:, 0] - top[:, 1]).min()) > 1.0, (key, float((top[:, 0] - top[:, 1]).min()))
+
+
+def test_score_functions_equal_live_reference_when_staged():
+    """libs/vl_scores.py of the staged, unmodified reference next to the oracle's restatement on random inputs: MLM accuracy
+    over the labelled positions, argmax scoring of the ITM / category heads, PSNR; and the rank of candidate 0 as
+    engine_grid_masking.py:360-384 computes it (softmax, descending sort, position of index 0)."""
+    import importlib.util
+    import pytest
+    from baseline import ref_loader
+    path = os.path.join(ref_loader.REF_DIR, "libs", "vl_scores.py")
+    if not os.path.isfile(path):
+        pytest.skip("baseline/_ref not staged")
+    spec = importlib.util.spec_from_file_location("ref_vl_scores", path)
+    R = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(R)
+    g = torch.Generator().manual_seed(0)
+    for trial in range(8):
+        logits = torch.randn((3, 16, 50), generator=g)
+        target = torch.randint(0, 50, (3, 16), generator=g)
+        target[torch.rand((3, 16), generator=g) < 0.7] = -1
+        target[0, 0] = int(logits[0, 0].argmax())                   # at least one labelled (and correct) position
+        assert abs(O.compute_mlm_score(logits, target) - R.compute_mlm_score(logits, target)) < 1e-7
+        n_cls = (2, 48, 122)[trial % 3]
+        lg = torch.randn((9, n_cls), generator=g)
+        lab = torch.randint(0, n_cls, (9,), generator=g)
+        assert torch.equal(O.compute_score_with_logits(lg, lab), R.compute_score_with_logits(lg, lab))
+        a, b = torch.rand((2, 3, 32, 32), generator=g), torch.rand((2, 3, 32, 32), generator=g)
+        assert abs(O.compute_psnr(a, b) - R.compute_psnr(a, b)) < 1e-9
+        itm = torch.randn((101, 1, 2), generator=g)
+        p = torch.nn.functional.softmax(itm.view(-1, 2), dim=-1)
+        order = torch.sort(p[:, 1], dim=-1, descending=True)[1]
+        assert O.retrieval_rank(itm) == int(np.argwhere(order.numpy() == 0)[0, 0])
+    assert R.compute_psnr(a, a) == 100 == O.compute_psnr(a, a)
