@@ -449,3 +449,42 @@ def test_token_mask_bit_exact_vs_oracle_and_reference_golden():
         assert (ids[b] == i2).all() and (labels[b] == l2).all(), b
     frac = (labels != -1).sum() / (rows[:, 1:] > 102).sum()
     assert 0.13 < frac < 0.17
+
+
+def test_vl_scores_equal_live_reference_functions():
+    """mvlt_b200.libs.vl_scores (reductions in csrc/loss.cu) next to the staged, unmodified reference's
+    libs/vl_scores.py on the same CUDA tensors: MLM accuracy over labelled positions at the real vocabulary width, argmax scoring
+    of 2 / 48 / 122-way heads, the single-logit sigmoid branch, PSNR."""
+    import importlib.util
+    import os
+    from baseline import ref_loader
+    from mvlt_b200.libs import vl_scores as S
+    path = os.path.join(ref_loader.REF_DIR, "libs", "vl_scores.py")
+    if not os.path.isfile(path):
+        pytest.skip("baseline/_ref not staged")
+    spec = importlib.util.spec_from_file_location("ref_vl_scores_gpu", path)
+    R = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(R)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for trial in range(3):
+        logits = torch.randn((2, 64, 30522), generator=g, device="cuda")
+        target = torch.randint(0, 30522, (2, 64), generator=g, device="cuda")
+        target[torch.rand((2, 64), generator=g, device="cuda") < 0.6] = -1
+        am = logits.argmax(-1)
+        keep = torch.rand((2, 64), generator=g, device="cuda") < 0.5
+        target = torch.where((target != -1) & keep, am, target)        # about half of the labelled positions are "correct"
+        target[0, 0] = am[0, 0]
+        got, want = S.compute_mlm_score(logits, target), R.compute_mlm_score(logits, target)
+        assert 0.2 < want < 0.9 and abs(got - want) < 1e-6, (got, want)
+        for n_cls in (2, 48, 122):
+            lg = torch.randn((37, n_cls), generator=g, device="cuda")
+            lab = torch.where(torch.rand((37,), generator=g, device="cuda") < 0.5, lg.argmax(-1),
+                              torch.randint(0, n_cls, (37,), generator=g, device="cuda"))
+            assert torch.equal(S.compute_score_with_logits(lg, lab), R.compute_score_with_logits(lg, lab))
+        lg1 = torch.randn((11, 1), generator=g, device="cuda")
+        lab1 = torch.randint(0, 2, (11,), generator=g, device="cuda")
+        assert torch.equal(S.compute_score_with_logits(lg1, lab1), R.compute_score_with_logits(lg1, lab1))
+        a = torch.rand((2, 3, 256, 256), generator=g, device="cuda")
+        b = torch.rand((2, 3, 256, 256), generator=g, device="cuda")
+        assert abs(S.compute_psnr(a, b) - R.compute_psnr(a, b)) < 1e-3
+    assert S.compute_psnr(a, a) == 100 == R.compute_psnr(a, a)
