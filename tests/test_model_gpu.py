@@ -268,3 +268,30 @@ def test_supplied_mlm_count_is_a_claim_not_an_index_bound():
     assert float(over[6]) == float(base[6])                        # correct-prediction counter: padded rows never count
     assert torch.allclose(over[2:6], base[2:6], rtol=1e-4, atol=1e-6)
     assert torch.isfinite(under).all() and 0 < float(under[1]) * (n - 1) <= float(base[1]) * n * (1 + 1e-3), (under, base)
+
+
+def test_forward_logits_match_live_reference_model_on_the_same_gpu():
+    """No intermediary: the staged, unmodified reference model (baseline/_ref/libs/pvlt.py; fp32, eval) on the same GPU with the
+    same weights and the same batch, next to the sm_100a kernels (bf16 operands): every head's logits within the stated 2e-2."""
+    import contextlib
+    import io
+    from baseline import ref_loader
+    from oracle import pvlt_oracle as O
+    if not ref_loader.available():
+        pytest.skip("baseline/_ref not staged")
+    m, sd = _model(PRE)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = ref_loader.build_model("pvlt_tiny", PRE, state_dict=sd).cuda().eval()
+    batch = O.make_inputs(2, seed=7)
+    img, ids = batch["images"].cuda(), batch["input_ids"].cuda()
+    m.eval()
+    with torch.no_grad():
+        out = m(img, ids)
+        want = ref(img, ids)
+    errs = {}
+    for key in ("mlm_logits", "itm_logits", "t2i_logits"):
+        assert tuple(out[key].shape) == tuple(want[key].shape), key
+        errs[key] = _rel(out[key], want[key])
+    _report("fwd_vs_live_reference.json", errs)
+    assert max(errs.values()) <= 2e-2, errs
+    assert out["sup_cls_logits"] is None and want["sup_cls_logits"] is None
