@@ -207,3 +207,20 @@ def test_validated_defaults_are_the_ones_shipped():
         assert kernels.MLP_FUSED_DIMS == (64, 128) and kernels.MLP_FUSED_BWD_DIMS == (64,)
     src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "mvlt_b200", "csrc", "common.cuh")).read()
     assert "#define MVLT_PDL_DEFAULT 1" in src
+
+
+def test_split_k_heuristic_invariants():
+    """engine_util.split_k (dW = dy^T x and the vocabulary dH GEMMs): 1 <= s <= k-blocks / 4, more splits never leave the persistent
+    grid with fewer than one wave of work per split, long-K / tiny-output shapes are split, full-grid shapes are not."""
+    from mvlt_b200.engine_util import pick_block_n, split_k
+    shapes = [(64, 64, 540672), (128, 128, 147456), (320, 320, 49152), (512, 2048, 24576), (30522, 768, 896), (896, 768, 30522),
+              (192, 1728, 131072), (64, 48, 524288), (2, 768, 128), (147456, 128, 1024)]
+    for M, N, K in shapes:
+        s = split_k(M, N, K)
+        kb = (K + 63) // 64
+        assert 1 <= s <= max(1, kb // 4), (M, N, K, s)
+        assert s == split_k(M, N, K)
+    assert split_k(64, 64, 540672) > 32 and split_k(896, 768, 30522) > 1        # tiny outputs, long K: fill the 148 SMs
+    assert split_k(147456, 128, 1024) == 1 and split_k(30522, 768, 896) == 1     # already >= several waves of tiles
+    for n, want in ((64, 64), (192, 192), (320, 128), (512, 256), (768, 256), (1728, 192), (30522, 128)):
+        assert pick_block_n(n) == want, (n, pick_block_n(n), want)
